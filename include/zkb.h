@@ -1,0 +1,196 @@
+/* zkb — C ABI of the B200 batched out-of-circuit EraVM witness generator.
+ *
+ * The reference (matter-labs/era-zk_evm, crate zk_evm 1.4.1) has no FFI boundary: its seam is the generic
+ * `VmState<S, M, EV, PP, DP, WT>` (/root/reference/src/vm_state/mod.rs:157-207) driven by a caller loop
+ * `while !vm.execution_has_ended() { vm.cycle(&mut tracer)? }` (cycle.rs:257, mod.rs:214).  This header is what a
+ * Rust `-sys` crate would bind so that a `Vec<VmState<InMemoryStorage, SimpleMemory, InMemoryEventSink,
+ * DefaultPrecompilesProcessor, SimpleDecommitter, WT>>` plus that loop can be replaced by ONE batch object that
+ * lives on one B200 (see INTEGRATION.md for the Rust shim that replays the recorded streams into a
+ * `VmWitnessTracer` in the reference's callback order).
+ *
+ * Conventions: every function returns an int32 status (ZKB_OK == 0); no exceptions or callbacks cross the
+ * boundary; pointers are plain host pointers unless named `dptr`; U256 values cross as 32 big-endian bytes
+ * (the reference's own byte convention, src/utils.rs:12-15,36-48); a ZkbBatch is single-owner and
+ * non-reentrant, distinct batches may be driven from distinct threads.
+ */
+#ifndef ZKB_H
+#define ZKB_H
+#include <stdint.h>
+#include "zkb_records.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------------------------------- */
+enum ZkbStatus {
+  ZKB_OK = 0,
+  ZKB_ERR_INVALID_ARGUMENT = 1,
+  ZKB_ERR_CUDA = 2,
+  ZKB_ERR_OUT_OF_MEMORY = 3,
+  ZKB_ERR_UNKNOWN_BYTECODE = 4,
+  ZKB_ERR_NO_DEVICE = 5
+};
+
+/* per-VM status (ZkbVmStatus.code) */
+enum ZkbVmCode {
+  ZKB_VM_RUNNING = 0,               /* not finished: call zkb_run again to continue                               */
+  ZKB_VM_ENDED = 1,                 /* execution_has_ended() (mod.rs:214)                                         */
+  ZKB_VM_UNKNOWN_CODE_HASH = 2,     /* the crate's only Err: decommitter.rs:50-56 via far_call.rs:448             */
+  ZKB_VM_REFERENCE_PANIC = 3,       /* a reference assert!/expect would have fired (e.g. memory.rs:415-437,483)   */
+  ZKB_VM_CAP_STREAM = 16,           /* a per-VM stream slab is full                                               */
+  ZKB_VM_CAP_STACK = 17,            /* stack index beyond ZkbConfig.stack_words                                   */
+  ZKB_VM_CAP_HEAP = 18,             /* heap access beyond ZkbConfig.heap_bytes, or no free heap slab              */
+  ZKB_VM_CAP_DEPTH = 19,            /* callstack deeper than max_depth / max_far_depth                            */
+  ZKB_VM_CAP_STORAGE = 20,          /* per-VM storage table or rollback journal full                              */
+  ZKB_VM_CAP_PAGES = 21,            /* page-indirection / decommit-history table full                             */
+  ZKB_VM_UNSUPPORTED = 22           /* reached a precompile that is not implemented in this build                 */
+};
+
+/* ---- configuration ------------------------------------------------------------------------------- */
+typedef struct ZkbConfig {
+  uint32_t n_vms;
+  int32_t device;            /* CUDA device ordinal */
+  uint32_t witness_mode;     /* 1 = record all streams (recording tracer); 0 = DummyTracer (witness_trace/mod.rs:75) */
+  uint32_t cap_records[ZKB_N_STREAMS]; /* per-VM capacity of each stream, in records */
+  uint32_t stack_words;      /* per far frame; bounded analogue of MAX_STACK_PAGE_SIZE_IN_WORDS (memory.rs:176) */
+  uint32_t heap_bytes;       /* per heap page slab, multiple of 32 (reference heaps grow on demand, memory.rs:194) */
+  uint32_t n_heap_slabs;     /* heap + aux heap of live far frames + extended-lifetime returndata pages, <= 32 */
+  uint32_t max_far_depth;    /* far-call frames incl. bootloader */
+  uint32_t max_depth;        /* all frames (near + far) */
+  uint32_t storage_slots;    /* per-VM open-addressed storage table, power of two */
+  uint32_t journal_entries;  /* per-VM storage rollback journal (storage.rs:98-120) */
+  uint32_t host_mirror;      /* 1 = allocate pinned host mirrors for zkb_fetch_streams */
+  uint32_t reserved[4];
+} ZkbConfig;
+
+/* mirror of CallStackEntry (execution_stack.rs:6-24) */
+typedef struct ZkbFrame {
+  uint8_t this_address[20];
+  uint8_t msg_sender[20];
+  uint8_t code_address[20];
+  uint32_t base_memory_page;
+  uint32_t code_page;
+  uint16_t sp;
+  uint16_t pc;
+  uint16_t exception_handler_location;
+  uint16_t reserved0;
+  uint32_t ergs_remaining;
+  uint8_t this_shard_id;
+  uint8_t caller_shard_id;
+  uint8_t code_shard_id;
+  uint8_t is_static;
+  uint8_t is_local_frame;
+  uint8_t reserved1[3];
+  uint32_t context_u128_value[4];
+  uint32_t heap_bound;
+  uint32_t aux_heap_bound;
+} ZkbFrame;
+
+/* mirror of VmLocalState (vm_state/mod.rs:54-73) with the callstack flattened to its current entry + depth */
+typedef struct ZkbLocalState {
+  uint32_t previous_code_word[8];
+  uint32_t previous_code_memory_page;
+  uint32_t registers[15][8];
+  uint16_t register_is_pointer;   /* bit i = registers[i].is_pointer */
+  uint8_t flags;                  /* bit0 LT/OF, bit1 EQ, bit2 GT */
+  uint8_t pending_exception;
+  uint32_t timestamp;
+  uint32_t monotonic_cycle_counter;
+  uint32_t spent_pubdata_counter;
+  uint32_t memory_page_counter;
+  uint32_t absolute_execution_step;
+  uint32_t current_ergs_per_pubdata_byte;
+  uint16_t tx_number_in_block;
+  uint16_t previous_super_pc;
+  uint32_t context_u128_register[4];
+  uint32_t callstack_depth;
+  ZkbFrame current_frame;
+} ZkbLocalState;
+
+typedef struct ZkbVmStatus {
+  uint32_t code;     /* ZkbVmCode */
+  uint32_t cycles;   /* cycles executed so far (== monotonic_cycle_counter) */
+} ZkbVmStatus;
+
+typedef struct ZkbStorageInit {
+  uint8_t shard_id;
+  uint8_t reserved[3];
+  uint8_t address[20];
+  uint8_t key_be[32];
+  uint8_t value_be[32];
+} ZkbStorageInit;
+
+enum ZkbLocalField {
+  ZKB_FIELD_MEMORY_PAGE_COUNTER = 0,
+  ZKB_FIELD_ERGS_PER_PUBDATA = 1,
+  ZKB_FIELD_TX_NUMBER = 2,
+  ZKB_FIELD_TIMESTAMP = 3
+};
+
+typedef struct ZkbBatch ZkbBatch;
+
+/* ---- lifecycle: replaces VmState::empty_state for n_vms instances (mod.rs:188-207) --------------- */
+int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out);
+int32_t zkb_destroy(ZkbBatch* b);
+const char* zkb_last_error(void);
+/* re-initialise every VM to empty_state, keeping bytecodes / block properties (new batch, same allocation) */
+int32_t zkb_reset(ZkbBatch* b);
+
+/* ---- population ---------------------------------------------------------------------------------- */
+/* = SimpleDecommitter::populate (decommitter.rs:23-28); words are 32-byte big-endian code words */
+int32_t zkb_load_bytecode(ZkbBatch* b, const uint8_t hash_be[32], const uint8_t* words_be, uint32_t n_words);
+/* = BlockProperties (block_properties/mod.rs:4-7) */
+int32_t zkb_set_block_properties(ZkbBatch* b, const uint8_t default_aa_code_hash_be[32], uint8_t zkporter_is_available);
+/* = InMemoryStorage::populate (storage.rs:26-32).  per_vm == 0: the n entries are applied to every VM in
+ * [vm_lo, vm_hi); per_vm != 0: `entries` holds (vm_hi - vm_lo) * n records, n per VM. */
+int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const ZkbStorageInit* entries, uint32_t n,
+                             uint32_t per_vm);
+/* = SimpleMemory::populate_code (memory.rs:271-284): bind a code page number to a loaded bytecode */
+int32_t zkb_populate_code(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t page, const uint8_t hash_be[32]);
+/* = VmState::push_bootloader_context (helpers.rs:289-316) */
+int32_t zkb_push_bootloader_context(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const ZkbFrame* frame);
+/* = SimpleMemory::populate_heap (memory.rs:287-291) on the current (bootloader) frame's heap; bytes are the
+ * big-endian memory image.  per_vm as in zkb_populate_storage (n_bytes per VM). */
+int32_t zkb_populate_heap(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* bytes, uint32_t n_bytes,
+                          uint32_t per_vm);
+/* local_state.registers[reg] = value (reg 0-based, 0..14) */
+int32_t zkb_set_register(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t reg, const uint8_t value_be[32],
+                         uint8_t is_pointer, uint32_t per_vm);
+int32_t zkb_set_local_field(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t field, uint32_t value);
+
+/* ---- execution: replaces the caller's `while !ended { cycle() }` loop ----------------------------- */
+/* run every VM for at most max_cycles_per_vm further cycles (0 = until ended). Asynchronous on `cuda_stream`
+ * (a cudaStream_t, may be NULL); resumable. */
+int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream);
+int32_t zkb_sync(ZkbBatch* b);
+/* elapsed device time (ms, CUDA events on the launch stream) of the last zkb_run, valid after zkb_sync */
+int32_t zkb_last_run_ms(ZkbBatch* b, float* ms, uint32_t* n_kernel_launches);
+
+/* ---- results ------------------------------------------------------------------------------------- */
+int32_t zkb_vm_status(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, ZkbVmStatus* out);
+int32_t zkb_read_local_state(ZkbBatch* b, uint32_t vm, ZkbLocalState* out);
+/* per-VM record counts of one stream */
+int32_t zkb_stream_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out);
+/* total bytes over all streams and VMs (the "algorithmic bytes" of SURVEY.md §8d) and total cycles */
+int32_t zkb_totals(ZkbBatch* b, uint64_t* total_cycles, uint64_t stream_bytes[ZKB_N_STREAMS]);
+/* device view: VM v's records of `kind` start at dptr + v * stride_bytes */
+int32_t zkb_stream_device_view(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* stride_bytes);
+/* copy one VM's stream to host memory (at most max_bytes); returns the byte length in *n_bytes */
+int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
+/* pack every VM's stream `kind` contiguously (VM order) on the device and copy it to `host_dst`
+ * (must hold the stream's total bytes); offsets_out[n_vms + 1] receives the byte offset of each VM. */
+int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity,
+                                uint64_t* offsets_out);
+/* device-only variant: returns the packed device buffer (valid until the next run/fetch/destroy) */
+int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
+/* final storage value of one slot (== InMemoryStorage.inner lookup, storage.rs:9) */
+int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8_t address[20],
+                         const uint8_t key_be[32], uint8_t value_be_out[32]);
+/* read back memory of the current frame's heap (debug / tests; = dump_page_content, memory.rs:300-313) */
+int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n_bytes, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
