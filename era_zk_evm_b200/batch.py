@@ -1,0 +1,64 @@
+"""GpuVmBatch — the product entry point: n independent EraVM instances on one B200 behind the C ABI of
+include/zkb.h (`libzkb.so`, hand-written sm_100a CUDA).  Stands in for the reference's
+`Vec<VmState<InMemoryStorage, SimpleMemory, InMemoryEventSink, DefaultPrecompilesProcessor, SimpleDecommitter, WT>>`
+plus the caller loop `while !vm.execution_has_ended() { vm.cycle(&mut tracer)? }`
+(/root/reference/src/vm_state/mod.rs:157-216, cycle.rs:257).
+
+There is NO CPU fallback: construction raises if the CUDA extension is not built or no GPU is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _binding, records
+from ._binding import ZkbConfig, ZkbError  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb.so")
+_LIB = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library; never builds, never falls back."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZkbError(f"{LIB_PATH} is missing: run `python -m era_zk_evm_b200.build` (nvcc, sm_100a). "
+                           "This package has no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+    return _LIB
+
+
+class GpuVmBatch(_binding.Batch):
+    def __init__(self, cfg: ZkbConfig):
+        super().__init__(load_library(), "zkb_", cfg)
+        lib, vp, u32, u64 = self._lib, C.c_void_p, C.c_uint32, C.c_uint64
+        lib.zkb_stream_device_view.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+        lib.zkb_fetch_stream_packed.argtypes = [vp, u32, vp, u64, vp]
+        lib.zkb_pack_stream_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp]
+        for name in ("stream_device_view", "fetch_stream_packed", "pack_stream_device"):
+            getattr(lib, "zkb_" + name).restype = C.c_int32
+
+    def stream_device_view(self, kind: int):
+        p, stride = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.zkb_stream_device_view(self._h, kind, C.byref(p), C.byref(stride)))
+        return p.value, stride.value
+
+    def pack_stream_device(self, kind: int, stream=None):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.zkb_pack_stream_device(self._h, kind, C.byref(p), C.byref(n), stream))
+        return p.value, n.value
+
+    def fetch_stream_packed(self, kind: int, host_ptr: int | None = None, host_capacity: int = 0):
+        """All VMs' records of `kind`, VM-major, as (uint8 array or None, offsets[n_vms + 1])."""
+        offsets = np.zeros(self.n_vms + 1, dtype=np.uint64)
+        if host_ptr is None:
+            total = int(self.stream_counts(kind).astype(np.uint64).sum()) * records.RECORD_BYTES[kind]
+            buf = np.empty(max(total, 1), dtype=np.uint8)
+            self._check(self._lib.zkb_fetch_stream_packed(self._h, kind, buf.ctypes.data, buf.size, offsets.ctypes.data))
+            return buf[:total], offsets
+        self._check(self._lib.zkb_fetch_stream_packed(self._h, kind, host_ptr, host_capacity, offsets.ctypes.data))
+        return None, offsets

@@ -1,0 +1,1639 @@
+// The batched EraVM interpreter: ONE WARP = ONE VM for the whole run.
+//
+// Replaces (reference, /root/reference/src): vm_state/cycle.rs:19-429 (read_and_decode + cycle),
+// vm_state/mem_ops.rs:14-125, vm_state/helpers.rs:10-338, every handler in opcodes/execution/*.rs and the
+// backends reference_impls/{memory,decommitter}.rs + testing/storage.rs, re-designed for sm_100a:
+//   * opcode dispatch is warp-uniform; the 32 lanes are used for limb-parallel U256 arithmetic (u256.cuh),
+//     the 25-lane keccak state (keccak.cuh) and coalesced record stores;
+//   * architectural state lives in shared memory (15 x 256-bit registers, current frame, the "live" tail of
+//     the cycle row) and warp-uniform registers (pc, sp, ergs, flags, timestamp ...);
+//   * SimpleMemory's growable pages become bounded per-VM slabs in HBM (stack per far-call level, a pool of heap
+//     slabs with a free mask, a 16-entry page-indirection table), InMemoryStorage becomes a per-VM open-addressed
+//     table + one rollback journal whose frame marks give the reference's rollback semantics;
+//   * every VmWitnessTracer callback becomes a packed record (include/zkb_records.h) appended to the VM's stream
+//     slab: the 256-byte cycle row is one 8-byte store per lane, a LogQuery/Frame record one 4-byte store per lane.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/zkb.h"
+#define ZK_TABLE_QUALIFIER __device__ __constant__
+#include "isa_tables.inc"
+#include "keccak.cuh"
+#include "u256.cuh"
+
+namespace zkb {
+
+// ---------------------------------------------------------------------------------------------------
+// per-VM hot state as stored in HBM between runs (loaded into shared memory / registers by run_vm)
+// ---------------------------------------------------------------------------------------------------
+// frame layout (32 words) == ZkbFrameRec words 2..28, then device-only fields
+enum {
+  F_THIS = 0, F_SENDER = 5, F_CODE_ADDR = 10, F_BASE_PAGE = 15, F_CODE_PAGE = 16, F_SP_PC = 17, F_EH_SHARDS = 18,
+  F_ERGS = 19, F_MISC = 20 /* code_shard | is_static << 8 | is_local << 16 */, F_CTX = 21, F_HEAP_BOUND = 25,
+  F_AUX_BOUND = 26, F_CODE_ID = 27, F_JOURNAL_MARK = 28, F_FAR_LEVEL = 29
+};
+// live tail of the cycle row (row words 40..55), kept current in shared memory
+enum {
+  L_DEPTH = 40, L_SPENT_PUBDATA = 41, L_PAGE_COUNTER = 42, L_COUNTS = 43, L_CTX = 44, L_TX_PSP = 48, L_EPP = 49,
+  L_CODE_PAGE = 50, L_BASE_PAGE = 51, L_HEAP_BOUND = 52, L_AUX_BOUND = 53, L_EH_BITS = 54
+};
+enum {
+  X_TIMESTAMP = 0, X_CYCLE = 1, X_FLAGS = 2, X_PENDING = 3, X_STATUS = 4, X_PTRMASK = 5, X_PREV_CODE_PAGE = 6,
+  X_FAR_DEPTH = 7, X_JOURNAL_LEN = 8, X_N_DECOMMIT = 9, X_SLAB_FREE = 10, X_COUNT0 = 11 /* ..16 */, X_ABS_STEP = 17
+};
+
+struct VmHot {
+  uint32_t regs[16][8];  // regs[0] is the constant-zero r0
+  uint32_t F[32];
+  uint32_t live[16];
+  uint32_t prev_word[8];
+  uint32_t x[32];
+};
+
+#define ZKB_NO_SLAB 0xFFu
+#define ZKB_NO_CODE 0xFFFFFFFFu
+#define ZKB_PT_ENTRIES 16u
+#define ZKB_DEC_ENTRIES 16u
+#define ZKB_PT_FREE 0xFFFFFFFFu
+enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
+
+struct DevBatch {
+  uint32_t n_vms, witness;
+  uint32_t cap[ZKB_N_STREAMS];
+  uint32_t stack_words, heap_words, n_slabs, max_far_depth, max_depth, storage_slots, journal_entries;
+  const uint32_t* code_words;  // 8 u32 (LE limbs) per 256-bit code word, all bytecodes back to back
+  const uint32_t* code_meta;   // per bytecode: offset_words, len_words, hash limbs[8]
+  uint32_t n_codes;
+  uint32_t default_aa[8];
+  uint32_t zkporter;
+  VmHot* hot;
+  uint32_t* callstack;  // [vm][max_depth][32]
+  uint32_t* stack_mem;  // [vm][max_far_depth + 1][stack_words][8]
+  uint8_t* stack_ptr;   // [vm][max_far_depth + 1][stack_words]
+  uint32_t* heap_mem;   // [vm][n_slabs][heap_words][8]
+  uint32_t* lvl;        // [vm][max_far_depth + 1][4]: heap slab, aux slab, stack hwm, -
+  uint32_t* slab_hwm;   // [vm][n_slabs]   words touched
+  uint32_t* pt;         // [vm][16][2]     page, kind | slab << 8 | cleanup_level << 16
+  uint32_t* dec;        // [vm][16][2]     code id, page
+  uint32_t* st_tags;    // [vm][slots]
+  uint32_t* st_keys;    // [vm][slots][8]
+  uint32_t* st_addr;    // [vm][slots][8]  5 address words, shard, -, -
+  uint32_t* st_vals;    // [vm][slots][8]
+  uint32_t* j_slot;     // [vm][journal]
+  uint32_t* j_val;      // [vm][journal][8]
+  uint8_t* streams[ZKB_N_STREAMS];
+  unsigned int* queue;
+};
+
+__device__ __forceinline__ uint32_t rec_bytes(int kind) {
+  return kind == ZKB_STREAM_ROWS ? ZKB_ROW_BYTES : kind == ZKB_STREAM_MEM ? ZKB_MEM_BYTES : kind == ZKB_STREAM_LOG ? ZKB_LOG_BYTES
+         : kind == ZKB_STREAM_DECOMMIT ? ZKB_DECOMMIT_BYTES : kind == ZKB_STREAM_FRAME ? ZKB_FRAME_BYTES : ZKB_REFUND_BYTES;
+}
+
+// shared memory per warp
+struct WarpSmem {
+  uint32_t regs[16][8];
+  uint32_t row[64];
+  uint32_t F[32];
+  uint32_t kbuf[64];
+};
+
+struct Vm {
+  const DevBatch& B;
+  WarpSmem& S;
+  const uint32_t vm;
+  const uint32_t lane;
+  // warp-uniform registers
+  uint32_t pc, sp, ergs, flags, timestamp, cycle, pending, ptr_mask, status;
+  uint32_t prev_code_page, far_depth, journal_len, n_decommit, slab_free;
+  uint32_t count[ZKB_N_STREAMS];
+  uint32_t rowbits;
+  uint32_t cm, cl, cd, cf, cr;  // per-cycle record counts
+  const uint32_t* code;
+  uint32_t code_len;
+  u256l prev_word;  // distributed
+  // decoded opcode (warp-uniform)
+  uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
+  uint32_t dst_loc_valid, dst_loc_index;
+  // per-VM global bases
+  uint32_t* g_stack;
+  uint8_t* g_stack_ptr;
+  uint32_t* g_heap;
+  uint32_t* g_lvl;
+  uint32_t* g_slab_hwm;
+  uint32_t* g_pt;
+
+  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {
+    g_stack = B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8;
+    g_stack_ptr = B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words;
+    g_heap = B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8;
+    g_lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
+    g_slab_hwm = B.slab_hwm + (size_t)vm * B.n_slabs;
+    g_pt = B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2;
+  }
+
+  // ---- small helpers -------------------------------------------------------------------------------
+  __device__ __forceinline__ void fail(uint32_t code) {
+    if (status == ZKB_VM_RUNNING) status = code;
+  }
+  __device__ __forceinline__ uint32_t L(int w) const { return S.row[w]; }
+  __device__ __forceinline__ void setL(int w, uint32_t v) {
+    if (lane == 0) S.row[w] = v;
+    __syncwarp();
+  }
+  __device__ __forceinline__ bool is_kernel() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_KERNEL; }
+  __device__ __forceinline__ bool is_static() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_STATIC; }
+  __device__ __forceinline__ bool is_local() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_LOCAL; }
+  __device__ __forceinline__ u256l reg_read(uint32_t idx) const { return lane < 8 ? S.regs[idx][lane] : 0u; }
+  __device__ __forceinline__ void reg_write(uint32_t idx, u256l v, bool is_ptr) {
+    if (idx != 0) {
+      if (lane < 8) S.regs[idx][lane] = v;
+      ptr_mask = (ptr_mask & ~(1u << idx)) | ((is_ptr ? 1u : 0u) << idx);
+      __syncwarp();
+    }
+  }
+  // address (5 LE-loaded words holding 20 BE bytes, in lanes 0..4) <-> U256 (address_to_u256, utils.rs:29-41)
+  __device__ __forceinline__ u256l addr_words_to_u256(uint32_t aw) const {
+    uint32_t v = __shfl_sync(ZK_FULL, aw, (4 - (int)lane) & 31);
+    return lane < 5 ? bswap32(v) : 0u;
+  }
+  __device__ __forceinline__ uint32_t u256_to_addr_words(u256l v) const {
+    uint32_t x = __shfl_sync(ZK_FULL, v, (4 - (int)lane) & 31);
+    return lane < 5 ? bswap32(x) : 0u;
+  }
+
+  // ---- record emission (VmWitnessTracer callbacks -> packed records) ---------------------------------
+  __device__ __forceinline__ uint8_t* stream_slot(int kind) {
+    uint32_t n = count[kind];
+    if (n >= B.cap[kind]) {
+      fail(ZKB_VM_CAP_STREAM);
+      return nullptr;
+    }
+    count[kind] = n + 1;
+    if (!B.witness) return nullptr;
+    return B.streams[kind] + ((size_t)vm * B.cap[kind] + n) * rec_bytes(kind);
+  }
+
+  // witness_tracer.add_memory_query (helpers.rs:36,70,111) / precompile memory witness (helpers.rs:215-221)
+  __device__ __forceinline__ void emit_mem(uint32_t ts, uint32_t page, uint32_t index, uint32_t mtype, uint32_t rw, uint32_t is_ptr,
+                                           uint32_t origin, u256l value) {
+    cm++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_MEM);
+    uint32_t v = __shfl_sync(ZK_FULL, value, (lane - 4) & 31);
+    if (p) {
+      uint32_t w = lane == 0 ? ts : lane == 1 ? page : lane == 2 ? index : lane == 3 ? (mtype | rw << 8 | is_ptr << 16 | origin << 24) : v;
+      if (lane < 12) p[lane] = w;
+    }
+  }
+
+  // witness_tracer.add_log_query (helpers.rs:151,161,208); aw = address words in lanes 0..4
+  __device__ __forceinline__ void emit_log(uint32_t ts, uint32_t aux, uint32_t shard, uint32_t aw, uint32_t rw, uint32_t is_service,
+                                           u256l key, u256l read_value, u256l written_value) {
+    cl++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_LOG);
+    uint32_t tx = S.row[L_TX_PSP] & 0xFFFFu;
+    uint32_t a = __shfl_sync(ZK_FULL, aw, (lane - 2) & 31);
+    uint32_t k = __shfl_sync(ZK_FULL, key, (lane - 8) & 31);
+    uint32_t r = __shfl_sync(ZK_FULL, read_value, (lane - 16) & 31);
+    uint32_t wv = __shfl_sync(ZK_FULL, written_value, (lane - 24) & 31);
+    if (p) {
+      uint32_t w = lane == 0 ? ts : lane == 1 ? (tx | aux << 16 | shard << 24) : lane < 7 ? a : lane == 7 ? (rw | is_service << 16) : lane < 16 ? k : lane < 24 ? r : wv;
+      p[lane] = w;
+    }
+  }
+
+  // witness_tracer.add_decommittment (helpers.rs:185-191)
+  __device__ __forceinline__ void emit_decommit(uint32_t ts, uint32_t page, uint32_t len, uint32_t fresh, u256l hash) {
+    cd++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_DECOMMIT);
+    uint32_t v = __shfl_sync(ZK_FULL, hash, (lane - 4) & 31);
+    if (p) {
+      uint32_t w = lane == 0 ? ts : lane == 1 ? page : lane == 2 ? ((len & 0xFFFFu) | fresh << 16) : lane == 3 ? 0u : v;
+      if (lane < 12) p[lane] = w;
+    }
+  }
+
+  // witness_tracer.record_refund_for_query (helpers.rs:130-134); InMemoryStorage => RefundType::None (storage.rs:80-86)
+  __device__ __forceinline__ void emit_refund() {
+    cr++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_REFUND);
+    if (p && lane < 2) p[lane] = 0u;
+  }
+
+  // start_new_execution_context (helpers.rs:237-241): the new frame must already be in S.F
+  __device__ __forceinline__ void emit_frame_start(uint32_t prev_ergs, uint32_t prev_pc, uint32_t prev_sp) {
+    cf++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
+    if (p) {
+      uint32_t w = lane == 0 ? ZKB_FRAMEKIND_START : lane == 1 ? cycle : lane < 29 ? S.F[(lane - 2) & 31] : lane == 29 ? prev_ergs
+                   : lane == 30 ? (prev_pc | prev_sp << 16) : 0u;
+      p[lane] = w;
+    }
+  }
+  // finish_execution_context (helpers.rs:258-259)
+  __device__ __forceinline__ void emit_frame_finish(bool panicked) {
+    cf++;
+    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
+    if (p) p[lane] = lane == 0 ? (ZKB_FRAMEKIND_FINISH | (panicked ? 1u : 0u) << 8) : lane == 1 ? cycle : 0u;
+  }
+
+  // ---- stack page of the current far level (SimpleMemory stack_pages, memory.rs:412-437) ----------
+  __device__ __forceinline__ u256l stack_read(uint32_t index, uint32_t& is_ptr) {
+    is_ptr = 0;
+    if (index >= B.stack_words) return 0u;  // never written (writes beyond the cap stop the VM) => still zero
+    size_t off = (size_t)far_depth * B.stack_words + index;
+    is_ptr = g_stack_ptr[off];
+    return lane < 8 ? g_stack[off * 8 + lane] : 0u;
+  }
+  __device__ __forceinline__ void stack_write(uint32_t index, u256l v, uint32_t is_ptr) {
+    if (index >= B.stack_words) {
+      fail(ZKB_VM_CAP_STACK);
+      return;
+    }
+    size_t off = (size_t)far_depth * B.stack_words + index;
+    if (lane < 8) g_stack[off * 8 + lane] = v;
+    if (lane == 8) g_stack_ptr[off] = (uint8_t)is_ptr;
+    uint32_t hwm = g_lvl[far_depth * 4 + 2];
+    if (index + 1 > hwm && lane == 0) g_lvl[far_depth * 4 + 2] = index + 1;
+    __syncwarp();
+  }
+
+  // ---- heap slabs (SimpleMemory heaps / pages_with_extended_lifetime, memory.rs:439-521) ----------
+  __device__ __forceinline__ uint32_t slab_alloc() {
+    if (slab_free == 0) {
+      fail(ZKB_VM_CAP_HEAP);
+      return ZKB_NO_SLAB;
+    }
+    uint32_t s = __ffs(slab_free) - 1;
+    slab_free &= ~(1u << s);
+    return s;
+  }
+  __device__ __forceinline__ void slab_release(uint32_t s) {
+    if (s == ZKB_NO_SLAB) return;
+    uint32_t hwm = g_slab_hwm[s];
+    uint32_t* base = g_heap + (size_t)s * B.heap_words * 8;
+    for (uint32_t i = lane; i < hwm * 8; i += 32) base[i] = 0u;  // == heap_on_return fill (memory.rs:181-183)
+    if (lane == 0) g_slab_hwm[s] = 0;
+    slab_free |= 1u << s;
+    __syncwarp();
+  }
+  __device__ __forceinline__ u256l slab_read(uint32_t s, uint32_t word) {
+    if (s == ZKB_NO_SLAB || word >= B.heap_words) return 0u;
+    return lane < 8 ? g_heap[((size_t)s * B.heap_words + word) * 8 + lane] : 0u;
+  }
+  __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
+    if (lane < 8) g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
+    if (word + 1 > g_slab_hwm[s] && lane == 0) g_slab_hwm[s] = word + 1;
+    __syncwarp();
+  }
+  // slab of the current frame's heap (which = 0) / aux heap (which = 1); allocate lazily on first write
+  __device__ __forceinline__ uint32_t cur_slab(uint32_t which, bool for_write, uint32_t word) {
+    uint32_t s = g_lvl[far_depth * 4 + which];
+    if (for_write) {
+      if (word >= B.heap_words) {
+        fail(ZKB_VM_CAP_HEAP);
+        return ZKB_NO_SLAB;
+      }
+      if (s == ZKB_NO_SLAB) {
+        s = slab_alloc();
+        if (lane == 0) g_lvl[far_depth * 4 + which] = s;
+        __syncwarp();
+      }
+    }
+    return s;
+  }
+
+  // ---- page indirections (SimpleMemory.page_numbers_indirections, memory.rs:160-171,475-521) ------
+  __device__ __forceinline__ int pt_find(uint32_t page) {
+    uint32_t p = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2] : ZKB_PT_FREE;
+    uint32_t m = __ballot_sync(ZK_FULL, p == page);
+    return m ? __ffs(m) - 1 : -1;
+  }
+  __device__ __forceinline__ void pt_upsert(uint32_t page, uint32_t kind, uint32_t slab_or_level, uint32_t cleanup_level) {
+    int e = pt_find(page);
+    if (e < 0) e = pt_find(ZKB_PT_FREE);
+    if (e < 0) {
+      fail(ZKB_VM_CAP_PAGES);
+      return;
+    }
+    if (lane == 0) {
+      g_pt[e * 2] = page;
+      g_pt[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
+    }
+    __syncwarp();
+  }
+  // fat-pointer read of one word (memory.rs:475-521); ok = false => reference panic (unreachable page)
+  __device__ __forceinline__ u256l fatptr_read(uint32_t page, uint32_t word, bool& ok) {
+    ok = true;
+    if (page == 0) return 0u;  // Indirection::Empty (memory.rs:226)
+    int e = pt_find(page);
+    if (e < 0) {
+      ok = false;
+      return 0u;
+    }
+    uint32_t info = g_pt[e * 2 + 1];
+    uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
+    uint32_t s = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+    return slab_read(s, word);
+  }
+
+  // ---- storage (InMemoryStorage, storage.rs:88-186) ----------------------------------------------
+  // aw: address words in lanes 0..4.  Returns the previous value; on writes stores `nv` and journals.
+  __device__ __forceinline__ u256l storage_access(uint32_t shard, uint32_t aw, u256l key, bool is_write, u256l nv, bool journal) {
+    uint32_t* tags = B.st_tags + (size_t)vm * B.storage_slots;
+    uint32_t* keys = B.st_keys + (size_t)vm * B.storage_slots * 8;
+    uint32_t* addrs = B.st_addr + (size_t)vm * B.storage_slots * 8;
+    uint32_t* vals = B.st_vals + (size_t)vm * B.storage_slots * 8;
+    // lanes 0..7 carry the key, lanes 8..12 the address, lane 13 the shard
+    uint32_t a_sh = __shfl_sync(ZK_FULL, aw, (lane - 8) & 31);
+    uint32_t ident = lane < 8 ? key : lane < 13 ? a_sh : lane == 13 ? shard : 0u;
+    uint32_t h = (ident + 0x9E3779B9u * (lane + 1u)) * 0x85EBCA6Bu;
+    h ^= h >> 15;
+    h *= 0xC2B2AE35u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) h += __shfl_xor_sync(ZK_FULL, h, o) * 0x27D4EB2Fu + (h >> 13);
+    h = __shfl_sync(ZK_FULL, h, 0);
+    uint32_t tag = h | 0x80000000u;
+    uint32_t mask = B.storage_slots - 1;
+    int found = -1, insert_at = -1;
+    for (uint32_t base = 0; base < B.storage_slots && found < 0 && insert_at < 0; base += 32) {
+      uint32_t idx = (h + base + lane) & mask;
+      uint32_t t = tags[idx];
+      uint32_t m_match = __ballot_sync(ZK_FULL, t == tag);
+      uint32_t m_empty = __ballot_sync(ZK_FULL, t == 0u);
+      uint32_t before_empty = m_empty ? ((1u << (__ffs(m_empty) - 1)) - 1u) : 0xFFFFFFFFu;
+      m_match &= before_empty;
+      while (m_match) {
+        int c = __ffs(m_match) - 1;
+        m_match &= m_match - 1;
+        uint32_t ci = (h + base + c) & mask;
+        uint32_t stored = lane < 8 ? keys[ci * 8 + lane] : lane < 14 ? addrs[ci * 8 + lane - 8] : 0u;
+        if (__all_sync(ZK_FULL, stored == ident)) {
+          found = (int)ci;
+          break;
+        }
+      }
+      if (found < 0 && m_empty) insert_at = (int)((h + base + __ffs(m_empty) - 1) & mask);
+    }
+    u256l old = 0u;
+    if (found >= 0) old = lane < 8 ? vals[found * 8 + lane] : 0u;
+    if (is_write) {
+      int slot = found;
+      if (slot < 0) {
+        if (insert_at < 0) {
+          fail(ZKB_VM_CAP_STORAGE);
+          return 0u;
+        }
+        slot = insert_at;
+        if (lane < 8) keys[slot * 8 + lane] = ident;
+        else if (lane < 14) addrs[slot * 8 + lane - 8] = ident;
+        if (lane == 14) tags[slot] = tag;
+      }
+      if (lane < 8) vals[slot * 8 + lane] = nv;
+      if (journal) {
+        if (journal_len >= B.journal_entries) {
+          fail(ZKB_VM_CAP_STORAGE);
+        } else {
+          uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
+          uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
+          if (lane < 8) jv[journal_len * 8 + lane] = old;
+          if (lane == 8) js[journal_len] = (uint32_t)slot;
+          journal_len++;
+        }
+      }
+      __syncwarp();
+    }
+    return old;
+  }
+  // storage.finish_frame(panicked = true): undo the frame's writes in reverse (storage.rs:156-176)
+  __device__ __forceinline__ void storage_rollback(uint32_t mark) {
+    uint32_t* vals = B.st_vals + (size_t)vm * B.storage_slots * 8;
+    const uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
+    const uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
+    while (journal_len > mark) {
+      journal_len--;
+      uint32_t slot = js[journal_len];
+      if (lane < 8) vals[slot * 8 + lane] = jv[journal_len * 8 + lane];
+      __syncwarp();
+    }
+  }
+
+  // ---- frames --------------------------------------------------------------------------------------
+  // sync the register/row-resident fields of the current frame into S.F
+  __device__ __forceinline__ void sync_frame_to_F() {
+    if (lane == 0) {
+      S.F[F_SP_PC] = sp | pc << 16;
+      S.F[F_ERGS] = ergs;
+      S.F[F_BASE_PAGE] = S.row[L_BASE_PAGE];
+      S.F[F_CODE_PAGE] = S.row[L_CODE_PAGE];
+      S.F[F_HEAP_BOUND] = S.row[L_HEAP_BOUND];
+      S.F[F_AUX_BOUND] = S.row[L_AUX_BOUND];
+      S.F[F_EH_SHARDS] = (S.F[F_EH_SHARDS] & 0xFFFF0000u) | (S.row[L_EH_BITS] & 0xFFFFu);
+    }
+    __syncwarp();
+  }
+  // derive the register/row-resident fields from S.F (after a push of a new frame or a pop)
+  __device__ __forceinline__ void load_frame_from_F() {
+    __syncwarp();
+    uint32_t sp_pc = S.F[F_SP_PC];
+    sp = sp_pc & 0xFFFFu;
+    pc = sp_pc >> 16;
+    ergs = S.F[F_ERGS];
+    uint32_t misc = S.F[F_MISC];
+    bool kernel = S.F[0] == 0 && S.F[1] == 0 && S.F[2] == 0 && S.F[3] == 0 && (S.F[4] & 0xFFFFu) == 0;  // execution_stack.rs:83-87
+    uint32_t bits = (((misc >> 8) & 1u) ? ZKB_FRAMEBIT_STATIC : 0u) | (((misc >> 16) & 1u) ? ZKB_FRAMEBIT_LOCAL : 0u) | (kernel ? ZKB_FRAMEBIT_KERNEL : 0u);
+    if (lane == 0) {
+      S.row[L_BASE_PAGE] = S.F[F_BASE_PAGE];
+      S.row[L_CODE_PAGE] = S.F[F_CODE_PAGE];
+      S.row[L_HEAP_BOUND] = S.F[F_HEAP_BOUND];
+      S.row[L_AUX_BOUND] = S.F[F_AUX_BOUND];
+      S.row[L_EH_BITS] = (S.F[F_EH_SHARDS] & 0xFFFFu) | bits << 16;
+    }
+    uint32_t id = S.F[F_CODE_ID];
+    if (id == ZKB_NO_CODE) {
+      code = nullptr;
+      code_len = 0;
+    } else {
+      code = B.code_words + (size_t)B.code_meta[id * 10] * 8;
+      code_len = B.code_meta[id * 10 + 1];
+    }
+    far_depth = S.F[F_FAR_LEVEL];
+    __syncwarp();
+  }
+  // vm_state.start_frame (helpers.rs:225-246) for a frame already described in `nf` (lane i holds word i)
+  __device__ __forceinline__ void push_frame(uint32_t nf) {
+    uint32_t depth = S.row[L_DEPTH];
+    if (depth >= B.max_depth) {
+      fail(ZKB_VM_CAP_DEPTH);
+      return;
+    }
+    sync_frame_to_F();
+    uint32_t prev_ergs = ergs, prev_pc = pc, prev_sp = sp;
+    B.callstack[((size_t)vm * B.max_depth + depth) * 32 + lane] = S.F[lane];
+    __syncwarp();
+    S.F[lane] = nf;
+    __syncwarp();
+    if (lane == 0) {
+      S.F[F_JOURNAL_MARK] = journal_len;  // storage.start_frame / event_sink.start_frame
+      S.row[L_DEPTH] = depth + 1;
+    }
+    __syncwarp();
+    emit_frame_start(prev_ergs, prev_pc, prev_sp);
+    load_frame_from_F();
+  }
+  // vm_state.finish_frame (helpers.rs:248-264); leaves the finished frame in S.kbuf[0..31], the parent in S.F
+  __device__ __forceinline__ void pop_frame(bool panicked) {
+    sync_frame_to_F();
+    if (panicked) storage_rollback(S.F[F_JOURNAL_MARK]);
+    emit_frame_finish(panicked);
+    uint32_t depth = S.row[L_DEPTH];
+    S.kbuf[lane] = S.F[lane];
+    __syncwarp();
+    S.F[lane] = B.callstack[((size_t)vm * B.max_depth + depth - 1) * 32 + lane];
+    if (lane == 0) S.row[L_DEPTH] = depth - 1;
+    __syncwarp();
+    load_frame_from_F();
+  }
+
+  // ---- operand write-back (helpers.rs:266-287) ------------------------------------------------------
+  __device__ __forceinline__ void dst0_update(u256l v, bool is_ptr) {
+    if (lane < 8) S.row[24 + lane] = v;
+    rowbits |= ZKB_ROWBIT_DST0_VALID | (is_ptr ? ZKB_ROWBIT_DST0_PTR : 0u);
+    if (dst_loc_valid) {
+      stack_write(dst_loc_index, v, is_ptr ? 1u : 0u);
+      emit_mem(timestamp + 3, L(L_BASE_PAGE) + 1, dst_loc_index, ZK_MEM_STACK, 1, is_ptr ? 1u : 0u, ZKB_MEMORIGIN_VM, v);
+    } else {
+      reg_write(dst0_reg, v, is_ptr);
+    }
+  }
+  __device__ __forceinline__ void dst1_update(u256l v, bool is_ptr) {
+    if (lane < 8) S.row[32 + lane] = v;
+    rowbits |= ZKB_ROWBIT_DST1_VALID | (is_ptr ? ZKB_ROWBIT_DST1_PTR : 0u);
+    reg_write(dst1_reg, v, is_ptr);
+  }
+
+  // handlers
+  __device__ void op_context(uint32_t sub, u256l src0);
+  __device__ void op_shift(uint32_t sub, u256l src0, u256l src1);
+  __device__ void op_ptr(uint32_t sub, u256l src0, u256l src1, bool src0_ptr, bool src1_ptr);
+  __device__ void op_near_call(u256l src0, uint32_t new_pc);
+  __device__ void op_log(uint32_t sub, u256l src0, u256l src1);
+  __device__ void op_far_call(uint32_t sub, u256l src0, u256l src1, bool src0_ptr, uint32_t new_pc, bool kernel_mode);
+  __device__ void op_ret(uint32_t sub, u256l src0, bool src0_ptr);
+  __device__ void op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr);
+  __device__ void keccak_precompile(u256l abi);
+  __device__ void memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page);
+  __device__ void memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page);
+  __device__ void cycle_once();
+};
+
+// ===================================================================================================
+// one VM cycle (cycle.rs:19-429)
+// ===================================================================================================
+__device__ __forceinline__ void Vm::cycle_once() {
+  const uint32_t row_cycle = cycle, row_ts = timestamp, pc_before = pc;
+  if (lane < 16) S.row[24 + lane] = 0u;  // dst0 / dst1 fields default to zero
+  rowbits = 0;
+  cm = cl = cd = cf = cr = 0;
+  dst_loc_valid = 0;
+
+  // ---- fetch (cycle.rs:46-130) ----
+  const uint32_t code_page = S.row[L_CODE_PAGE];
+  const uint32_t super_pc = pc >> 2, sub_pc = pc & 3u;
+  uint32_t prev_super_pc = S.row[L_TX_PSP] >> 16;
+  uint32_t raw_lo, raw_hi;
+  if (!pending) {
+    if (code_page != prev_code_page || prev_super_pc != super_pc) {
+      u256l w = (lane < 8 && super_pc < code_len) ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
+      prev_word = w;
+      prev_super_pc = super_pc;
+      emit_mem(timestamp, code_page, super_pc, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, w);
+    }
+    raw_lo = __shfl_sync(ZK_FULL, prev_word, 6 - 2 * (int)sub_pc);
+    raw_hi = __shfl_sync(ZK_FULL, prev_word, 7 - 2 * (int)sub_pc);
+  } else {
+    pending = 0;
+    prev_super_pc = super_pc;
+    raw_lo = (uint32_t)ZK_EXCEPTION_REVERT_ENCODING;
+    raw_hi = 0;
+  }
+  prev_code_page = code_page;
+
+  // ---- decode, price, exceptions, condition (cycle.rs:132-217) ----
+  uint32_t vidx = raw_lo & ((1u << ZK_VARIANT_BITS) - 1u);
+  entry = ZK_OPCODE_TABLE[vidx];
+  uint32_t price = ZK_OPCODE_PRICES[vidx];
+  uint32_t cond = (raw_lo >> ZK_COND_SHIFT) & 7u;
+  uint32_t src0_reg = (raw_lo >> 16) & 15u, src1_reg = (raw_lo >> 20) & 15u;
+  dst0_reg = (raw_lo >> 24) & 15u;
+  dst1_reg = raw_lo >> 28;
+  imm0 = raw_hi & 0xFFFFu;
+  imm1 = raw_hi >> 16;
+  uint32_t err = (entry & ZK_E_INVALID) ? 1u : 0u;
+  if (ergs < price) {
+    ergs = 0;
+    err |= 2u;
+  } else {
+    ergs -= price;
+  }
+  const uint32_t fbits = S.row[L_EH_BITS] >> 16;
+  const bool kernel_mode = fbits & ZKB_FRAMEBIT_KERNEL;
+  if ((entry & ZK_E_KERNEL_ONLY) && !kernel_mode) err |= 4u;
+  if ((entry & ZK_E_STATIC_FORBIDDEN) && (fbits & ZKB_FRAMEBIT_STATIC)) err |= 8u;
+  if (S.row[L_DEPTH] == ZK_VM_MAX_STACK_DEPTH) err |= 16u;
+  if (err) {
+    vidx = ZK_PANIC_VARIANT_IDX;
+    entry = ZK_OPCODE_TABLE[ZK_PANIC_VARIANT_IDX];
+    cond = 0;
+    src0_reg = src1_reg = dst0_reg = dst1_reg = 0;
+    imm0 = imm1 = 0;
+  }
+  // flags: bit0 LT/OF, bit1 EQ, bit2 GT.  cond -> mask of flag bits that satisfy it (Ne handled apart)
+  const uint32_t cond_mask = cond == 1 ? 4u : cond == 2 ? 1u : cond == 3 ? 2u : cond == 4 ? 6u : cond == 5 ? 3u : cond == 7 ? 5u : 0u;
+  bool resolved = cond == 0 ? true : cond == 6 ? !(flags & 2u) : (flags & cond_mask) != 0;
+  if (!resolved && !err) {
+    vidx = ZK_NOP_VARIANT_IDX;
+    entry = ZK_OPCODE_TABLE[ZK_NOP_VARIANT_IDX];
+    src0_reg = src1_reg = dst0_reg = dst1_reg = 0;
+    imm0 = imm1 = 0;
+  }
+  // delayed changes (mod.rs:134-153): previous_super_pc lives in the row tail
+  __syncwarp();
+  if (lane == 0) S.row[L_TX_PSP] = (S.row[L_TX_PSP] & 0xFFFFu) | prev_super_pc << 16;
+
+  // ---- operand addressing (mem_ops.rs:14-125, cycle.rs:275-345) ----
+  const uint32_t family = entry & 15u, sub = (entry >> ZK_E_SUB_SHIFT) & 15u;
+  const uint32_t src_mode = (entry >> ZK_E_SRC_SHIFT) & 7u, dst_mode = (entry >> ZK_E_DST_SHIFT) & 3u;
+  u256l src0 = reg_read(src0_reg);
+  uint32_t src0_ptr = (ptr_mask >> src0_reg) & 1u;
+  if (src_mode != ZK_SRC_REG) {
+    uint32_t vaddr = (__shfl_sync(ZK_FULL, src0, 0) + imm0) & 0xFFFFu;
+    if (src_mode == ZK_SRC_IMM) {
+      src0 = lane == 0 ? imm0 : 0u;
+      src0_ptr = 0;
+    } else {
+      uint32_t index;
+      if (src_mode == ZK_SRC_STACK_POP) {
+        sp = (sp - vaddr) & 0xFFFFu;
+        index = sp;
+      } else if (src_mode == ZK_SRC_STACK_REL) {
+        index = (sp - vaddr) & 0xFFFFu;
+      } else {
+        index = vaddr;  // absolute stack or code page
+      }
+      if (family == ZK_OP_NOP) {
+        src0 = 0u;  // NOP moves SP but never reads (cycle.rs:298-301)
+        src0_ptr = 0;
+      } else if (src_mode == ZK_SRC_CODE) {
+        src0 = (lane < 8 && index < code_len) ? __ldg(code + (size_t)index * 8 + lane) : 0u;
+        src0_ptr = 0;
+        emit_mem(timestamp, code_page, index, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, src0);
+      } else {
+        src0 = stack_read(index, src0_ptr);
+        emit_mem(timestamp, L(L_BASE_PAGE) + 1, index, ZK_MEM_STACK, 0, src0_ptr, ZKB_MEMORIGIN_VM, src0);
+      }
+    }
+  }
+  if (dst_mode != ZK_DST_REG) {
+    uint32_t vaddr = (S.regs[dst0_reg][0] + imm1) & 0xFFFFu;
+    if (dst_mode == ZK_DST_STACK_PUSH) {
+      dst_loc_index = sp;
+      sp = (sp + vaddr) & 0xFFFFu;
+    } else if (dst_mode == ZK_DST_STACK_REL) {
+      dst_loc_index = (sp - vaddr) & 0xFFFFu;
+    } else {
+      dst_loc_index = vaddr;
+    }
+    dst_loc_valid = 1;
+  }
+  u256l src1 = reg_read(src1_reg);
+  uint32_t src1_ptr = (ptr_mask >> src1_reg) & 1u;
+  if (entry & ZK_E_SWAP) {
+    u256l t = src0;
+    src0 = src1;
+    src1 = t;
+    uint32_t tp = src0_ptr;
+    src0_ptr = src1_ptr;
+    src1_ptr = tp;
+  }
+  const uint32_t new_pc = (pc + 1u) & 0xFFFFu;
+  rowbits |= (src0_ptr ? ZKB_ROWBIT_SRC0_PTR : 0u) | (src1_ptr ? ZKB_ROWBIT_SRC1_PTR : 0u);
+  // erase_fat_pointer_metadata (cycle.rs:374-396)
+  if (!(entry & ZK_E_SRC0_PTR_OK) && src0_ptr && !kernel_mode) {
+    src0 = lane < 4 ? src0 : 0u;
+    src0_ptr = 0;
+  }
+  if (!(entry & ZK_E_SRC1_PTR_OK) && src1_ptr && !kernel_mode) {
+    src1 = lane < 4 ? src1 : 0u;
+    src1_ptr = 0;
+  }
+  if (lane < 8) {
+    S.row[8 + lane] = src0;
+    S.row[16 + lane] = src1;
+  }
+  const bool set_flags = entry & ZK_E_FLAG0;
+
+  // ---- dispatch (parsing.rs:47-79) ----
+  switch (family) {
+    case ZK_OP_NOP:  // noop.rs
+      pc = new_pc;
+      break;
+    case ZK_OP_ADD: {  // add.rs:35-43 (no flags reset; all three assigned)
+      pc = new_pc;
+      bool of;
+      u256l r = u_add(src0, src1, lane, of);
+      if (set_flags) {
+        bool eq = u_is_zero(r);
+        flags = (of ? 1u : 0u) | (eq ? 2u : 0u) | ((!eq && !of) ? 4u : 0u);
+      }
+      dst0_update(r, false);
+      break;
+    }
+    case ZK_OP_SUB: {  // sub.rs:35-44
+      pc = new_pc;
+      bool of;
+      u256l r = u_sub(src0, src1, lane, of);
+      if (set_flags) {
+        bool eq = u_is_zero(r);
+        flags = (of ? 1u : 0u) | (eq ? 2u : 0u) | ((!eq && !of) ? 4u : 0u);
+      }
+      dst0_update(r, false);
+      break;
+    }
+    case ZK_OP_MUL: {  // mul.rs:35-65
+      pc = new_pc;
+      u256l lo, hi;
+      u_mul(src0, src1, lane, lo, hi);
+      if (set_flags) {
+        bool of = !u_is_zero(hi), eq = u_is_zero(lo);
+        flags = (of ? 1u : 0u) | (eq ? 2u : 0u) | ((!of && !eq) ? 4u : 0u);
+      }
+      dst0_update(lo, false);
+      dst1_update(hi, false);
+      break;
+    }
+    case ZK_OP_DIV: {  // div.rs:36-75
+      pc = new_pc;
+      if (u_is_zero(src1)) {
+        if (set_flags) flags = 1u;
+        dst0_update(0u, false);
+        dst1_update(0u, false);
+      } else {
+        u256l q, r;
+        u_divmod(src0, src1, lane, q, r);
+        if (set_flags) flags = (u_is_zero(q) ? 2u : 0u) | (u_is_zero(r) ? 4u : 0u);
+        dst0_update(q, false);
+        dst1_update(r, false);
+      }
+      break;
+    }
+    case ZK_OP_JUMP:  // jump.rs:24-25
+      pc = __shfl_sync(ZK_FULL, src0, 0) & 0xFFFFu;
+      break;
+    case ZK_OP_CONTEXT:
+      pc = new_pc;
+      op_context(sub, src0);
+      break;
+    case ZK_OP_SHIFT:
+      pc = new_pc;
+      op_shift(sub, src0, src1);
+      break;
+    case ZK_OP_BINOP: {  // binop.rs:42-51
+      pc = new_pc;
+      u256l r = sub == ZK_XOR ? (src0 ^ src1) : sub == ZK_AND ? (src0 & src1) : (src0 | src1);
+      if (set_flags) flags = u_is_zero(r) ? 2u : 0u;
+      dst0_update(r, false);
+      break;
+    }
+    case ZK_OP_PTR:
+      pc = new_pc;
+      op_ptr(sub, src0, src1, src0_ptr, src1_ptr);
+      break;
+    case ZK_OP_NEAR_CALL:
+      op_near_call(src0, new_pc);
+      break;
+    case ZK_OP_LOG:
+      pc = new_pc;
+      op_log(sub, src0, src1);
+      break;
+    case ZK_OP_FAR_CALL:
+      op_far_call(sub, src0, src1, src0_ptr, new_pc, kernel_mode);
+      break;
+    case ZK_OP_RET:
+      op_ret(sub, src0, src0_ptr);
+      break;
+    case ZK_OP_UMA:
+      pc = new_pc;
+      op_uma(sub, src0, src1, src0_ptr);
+      break;
+    default:
+      fail(ZKB_VM_REFERENCE_PANIC);
+      break;
+  }
+  // the reference returns Err / panics before end_execution_cycle (cycle.rs:406): no row for a cycle that stopped the VM
+  if (status != ZKB_VM_RUNNING) return;
+
+  timestamp += ZK_TIME_DELTA_PER_CYCLE;
+  cycle += 1;
+
+  // ---- end_execution_cycle: emit the 256-byte row, one 8-byte store per lane ----
+  __syncwarp();
+  uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
+  if (lane == 0) v = make_uint2(row_cycle, row_ts);
+  if (lane == 1) v = make_uint2(raw_lo, raw_hi);
+  if (lane == 2) v = make_uint2(vidx | (resolved ? 1u : 0u) << 16 | err << 24, pc_before | pc << 16);
+  if (lane == 3) v = make_uint2(sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
+  if (lane == 21) v.y = (cm & 0xFFFFu) | (cl & 0xFFu) << 16 | ((cd & 3u) | (cf & 3u) << 2 | (cr & 3u) << 4) << 24;
+  uint8_t* p = stream_slot(ZKB_STREAM_ROWS);
+  if (p) *reinterpret_cast<uint2*>(p + 8 * lane) = v;
+}
+
+// context.rs:36-99
+__device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
+  if (sub == ZK_CTX_SET_U128) {
+    if (lane < 4) S.row[L_CTX + lane] = src0;
+    __syncwarp();
+    return;
+  }
+  if (sub == ZK_CTX_SET_ERGS_PER_PUBDATA) {
+    setL(L_EPP, __shfl_sync(ZK_FULL, src0, 0));
+    return;
+  }
+  if (sub == ZK_CTX_INC_TX) {
+    uint32_t t = S.row[L_TX_PSP];
+    __syncwarp();
+    setL(L_TX_PSP, (t & 0xFFFF0000u) | ((t + 1u) & 0xFFFFu));
+    return;
+  }
+  u256l v = 0u;
+  switch (sub) {
+    case ZK_CTX_THIS: v = addr_words_to_u256(lane < 5 ? S.F[F_THIS + lane] : 0u); break;
+    case ZK_CTX_CALLER: v = addr_words_to_u256(lane < 5 ? S.F[F_SENDER + lane] : 0u); break;
+    case ZK_CTX_CODE_ADDRESS: v = addr_words_to_u256(lane < 5 ? S.F[F_CODE_ADDR + lane] : 0u); break;
+    case ZK_CTX_META: {  // VmMetaParameters::to_u256 (external layout; same reconstruction as the ISA table)
+      uint32_t sh = S.F[F_EH_SHARDS], misc = S.F[F_MISC];
+      uint32_t this_shard = (sh >> 16) & 0xFFu, caller_shard = sh >> 24, code_shard = misc & 0xFFu;
+      v = lane == 0 ? L(L_EPP) : lane == 4 ? L(L_HEAP_BOUND) : lane == 5 ? L(L_AUX_BOUND)
+          : lane == 7 ? (this_shard << 24 | caller_shard << 16 | code_shard << 8) : 0u;
+      break;
+    }
+    case ZK_CTX_ERGS_LEFT: v = lane == 0 ? ergs : 0u; break;
+    case ZK_CTX_SP: v = lane == 0 ? sp : 0u; break;
+    case ZK_CTX_GET_U128: v = lane < 4 ? S.F[F_CTX + lane] : 0u; break;
+    default: fail(ZKB_VM_REFERENCE_PANIC); return;
+  }
+  dst0_update(v, false);
+}
+
+// shift.rs:44-67
+__device__ __forceinline__ void Vm::op_shift(uint32_t sub, u256l src0, u256l src1) {
+  uint32_t n = __shfl_sync(ZK_FULL, src1, 0) & 0xFFu;
+  bool cyclic = sub == ZK_ROL || sub == ZK_ROR, right = sub == ZK_SHR || sub == ZK_ROR;
+  u256l r;
+  if (right) {
+    r = u_shr(src0, n, lane);
+    if (cyclic) r |= u_shl(src0, 256u - n, lane);
+  } else {
+    r = u_shl(src0, n, lane);
+    if (cyclic) r |= u_shr(src0, 256u - n, lane);
+  }
+  if (entry & ZK_E_FLAG0) flags = u_is_zero(r) ? 2u : 0u;
+  dst0_update(r, false);
+}
+
+// ptr.rs:32-193
+__device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1, bool src0_ptr, bool src1_ptr) {
+  if (!src0_ptr || src1_ptr) {
+    pending = 1;
+    return;
+  }
+  uint32_t s1_nz = __ballot_sync(ZK_FULL, src1 != 0) & 0xFFu;
+  uint32_t off1 = __shfl_sync(ZK_FULL, src1, 0);
+  if (sub == ZK_PTR_ADD || sub == ZK_PTR_SUB) {
+    if (s1_nz & 0xFEu) {  // src1 >= 2^32 (MAX_OFFSET_FOR_ADD_SUB, ptr.rs:47)
+      pending = 1;
+      return;
+    }
+    uint32_t off0 = __shfl_sync(ZK_FULL, src0, 0);
+    uint32_t r = sub == ZK_PTR_ADD ? off0 + off1 : off0 - off1;
+    bool of = sub == ZK_PTR_ADD ? r < off0 : off0 < off1;
+    if (of) {
+      pending = 1;
+      return;
+    }
+    dst0_update(lane == 0 ? r : src0, true);
+  } else if (sub == ZK_PTR_PACK) {
+    if (s1_nz & 0x0Fu) {  // src1.low_u128() != 0 (ptr.rs:110)
+      pending = 1;
+      return;
+    }
+    dst0_update(lane < 4 ? src0 : src1, true);
+  } else {  // Shrink (ptr.rs:140-192)
+    uint32_t len = __shfl_sync(ZK_FULL, src0, 3);
+    if (len < off1) {
+      pending = 1;
+      return;
+    }
+    dst0_update(lane == 3 ? len - off1 : src0, true);
+  }
+}
+
+// near_call.rs:6-68
+__device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
+  flags = 0;
+  uint32_t abi_ergs = __shfl_sync(ZK_FULL, src0, 0);
+  uint32_t passed, remaining;
+  if (abi_ergs == 0 || ergs < abi_ergs) {
+    passed = ergs;
+    remaining = 0;
+  } else {
+    passed = abi_ergs;
+    remaining = ergs - abi_ergs;
+  }
+  ergs = remaining;
+  pc = new_pc;
+  sync_frame_to_F();
+  uint32_t nf = S.F[lane];
+  if (lane == F_SP_PC) nf = sp | imm0 << 16;
+  if (lane == F_EH_SHARDS) nf = (nf & 0xFFFF0000u) | imm1;
+  if (lane == F_ERGS) nf = passed;
+  if (lane == F_MISC) nf |= 1u << 16;
+  push_frame(nf);
+}
+
+// log.rs:11-330
+__device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1) {
+  const bool is_first = entry & ZK_E_FLAG0;
+  const uint32_t shard = (S.F[F_EH_SHARDS] >> 16) & 0xFFu;
+  const uint32_t ergs_available = ergs;
+  const uint32_t ts_log = timestamp + 1;
+  const uint32_t aw = lane < 5 ? S.F[F_THIS + lane] : 0u;
+  const uint32_t epp = L(L_EPP);
+  uint32_t ergs_on_pubdata = 0;
+  if (sub == ZK_LOG_SSTORE) {
+    emit_refund();  // refund_for_partial_query (log.rs:99-102)
+    uint32_t net = shard == 0 ? ZK_INITIAL_STORAGE_WRITE_PUBDATA_BYTES : 0u;
+    ergs_on_pubdata = epp * net;
+  } else if (sub == ZK_LOG_TO_L1) {
+    ergs_on_pubdata = epp * ZK_L1_MESSAGE_PUBDATA_BYTES;
+  }
+  uint32_t extra = sub == ZK_LOG_PRECOMPILE ? __shfl_sync(ZK_FULL, src1, 0) : 0u;
+  uint32_t total = extra + ergs_on_pubdata;
+  bool not_enough = ergs_available < total;
+  uint32_t spent = S.row[L_SPENT_PUBDATA];
+  __syncwarp();
+  if (not_enough) {
+    ergs = 0;
+    setL(L_SPENT_PUBDATA, spent + min(ergs_available, ergs_on_pubdata));
+  } else {
+    ergs = ergs_available - total;
+    if (ergs_on_pubdata) setL(L_SPENT_PUBDATA, spent + ergs_on_pubdata);
+  }
+  switch (sub) {
+    case ZK_LOG_SLOAD: {
+      u256l v = storage_access(shard, aw, src0, false, 0u, false);
+      emit_log(ts_log, ZK_STORAGE_AUX_BYTE, shard, aw, 0, is_first, src0, v, v);  // written := read (helpers.rs:145-148)
+      dst0_update(v, false);
+      break;
+    }
+    case ZK_LOG_SSTORE: {
+      if (not_enough) return;
+      u256l old = storage_access(shard, aw, src0, true, src1, true);
+      emit_log(ts_log, ZK_STORAGE_AUX_BYTE, shard, aw, 1, is_first, src0, old, src1);
+      break;
+    }
+    case ZK_LOG_EVENT:
+    case ZK_LOG_TO_L1: {
+      if (not_enough) return;
+      emit_log(ts_log, sub == ZK_LOG_EVENT ? ZK_EVENT_AUX_BYTE : ZK_L1_MESSAGE_AUX_BYTE, shard, aw, 1, is_first, src0, 0u, src1);
+      break;
+    }
+    default: {  // PrecompileCall (log.rs:252-328)
+      if (not_enough) {
+        dst0_update(0u, false);
+        return;
+      }
+      uint32_t heap_page = L(L_BASE_PAGE) + 2;
+      u256l abi = src0;
+      if (lane == 4 && abi == 0) abi = heap_page;  // memory_page_to_read
+      if (lane == 5 && abi == 0) abi = heap_page;  // memory_page_to_write
+      emit_log(ts_log, ZK_PRECOMPILE_AUX_BYTE, shard, aw, 0, is_first, abi, 0u, 0u);
+      uint32_t addr_low = bswap32(S.F[F_THIS + 4]) & 0xFFFFu;
+      if (addr_low == ZK_KECCAK256_PRECOMPILE_ADDRESS) {
+        keccak_precompile(abi);
+      } else if (addr_low == ZK_SHA256_PRECOMPILE_ADDRESS || addr_low == ZK_ECRECOVER_PRECOMPILE_ADDRESS) {
+        fail(ZKB_VM_UNSUPPORTED);
+      }
+      u256l one = lane == 0 ? 1u : 0u;
+      dst0_update(one, false);
+      break;
+    }
+  }
+}
+
+// keccak256 precompile (external DefaultPrecompilesProcessor; memory ABI pinned by keccak256.rs:100-139):
+// byte offset/length in, one output word (word index) out; one FatPointer-type read per distinct input word.
+__device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
+  const uint32_t in_off = __shfl_sync(ZK_FULL, abi, 0), in_len = __shfl_sync(ZK_FULL, abi, 1);
+  const uint32_t out_word = __shfl_sync(ZK_FULL, abi, 2);
+  const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
+  const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
+  // resolve the source page once (fat-pointer indirection, memory.rs:475-521)
+  uint32_t src_slab = ZKB_NO_SLAB;
+  if (in_len > 0 && page_read != 0) {
+    int e = pt_find(page_read);
+    if (e < 0) {
+      fail(ZKB_VM_REFERENCE_PANIC);
+      return;
+    }
+    uint32_t info = g_pt[e * 2 + 1];
+    uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
+    src_slab = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+  }
+  const KeccakLanes kl = keccak_lanes(lane);
+  uint64_t st = 0;
+  const uint64_t end = (uint64_t)in_off + in_len;
+  uint64_t next_emit_word = in_off / 32;
+  const uint32_t n_blocks = in_len / 136 + 1;
+  for (uint32_t blk = 0; blk < n_blocks; blk++) {
+    const uint64_t a0 = (uint64_t)in_off + (uint64_t)blk * 136;
+    const uint32_t nb = (uint32_t)min((uint64_t)136, end - a0);  // valid bytes in this block
+    const uint64_t w0 = a0 / 32;
+    if (nb > 0) {
+      const uint64_t w1 = (a0 + nb - 1) / 32;
+      for (uint64_t w = w0; w <= w1; w++) {
+        u256l word = slab_read(src_slab, (uint32_t)min(w, (uint64_t)0xFFFFFFFFu));
+        if (w >= next_emit_word) {
+          emit_mem(ts_read, page_read, (uint32_t)w, ZK_MEM_FAT_PTR, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, word);
+          next_emit_word = w + 1;
+        }
+        if (lane < 8) S.kbuf[(uint32_t)(w - w0) * 8 + (7 - lane)] = bswap32(word);  // byte stream order
+      }
+    }
+    __syncwarp();
+    uint64_t v = 0;
+    if (lane < 17) {
+      uint32_t o = (uint32_t)(a0 - w0 * 32) + 8 * lane;  // byte offset into kbuf
+      uint32_t i = o >> 2, sh = (o & 3u) * 8;
+      uint32_t x0 = S.kbuf[i], x1 = S.kbuf[i + 1], x2 = S.kbuf[(i + 2) & 63];
+      uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+      v = ((uint64_t)hi << 32) | lo;
+      uint32_t b0 = 8 * lane;
+      if (b0 >= nb) v = 0;
+      else if (b0 + 8 > nb) v &= (1ull << (8 * (nb - b0))) - 1ull;
+      if (nb < 136) {  // final block: pad10*1 with the keccak domain byte 0x01
+        if (lane == nb / 8) v ^= 1ull << (8 * (nb % 8));
+        if (lane == 16) v ^= 0x80ull << 56;
+      }
+    }
+    __syncwarp();
+    st ^= v;
+    st = keccak_f1600(st, kl, lane);
+  }
+  // digest = first 32 bytes of the state (little-endian lanes) read as one big-endian word
+  int t = 7 - (int)lane;
+  uint32_t lo = __shfl_sync(ZK_FULL, (uint32_t)st, (t >> 1) & 31), hi = __shfl_sync(ZK_FULL, (uint32_t)(st >> 32), (t >> 1) & 31);
+  u256l digest = lane < 8 ? bswap32((t & 1) ? hi : lo) : 0u;
+  // the write goes through MemoryType::Heap: the reference checks the page only by debug_assert (memory.rs:447)
+  if (page_write != L(L_BASE_PAGE) + 2) {
+    fail(ZKB_VM_REFERENCE_PANIC);
+    return;
+  }
+  uint32_t s = cur_slab(0, true, out_word);
+  if (status != ZKB_VM_RUNNING) return;
+  slab_write(s, out_word, digest);
+  emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, digest);
+}
+
+// SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth (already incremented)
+__device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
+  uint32_t level = far_depth;
+  if (lane == 0) {
+    g_lvl[level * 4 + 0] = ZKB_NO_SLAB;
+    g_lvl[level * 4 + 1] = ZKB_NO_SLAB;
+    g_lvl[level * 4 + 2] = 0;
+  }
+  __syncwarp();
+  // the root "heaps" entry has page numbers 0/0 (memory.rs:230-233)
+  uint32_t cur_heap = caller_level == 0 ? 0u : caller_base + 2, cur_aux = caller_level == 0 ? 0u : caller_base + 3;
+  if (calldata_page == 0) {
+  } else if (calldata_page == cur_heap) {
+    pt_upsert(cur_heap, PT_HEAP_LIVE, caller_level, level);
+  } else if (calldata_page == cur_aux) {
+    pt_upsert(cur_aux, PT_AUX_LIVE, caller_level, level);
+  } else {
+    int e = pt_find(calldata_page);
+    if (e < 0) {
+      fail(ZKB_VM_REFERENCE_PANIC);  // "fat pointer must only point to reachable memory" (memory.rs:641)
+      return;
+    }
+    uint32_t kind = g_pt[e * 2 + 1] & 0xFFu;
+    if (kind != PT_HEAP_LIVE && kind != PT_AUX_LIVE) fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:645
+  }
+}
+
+// SimpleMemory::finish_global_frame (memory.rs:660-758)
+__device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
+  // stack page goes back to the pool: clear what was touched (stack_on_return, memory.rs:185-188)
+  uint32_t hwm = g_lvl[level * 4 + 2];
+  uint32_t* sbase = g_stack + (size_t)level * B.stack_words * 8;
+  uint8_t* pbase = g_stack_ptr + (size_t)level * B.stack_words;
+  for (uint32_t i = lane; i < hwm * 8; i += 32) sbase[i] = 0u;
+  for (uint32_t i = lane; i < hwm; i += 32) pbase[i] = 0;
+  uint32_t heap_slab = g_lvl[level * 4 + 0], aux_slab = g_lvl[level * 4 + 1];
+  __syncwarp();
+  uint32_t heap_page = base_page + 2, aux_page = base_page + 3;
+  if (returndata_page == heap_page) {
+    pt_upsert(heap_page, PT_EXT, heap_slab, level - 1);
+    slab_release(aux_slab);
+  } else if (returndata_page == aux_page) {
+    pt_upsert(aux_page, PT_EXT, aux_slab, level - 1);
+    slab_release(heap_slab);
+  } else {
+    if (returndata_page != 0) {
+      int e = pt_find(returndata_page);
+      if (e < 0) {
+        fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:735
+        return;
+      }
+      if (lane == 0) g_pt[e * 2 + 1] = (g_pt[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
+      __syncwarp();
+    }
+    slab_release(heap_slab);
+    slab_release(aux_slab);
+  }
+  // drop every indirection still owned by the finished level
+  uint32_t page = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2] : ZKB_PT_FREE;
+  uint32_t info = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2 + 1] : 0u;
+  uint32_t drop = __ballot_sync(ZK_FULL, page != ZKB_PT_FREE && (info >> 16) == level);
+  while (drop) {
+    int e = __ffs(drop) - 1;
+    drop &= drop - 1;
+    uint32_t einfo = __shfl_sync(ZK_FULL, info, e);
+    if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
+    if (lane == 0) g_pt[e * 2] = ZKB_PT_FREE;
+  }
+  __syncwarp();
+}
+
+// far_call.rs:35-613
+__device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l src1, bool abi_is_ptr, uint32_t new_pc, bool kernel_mode) {
+  enum { EX_NOT_PTR = 1, EX_HASH_FORMAT = 2, EX_ERGS_DECOMMIT = 4, EX_ERGS_GROW = 8, EX_MALFORMED_PTR = 16, EX_CONSTRUCTED_SYSTEM = 32 };
+  flags = 0;
+  const bool is_call_shard = entry & ZK_E_FLAG0, is_static_call = entry & ZK_E_FLAG1;
+  const uint32_t eh = imm0;
+  // called address / kernel test
+  const uint32_t dest_nz = __ballot_sync(ZK_FULL, src1 != 0) & 0x1Fu;  // limbs 0..4 = low 160 bits
+  const bool dst_is_kernel = (dest_nz & 0x1Eu) == 0 && __shfl_sync(ZK_FULL, src1, 0) < 65536u;
+  const u256l dest_key = lane < 5 ? src1 : 0u;             // value & U256_TO_ADDRESS_MASK
+  const uint32_t dest_aw = u256_to_addr_words(src1);       // lanes 0..4
+  // FarCallABI::from_u256
+  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
+  uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
+  const uint32_t abi_ergs = __shfl_sync(ZK_FULL, src0, 6), top = __shfl_sync(ZK_FULL, src0, 7);
+  const uint32_t fwd_byte = top & 0xFFu, abi_shard = (top >> 8) & 0xFFu;
+  const uint32_t fwd = fwd_byte == ZK_FWD_FORWARD_FAT_POINTER ? ZK_FWD_FORWARD_FAT_POINTER : fwd_byte == ZK_FWD_USE_AUX_HEAP ? ZK_FWD_USE_AUX_HEAP : ZK_FWD_USE_HEAP;
+  const bool constructor_call = ((top >> 16) & 0xFFu) != 0 && kernel_mode;
+  const bool to_system = (top >> 24) != 0 && dst_is_kernel;
+
+  const uint32_t cur_base = L(L_BASE_PAGE);
+  const uint32_t shards = S.F[F_EH_SHARDS];
+  const uint32_t caller_shard = (shards >> 16) & 0xFFu;
+  const uint32_t remaining_ergs = ergs;
+  const uint32_t new_code_shard = is_call_shard ? abi_shard : caller_shard;
+  const uint32_t new_this_shard = sub == ZK_FC_DELEGATE ? caller_shard : new_code_shard;
+  const uint32_t new_base = L(L_PAGE_COUNTER);
+  const uint32_t ts1 = timestamp + 1;
+
+  u256l code_hash;
+  bool map_to_trivial;
+  if (new_code_shard != 0 && !B.zkporter) {
+    code_hash = 0u;
+    map_to_trivial = true;
+  } else {
+    if (new_code_shard >= 2) {
+      fail(ZKB_VM_REFERENCE_PANIC);  // InMemoryStorage has NUM_SHARDS = 2 (storage.rs:93 index)
+      return;
+    }
+    const uint32_t deployer_aw = lane == 4 ? bswap32(ZK_DEPLOYER_SYSTEM_CONTRACT_ADDRESS) : 0u;
+    u256l v = storage_access(new_code_shard, deployer_aw, dest_key, false, 0u, false);
+    emit_log(ts1, ZK_STORAGE_AUX_BYTE, new_code_shard, deployer_aw, 0, 0, dest_key, v, v);
+    bool mask_aa = u_is_zero(v) && !dst_is_kernel;
+    code_hash = mask_aa ? (lane < 8 ? B.default_aa[lane] : 0u) : v;
+    map_to_trivial = false;
+  }
+  const uint32_t page_candidate = map_to_trivial ? ZK_UNMAPPED_PAGE : new_base;
+
+  uint32_t ex = 0;
+  uint32_t code_len_words = 0;
+  {
+    uint32_t top_limb = __shfl_sync(ZK_FULL, code_hash, 7);
+    uint32_t version = top_limb >> 24, marker = (top_limb >> 16) & 0xFFu;
+    if (version == ZK_CODE_HASH_VERSION_BYTE) {
+      bool at_rest = marker == ZK_CODE_AT_REST_MARKER, constructed_now = marker == ZK_YET_CONSTRUCTED_MARKER;
+      if (!(at_rest || constructed_now)) {
+        ex |= EX_HASH_FORMAT;
+        code_hash = 0u;
+      } else if ((!constructor_call && at_rest) || (constructor_call && constructed_now)) {
+        if (lane == 7) code_hash &= 0xFF00FFFFu;  // serialize_to_stored: marker := at rest
+        code_len_words = top_limb & 0xFFFFu;
+      } else if (!dst_is_kernel) {
+        uint32_t aa_top = B.default_aa[7];
+        if ((aa_top >> 24) != ZK_CODE_HASH_VERSION_BYTE || ((aa_top >> 16) & 0xFFu) != ZK_CODE_AT_REST_MARKER) {
+          fail(ZKB_VM_REFERENCE_PANIC);  // far_call.rs:222-227
+          return;
+        }
+        code_hash = lane < 8 ? B.default_aa[lane] : 0u;
+        code_len_words = aa_top & 0xFFFFu;
+      } else {
+        ex |= EX_CONSTRUCTED_SYSTEM;
+        code_hash = 0u;
+      }
+    } else {
+      ex |= EX_HASH_FORMAT;
+      code_hash = 0u;
+    }
+  }
+  if (fwd == ZK_FWD_FORWARD_FAT_POINTER && !abi_is_ptr) ex |= EX_NOT_PTR;
+  // FatPointer::validate / validate_as_slice
+  const bool fresh = fwd != ZK_FWD_FORWARD_FAT_POINTER;
+  const bool deref_beyond = (uint64_t)p_start + (uint64_t)p_len > 0xFFFFFFFFull;
+  if ((fresh && p_off != 0) || deref_beyond) ex |= EX_MALFORMED_PTR;
+  if (p_off > p_len) ex |= EX_MALFORMED_PTR;
+  if (fwd == ZK_FWD_FORWARD_FAT_POINTER) {
+    p_start += p_off;
+    p_len -= p_off;
+    p_off = 0;
+  } else {
+    p_page = cur_base + (fwd == ZK_FWD_USE_HEAP ? 2u : 3u);
+  }
+  if (ex) p_off = p_page = p_start = p_len = 0;
+
+  uint32_t growth = 0;
+  if (fwd != ZK_FWD_FORWARD_FAT_POINTER) {
+    uint32_t upper = p_start + p_len;
+    if (deref_beyond) upper = 0xFFFFFFFFu;
+    int w = fwd == ZK_FWD_USE_HEAP ? L_HEAP_BOUND : L_AUX_BOUND;
+    uint32_t bound = S.row[w];
+    __syncwarp();
+    if (upper >= bound) {
+      growth = upper - bound;
+      setL(w, upper);
+    }
+  }
+  uint32_t ergs_after_growth;
+  if (remaining_ergs >= growth) {
+    ergs_after_growth = remaining_ergs - growth;
+  } else {
+    ex |= EX_ERGS_GROW;
+    ergs_after_growth = 0;
+  }
+  const uint32_t decommit_cost = ZK_ERGS_PER_CODE_WORD_DECOMMITTMENT * code_len_words;
+  uint32_t ergs_after_decommit;
+  if (ergs_after_growth >= decommit_cost) {
+    ergs_after_decommit = ergs_after_growth - decommit_cost;
+  } else {
+    ex |= EX_ERGS_DECOMMIT;
+    ergs_after_decommit = ergs_after_growth;
+  }
+  uint32_t mapped_code_page, new_code_id = ZKB_NO_CODE;
+  if (ex) {
+    pending = 1;
+    mapped_code_page = ZK_UNMAPPED_PAGE;
+  } else {
+    // SimpleDecommitter::decommit_into_memory (decommitter.rs:32-99)
+    int id = -1;
+    for (uint32_t c = 0; c < B.n_codes && id < 0; c++) {
+      uint32_t hw = lane < 8 ? B.code_meta[c * 10 + 2 + lane] : 0u;
+      if (u_eq(hw, code_hash)) id = (int)c;
+    }
+    uint32_t* dec = B.dec + (size_t)vm * ZKB_DEC_ENTRIES * 2;
+    uint32_t e_id = lane < n_decommit ? dec[lane * 2] : ZKB_NO_CODE;
+    // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it
+    uint32_t hist = id >= 0 ? __ballot_sync(ZK_FULL, e_id == (uint32_t)id) : (__ballot_sync(ZK_FULL, false));
+    uint32_t fresh_flag, len16;
+    if (hist) {
+      mapped_code_page = dec[(__ffs(hist) - 1) * 2 + 1];
+      fresh_flag = 0;
+      len16 = B.code_meta[id * 10 + 1] & 0xFFFFu;
+      ergs_after_decommit += decommit_cost;  // refund (far_call.rs:450-453)
+    } else {
+      if (id < 0) {
+        status = ZKB_VM_UNKNOWN_CODE_HASH;  // anyhow::Err (decommitter.rs:50-56)
+        return;
+      }
+      if (n_decommit >= ZKB_DEC_ENTRIES) {
+        fail(ZKB_VM_CAP_PAGES);
+        return;
+      }
+      if (lane == 0) {
+        dec[n_decommit * 2] = (uint32_t)id;
+        dec[n_decommit * 2 + 1] = page_candidate;
+      }
+      n_decommit++;
+      __syncwarp();
+      mapped_code_page = page_candidate;
+      fresh_flag = 1;
+      len16 = B.code_meta[id * 10 + 1] & 0xFFFFu;
+    }
+    new_code_id = (uint32_t)id;
+    emit_decommit(ts1, mapped_code_page, len16, fresh_flag, code_hash);
+  }
+  // 63/64 rule (far_call.rs:468-487)
+  const uint32_t max_passable = (ergs_after_decommit / 64u) * 63u;
+  const uint32_t leftover = ergs_after_decommit - max_passable;
+  uint32_t passed, remaining_for_this;
+  if (max_passable < abi_ergs) {
+    passed = max_passable;
+    remaining_for_this = leftover;
+  } else {
+    passed = abi_ergs;
+    remaining_for_this = leftover + (max_passable - abi_ergs);
+  }
+  ergs = remaining_for_this;
+  pc = new_pc;
+  const bool new_static = is_static() || is_static_call;
+  uint32_t page_counter = S.row[L_PAGE_COUNTER];
+  __syncwarp();
+  setL(L_PAGE_COUNTER, page_counter + ZK_NEW_MEMORY_PAGES_PER_FAR_CALL);
+
+  // new frame, lane i = word i
+  const uint32_t r15_aw = u256_to_addr_words(reg_read(ZK_CALL_IMPLICIT_PARAMETER_REG_IDX + 1));
+  const uint32_t caller_level = far_depth;
+  if (far_depth + 1 > B.max_far_depth) {
+    fail(ZKB_VM_CAP_DEPTH);
+    return;
+  }
+  sync_frame_to_F();
+  uint32_t nf = 0;
+  {
+    uint32_t this_w = lane < 5 ? S.F[F_THIS + lane] : 0u;          // lanes 0..4
+    uint32_t sender_w = lane < 5 ? S.F[F_SENDER + lane] : 0u;
+    uint32_t next_this = sub == ZK_FC_DELEGATE ? this_w : dest_aw;
+    uint32_t next_sender = sub == ZK_FC_NORMAL ? this_w : sub == ZK_FC_DELEGATE ? sender_w : r15_aw;
+    uint32_t a = __shfl_sync(ZK_FULL, next_this, lane & 7);
+    uint32_t b = __shfl_sync(ZK_FULL, next_sender, (lane - 5) & 7);
+    uint32_t c = __shfl_sync(ZK_FULL, dest_aw, (lane - 10) & 7);
+    uint32_t ctx_frame = lane >= F_CTX && lane < F_CTX + 4 ? S.F[lane] : 0u;
+    uint32_t ctx_reg = lane >= F_CTX && lane < F_CTX + 4 ? S.row[L_CTX + lane - F_CTX] : 0u;
+    if (lane < 5) nf = a;
+    else if (lane < 10) nf = b;
+    else if (lane < 15) nf = c;
+    else if (lane == F_BASE_PAGE) nf = new_base;
+    else if (lane == F_CODE_PAGE) nf = mapped_code_page;
+    else if (lane == F_SP_PC) nf = ZK_INITIAL_SP_ON_FAR_CALL;
+    else if (lane == F_EH_SHARDS) nf = eh | new_this_shard << 16 | caller_shard << 24;
+    else if (lane == F_ERGS) nf = passed;
+    else if (lane == F_MISC) nf = new_code_shard | (new_static ? 1u : 0u) << 8;
+    else if (lane >= F_CTX && lane < F_CTX + 4) nf = sub == ZK_FC_DELEGATE ? ctx_frame : ctx_reg;
+    else if (lane == F_HEAP_BOUND || lane == F_AUX_BOUND) nf = ZK_NEW_FRAME_MEMORY_STIPEND;
+    else if (lane == F_CODE_ID) nf = new_code_id;
+    else if (lane == F_FAR_LEVEL) nf = caller_level + 1;
+  }
+  __syncwarp();
+  if (lane < 4) S.row[L_CTX + lane] = 0u;  // context_u128_register = 0 (far_call.rs:558)
+  __syncwarp();
+  push_frame(nf);
+  if (status != ZKB_VM_RUNNING) return;
+  memory_start_global_frame(caller_level, cur_base, p_page);
+
+  // register ABI (far_call.rs:573-610)
+  u256l r1 = lane == 0 ? p_off : lane == 1 ? p_page : lane == 2 ? p_start : lane == 3 ? p_len : 0u;
+  u256l r2 = lane == 0 ? ((constructor_call ? 1u : 0u) | (to_system ? 2u : 0u)) : 0u;
+  if (lane < 8) {
+    S.regs[1][lane] = r1;
+    S.regs[2][lane] = r2;
+    S.row[24 + lane] = r1;
+    S.row[32 + lane] = r2;
+  }
+  // registers[] index i <-> r(i+1): system ABI regs r3..r12, reserved r13,r14, implicit r15
+  uint32_t clear_mask = 0xE000u | (to_system ? 0u : 0x1FF8u);
+  for (uint32_t r = 3; r < 16; r++)
+    if (((clear_mask >> r) & 1u) && lane < 8) S.regs[r][lane] = 0u;
+  ptr_mask = 0x0002u;  // only r1 is a pointer: r2 plain, r3..r12 markers removed or zeroed, r13..r15 zeroed
+  rowbits |= ZKB_ROWBIT_DST0_VALID | ZKB_ROWBIT_DST0_PTR | ZKB_ROWBIT_DST1_VALID;
+  __syncwarp();
+}
+
+// ret.rs:9-265
+__device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_ptr) {
+  uint32_t variant = sub;
+  flags = 0;
+  if (variant == ZK_RET_PANIC) {
+    src0 = 0u;
+    src0_ptr = false;
+  }
+  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
+  uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
+  const uint32_t fwd_byte = __shfl_sync(ZK_FULL, src0, 7) & 0xFFu;
+  const uint32_t fwd = fwd_byte == ZK_FWD_FORWARD_FAT_POINTER ? ZK_FWD_FORWARD_FAT_POINTER : fwd_byte == ZK_FWD_USE_AUX_HEAP ? ZK_FWD_USE_AUX_HEAP : ZK_FWD_USE_HEAP;
+  bool to_label = entry & ZK_E_FLAG0;
+  const uint32_t label_pc = imm0;
+  const bool local = is_local();
+  const uint32_t base = L(L_BASE_PAGE);
+  bool deref_beyond = false;
+  if (!local) {
+    if (fwd == ZK_FWD_FORWARD_FAT_POINTER) {
+      if (!src0_ptr) variant = ZK_RET_PANIC;
+      if (p_page < base) variant = ZK_RET_PANIC;
+    }
+    const bool fresh = fwd != ZK_FWD_FORWARD_FAT_POINTER;
+    deref_beyond = (uint64_t)p_start + (uint64_t)p_len > 0xFFFFFFFFull;
+    if ((fresh && p_off != 0) || deref_beyond) variant = ZK_RET_PANIC;
+    if (p_off > p_len) variant = ZK_RET_PANIC;
+    if (variant == ZK_RET_PANIC) p_off = p_page = p_start = p_len = 0;
+  }
+  uint32_t ergs_remaining = ergs;
+  if (!local) {
+    if (variant != ZK_RET_PANIC) {
+      if (fwd == ZK_FWD_FORWARD_FAT_POINTER) {
+        p_start += p_off;
+        p_len -= p_off;
+        p_off = 0;
+      } else {
+        p_page = base + (fwd == ZK_FWD_USE_HEAP ? 2u : 3u);
+      }
+    }
+    uint32_t growth = 0;
+    if (fwd != ZK_FWD_FORWARD_FAT_POINTER) {
+      uint32_t upper = p_start + p_len;
+      if (deref_beyond) upper = 0xFFFFFFFFu;
+      uint32_t bound = fwd == ZK_FWD_USE_HEAP ? L(L_HEAP_BOUND) : L(L_AUX_BOUND);
+      if (upper >= bound) growth = upper - bound;
+    }
+    if (ergs_remaining >= growth) {
+      ergs_remaining -= growth;
+    } else {
+      ergs_remaining = 0;
+      variant = ZK_RET_PANIC;
+      p_off = p_page = p_start = p_len = 0;
+    }
+  }
+  const bool panicked = variant == ZK_RET_REVERT || variant == ZK_RET_PANIC;
+  const uint32_t finished_level = far_depth;
+  const uint32_t finished_eh = L(L_EH_BITS) & 0xFFFFu;
+  const uint32_t fin_heap_bound = L(L_HEAP_BOUND), fin_aux_bound = L(L_AUX_BOUND);
+  if (S.row[L_DEPTH] == 0) {
+    fail(ZKB_VM_REFERENCE_PANIC);  // pop of the root frame (execution_stack.rs:113 unwrap)
+    return;
+  }
+  __syncwarp();
+  pop_frame(panicked);
+  to_label = to_label && local;
+  if (!local) {
+    memory_finish_global_frame(finished_level, base, p_page);
+    u256l r1 = lane == 0 ? p_off : lane == 1 ? p_page : lane == 2 ? p_start : lane == 3 ? p_len : 0u;
+    if (lane < 8) {
+      S.regs[1][lane] = r1;
+      S.row[24 + lane] = r1;
+#pragma unroll
+      for (int r = 2; r < 16; r++) S.regs[r][lane] = 0u;
+    }
+    if (lane < 4) S.row[L_CTX + lane] = 0u;
+    ptr_mask = 0x0002u;
+    rowbits |= ZKB_ROWBIT_DST0_VALID | ZKB_ROWBIT_DST0_PTR;
+    __syncwarp();
+  }
+  ergs += ergs_remaining;  // ret.rs:243
+  if (to_label) pc = label_pc;
+  else if (panicked) pc = finished_eh;
+  if (local) {
+    if (fin_heap_bound < L(L_HEAP_BOUND) || fin_aux_bound < L(L_AUX_BOUND)) {
+      fail(ZKB_VM_REFERENCE_PANIC);  // ret.rs:255-256
+      return;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      S.row[L_HEAP_BOUND] = fin_heap_bound;
+      S.row[L_AUX_BOUND] = fin_aux_bound;
+    }
+    __syncwarp();
+  }
+  if (variant == ZK_RET_PANIC) flags = 1u;
+}
+
+// uma.rs:26-425
+__device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr) {
+  const bool inc = entry & ZK_E_FLAG0;
+  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
+  const uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
+  const bool is_ptr_read = sub == ZK_UMA_PTR_READ;
+  const bool is_heap = sub == ZK_UMA_HEAP_READ || sub == ZK_UMA_HEAP_WRITE;
+  const bool is_write = sub == ZK_UMA_HEAP_WRITE || sub == ZK_UMA_AUX_WRITE;
+  bool ex = false, ex_deref = false, skip = false;
+  if (is_ptr_read && !src0_ptr) ex = true;
+  uint32_t mtype;
+  if (is_ptr_read) {
+    mtype = ZK_MEM_FAT_PTR;
+  } else {
+    p_page = L(L_BASE_PAGE) + (is_heap ? 2u : 3u);
+    mtype = is_heap ? ZK_MEM_HEAP : ZK_MEM_AUX_HEAP;
+  }
+  uint32_t src_offset;
+  if (is_ptr_read) {
+    if (!(p_off < p_len)) skip = true;
+    src_offset = p_start + p_off;
+  } else {
+    uint32_t hi_nz = __ballot_sync(ZK_FULL, src0 != 0) & 0xFEu;
+    if (hi_nz || p_off > (uint32_t)ZK_MAX_OFFSET_TO_DEREF) {
+      ex = ex_deref = true;
+      skip = true;
+    }
+    src_offset = p_off;
+  }
+  const uint32_t incremented = p_off + 32u;
+  if (incremented < p_off) ex = true;
+  uint32_t growth = 0;
+  if (!is_ptr_read) {
+    int w = is_heap ? L_HEAP_BOUND : L_AUX_BOUND;
+    uint32_t bound = S.row[w];
+    __syncwarp();
+    if (incremented >= bound) {
+      growth = incremented - bound;
+      setL(w, incremented);
+    }
+  }
+  if (ex_deref) growth = 0xFFFFFFFFu;
+  if (ergs < growth) {
+    ergs = 0;
+    ex = true;
+  } else {
+    ergs -= growth;
+  }
+  const bool set_panic = ex;
+  const bool skip_access = skip || set_panic;
+  const uint32_t word0 = src_offset >> 5, word1 = word0 + 1, un = src_offset & 31u;
+  const bool unaligned = un != 0;
+  u256l w0 = 0u, w1 = 0u;
+  uint32_t slab = ZKB_NO_SLAB;
+  if (!skip_access) {
+    if (is_ptr_read) {
+      bool ok;
+      w0 = fatptr_read(p_page, word0, ok);
+      if (!ok) {
+        fail(ZKB_VM_REFERENCE_PANIC);
+        return;
+      }
+      emit_mem(timestamp, p_page, word0, mtype, 0, 0, ZKB_MEMORIGIN_VM, w0);
+      if (unaligned) {
+        w1 = fatptr_read(p_page, word1, ok);
+        emit_mem(timestamp, p_page, word1, mtype, 0, 0, ZKB_MEMORIGIN_VM, w1);
+      }
+    } else {
+      slab = cur_slab(is_heap ? 0 : 1, is_write, unaligned ? word1 : word0);
+      if (status != ZKB_VM_RUNNING) return;
+      w0 = slab_read(slab, word0);
+      emit_mem(timestamp, p_page, word0, mtype, 0, 0, ZKB_MEMORIGIN_VM, w0);
+      if (unaligned) {
+        w1 = slab_read(slab, word1);
+        emit_mem(timestamp, p_page, word1, mtype, 0, 0, ZKB_MEMORIGIN_VM, w1);
+      }
+    }
+  }
+  if (!is_write) {
+    u256l r = u_shl(w0, un * 8u, lane) | u_shr(w1, (32u - un) * 8u, lane);
+    if (is_ptr_read) {
+      uint32_t beyond = incremented - p_len;
+      if (incremented < p_len || skip_access) beyond = 0;
+      beyond &= 31u;
+      r = u_shl(u_shr(r, beyond * 8u, lane), beyond * 8u, lane);
+    }
+    if (!set_panic) {
+      dst0_update(r, false);
+      if (inc) dst1_update(lane == 0 ? incremented : src0, src0_ptr);
+    } else {
+      pending = 1;
+    }
+  } else {
+    const uint32_t low0 = 32u - un;
+    u256l n0 = u_shl(u_shr(w0, low0 * 8u, lane), low0 * 8u, lane) | u_shr(src1, un * 8u, lane);
+    u256l n1 = u_shr(u_shl(w1, un * 8u, lane), un * 8u, lane) | u_shl(src1, (32u - un) * 8u, lane);
+    if (!skip_access) {
+      slab_write(slab, word0, n0);
+      emit_mem(timestamp + 3, p_page, word0, mtype, 1, 0, ZKB_MEMORIGIN_VM, n0);
+      if (unaligned) {
+        slab_write(slab, word1, n1);
+        emit_mem(timestamp + 3, p_page, word1, mtype, 1, 0, ZKB_MEMORIGIN_VM, n1);
+      }
+    }
+    if (!set_panic) {
+      if (inc) dst0_update(lane == 0 ? incremented : src0, false);
+    } else {
+      pending = 1;
+    }
+  }
+}
+
+// ===================================================================================================
+// load / run / store one VM
+// ===================================================================================================
+__device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
+  VmHot* hot = B.hot + vm_idx;
+  if (hot->x[X_STATUS] != ZKB_VM_RUNNING) return;
+  Vm v(B, S, vm_idx, lane);
+  uint32_t* sregs = &S.regs[0][0];
+  const uint32_t* hregs = &hot->regs[0][0];
+#pragma unroll
+  for (int i = 0; i < 4; i++) sregs[i * 32 + lane] = hregs[i * 32 + lane];
+  S.F[lane] = hot->F[lane];
+  S.row[lane] = 0u;
+  S.row[32 + lane] = lane >= 8 && lane < 24 ? hot->live[lane - 8] : 0u;
+  v.prev_word = lane < 8 ? hot->prev_word[lane] : 0u;
+  uint32_t x = hot->x[lane];
+  v.timestamp = __shfl_sync(ZK_FULL, x, X_TIMESTAMP);
+  v.cycle = __shfl_sync(ZK_FULL, x, X_CYCLE);
+  v.flags = __shfl_sync(ZK_FULL, x, X_FLAGS);
+  v.pending = __shfl_sync(ZK_FULL, x, X_PENDING);
+  v.status = ZKB_VM_RUNNING;
+  v.ptr_mask = __shfl_sync(ZK_FULL, x, X_PTRMASK);
+  v.prev_code_page = __shfl_sync(ZK_FULL, x, X_PREV_CODE_PAGE);
+  v.journal_len = __shfl_sync(ZK_FULL, x, X_JOURNAL_LEN);
+  v.n_decommit = __shfl_sync(ZK_FULL, x, X_N_DECOMMIT);
+  v.slab_free = __shfl_sync(ZK_FULL, x, X_SLAB_FREE);
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = __shfl_sync(ZK_FULL, x, X_COUNT0 + k);
+  v.rowbits = 0;
+  v.cm = v.cl = v.cd = v.cf = v.cr = 0;
+  v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
+  __syncwarp();
+  v.load_frame_from_F();
+
+  uint32_t n = 0;
+  while (v.status == ZKB_VM_RUNNING) {
+    if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
+      v.status = ZKB_VM_ENDED;
+      break;
+    }
+    if (max_cycles && n >= max_cycles) break;
+    v.cycle_once();
+    n++;
+  }
+
+  // store back
+  __syncwarp();
+  v.sync_frame_to_F();
+  uint32_t* gregs = &hot->regs[0][0];
+#pragma unroll
+  for (int i = 0; i < 4; i++) gregs[i * 32 + lane] = sregs[i * 32 + lane];
+  hot->F[lane] = S.F[lane];
+  if (lane < 16) hot->live[lane] = S.row[40 + lane];
+  if (lane < 8) hot->prev_word[lane] = v.prev_word;
+  uint32_t out = 0;
+  out = lane == X_TIMESTAMP ? v.timestamp : out;
+  out = lane == X_CYCLE ? v.cycle : out;
+  out = lane == X_FLAGS ? v.flags : out;
+  out = lane == X_PENDING ? v.pending : out;
+  out = lane == X_STATUS ? v.status : out;
+  out = lane == X_PTRMASK ? v.ptr_mask : out;
+  out = lane == X_PREV_CODE_PAGE ? v.prev_code_page : out;
+  out = lane == X_FAR_DEPTH ? v.far_depth : out;
+  out = lane == X_JOURNAL_LEN ? v.journal_len : out;
+  out = lane == X_N_DECOMMIT ? v.n_decommit : out;
+  out = lane == X_SLAB_FREE ? v.slab_free : out;
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) out = lane == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
+  hot->x[lane] = out;
+  __syncwarp();
+}
+
+}  // namespace zkb

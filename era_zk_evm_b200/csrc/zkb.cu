@@ -1,0 +1,780 @@
+// zkb.cu — kernels + the C ABI of include/zkb.h (host side) for the B200 batched EraVM witness generator.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vm.cuh"
+
+using namespace zkb;
+
+#ifndef ZKB_WARPS_PER_CTA
+#define ZKB_WARPS_PER_CTA 4
+#endif
+#ifndef ZKB_MIN_CTAS_PER_SM
+#define ZKB_MIN_CTAS_PER_SM 4
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+// K1: persistent interpreter — each warp pulls VM indices from an atomic queue and runs the VM to completion
+// (or for max_cycles cycles).  Replaces the caller loop `while !vm.execution_has_ended() { vm.cycle() }`.
+__global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) zkb_run_kernel(const DevBatch B, uint32_t max_cycles) {
+  __shared__ WarpSmem smem[ZKB_WARPS_PER_CTA];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  WarpSmem& S = smem[warp];
+  while (true) {
+    uint32_t vm_idx = 0;
+    if (lane == 0) vm_idx = atomicAdd(B.queue, 1u);
+    vm_idx = __shfl_sync(ZK_FULL, vm_idx, 0);
+    if (vm_idx >= B.n_vms) break;
+    run_vm(B, S, vm_idx, lane, max_cycles);
+  }
+}
+
+// K6a: per-VM cold-state initialisation (level table, page indirections)
+__global__ void zkb_init_kernel(const DevBatch B) {
+  uint32_t vm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vm >= B.n_vms) return;
+  uint32_t* lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
+  for (uint32_t l = 0; l <= B.max_far_depth; l++) {
+    lvl[l * 4 + 0] = ZKB_NO_SLAB;
+    lvl[l * 4 + 1] = ZKB_NO_SLAB;
+    lvl[l * 4 + 2] = 0;
+    lvl[l * 4 + 3] = 0;
+  }
+  uint32_t* pt = B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2;
+  for (uint32_t e = 0; e < ZKB_PT_ENTRIES; e++) {
+    pt[e * 2] = ZKB_PT_FREE;
+    pt[e * 2 + 1] = 0;
+  }
+}
+
+struct DevStorageInit {
+  uint32_t shard;
+  uint32_t addr[5];
+  uint32_t key[8];
+  uint32_t value[8];
+};
+
+// K6b: InMemoryStorage::populate (storage.rs:26-32): one warp per VM inserts n entries through the same
+// open-addressed insert the interpreter uses (no journal).
+__global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, uint32_t vm_hi, const DevStorageInit* entries, uint32_t n,
+                                            uint32_t per_vm, uint32_t* fail_flag) {
+  __shared__ WarpSmem smem[4];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t vm = vm_lo + blockIdx.x * 4 + warp;
+  if (vm >= vm_hi) return;
+  Vm v(B, smem[warp], vm, lane);
+  v.status = ZKB_VM_RUNNING;
+  v.journal_len = 0;
+  const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
+    u256l key = lane < 8 ? e[i].key[lane] : 0u;
+    u256l val = lane < 8 ? e[i].value[lane] : 0u;
+    v.storage_access(e[i].shard, aw, key, true, val, false);
+  }
+  if (v.status != ZKB_VM_RUNNING && lane == 0) atomicExch(fail_flag, v.status);
+}
+
+// K6c: SimpleMemory::populate_heap (memory.rs:287-291) into slab 0 (the bootloader frame's heap).
+// bytes: big-endian memory image; word w limb l = BE bytes [32w + 28 - 4l, +4)
+__global__ void zkb_populate_heap_kernel(const DevBatch B, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* bytes, uint32_t n_bytes,
+                                         uint32_t per_vm, uint32_t level) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t vm = vm_lo + blockIdx.x * 4 + warp;
+  if (vm >= vm_hi) return;
+  const uint8_t* src = per_vm ? bytes + (size_t)(vm - vm_lo) * n_bytes : bytes;
+  uint32_t n_words = (n_bytes + 31) / 32;
+  uint32_t* heap = B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8;  // slab 0
+  for (uint32_t i = lane; i < n_words * 8; i += 32) {
+    uint32_t w = i >> 3, l = i & 7u;
+    uint32_t off = 32 * w + 28 - 4 * l;
+    uint32_t v = 0;
+    for (int k = 0; k < 4; k++) {
+      uint32_t a = off + k;
+      uint32_t byte = a < n_bytes ? src[a] : 0u;
+      v = (v << 8) | byte;
+    }
+    heap[i] = v;
+  }
+  if (lane == 0) {
+    B.slab_hwm[(size_t)vm * B.n_slabs] = n_words;
+    B.lvl[((size_t)vm * (B.max_far_depth + 1) + level) * 4 + 0] = 0;
+  }
+}
+
+// K5: pack one stream kind of every VM contiguously (VM order) for a single D2H / NCCL send.
+__global__ void zkb_pack_kernel(const uint8_t* __restrict__ src, uint64_t stride, const uint64_t* __restrict__ offsets, uint8_t* __restrict__ dst,
+                                uint32_t n_vms) {
+  uint32_t vm = blockIdx.x;
+  if (vm >= n_vms) return;
+  uint64_t begin = offsets[vm], n = offsets[vm + 1] - begin;
+  const uint2* s = reinterpret_cast<const uint2*>(src + (size_t)vm * stride);
+  uint2* d = reinterpret_cast<uint2*>(dst + begin);
+  for (uint64_t i = threadIdx.x; i < n / 8; i += blockDim.x) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t set_err(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) return set_err(ZKB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static const uint32_t REC_BYTES[ZKB_N_STREAMS] = {ZKB_ROW_BYTES, ZKB_MEM_BYTES, ZKB_LOG_BYTES, ZKB_DECOMMIT_BYTES, ZKB_FRAME_BYTES, ZKB_REFUND_BYTES};
+
+struct Bytecode {
+  uint32_t hash[8];
+  uint32_t offset_words, len_words;
+};
+
+struct ZkbBatch {
+  ZkbConfig cfg;
+  DevBatch d;
+  std::vector<VmHot> h_hot;
+  std::vector<uint32_t> h_root;  // [n_vms][32] root frames (callstack slot 0)
+  std::vector<uint32_t> h_bootrec;  // [n_vms][32] FrameRec of the bootloader push (start_new_execution_context)
+  bool hot_dirty = true;         // host mirror newer than device
+  bool hot_stale = false;        // device newer than host mirror
+  bool root_dirty = true;
+  std::vector<Bytecode> codes;
+  std::vector<uint32_t> h_code_words;
+  bool codes_dirty = true;
+  uint32_t* d_code_words = nullptr;
+  uint32_t* d_code_meta = nullptr;
+  std::vector<int32_t> boot_code;  // per VM: code id bound by populate_code (page in boot_page)
+  std::vector<uint32_t> boot_page;
+  uint32_t* d_fail = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t last_stream = nullptr;
+  uint32_t n_launches = 0;
+  int grid = 0;
+  uint8_t* d_pack = nullptr;
+  uint64_t pack_capacity = 0;
+  uint64_t* d_offsets = nullptr;
+  std::vector<void*> allocs;
+};
+
+static void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {
+  for (int l = 0; l < 8; l++) {
+    const uint8_t* p = be + 28 - 4 * l;
+    limbs[l] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+  }
+}
+static void limbs_to_be32(const uint32_t* limbs, uint8_t* be) {
+  for (int l = 0; l < 8; l++) {
+    uint8_t* p = be + 28 - 4 * l;
+    p[0] = (uint8_t)(limbs[l] >> 24);
+    p[1] = (uint8_t)(limbs[l] >> 16);
+    p[2] = (uint8_t)(limbs[l] >> 8);
+    p[3] = (uint8_t)limbs[l];
+  }
+}
+
+static void init_hot(const ZkbBatch* b, VmHot& h) {
+  memset(&h, 0, sizeof(h));
+  // CallStackEntry::empty_context (execution_stack.rs:35-55)
+  h.F[F_SP_PC] = ZK_INITIAL_SP_ON_FAR_CALL;
+  h.F[F_ERGS] = ZK_VM_INITIAL_FRAME_ERGS;
+  h.F[F_CODE_ID] = ZKB_NO_CODE;
+  h.F[F_FAR_LEVEL] = 0;
+  // VmLocalState::empty_state (vm_state/mod.rs:76-94)
+  h.live[L_PAGE_COUNTER - 40] = ZK_STARTING_BASE_PAGE;
+  h.live[L_EH_BITS - 40] = ZKB_FRAMEBIT_KERNEL << 16;  // address 0 is a kernel address
+  h.x[X_TIMESTAMP] = ZK_STARTING_TIMESTAMP;
+  h.x[X_STATUS] = ZKB_VM_RUNNING;
+  h.x[X_SLAB_FREE] = b->cfg.n_heap_slabs >= 32 ? 0xFFFFFFFFu : ((1u << b->cfg.n_heap_slabs) - 1u);
+}
+
+template <class T>
+static cudaError_t dalloc(ZkbBatch* b, T** p, size_t count, bool zero) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return e;
+  b->allocs.push_back(q);
+  if (zero) e = cudaMemset(q, 0, bytes);
+  *p = (T*)q;
+  return e;
+}
+
+static int32_t clear_cold_state(ZkbBatch* b) {
+  const ZkbConfig& c = b->cfg;
+  size_t n = c.n_vms, levels = c.max_far_depth + 1;
+  CUDA_OK(cudaMemset(b->d.stack_mem, 0, n * levels * c.stack_words * 32));
+  CUDA_OK(cudaMemset(b->d.stack_ptr, 0, n * levels * c.stack_words));
+  CUDA_OK(cudaMemset(b->d.heap_mem, 0, n * c.n_heap_slabs * (size_t)c.heap_bytes));
+  CUDA_OK(cudaMemset(b->d.slab_hwm, 0, n * c.n_heap_slabs * 4));
+  CUDA_OK(cudaMemset(b->d.st_tags, 0, n * c.storage_slots * 4));
+  CUDA_OK(cudaMemset(b->d.st_vals, 0, n * c.storage_slots * 32));
+  zkb_init_kernel<<<(c.n_vms + 127) / 128, 128>>>(b->d);
+  CUDA_OK(cudaGetLastError());
+  return ZKB_OK;
+}
+
+static int32_t upload(ZkbBatch* b) {
+  if (b->codes_dirty) {
+    if (b->d_code_words) cudaFree(b->d_code_words);
+    if (b->d_code_meta) cudaFree(b->d_code_meta);
+    b->d_code_words = b->d_code_meta = nullptr;
+    size_t nw = std::max<size_t>(b->h_code_words.size(), 8);
+    CUDA_OK(cudaMalloc(&b->d_code_words, nw * 4));
+    CUDA_OK(cudaMalloc(&b->d_code_meta, std::max<size_t>(b->codes.size(), 1) * 40));
+    if (!b->h_code_words.empty()) CUDA_OK(cudaMemcpy(b->d_code_words, b->h_code_words.data(), b->h_code_words.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> meta(b->codes.size() * 10);
+    for (size_t i = 0; i < b->codes.size(); i++) {
+      meta[i * 10] = b->codes[i].offset_words;
+      meta[i * 10 + 1] = b->codes[i].len_words;
+      memcpy(&meta[i * 10 + 2], b->codes[i].hash, 32);
+    }
+    if (!meta.empty()) CUDA_OK(cudaMemcpy(b->d_code_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    b->d.code_words = b->d_code_words;
+    b->d.code_meta = b->d_code_meta;
+    b->d.n_codes = (uint32_t)b->codes.size();
+    b->codes_dirty = false;
+  }
+  if (b->hot_dirty) {
+    CUDA_OK(cudaMemcpy(b->d.hot, b->h_hot.data(), b->h_hot.size() * sizeof(VmHot), cudaMemcpyHostToDevice));
+    b->hot_dirty = false;
+  }
+  if (b->root_dirty) {
+    CUDA_OK(cudaMemcpy2D(b->d.callstack, (size_t)b->cfg.max_depth * 128, b->h_root.data(), 128, 128, b->cfg.n_vms, cudaMemcpyHostToDevice));
+    if (b->cfg.witness_mode && b->cfg.cap_records[ZKB_STREAM_FRAME] > 0)
+      CUDA_OK(cudaMemcpy2D(b->d.streams[ZKB_STREAM_FRAME], (size_t)b->cfg.cap_records[ZKB_STREAM_FRAME] * ZKB_FRAME_BYTES, b->h_bootrec.data(), 128,
+                           128, b->cfg.n_vms, cudaMemcpyHostToDevice));
+    b->root_dirty = false;
+  }
+  return ZKB_OK;
+}
+
+static int32_t download_hot(ZkbBatch* b) {
+  if (b->hot_stale) {
+    CUDA_OK(cudaSetDevice(b->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(b->last_stream));
+    CUDA_OK(cudaMemcpy(b->h_hot.data(), b->d.hot, b->h_hot.size() * sizeof(VmHot), cudaMemcpyDeviceToHost));
+    b->hot_stale = false;
+  }
+  return ZKB_OK;
+}
+
+static bool range_ok(ZkbBatch* b, uint32_t lo, uint32_t hi) { return b && lo <= hi && hi <= b->cfg.n_vms; }
+
+static int find_code(ZkbBatch* b, const uint8_t hash_be[32]) {
+  uint32_t limbs[8];
+  be32_to_limbs(hash_be, limbs);
+  for (size_t i = 0; i < b->codes.size(); i++)
+    if (memcmp(b->codes[i].hash, limbs, 32) == 0) return (int)i;
+  return -1;
+}
+
+extern "C" {
+
+const char* zkb_last_error(void) { return g_err.c_str(); }
+
+int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
+  if (!cfg || !out || cfg->n_vms == 0) return set_err(ZKB_ERR_INVALID_ARGUMENT, "null config / zero VMs");
+  if (cfg->heap_bytes % 32 || cfg->n_heap_slabs == 0 || cfg->n_heap_slabs > 32 || cfg->storage_slots < 32 ||
+      (cfg->storage_slots & (cfg->storage_slots - 1)) || cfg->max_far_depth == 0 || cfg->max_depth < 2 || cfg->stack_words == 0 ||
+      cfg->max_far_depth > 250)
+    return set_err(ZKB_ERR_INVALID_ARGUMENT, "bad capacity in ZkbConfig");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return set_err(ZKB_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  CUDA_OK(cudaSetDevice(cfg->device));
+  ZkbBatch* b = new ZkbBatch();
+  b->cfg = *cfg;
+  const ZkbConfig& c = b->cfg;
+  DevBatch& d = b->d;
+  memset(&d, 0, sizeof(d));
+  d.n_vms = c.n_vms;
+  d.witness = c.witness_mode;
+  for (int k = 0; k < ZKB_N_STREAMS; k++) d.cap[k] = c.cap_records[k];
+  d.stack_words = c.stack_words;
+  d.heap_words = c.heap_bytes / 32;
+  d.n_slabs = c.n_heap_slabs;
+  d.max_far_depth = c.max_far_depth;
+  d.max_depth = c.max_depth;
+  d.storage_slots = c.storage_slots;
+  d.journal_entries = std::max(1u, c.journal_entries);
+  size_t n = c.n_vms, levels = c.max_far_depth + 1;
+  cudaError_t e = cudaSuccess;
+#define ALLOC(ptr, count, zero)                                                                    \
+  if (e == cudaSuccess) e = dalloc(b, &(ptr), (count), (zero));
+  ALLOC(d.hot, n, false);
+  ALLOC(d.callstack, n * c.max_depth * 32, false);
+  ALLOC(d.stack_mem, n * levels * c.stack_words * 8, false);
+  ALLOC(d.stack_ptr, n * levels * c.stack_words, false);
+  ALLOC(d.heap_mem, n * c.n_heap_slabs * (size_t)d.heap_words * 8, false);
+  ALLOC(d.lvl, n * levels * 4, false);
+  ALLOC(d.slab_hwm, n * c.n_heap_slabs, false);
+  ALLOC(d.pt, n * ZKB_PT_ENTRIES * 2, false);
+  ALLOC(d.dec, n * ZKB_DEC_ENTRIES * 2, true);
+  ALLOC(d.st_tags, n * c.storage_slots, false);
+  ALLOC(d.st_keys, n * c.storage_slots * 8, true);
+  ALLOC(d.st_addr, n * c.storage_slots * 8, true);
+  ALLOC(d.st_vals, n * c.storage_slots * 8, false);
+  ALLOC(d.j_slot, n * d.journal_entries, true);
+  ALLOC(d.j_val, n * d.journal_entries * 8, true);
+  if (c.witness_mode)
+    for (int k = 0; k < ZKB_N_STREAMS; k++) ALLOC(d.streams[k], n * (size_t)c.cap_records[k] * REC_BYTES[k], false);
+  ALLOC(d.queue, 4, true);
+  ALLOC(b->d_fail, 4, true);
+  ALLOC(b->d_offsets, n + 1, false);
+#undef ALLOC
+  if (e != cudaSuccess) {
+    std::string msg = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    for (void* p : b->allocs) cudaFree(p);
+    delete b;
+    cudaGetLastError();
+    return set_err(ZKB_ERR_OUT_OF_MEMORY, msg);
+  }
+  b->h_hot.resize(n);
+  b->h_root.assign(n * 32, 0);
+  b->h_bootrec.assign(n * 32, 0);
+  b->boot_code.assign(n, -1);
+  b->boot_page.assign(n, 0);
+  for (auto& h : b->h_hot) init_hot(b, h);
+  memset(d.default_aa, 0, sizeof(d.default_aa));
+  int32_t rc = clear_cold_state(b);
+  if (rc != ZKB_OK) return rc;
+  CUDA_OK(cudaEventCreate(&b->ev0));
+  CUDA_OK(cudaEventCreate(&b->ev1));
+  int per_sm = 0, n_sm = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel, ZKB_WARPS_PER_CTA * 32, 0));
+  CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+  b->grid = std::max(1, per_sm * n_sm);  // persistent grid: a multiple of the SM count (148 on B200)
+  *out = b;
+  return ZKB_OK;
+}
+
+int32_t zkb_destroy(ZkbBatch* b) {
+  if (!b) return ZKB_OK;
+  cudaSetDevice(b->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->d_code_words) cudaFree(b->d_code_words);
+  if (b->d_code_meta) cudaFree(b->d_code_meta);
+  if (b->d_pack) cudaFree(b->d_pack);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  delete b;
+  return ZKB_OK;
+}
+
+int32_t zkb_reset(ZkbBatch* b) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  CUDA_OK(cudaDeviceSynchronize());
+  for (auto& h : b->h_hot) init_hot(b, h);
+  std::fill(b->h_root.begin(), b->h_root.end(), 0u);
+  std::fill(b->h_bootrec.begin(), b->h_bootrec.end(), 0u);
+  std::fill(b->boot_code.begin(), b->boot_code.end(), -1);
+  b->hot_dirty = b->root_dirty = true;
+  b->hot_stale = false;
+  return clear_cold_state(b);
+}
+
+int32_t zkb_load_bytecode(ZkbBatch* b, const uint8_t hash_be[32], const uint8_t* words_be, uint32_t n_words) {
+  if (!b || !hash_be || (!words_be && n_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (find_code(b, hash_be) >= 0) return set_err(ZKB_ERR_INVALID_ARGUMENT, "bytecode hash already loaded (decommitter.rs:25)");
+  Bytecode bc;
+  be32_to_limbs(hash_be, bc.hash);
+  bc.offset_words = (uint32_t)(b->h_code_words.size() / 8);
+  bc.len_words = n_words;
+  b->h_code_words.resize(b->h_code_words.size() + (size_t)n_words * 8);
+  for (uint32_t i = 0; i < n_words; i++) be32_to_limbs(words_be + 32 * (size_t)i, &b->h_code_words[((size_t)bc.offset_words + i) * 8]);
+  b->codes.push_back(bc);
+  b->codes_dirty = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_set_block_properties(ZkbBatch* b, const uint8_t default_aa_code_hash_be[32], uint8_t zkporter_is_available) {
+  if (!b || !default_aa_code_hash_be) return ZKB_ERR_INVALID_ARGUMENT;
+  be32_to_limbs(default_aa_code_hash_be, b->d.default_aa);
+  b->d.zkporter = zkporter_is_available ? 1u : 0u;
+  return ZKB_OK;
+}
+
+int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const ZkbStorageInit* entries, uint32_t n, uint32_t per_vm) {
+  if (!range_ok(b, vm_lo, vm_hi) || (!entries && n)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (n == 0 || vm_lo == vm_hi) return ZKB_OK;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  size_t total = per_vm ? (size_t)(vm_hi - vm_lo) * n : n;
+  std::vector<DevStorageInit> h(total);
+  for (size_t i = 0; i < total; i++) {
+    h[i].shard = entries[i].shard_id;
+    memcpy(h[i].addr, entries[i].address, 20);
+    be32_to_limbs(entries[i].key_be, h[i].key);
+    be32_to_limbs(entries[i].value_be, h[i].value);
+  }
+  DevStorageInit* d_e = nullptr;
+  CUDA_OK(cudaMalloc(&d_e, total * sizeof(DevStorageInit)));
+  CUDA_OK(cudaMemcpy(d_e, h.data(), total * sizeof(DevStorageInit), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(b->d_fail, 0, 4));
+  zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
+  CUDA_OK(cudaGetLastError());
+  uint32_t fail = 0;
+  CUDA_OK(cudaMemcpy(&fail, b->d_fail, 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaFree(d_e));
+  if (fail) return set_err(ZKB_ERR_INVALID_ARGUMENT, "storage table capacity exceeded while populating (raise ZkbConfig.storage_slots)");
+  return ZKB_OK;
+}
+
+int32_t zkb_populate_code(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t page, const uint8_t hash_be[32]) {
+  if (!range_ok(b, vm_lo, vm_hi) || !hash_be) return ZKB_ERR_INVALID_ARGUMENT;
+  int id = find_code(b, hash_be);
+  if (id < 0) return set_err(ZKB_ERR_UNKNOWN_BYTECODE, "populate_code: bytecode hash not loaded");
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    b->boot_code[v] = id;
+    b->boot_page[v] = page;
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_push_bootloader_context(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const ZkbFrame* f) {
+  if (!range_ok(b, vm_lo, vm_hi) || !f) return ZKB_ERR_INVALID_ARGUMENT;
+  if (b->cfg.max_depth < 2 || b->cfg.max_far_depth < 1) return ZKB_ERR_INVALID_ARGUMENT;
+  if (download_hot(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    VmHot& h = b->h_hot[v];
+    if (h.live[L_DEPTH - 40] != 0) return set_err(ZKB_ERR_INVALID_ARGUMENT, "bootloader context already pushed");
+    // helpers.rs:295-303: the root frame keeps the difference
+    if (h.F[F_ERGS] < f->ergs_remaining) return set_err(ZKB_ERR_INVALID_ARGUMENT, "trying to create bootloader frame with more ergs than VM has available");
+    h.F[F_ERGS] -= f->ergs_remaining;
+    h.F[F_JOURNAL_MARK] = 0;
+    memcpy(&b->h_root[(size_t)v * 32], h.F, 128);
+    uint32_t* F = h.F;
+    memset(F, 0, 128);
+    memcpy(&F[F_THIS], f->this_address, 20);
+    memcpy(&F[F_SENDER], f->msg_sender, 20);
+    memcpy(&F[F_CODE_ADDR], f->code_address, 20);
+    F[F_BASE_PAGE] = f->base_memory_page;
+    F[F_CODE_PAGE] = f->code_page;
+    F[F_SP_PC] = (uint32_t)f->sp | (uint32_t)f->pc << 16;
+    F[F_EH_SHARDS] = (uint32_t)f->exception_handler_location | (uint32_t)f->this_shard_id << 16 | (uint32_t)f->caller_shard_id << 24;
+    F[F_ERGS] = f->ergs_remaining;
+    F[F_MISC] = (uint32_t)f->code_shard_id | (uint32_t)(f->is_static ? 1 : 0) << 8 | (uint32_t)(f->is_local_frame ? 1 : 0) << 16;
+    memcpy(&F[F_CTX], f->context_u128_value, 16);
+    F[F_HEAP_BOUND] = f->heap_bound;
+    F[F_AUX_BOUND] = f->aux_heap_bound;
+    F[F_CODE_ID] = (b->boot_code[v] >= 0 && b->boot_page[v] == f->code_page) ? (uint32_t)b->boot_code[v] : ZKB_NO_CODE;
+    F[F_JOURNAL_MARK] = 0;
+    F[F_FAR_LEVEL] = 1;  // memory.start_global_frame(UNMAPPED_PAGE, base, empty ptr) (helpers.rs:308-315)
+    bool kernel = F[0] == 0 && F[1] == 0 && F[2] == 0 && F[3] == 0 && (F[4] & 0xFFFFu) == 0;
+    uint32_t bits = (f->is_static ? ZKB_FRAMEBIT_STATIC : 0u) | (f->is_local_frame ? ZKB_FRAMEBIT_LOCAL : 0u) | (kernel ? ZKB_FRAMEBIT_KERNEL : 0u);
+    h.live[L_DEPTH - 40] = 1;
+    h.live[L_CODE_PAGE - 40] = f->code_page;
+    h.live[L_BASE_PAGE - 40] = f->base_memory_page;
+    h.live[L_HEAP_BOUND - 40] = f->heap_bound;
+    h.live[L_AUX_BOUND - 40] = f->aux_heap_bound;
+    h.live[L_EH_BITS - 40] = (uint32_t)f->exception_handler_location | bits << 16;
+    h.x[X_FAR_DEPTH] = 1;
+    // start_frame -> witness_tracer.start_new_execution_context (helpers.rs:237-241): the VM's first frame record
+    uint32_t* rec = &b->h_bootrec[(size_t)v * 32];
+    memset(rec, 0, 128);
+    rec[0] = ZKB_FRAMEKIND_START;
+    rec[1] = h.x[X_CYCLE];
+    memcpy(&rec[2], F, 27 * 4);
+    rec[29] = b->h_root[(size_t)v * 32 + F_ERGS];
+    rec[30] = b->h_root[(size_t)v * 32 + F_SP_PC] >> 16 | (b->h_root[(size_t)v * 32 + F_SP_PC] & 0xFFFFu) << 16;
+    if (h.x[X_COUNT0 + ZKB_STREAM_FRAME] == 0) h.x[X_COUNT0 + ZKB_STREAM_FRAME] = 1;
+  }
+  b->hot_dirty = b->root_dirty = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_populate_heap(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* bytes, uint32_t n_bytes, uint32_t per_vm) {
+  if (!range_ok(b, vm_lo, vm_hi) || (!bytes && n_bytes)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (n_bytes > b->cfg.heap_bytes) return set_err(ZKB_ERR_INVALID_ARGUMENT, "populate_heap: image larger than ZkbConfig.heap_bytes");
+  if (n_bytes == 0 || vm_lo == vm_hi) return ZKB_OK;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  if (download_hot(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    VmHot& h = b->h_hot[v];
+    if (h.x[X_FAR_DEPTH] != 1) return set_err(ZKB_ERR_INVALID_ARGUMENT, "populate_heap: push the bootloader context first");
+    h.x[X_SLAB_FREE] &= ~1u;  // slab 0 = heap of the bootloader frame
+  }
+  b->hot_dirty = true;
+  size_t total = per_vm ? (size_t)(vm_hi - vm_lo) * n_bytes : n_bytes;
+  uint8_t* d_bytes = nullptr;
+  CUDA_OK(cudaMalloc(&d_bytes, total));
+  CUDA_OK(cudaMemcpy(d_bytes, bytes, total, cudaMemcpyHostToDevice));
+  zkb_populate_heap_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_bytes, n_bytes, per_vm, 1);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaFree(d_bytes));
+  return ZKB_OK;
+}
+
+int32_t zkb_set_register(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t reg, const uint8_t* value_be, uint8_t is_pointer, uint32_t per_vm) {
+  if (!range_ok(b, vm_lo, vm_hi) || reg >= ZK_REGISTERS_COUNT || !value_be) return ZKB_ERR_INVALID_ARGUMENT;
+  if (download_hot(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    VmHot& h = b->h_hot[v];
+    be32_to_limbs(per_vm ? value_be + (size_t)(v - vm_lo) * 32 : value_be, h.regs[reg + 1]);
+    h.x[X_PTRMASK] = (h.x[X_PTRMASK] & ~(1u << (reg + 1))) | (is_pointer ? 1u << (reg + 1) : 0u);
+  }
+  b->hot_dirty = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_set_local_field(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t field, uint32_t value) {
+  if (!range_ok(b, vm_lo, vm_hi)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (download_hot(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    VmHot& h = b->h_hot[v];
+    switch (field) {
+      case ZKB_FIELD_MEMORY_PAGE_COUNTER: h.live[L_PAGE_COUNTER - 40] = value; break;
+      case ZKB_FIELD_ERGS_PER_PUBDATA: h.live[L_EPP - 40] = value; break;
+      case ZKB_FIELD_TX_NUMBER: h.live[L_TX_PSP - 40] = (h.live[L_TX_PSP - 40] & 0xFFFF0000u) | (value & 0xFFFFu); break;
+      case ZKB_FIELD_TIMESTAMP: h.x[X_TIMESTAMP] = value; break;
+      default: return ZKB_ERR_INVALID_ARGUMENT;
+    }
+  }
+  b->hot_dirty = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = upload(b);
+  if (rc != ZKB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  b->last_stream = st;
+  CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 4, st));
+  CUDA_OK(cudaEventRecord(b->ev0, st));
+  int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_WARPS_PER_CTA - 1) / ZKB_WARPS_PER_CTA));
+  zkb_run_kernel<<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(b->ev1, st));
+  b->n_launches = 1;
+  b->hot_stale = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_sync(ZkbBatch* b) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(b->last_stream));
+  return ZKB_OK;
+}
+
+int32_t zkb_last_run_ms(ZkbBatch* b, float* ms, uint32_t* n_kernel_launches) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaEventSynchronize(b->ev1));
+  float t = 0;
+  CUDA_OK(cudaEventElapsedTime(&t, b->ev0, b->ev1));
+  if (ms) *ms = t;
+  if (n_kernel_launches) *n_kernel_launches = b->n_launches;
+  return ZKB_OK;
+}
+
+int32_t zkb_vm_status(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, ZkbVmStatus* out) {
+  if (!range_ok(b, vm_lo, vm_hi) || !out) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    const VmHot& h = b->h_hot[v];
+    uint32_t code = h.x[X_STATUS];
+    if (code == ZKB_VM_RUNNING && h.live[L_DEPTH - 40] == 0 && h.x[X_CYCLE] > 0) code = ZKB_VM_ENDED;
+    out[v - vm_lo].code = code;
+    out[v - vm_lo].cycles = h.x[X_CYCLE];
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_read_local_state(ZkbBatch* b, uint32_t vm, ZkbLocalState* out) {
+  if (!b || vm >= b->cfg.n_vms || !out) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  const VmHot& h = b->h_hot[vm];
+  memset(out, 0, sizeof(*out));
+  memcpy(out->previous_code_word, h.prev_word, 32);
+  out->previous_code_memory_page = h.x[X_PREV_CODE_PAGE];
+  for (int i = 0; i < 15; i++) memcpy(out->registers[i], h.regs[i + 1], 32);
+  out->register_is_pointer = (uint16_t)(h.x[X_PTRMASK] >> 1);
+  out->flags = (uint8_t)h.x[X_FLAGS];
+  out->pending_exception = (uint8_t)h.x[X_PENDING];
+  out->timestamp = h.x[X_TIMESTAMP];
+  out->monotonic_cycle_counter = h.x[X_CYCLE];
+  out->spent_pubdata_counter = h.live[L_SPENT_PUBDATA - 40];
+  out->memory_page_counter = h.live[L_PAGE_COUNTER - 40];
+  out->absolute_execution_step = 0;
+  out->current_ergs_per_pubdata_byte = h.live[L_EPP - 40];
+  out->tx_number_in_block = (uint16_t)(h.live[L_TX_PSP - 40] & 0xFFFFu);
+  out->previous_super_pc = (uint16_t)(h.live[L_TX_PSP - 40] >> 16);
+  memcpy(out->context_u128_register, &h.live[L_CTX - 40], 16);
+  out->callstack_depth = h.live[L_DEPTH - 40];
+  ZkbFrame& f = out->current_frame;
+  const uint32_t* F = h.F;
+  memcpy(f.this_address, &F[F_THIS], 20);
+  memcpy(f.msg_sender, &F[F_SENDER], 20);
+  memcpy(f.code_address, &F[F_CODE_ADDR], 20);
+  f.base_memory_page = F[F_BASE_PAGE];
+  f.code_page = F[F_CODE_PAGE];
+  f.sp = (uint16_t)(F[F_SP_PC] & 0xFFFFu);
+  f.pc = (uint16_t)(F[F_SP_PC] >> 16);
+  f.exception_handler_location = (uint16_t)(F[F_EH_SHARDS] & 0xFFFFu);
+  f.ergs_remaining = F[F_ERGS];
+  f.this_shard_id = (uint8_t)(F[F_EH_SHARDS] >> 16);
+  f.caller_shard_id = (uint8_t)(F[F_EH_SHARDS] >> 24);
+  f.code_shard_id = (uint8_t)(F[F_MISC] & 0xFFu);
+  f.is_static = (uint8_t)((F[F_MISC] >> 8) & 1u);
+  f.is_local_frame = (uint8_t)((F[F_MISC] >> 16) & 1u);
+  memcpy(f.context_u128_value, &F[F_CTX], 16);
+  f.heap_bound = F[F_HEAP_BOUND];
+  f.aux_heap_bound = F[F_AUX_BOUND];
+  return ZKB_OK;
+}
+
+int32_t zkb_stream_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out) {
+  if (!range_ok(b, vm_lo, vm_hi) || kind >= ZKB_N_STREAMS || !counts_out) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) counts_out[v - vm_lo] = b->h_hot[v].x[X_COUNT0 + kind];
+  return ZKB_OK;
+}
+
+int32_t zkb_totals(ZkbBatch* b, uint64_t* total_cycles, uint64_t stream_bytes[ZKB_N_STREAMS]) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  uint64_t cyc = 0, sb[ZKB_N_STREAMS] = {0, 0, 0, 0, 0, 0};
+  for (const VmHot& h : b->h_hot) {
+    cyc += h.x[X_CYCLE];
+    for (int k = 0; k < ZKB_N_STREAMS; k++) sb[k] += (uint64_t)h.x[X_COUNT0 + k] * REC_BYTES[k];
+  }
+  if (total_cycles) *total_cycles = cyc;
+  if (stream_bytes) memcpy(stream_bytes, sb, sizeof(sb));
+  return ZKB_OK;
+}
+
+int32_t zkb_stream_device_view(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* stride_bytes) {
+  if (!b || kind >= ZKB_N_STREAMS) return ZKB_ERR_INVALID_ARGUMENT;
+  if (dptr) *dptr = b->d.streams[kind];
+  if (stride_bytes) *stride_bytes = (uint64_t)b->cfg.cap_records[kind] * REC_BYTES[kind];
+  return ZKB_OK;
+}
+
+int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
+  if (!b || vm >= b->cfg.n_vms || kind >= ZKB_N_STREAMS) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  uint64_t n = b->cfg.witness_mode ? (uint64_t)b->h_hot[vm].x[X_COUNT0 + kind] * REC_BYTES[kind] : 0;
+  if (n_bytes) *n_bytes = n;
+  uint64_t take = std::min(n, max_bytes);
+  if (dst && take) {
+    CUDA_OK(cudaSetDevice(b->cfg.device));
+    CUDA_OK(cudaMemcpy(dst, b->d.streams[kind] + (size_t)vm * b->cfg.cap_records[kind] * REC_BYTES[kind], take, cudaMemcpyDeviceToHost));
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || kind >= ZKB_N_STREAMS || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  uint32_t n = b->cfg.n_vms;
+  std::vector<uint64_t> off(n + 1);
+  off[0] = 0;
+  for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_hot[v].x[X_COUNT0 + kind] * REC_BYTES[kind];
+  uint64_t total = off[n];
+  if (total > b->pack_capacity) {
+    if (b->d_pack) CUDA_OK(cudaFree(b->d_pack));
+    b->d_pack = nullptr;
+    b->pack_capacity = 0;
+    CUDA_OK(cudaMalloc(&b->d_pack, total));
+    b->pack_capacity = total;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_OK(cudaMemcpyAsync(b->d_offsets, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (total) {
+    zkb_pack_kernel<<<n, 128, 0, st>>>(b->d.streams[kind], (uint64_t)b->cfg.cap_records[kind] * REC_BYTES[kind], b->d_offsets, b->d_pack, n);
+    CUDA_OK(cudaGetLastError());
+  }
+  CUDA_OK(cudaStreamSynchronize(st));  // `off` is a host temporary
+  if (dptr) *dptr = b->d_pack;
+  if (n_bytes) *n_bytes = total;
+  return ZKB_OK;
+}
+
+int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity, uint64_t* offsets_out) {
+  if (!b || kind >= ZKB_N_STREAMS) return ZKB_ERR_INVALID_ARGUMENT;
+  void* dptr = nullptr;
+  uint64_t total = 0;
+  int32_t rc = zkb_pack_stream_device(b, kind, &dptr, &total, nullptr);
+  if (rc != ZKB_OK) return rc;
+  if (offsets_out) {
+    uint64_t acc = 0;
+    for (uint32_t v = 0; v < b->cfg.n_vms; v++) {
+      offsets_out[v] = acc;
+      acc += (uint64_t)b->h_hot[v].x[X_COUNT0 + kind] * REC_BYTES[kind];
+    }
+    offsets_out[b->cfg.n_vms] = acc;
+  }
+  if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_stream_packed: host buffer too small");
+  if (total && host_dst) CUDA_OK(cudaMemcpy(host_dst, dptr, total, cudaMemcpyDeviceToHost));
+  return ZKB_OK;
+}
+
+int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8_t address[20], const uint8_t key_be[32], uint8_t value_be_out[32]) {
+  if (!b || vm >= b->cfg.n_vms || !address || !key_be || !value_be_out) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  uint32_t slots = b->cfg.storage_slots;
+  std::vector<uint32_t> tags(slots), keys((size_t)slots * 8), addrs((size_t)slots * 8), vals((size_t)slots * 8);
+  CUDA_OK(cudaMemcpy(tags.data(), b->d.st_tags + (size_t)vm * slots, slots * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(keys.data(), b->d.st_keys + (size_t)vm * slots * 8, (size_t)slots * 32, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(addrs.data(), b->d.st_addr + (size_t)vm * slots * 8, (size_t)slots * 32, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(vals.data(), b->d.st_vals + (size_t)vm * slots * 8, (size_t)slots * 32, cudaMemcpyDeviceToHost));
+  uint32_t key[8], aw[5];
+  be32_to_limbs(key_be, key);
+  memcpy(aw, address, 20);
+  memset(value_be_out, 0, 32);
+  for (uint32_t s = 0; s < slots; s++) {
+    if (!tags[s]) continue;
+    if (memcmp(&keys[(size_t)s * 8], key, 32) == 0 && memcmp(&addrs[(size_t)s * 8], aw, 20) == 0 && addrs[(size_t)s * 8 + 5] == shard_id) {
+      limbs_to_be32(&vals[(size_t)s * 8], value_be_out);
+      break;
+    }
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n_bytes, uint8_t* out) {
+  if (!b || vm >= b->cfg.n_vms || (!out && n_bytes)) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  uint32_t level = b->h_hot[vm].x[X_FAR_DEPTH];
+  uint32_t lv[4];
+  CUDA_OK(cudaMemcpy(lv, b->d.lvl + ((size_t)vm * (b->cfg.max_far_depth + 1) + level) * 4, 16, cudaMemcpyDeviceToHost));
+  memset(out, 0, n_bytes);
+  if (lv[0] == ZKB_NO_SLAB) return ZKB_OK;
+  uint32_t hw = b->cfg.heap_bytes / 32;
+  std::vector<uint32_t> slab((size_t)hw * 8);
+  CUDA_OK(cudaMemcpy(slab.data(), b->d.heap_mem + ((size_t)vm * b->cfg.n_heap_slabs + lv[0]) * hw * 8, (size_t)hw * 32, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n_bytes; i++) {
+    uint32_t a = byte_offset + i, w = a / 32, k = a % 32;
+    if (w >= hw) break;
+    uint32_t limb = slab[(size_t)w * 8 + (31 - k) / 4];
+    out[i] = (uint8_t)(limb >> (8 * ((31 - k) % 4)));
+  }
+  return ZKB_OK;
+}
+
+}  // extern "C"

@@ -444,7 +444,7 @@ class KeccakHeavy(Workload):
         cfg.n_heap_slabs = 6
         cfg.max_far_depth = 3
         cfg.max_depth = 4
-        cfg.storage_slots = 16
+        cfg.storage_slots = 32
         cfg.journal_entries = 8
         return cfg
 
