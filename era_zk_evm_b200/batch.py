@@ -39,7 +39,11 @@ class GpuVmBatch(_binding.Batch):
         lib.zkb_stream_device_view.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
         lib.zkb_fetch_stream_packed.argtypes = [vp, u32, vp, u64, vp]
         lib.zkb_pack_stream_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp]
-        for name in ("stream_device_view", "fetch_stream_packed", "pack_stream_device"):
+        lib.zkb_snapshot.argtypes = [vp]
+        lib.zkb_restore.argtypes = [vp, vp]
+        lib.zkb_transfer_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), u32]
+        for name in ("stream_device_view", "fetch_stream_packed", "pack_stream_device", "snapshot", "restore",
+                     "transfer_stats"):
             getattr(lib, "zkb_" + name).restype = C.c_int32
 
     def stream_device_view(self, kind: int):
@@ -62,3 +66,14 @@ class GpuVmBatch(_binding.Batch):
             return buf[:total], offsets
         self._check(self._lib.zkb_fetch_stream_packed(self._h, kind, host_ptr, host_capacity, offsets.ctypes.data))
         return None, offsets
+
+    def snapshot(self):
+        self._check(self._lib.zkb_snapshot(self._h))
+
+    def restore(self, stream=None):
+        self._check(self._lib.zkb_restore(self._h, stream))
+
+    def transfer_stats(self, reset: bool = False):
+        h2d, d2h = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.zkb_transfer_stats(self._h, C.byref(h2d), C.byref(d2h), int(reset)))
+        return h2d.value, d2h.value

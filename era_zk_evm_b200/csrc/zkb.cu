@@ -167,6 +167,15 @@ struct ZkbBatch {
   uint64_t pack_capacity = 0;
   uint64_t* d_offsets = nullptr;
   std::vector<void*> allocs;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;
+  // checkpoint (VmLocalState: Clone, vm_state/mod.rs:53): device copies of every mutable per-VM array
+  struct Region {
+    void* live;
+    void* saved;
+    size_t bytes;
+  };
+  std::vector<Region> snap;
+  bool has_snapshot = false;
 };
 
 static void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {
@@ -249,6 +258,7 @@ static int32_t upload(ZkbBatch* b) {
   }
   if (b->hot_dirty) {
     CUDA_OK(cudaMemcpy(b->d.hot, b->h_hot.data(), b->h_hot.size() * sizeof(VmHot), cudaMemcpyHostToDevice));
+    b->h2d_bytes += b->h_hot.size() * sizeof(VmHot);
     b->hot_dirty = false;
   }
   if (b->root_dirty) {
@@ -256,6 +266,7 @@ static int32_t upload(ZkbBatch* b) {
     if (b->cfg.witness_mode && b->cfg.cap_records[ZKB_STREAM_FRAME] > 0)
       CUDA_OK(cudaMemcpy2D(b->d.streams[ZKB_STREAM_FRAME], (size_t)b->cfg.cap_records[ZKB_STREAM_FRAME] * ZKB_FRAME_BYTES, b->h_bootrec.data(), 128,
                            128, b->cfg.n_vms, cudaMemcpyHostToDevice));
+    b->h2d_bytes += (size_t)b->cfg.n_vms * 256;
     b->root_dirty = false;
   }
   return ZKB_OK;
@@ -266,6 +277,7 @@ static int32_t download_hot(ZkbBatch* b) {
     CUDA_OK(cudaSetDevice(b->cfg.device));
     CUDA_OK(cudaStreamSynchronize(b->last_stream));
     CUDA_OK(cudaMemcpy(b->h_hot.data(), b->d.hot, b->h_hot.size() * sizeof(VmHot), cudaMemcpyDeviceToHost));
+    b->d2h_bytes += b->h_hot.size() * sizeof(VmHot);
     b->hot_stale = false;
   }
   return ZKB_OK;
@@ -368,6 +380,8 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->d_code_words) cudaFree(b->d_code_words);
   if (b->d_code_meta) cudaFree(b->d_code_meta);
   if (b->d_pack) cudaFree(b->d_pack);
+  for (auto& r : b->snap)
+    if (r.saved) cudaFree(r.saved);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   delete b;
@@ -423,6 +437,7 @@ int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const 
   DevStorageInit* d_e = nullptr;
   CUDA_OK(cudaMalloc(&d_e, total * sizeof(DevStorageInit)));
   CUDA_OK(cudaMemcpy(d_e, h.data(), total * sizeof(DevStorageInit), cudaMemcpyHostToDevice));
+  b->h2d_bytes += total * sizeof(DevStorageInit);
   CUDA_OK(cudaMemset(b->d_fail, 0, 4));
   zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
   CUDA_OK(cudaGetLastError());
@@ -512,6 +527,7 @@ int32_t zkb_populate_heap(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uin
   uint8_t* d_bytes = nullptr;
   CUDA_OK(cudaMalloc(&d_bytes, total));
   CUDA_OK(cudaMemcpy(d_bytes, bytes, total, cudaMemcpyHostToDevice));
+  b->h2d_bytes += total;
   zkb_populate_heap_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_bytes, n_bytes, per_vm, 1);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
@@ -728,7 +744,10 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
     offsets_out[b->cfg.n_vms] = acc;
   }
   if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_stream_packed: host buffer too small");
-  if (total && host_dst) CUDA_OK(cudaMemcpy(host_dst, dptr, total, cudaMemcpyDeviceToHost));
+  if (total && host_dst) {
+    CUDA_OK(cudaMemcpy(host_dst, dptr, total, cudaMemcpyDeviceToHost));
+    b->d2h_bytes += total;
+  }
   return ZKB_OK;
 }
 
@@ -774,6 +793,66 @@ int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n
     uint32_t limb = slab[(size_t)w * 8 + (31 - k) / 4];
     out[i] = (uint8_t)(limb >> (8 * ((31 - k) % 4)));
   }
+  return ZKB_OK;
+}
+
+int32_t zkb_transfer_stats(ZkbBatch* b, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint32_t reset) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  if (h2d_bytes) *h2d_bytes = b->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = b->d2h_bytes;
+  if (reset) b->h2d_bytes = b->d2h_bytes = 0;
+  return ZKB_OK;
+}
+
+int32_t zkb_snapshot(ZkbBatch* b) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = upload(b);
+  if (rc != ZKB_OK) return rc;
+  CUDA_OK(cudaDeviceSynchronize());
+  const ZkbConfig& c = b->cfg;
+  const DevBatch& d = b->d;
+  size_t n = c.n_vms, levels = c.max_far_depth + 1;
+  if (b->snap.empty()) {
+    auto add = [&](void* live, size_t bytes) { b->snap.push_back(ZkbBatch::Region{live, nullptr, bytes}); };
+    add(d.hot, n * sizeof(VmHot));
+    add(d.callstack, n * c.max_depth * 128);
+    add(d.stack_mem, n * levels * c.stack_words * 32);
+    add(d.stack_ptr, n * levels * c.stack_words);
+    add(d.heap_mem, n * c.n_heap_slabs * (size_t)c.heap_bytes);
+    add(d.lvl, n * levels * 16);
+    add(d.slab_hwm, n * c.n_heap_slabs * 4);
+    add(d.pt, n * ZKB_PT_ENTRIES * 8);
+    add(d.dec, n * ZKB_DEC_ENTRIES * 8);
+    add(d.st_tags, n * c.storage_slots * 4);
+    add(d.st_keys, n * c.storage_slots * 32);
+    add(d.st_addr, n * c.storage_slots * 32);
+    add(d.st_vals, n * c.storage_slots * 32);
+    for (auto& r : b->snap) {
+      cudaError_t e = cudaMalloc(&r.saved, std::max<size_t>(r.bytes, 16));
+      if (e != cudaSuccess) {
+        for (auto& q : b->snap)
+          if (q.saved) cudaFree(q.saved);
+        b->snap.clear();
+        return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("snapshot cudaMalloc: ") + cudaGetErrorString(e));
+      }
+    }
+  }
+  rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  for (auto& r : b->snap) CUDA_OK(cudaMemcpy(r.saved, r.live, r.bytes, cudaMemcpyDeviceToDevice));
+  b->has_snapshot = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
+  if (!b || !b->has_snapshot) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_restore without zkb_snapshot");
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  for (auto& r : b->snap) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
+  b->last_stream = st;
+  b->hot_dirty = false;
+  b->hot_stale = true;
   return ZKB_OK;
 }
 

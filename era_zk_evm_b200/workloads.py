@@ -342,7 +342,8 @@ class Erc20(Workload):
         cfg.cap_records[5] = 4 * self.n_transfers + 8
         cfg.stack_words = 16
         cfg.heap_bytes = 2048
-        cfg.n_heap_slabs = 8
+        # every returned token heap stays reachable from the bootloader frame until it ends (memory.rs:702-712)
+        cfg.n_heap_slabs = min(32, self.n_transfers + 6)
         cfg.max_far_depth = 5
         cfg.max_depth = 8
         cfg.storage_slots = 64

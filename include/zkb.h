@@ -190,6 +190,14 @@ int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8
 /* read back memory of the current frame's heap (debug / tests; = dump_page_content, memory.rs:300-313) */
 int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n_bytes, uint8_t* out);
 
+/* ---- checkpoint / accounting ---------------------------------------------------------------------- */
+/* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a
+ * device-side copy of every mutable per-VM array, restore puts it back (asynchronously on `cuda_stream`). */
+int32_t zkb_snapshot(ZkbBatch* b);
+int32_t zkb_restore(ZkbBatch* b, void* cuda_stream);
+/* host<->device bytes moved by this batch's API calls so far (optionally reset the counters) */
+int32_t zkb_transfer_stats(ZkbBatch* b, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint32_t reset);
+
 #ifdef __cplusplus
 }
 #endif
