@@ -18,6 +18,7 @@ N_STREAMS = records.N_STREAMS
 VM_RUNNING, VM_ENDED, VM_UNKNOWN_CODE_HASH, VM_REFERENCE_PANIC = 0, 1, 2, 3
 VM_CAP_STREAM, VM_CAP_STACK, VM_CAP_HEAP, VM_CAP_DEPTH, VM_CAP_STORAGE, VM_CAP_PAGES, VM_UNSUPPORTED = range(16, 23)
 
+SCHED_AUTO, SCHED_FREE, SCHED_LOCKSTEP = 0, 1, 2
 FIELD_MEMORY_PAGE_COUNTER, FIELD_ERGS_PER_PUBDATA, FIELD_TX_NUMBER, FIELD_TIMESTAMP = range(4)
 
 
@@ -26,7 +27,7 @@ class ZkbConfig(C.Structure):
                 ("cap_records", C.c_uint32 * N_STREAMS), ("stack_words", C.c_uint32), ("heap_bytes", C.c_uint32),
                 ("n_heap_slabs", C.c_uint32), ("max_far_depth", C.c_uint32), ("max_depth", C.c_uint32),
                 ("storage_slots", C.c_uint32), ("journal_entries", C.c_uint32), ("host_mirror", C.c_uint32),
-                ("reserved", C.c_uint32 * 4)]
+                ("schedule", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class ZkbFrame(C.Structure):

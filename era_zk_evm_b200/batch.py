@@ -17,7 +17,7 @@ from . import _binding, records
 from ._binding import ZkbConfig, ZkbError  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkb.so")
+LIB_PATH = os.environ.get("ZKB_LIB_PATH") or os.path.join(_HERE, "libzkb.so")   # override: kernel-variant experiments only
 _LIB = None
 
 

@@ -20,15 +20,23 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
+def build(force: bool = False, verbose: bool = False, extra=(), out: str = OUT) -> str:
     from . import isa
     isa.write_header()
-    if force or stale():
+    if force or out != OUT or stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
-            ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+            ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
         subprocess.check_call(cmd)
-    return OUT
+    return out
+
+
+def build_variant(tag: str, warps: int, min_ctas: int, extra=()) -> str:
+    """kernel-tuning experiments: build/variants/libzkb_<tag>.so (selected with ZKB_LIB_PATH)"""
+    d = os.path.join(HERE, "..", "build", "variants")
+    os.makedirs(d, exist_ok=True)
+    out = os.path.abspath(os.path.join(d, f"libzkb_{tag}.so"))
+    return build(force=True, extra=[f"-DZKB_WARPS_PER_CTA={warps}", f"-DZKB_MIN_CTAS_PER_SM={min_ctas}"] + list(extra), out=out)
 
 
 if __name__ == "__main__":

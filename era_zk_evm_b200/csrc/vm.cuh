@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t rec_bytes(int kind) {
 }
 
 // shared memory per warp
-struct WarpSmem {
+struct __align__(16) WarpSmem {
   uint32_t regs[16][8];
   uint32_t row[64];
   uint32_t F[32];
@@ -122,6 +122,8 @@ struct Vm {
   uint32_t* g_lvl;
   uint32_t* g_slab_hwm;
   uint32_t* g_pt;
+  uint8_t* row_base;  // this VM's slab of the ROWS / MEM streams (the two streams written every cycle)
+  uint8_t* mem_base;
 
   __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {
     g_stack = B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8;
@@ -130,6 +132,8 @@ struct Vm {
     g_lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
     g_slab_hwm = B.slab_hwm + (size_t)vm * B.n_slabs;
     g_pt = B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2;
+    row_base = B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES;
+    mem_base = B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES;
   }
 
   // ---- small helpers -------------------------------------------------------------------------------
@@ -163,6 +167,8 @@ struct Vm {
   }
 
   // ---- record emission (VmWitnessTracer callbacks -> packed records) ---------------------------------
+  // Every record is written straight from the registers that hold its fields: the scalar header by lane 0 as one
+  // 8/16-byte vector store, each U256 by lanes 0..7 (one 32-byte segment) -- no shuffles, no lane-select chains.
   __device__ __forceinline__ uint8_t* stream_slot(int kind) {
     uint32_t n = count[kind];
     if (n >= B.cap[kind]) {
@@ -178,12 +184,16 @@ struct Vm {
   __device__ __forceinline__ void emit_mem(uint32_t ts, uint32_t page, uint32_t index, uint32_t mtype, uint32_t rw, uint32_t is_ptr,
                                            uint32_t origin, u256l value) {
     cm++;
-    uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_MEM);
-    uint32_t v = __shfl_sync(ZK_FULL, value, (lane - 4) & 31);
-    if (p) {
-      uint32_t w = lane == 0 ? ts : lane == 1 ? page : lane == 2 ? index : lane == 3 ? (mtype | rw << 8 | is_ptr << 16 | origin << 24) : v;
-      if (lane < 12) p[lane] = w;
+    uint32_t n = count[ZKB_STREAM_MEM];
+    if (n >= B.cap[ZKB_STREAM_MEM]) {
+      fail(ZKB_VM_CAP_STREAM);
+      return;
     }
+    count[ZKB_STREAM_MEM] = n + 1;
+    if (!B.witness) return;
+    uint32_t* p = reinterpret_cast<uint32_t*>(mem_base + (size_t)n * ZKB_MEM_BYTES);
+    if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, index, mtype | rw << 8 | is_ptr << 16 | origin << 24);
+    if (lane < 8) p[4 + lane] = value;
   }
 
   // witness_tracer.add_log_query (helpers.rs:151,161,208); aw = address words in lanes 0..4
@@ -192,13 +202,17 @@ struct Vm {
     cl++;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_LOG);
     uint32_t tx = S.row[L_TX_PSP] & 0xFFFFu;
-    uint32_t a = __shfl_sync(ZK_FULL, aw, (lane - 2) & 31);
-    uint32_t k = __shfl_sync(ZK_FULL, key, (lane - 8) & 31);
-    uint32_t r = __shfl_sync(ZK_FULL, read_value, (lane - 16) & 31);
-    uint32_t wv = __shfl_sync(ZK_FULL, written_value, (lane - 24) & 31);
     if (p) {
-      uint32_t w = lane == 0 ? ts : lane == 1 ? (tx | aux << 16 | shard << 24) : lane < 7 ? a : lane == 7 ? (rw | is_service << 16) : lane < 16 ? k : lane < 24 ? r : wv;
-      p[lane] = w;
+      if (lane == 0) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(ts, tx | aux << 16 | shard << 24);
+        p[7] = rw | is_service << 16;
+      }
+      if (lane < 5) p[2 + lane] = aw;
+      if (lane < 8) {
+        p[8 + lane] = key;
+        p[16 + lane] = read_value;
+        p[24 + lane] = written_value;
+      }
     }
   }
 
@@ -206,10 +220,9 @@ struct Vm {
   __device__ __forceinline__ void emit_decommit(uint32_t ts, uint32_t page, uint32_t len, uint32_t fresh, u256l hash) {
     cd++;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_DECOMMIT);
-    uint32_t v = __shfl_sync(ZK_FULL, hash, (lane - 4) & 31);
     if (p) {
-      uint32_t w = lane == 0 ? ts : lane == 1 ? page : lane == 2 ? ((len & 0xFFFFu) | fresh << 16) : lane == 3 ? 0u : v;
-      if (lane < 12) p[lane] = w;
+      if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, (len & 0xFFFFu) | fresh << 16, 0u);
+      if (lane < 8) p[4 + lane] = hash;
     }
   }
 
@@ -562,13 +575,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   // ---- decode, price, exceptions, condition (cycle.rs:132-217) ----
   uint32_t vidx = raw_lo & ((1u << ZK_VARIANT_BITS) - 1u);
   entry = ZK_OPCODE_TABLE[vidx];
-  uint32_t price = ZK_OPCODE_PRICES[vidx];
-  uint32_t cond = (raw_lo >> ZK_COND_SHIFT) & 7u;
-  uint32_t src0_reg = (raw_lo >> 16) & 15u, src1_reg = (raw_lo >> 20) & 15u;
-  dst0_reg = (raw_lo >> 24) & 15u;
-  dst1_reg = raw_lo >> 28;
-  imm0 = raw_hi & 0xFFFFu;
-  imm1 = raw_hi >> 16;
+  const uint32_t price = ZK_OPCODE_PRICES[vidx];
   uint32_t err = (entry & ZK_E_INVALID) ? 1u : 0u;
   if (ergs < price) {
     ergs = 0;
@@ -581,22 +588,28 @@ __device__ __forceinline__ void Vm::cycle_once() {
   if ((entry & ZK_E_KERNEL_ONLY) && !kernel_mode) err |= 4u;
   if ((entry & ZK_E_STATIC_FORBIDDEN) && (fbits & ZKB_FRAMEBIT_STATIC)) err |= 8u;
   if (S.row[L_DEPTH] == ZK_VM_MAX_STACK_DEPTH) err |= 16u;
+  // flags: bit0 LT/OF, bit1 EQ, bit2 GT.  Byte `cond` of the table = the set of flag values that satisfy the condition
+  // {Always, Gt, Lt, Eq, Ge, Le, Ne, GtOrLt} (cycle.rs:193-210)
+  const uint32_t cond = (raw_lo >> ZK_COND_SHIFT) & 7u;
+  const uint64_t kCondTable = 0xFA33EEFCCCAAF0FFull;
+  bool resolved = (uint32_t)(kCondTable >> (cond * 8u + (flags & 7u))) & 1u;
+  // mask_into_panic / mask_into_nop (cycle.rs:187-217): the masked opcode has all-zero operands
+  uint32_t ops_lo = raw_lo, ops_hi = raw_hi;
   if (err) {
     vidx = ZK_PANIC_VARIANT_IDX;
-    entry = ZK_OPCODE_TABLE[ZK_PANIC_VARIANT_IDX];
-    cond = 0;
-    src0_reg = src1_reg = dst0_reg = dst1_reg = 0;
-    imm0 = imm1 = 0;
-  }
-  // flags: bit0 LT/OF, bit1 EQ, bit2 GT.  cond -> mask of flag bits that satisfy it (Ne handled apart)
-  const uint32_t cond_mask = cond == 1 ? 4u : cond == 2 ? 1u : cond == 3 ? 2u : cond == 4 ? 6u : cond == 5 ? 3u : cond == 7 ? 5u : 0u;
-  bool resolved = cond == 0 ? true : cond == 6 ? !(flags & 2u) : (flags & cond_mask) != 0;
-  if (!resolved && !err) {
+    resolved = true;
+  } else if (!resolved) {
     vidx = ZK_NOP_VARIANT_IDX;
-    entry = ZK_OPCODE_TABLE[ZK_NOP_VARIANT_IDX];
-    src0_reg = src1_reg = dst0_reg = dst1_reg = 0;
-    imm0 = imm1 = 0;
   }
+  if (err || !resolved) {
+    entry = ZK_OPCODE_TABLE[vidx];
+    ops_lo = ops_hi = 0u;
+  }
+  uint32_t src0_reg = (ops_lo >> 16) & 15u, src1_reg = (ops_lo >> 20) & 15u;
+  dst0_reg = (ops_lo >> 24) & 15u;
+  dst1_reg = ops_lo >> 28;
+  imm0 = ops_hi & 0xFFFFu;
+  imm1 = ops_hi >> 16;
   // delayed changes (mod.rs:134-153): previous_super_pc lives in the row tail
   __syncwarp();
   if (lane == 0) S.row[L_TX_PSP] = (S.row[L_TX_PSP] & 0xFFFFu) | prev_super_pc << 16;
@@ -777,15 +790,24 @@ __device__ __forceinline__ void Vm::cycle_once() {
   cycle += 1;
 
   // ---- end_execution_cycle: emit the 256-byte row, one 8-byte store per lane ----
+  // lane 0 drops the scalar head of the row next to the operand values already staged in shared memory
+  if (lane == 0) {
+    *reinterpret_cast<uint4*>(&S.row[0]) = make_uint4(row_cycle, row_ts, raw_lo, raw_hi);
+    *reinterpret_cast<uint4*>(&S.row[4]) = make_uint4(vidx | (resolved ? 1u : 0u) << 16 | err << 24, pc_before | pc << 16,
+                                                      sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
+    S.row[L_COUNTS] = (cm & 0xFFFFu) | (cl & 0xFFu) << 16 | ((cd & 3u) | (cf & 3u) << 2 | (cr & 3u) << 4) << 24;
+  }
+  const uint32_t n_rows = count[ZKB_STREAM_ROWS];
+  if (n_rows >= B.cap[ZKB_STREAM_ROWS]) {
+    fail(ZKB_VM_CAP_STREAM);
+    return;
+  }
+  count[ZKB_STREAM_ROWS] = n_rows + 1;
   __syncwarp();
-  uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
-  if (lane == 0) v = make_uint2(row_cycle, row_ts);
-  if (lane == 1) v = make_uint2(raw_lo, raw_hi);
-  if (lane == 2) v = make_uint2(vidx | (resolved ? 1u : 0u) << 16 | err << 24, pc_before | pc << 16);
-  if (lane == 3) v = make_uint2(sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
-  if (lane == 21) v.y = (cm & 0xFFFFu) | (cl & 0xFFu) << 16 | ((cd & 3u) | (cf & 3u) << 2 | (cr & 3u) << 4) << 24;
-  uint8_t* p = stream_slot(ZKB_STREAM_ROWS);
-  if (p) *reinterpret_cast<uint2*>(p + 8 * lane) = v;
+  if (B.witness) {
+    uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
+    *reinterpret_cast<uint2*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES + 8 * lane) = v;
+  }
 }
 
 // context.rs:36-99
@@ -1531,12 +1553,13 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
     }
   }
   if (!is_write) {
-    u256l r = u_shl(w0, un * 8u, lane) | u_shr(w1, (32u - un) * 8u, lane);
+    u256l r = w0;  // aligned accesses (the common case) need no byte shuffling
+    if (unaligned) r = u_shl(w0, un * 8u, lane) | u_shr(w1, (32u - un) * 8u, lane);
     if (is_ptr_read) {
       uint32_t beyond = incremented - p_len;
       if (incremented < p_len || skip_access) beyond = 0;
       beyond &= 31u;
-      r = u_shl(u_shr(r, beyond * 8u, lane), beyond * 8u, lane);
+      if (beyond) r = u_shl(u_shr(r, beyond * 8u, lane), beyond * 8u, lane);
     }
     if (!set_panic) {
       dst0_update(r, false);
@@ -1546,8 +1569,11 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
     }
   } else {
     const uint32_t low0 = 32u - un;
-    u256l n0 = u_shl(u_shr(w0, low0 * 8u, lane), low0 * 8u, lane) | u_shr(src1, un * 8u, lane);
-    u256l n1 = u_shr(u_shl(w1, un * 8u, lane), un * 8u, lane) | u_shl(src1, (32u - un) * 8u, lane);
+    u256l n0 = src1, n1 = 0u;
+    if (unaligned) {
+      n0 = u_shl(u_shr(w0, low0 * 8u, lane), low0 * 8u, lane) | u_shr(src1, un * 8u, lane);
+      n1 = u_shr(u_shl(w1, un * 8u, lane), un * 8u, lane) | u_shl(src1, (32u - un) * 8u, lane);
+    }
     if (!skip_access) {
       slab_write(slab, word0, n0);
       emit_mem(timestamp + 3, p_page, word0, mtype, 1, 0, ZKB_MEMORIGIN_VM, n0);
@@ -1567,10 +1593,10 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
 // ===================================================================================================
 // load / run / store one VM
 // ===================================================================================================
-__device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
-  VmHot* hot = B.hot + vm_idx;
-  if (hot->x[X_STATUS] != ZKB_VM_RUNNING) return;
-  Vm v(B, S, vm_idx, lane);
+// load VM `v.vm`'s hot state from HBM into shared memory / warp-uniform registers
+__device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
+  WarpSmem& S = v.S;
+  const uint32_t lane = v.lane;
   uint32_t* sregs = &S.regs[0][0];
   const uint32_t* hregs = &hot->regs[0][0];
 #pragma unroll
@@ -1597,21 +1623,15 @@ __device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t 
   v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
   __syncwarp();
   v.load_frame_from_F();
+}
 
-  uint32_t n = 0;
-  while (v.status == ZKB_VM_RUNNING) {
-    if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
-      v.status = ZKB_VM_ENDED;
-      break;
-    }
-    if (max_cycles && n >= max_cycles) break;
-    v.cycle_once();
-    n++;
-  }
-
-  // store back
+// write the hot state back to HBM (the batch is resumable: zkb_run may be called again)
+__device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
+  WarpSmem& S = v.S;
+  const uint32_t lane = v.lane;
   __syncwarp();
   v.sync_frame_to_F();
+  uint32_t* sregs = &S.regs[0][0];
   uint32_t* gregs = &hot->regs[0][0];
 #pragma unroll
   for (int i = 0; i < 4; i++) gregs[i * 32 + lane] = sregs[i * 32 + lane];
@@ -1634,6 +1654,53 @@ __device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t 
   for (int k = 0; k < ZKB_N_STREAMS; k++) out = lane == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
   hot->x[lane] = out;
   __syncwarp();
+}
+
+// free-running schedule: one warp runs one VM to the end (or for max_cycles cycles)
+__device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
+  VmHot* hot = B.hot + vm_idx;
+  if (hot->x[X_STATUS] != ZKB_VM_RUNNING) return;
+  Vm v(B, S, vm_idx, lane);
+  vm_load(v, hot);
+  uint32_t n = 0;
+  while (v.status == ZKB_VM_RUNNING) {
+    if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
+      v.status = ZKB_VM_ENDED;
+      break;
+    }
+    if (max_cycles && n >= max_cycles) break;
+    v.cycle_once();
+    n++;
+  }
+  vm_store(v, hot);
+}
+
+// lockstep schedule: the W warps of a CTA run W consecutive VMs cycle by cycle with one CTA barrier per VM
+// cycle.  Batches of transactions against the same contracts follow (nearly) the same path through the
+// interpreter, so the warps of a CTA execute the same handler at the same time and share its instruction-cache
+// lines (the interpreter is ~190 KB of SASS against a 32 KB L1.5 I-cache; the free-running schedule spends most
+// of its issue slots waiting for instruction fetch).
+__device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
+  const bool valid = vm_idx < B.n_vms && B.hot[vm_idx < B.n_vms ? vm_idx : 0].x[X_STATUS] == ZKB_VM_RUNNING;
+  VmHot* hot = B.hot + (valid ? vm_idx : 0);
+  Vm v(B, S, valid ? vm_idx : 0, lane);
+  v.status = ZKB_VM_ENDED;
+  if (valid) vm_load(v, hot);
+  uint32_t n = 0;
+  while (true) {
+    bool active = valid && v.status == ZKB_VM_RUNNING;
+    if (active && S.row[L_DEPTH] == 0) {
+      v.status = ZKB_VM_ENDED;
+      active = false;
+    }
+    if (active && max_cycles && n >= max_cycles) active = false;
+    if (!__syncthreads_or(active ? 1 : 0)) break;
+    if (active) {
+      v.cycle_once();
+      n++;
+    }
+  }
+  if (valid) vm_store(v, hot);
 }
 
 }  // namespace zkb

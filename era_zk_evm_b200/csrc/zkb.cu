@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,27 +14,41 @@
 using namespace zkb;
 
 #ifndef ZKB_WARPS_PER_CTA
-#define ZKB_WARPS_PER_CTA 4
+#define ZKB_WARPS_PER_CTA 16
 #endif
 #ifndef ZKB_MIN_CTAS_PER_SM
-#define ZKB_MIN_CTAS_PER_SM 4
+#define ZKB_MIN_CTAS_PER_SM 1
 #endif
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-// K1: persistent interpreter — each warp pulls VM indices from an atomic queue and runs the VM to completion
-// (or for max_cycles cycles).  Replaces the caller loop `while !vm.execution_has_ended() { vm.cycle() }`.
+// K1: persistent interpreter.  Replaces the caller loop `while !vm.execution_has_ended() { vm.cycle() }`.
+// LOCKSTEP = false: each warp pulls VM indices from an atomic queue and runs its VM to completion.
+// LOCKSTEP = true : each CTA pulls groups of W consecutive VMs and steps them together (run_vm_group).
+template <bool LOCKSTEP>
 __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) zkb_run_kernel(const DevBatch B, uint32_t max_cycles) {
   __shared__ WarpSmem smem[ZKB_WARPS_PER_CTA];
+  __shared__ uint32_t s_base;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   WarpSmem& S = smem[warp];
-  while (true) {
-    uint32_t vm_idx = 0;
-    if (lane == 0) vm_idx = atomicAdd(B.queue, 1u);
-    vm_idx = __shfl_sync(ZK_FULL, vm_idx, 0);
-    if (vm_idx >= B.n_vms) break;
-    run_vm(B, S, vm_idx, lane, max_cycles);
+  if (!LOCKSTEP) {
+    while (true) {
+      uint32_t vm_idx = 0;
+      if (lane == 0) vm_idx = atomicAdd(B.queue, 1u);
+      vm_idx = __shfl_sync(ZK_FULL, vm_idx, 0);
+      if (vm_idx >= B.n_vms) break;
+      run_vm(B, S, vm_idx, lane, max_cycles);
+    }
+  } else {
+    while (true) {
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue, (uint32_t)ZKB_WARPS_PER_CTA);
+      __syncthreads();
+      const uint32_t base = s_base;
+      if (base >= B.n_vms) break;
+      run_vm_group(B, S, base + warp, lane, max_cycles);
+      __syncthreads();
+    }
   }
 }
 
@@ -163,6 +178,7 @@ struct ZkbBatch {
   cudaStream_t last_stream = nullptr;
   uint32_t n_launches = 0;
   int grid = 0;
+  bool lockstep = false;
   uint8_t* d_pack = nullptr;
   uint64_t pack_capacity = 0;
   uint64_t* d_offsets = nullptr;
@@ -365,9 +381,12 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   CUDA_OK(cudaEventCreate(&b->ev0));
   CUDA_OK(cudaEventCreate(&b->ev1));
   int per_sm = 0, n_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel, ZKB_WARPS_PER_CTA * 32, 0));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, 0));
   CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   b->grid = std::max(1, per_sm * n_sm);  // persistent grid: a multiple of the SM count (148 on B200)
+  uint32_t sched = cfg->schedule;
+  if (const char* env = getenv("ZKB_SCHEDULE")) sched = (uint32_t)atoi(env);  // experiment override
+  b->lockstep = sched != ZKB_SCHED_FREE;
   *out = b;
   return ZKB_OK;
 }
@@ -574,7 +593,10 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 4, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_WARPS_PER_CTA - 1) / ZKB_WARPS_PER_CTA));
-  zkb_run_kernel<<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
+  if (b->lockstep)
+    zkb_run_kernel<true><<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
+  else
+    zkb_run_kernel<false><<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(b->ev1, st));
   b->n_launches = 1;

@@ -48,6 +48,13 @@ enum ZkbVmCode {
 };
 
 /* ---- configuration ------------------------------------------------------------------------------- */
+enum ZkbSchedule {
+  ZKB_SCHED_AUTO = 0,      /* library default (lockstep) */
+  ZKB_SCHED_FREE = 1,      /* every warp pulls the next VM from a queue and runs it to the end on its own   */
+  ZKB_SCHED_LOCKSTEP = 2   /* the warps of a CTA step consecutive VMs cycle by cycle (shared I-cache lines): */
+                           /* best when neighbouring VMs execute the same contracts                          */
+};
+
 typedef struct ZkbConfig {
   uint32_t n_vms;
   int32_t device;            /* CUDA device ordinal */
@@ -61,7 +68,8 @@ typedef struct ZkbConfig {
   uint32_t storage_slots;    /* per-VM open-addressed storage table, power of two */
   uint32_t journal_entries;  /* per-VM storage rollback journal (storage.rs:98-120) */
   uint32_t host_mirror;      /* 1 = allocate pinned host mirrors for zkb_fetch_streams */
-  uint32_t reserved[4];
+  uint32_t schedule;         /* ZkbSchedule: how warps are assigned to VMs (results are identical either way) */
+  uint32_t reserved[3];
 } ZkbConfig;
 
 /* mirror of CallStackEntry (execution_stack.rs:6-24) */
