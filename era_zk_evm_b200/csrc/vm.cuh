@@ -50,6 +50,9 @@ struct VmHot {
   uint32_t x[32];
 };
 
+#ifndef ZKB_LOCKSTEP_PERIOD
+#define ZKB_LOCKSTEP_PERIOD 4
+#endif
 #define ZKB_NO_SLAB 0xFFu
 #define ZKB_NO_CODE 0xFFFFFFFFu
 #define ZKB_PT_ENTRIES 16u
@@ -108,7 +111,8 @@ struct Vm {
   uint32_t prev_code_page, far_depth, journal_len, n_decommit, slab_free;
   uint32_t count[ZKB_N_STREAMS];
   uint32_t rowbits;
-  uint32_t cm, cl, cd, cf, cr;  // per-cycle record counts
+  uint32_t ccount;  // per-cycle record counts, packed as CycleRow.n_mem | n_log << 16 | n_dfr << 24
+  uint32_t forbid;  // ZK_E_* bits an opcode must not have in the current frame (kernel-only / not-in-static)
   const uint32_t* code;
   uint32_t code_len;
   u256l prev_word;  // distributed
@@ -183,7 +187,7 @@ struct Vm {
   // witness_tracer.add_memory_query (helpers.rs:36,70,111) / precompile memory witness (helpers.rs:215-221)
   __device__ __forceinline__ void emit_mem(uint32_t ts, uint32_t page, uint32_t index, uint32_t mtype, uint32_t rw, uint32_t is_ptr,
                                            uint32_t origin, u256l value) {
-    cm++;
+    ccount += 1u;
     uint32_t n = count[ZKB_STREAM_MEM];
     if (n >= B.cap[ZKB_STREAM_MEM]) {
       fail(ZKB_VM_CAP_STREAM);
@@ -199,7 +203,7 @@ struct Vm {
   // witness_tracer.add_log_query (helpers.rs:151,161,208); aw = address words in lanes 0..4
   __device__ __forceinline__ void emit_log(uint32_t ts, uint32_t aux, uint32_t shard, uint32_t aw, uint32_t rw, uint32_t is_service,
                                            u256l key, u256l read_value, u256l written_value) {
-    cl++;
+    ccount += 1u << 16;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_LOG);
     uint32_t tx = S.row[L_TX_PSP] & 0xFFFFu;
     if (p) {
@@ -218,7 +222,7 @@ struct Vm {
 
   // witness_tracer.add_decommittment (helpers.rs:185-191)
   __device__ __forceinline__ void emit_decommit(uint32_t ts, uint32_t page, uint32_t len, uint32_t fresh, u256l hash) {
-    cd++;
+    ccount += 1u << 24;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_DECOMMIT);
     if (p) {
       if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, (len & 0xFFFFu) | fresh << 16, 0u);
@@ -228,14 +232,14 @@ struct Vm {
 
   // witness_tracer.record_refund_for_query (helpers.rs:130-134); InMemoryStorage => RefundType::None (storage.rs:80-86)
   __device__ __forceinline__ void emit_refund() {
-    cr++;
+    ccount += 1u << 28;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_REFUND);
     if (p && lane < 2) p[lane] = 0u;
   }
 
   // start_new_execution_context (helpers.rs:237-241): the new frame must already be in S.F
   __device__ __forceinline__ void emit_frame_start(uint32_t prev_ergs, uint32_t prev_pc, uint32_t prev_sp) {
-    cf++;
+    ccount += 1u << 26;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
     if (p) {
       uint32_t w = lane == 0 ? ZKB_FRAMEKIND_START : lane == 1 ? cycle : lane < 29 ? S.F[(lane - 2) & 31] : lane == 29 ? prev_ergs
@@ -245,7 +249,7 @@ struct Vm {
   }
   // finish_execution_context (helpers.rs:258-259)
   __device__ __forceinline__ void emit_frame_finish(bool panicked) {
-    cf++;
+    ccount += 1u << 26;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
     if (p) p[lane] = lane == 0 ? (ZKB_FRAMEKIND_FINISH | (panicked ? 1u : 0u) << 8) : lane == 1 ? cycle : 0u;
   }
@@ -455,6 +459,7 @@ struct Vm {
     uint32_t misc = S.F[F_MISC];
     bool kernel = S.F[0] == 0 && S.F[1] == 0 && S.F[2] == 0 && S.F[3] == 0 && (S.F[4] & 0xFFFFu) == 0;  // execution_stack.rs:83-87
     uint32_t bits = (((misc >> 8) & 1u) ? ZKB_FRAMEBIT_STATIC : 0u) | (((misc >> 16) & 1u) ? ZKB_FRAMEBIT_LOCAL : 0u) | (kernel ? ZKB_FRAMEBIT_KERNEL : 0u);
+    forbid = (kernel ? 0u : (uint32_t)ZK_E_KERNEL_ONLY) | (((misc >> 8) & 1u) ? (uint32_t)ZK_E_STATIC_FORBIDDEN : 0u);
     if (lane == 0) {
       S.row[L_BASE_PAGE] = S.F[F_BASE_PAGE];
       S.row[L_CODE_PAGE] = S.F[F_CODE_PAGE];
@@ -547,7 +552,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   const uint32_t row_cycle = cycle, row_ts = timestamp, pc_before = pc;
   if (lane < 16) S.row[24 + lane] = 0u;  // dst0 / dst1 fields default to zero
   rowbits = 0;
-  cm = cl = cd = cf = cr = 0;
+  ccount = 0;
   dst_loc_valid = 0;
 
   // ---- fetch (cycle.rs:46-130) ----
@@ -583,10 +588,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
   } else {
     ergs -= price;
   }
-  const uint32_t fbits = S.row[L_EH_BITS] >> 16;
-  const bool kernel_mode = fbits & ZKB_FRAMEBIT_KERNEL;
-  if ((entry & ZK_E_KERNEL_ONLY) && !kernel_mode) err |= 4u;
-  if ((entry & ZK_E_STATIC_FORBIDDEN) && (fbits & ZKB_FRAMEBIT_STATIC)) err |= 8u;
+  const bool kernel_mode = !(forbid & ZK_E_KERNEL_ONLY);
+  if (entry & forbid) err |= ((entry & forbid & ZK_E_KERNEL_ONLY) ? 4u : 0u) | ((entry & forbid & ZK_E_STATIC_FORBIDDEN) ? 8u : 0u);
   if (S.row[L_DEPTH] == ZK_VM_MAX_STACK_DEPTH) err |= 16u;
   // flags: bit0 LT/OF, bit1 EQ, bit2 GT.  Byte `cond` of the table = the set of flag values that satisfy the condition
   // {Always, Gt, Lt, Eq, Ge, Le, Ne, GtOrLt} (cycle.rs:193-210)
@@ -795,7 +798,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
     *reinterpret_cast<uint4*>(&S.row[0]) = make_uint4(row_cycle, row_ts, raw_lo, raw_hi);
     *reinterpret_cast<uint4*>(&S.row[4]) = make_uint4(vidx | (resolved ? 1u : 0u) << 16 | err << 24, pc_before | pc << 16,
                                                       sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
-    S.row[L_COUNTS] = (cm & 0xFFFFu) | (cl & 0xFFu) << 16 | ((cd & 3u) | (cf & 3u) << 2 | (cr & 3u) << 4) << 24;
+    S.row[L_COUNTS] = ccount;
   }
   const uint32_t n_rows = count[ZKB_STREAM_ROWS];
   if (n_rows >= B.cap[ZKB_STREAM_ROWS]) {
@@ -1619,7 +1622,7 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
 #pragma unroll
   for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = __shfl_sync(ZK_FULL, x, X_COUNT0 + k);
   v.rowbits = 0;
-  v.cm = v.cl = v.cd = v.cf = v.cr = 0;
+  v.ccount = 0;
   v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
   __syncwarp();
   v.load_frame_from_F();
@@ -1688,17 +1691,24 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
   if (valid) vm_load(v, hot);
   uint32_t n = 0;
   while (true) {
+    // up to ZKB_LOCKSTEP_PERIOD cycles between two CTA barriers: the warps may drift by a few hundred instructions
+    // (still inside the I-cache window) and the barrier waits for the slowest SUM of cycles, not the slowest cycle
     bool active = valid && v.status == ZKB_VM_RUNNING;
-    if (active && S.row[L_DEPTH] == 0) {
-      v.status = ZKB_VM_ENDED;
-      active = false;
+#pragma unroll 1
+    for (int k = 0; k < ZKB_LOCKSTEP_PERIOD && active; k++) {
+      if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
+        v.status = ZKB_VM_ENDED;
+        active = false;
+      } else if (max_cycles && n >= max_cycles) {
+        active = false;
+      } else {
+        v.cycle_once();
+        n++;
+        active = v.status == ZKB_VM_RUNNING;
+      }
     }
     if (active && max_cycles && n >= max_cycles) active = false;
     if (!__syncthreads_or(active ? 1 : 0)) break;
-    if (active) {
-      v.cycle_once();
-      n++;
-    }
   }
   if (valid) vm_store(v, hot);
 }
