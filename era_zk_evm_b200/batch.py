@@ -39,6 +39,8 @@ class GpuVmBatch(_binding.Batch):
         lib.zkb_stream_device_view.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
         lib.zkb_fetch_stream_packed.argtypes = [vp, u32, vp, u64, vp]
         lib.zkb_pack_stream_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp]
+        lib.zkb_fetch_stream_packed_async.argtypes = [vp, u32, vp, u64, vp, vp]
+        lib.zkb_fetch_stream_packed_async.restype = C.c_int32
         lib.zkb_snapshot.argtypes = [vp]
         lib.zkb_restore.argtypes = [vp, vp]
         lib.zkb_transfer_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), u32]
@@ -66,6 +68,12 @@ class GpuVmBatch(_binding.Batch):
             return buf[:total], offsets
         self._check(self._lib.zkb_fetch_stream_packed(self._h, kind, host_ptr, host_capacity, offsets.ctypes.data))
         return None, offsets
+
+    def fetch_stream_packed_async(self, kind: int, host_ptr: int, host_capacity: int, stream=None, offsets=None):
+        """enqueue pack + D2H of stream `kind` into pinned host memory on `stream`; returns the per-VM byte offsets"""
+        offsets = np.zeros(self.n_vms + 1, dtype=np.uint64) if offsets is None else offsets
+        self._check(self._lib.zkb_fetch_stream_packed_async(self._h, kind, host_ptr, host_capacity, offsets.ctypes.data, stream))
+        return offsets
 
     def snapshot(self):
         self._check(self._lib.zkb_snapshot(self._h))

@@ -19,6 +19,7 @@
 #define ZK_TABLE_QUALIFIER __device__ __constant__
 #include "isa_tables.inc"
 #include "keccak.cuh"
+#include "sha256.cuh"
 #include "u256.cuh"
 
 namespace zkb {
@@ -51,11 +52,11 @@ struct VmHot {
 };
 
 #ifndef ZKB_LOCKSTEP_PERIOD
-#define ZKB_LOCKSTEP_PERIOD 4
+#define ZKB_LOCKSTEP_PERIOD 32
 #endif
 #define ZKB_NO_SLAB 0xFFu
 #define ZKB_NO_CODE 0xFFFFFFFFu
-#define ZKB_PT_ENTRIES 16u
+#define ZKB_PT_ENTRIES 32u   // one entry per lane
 #define ZKB_DEC_ENTRIES 16u
 #define ZKB_PT_FREE 0xFFFFFFFFu
 enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
@@ -322,8 +323,8 @@ struct Vm {
 
   // ---- page indirections (SimpleMemory.page_numbers_indirections, memory.rs:160-171,475-521) ------
   __device__ __forceinline__ int pt_find(uint32_t page) {
-    uint32_t p = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2] : ZKB_PT_FREE;
-    uint32_t m = __ballot_sync(ZK_FULL, p == page);
+    bool hit = lane < ZKB_PT_ENTRIES && g_pt[lane * 2] == page;  // lanes beyond the table never match (not even "free")
+    uint32_t m = __ballot_sync(ZK_FULL, hit);
     return m ? __ffs(m) - 1 : -1;
   }
   __device__ __forceinline__ void pt_upsert(uint32_t page, uint32_t kind, uint32_t slab_or_level, uint32_t cleanup_level) {
@@ -540,6 +541,7 @@ struct Vm {
   __device__ void op_ret(uint32_t sub, u256l src0, bool src0_ptr);
   __device__ void op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr);
   __device__ void keccak_precompile(u256l abi);
+  __device__ void sha256_precompile(u256l abi);
   __device__ void memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page);
   __device__ void memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page);
   __device__ void cycle_once();
@@ -986,9 +988,12 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
       uint32_t addr_low = bswap32(S.F[F_THIS + 4]) & 0xFFFFu;
       if (addr_low == ZK_KECCAK256_PRECOMPILE_ADDRESS) {
         keccak_precompile(abi);
-      } else if (addr_low == ZK_SHA256_PRECOMPILE_ADDRESS || addr_low == ZK_ECRECOVER_PRECOMPILE_ADDRESS) {
+      } else if (addr_low == ZK_SHA256_PRECOMPILE_ADDRESS) {
+        sha256_precompile(abi);
+      } else if (addr_low == ZK_ECRECOVER_PRECOMPILE_ADDRESS) {
         fail(ZKB_VM_UNSUPPORTED);
       }
+      if (status != ZKB_VM_RUNNING) return;
       u256l one = lane == 0 ? 1u : 0u;
       dst0_update(one, false);
       break;
@@ -1064,6 +1069,42 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
+  uint32_t s = cur_slab(0, true, out_word);
+  if (status != ZKB_VM_RUNNING) return;
+  slab_write(s, out_word, digest);
+  emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, digest);
+}
+
+// sha256 precompile (external DefaultPrecompilesProcessor; memory ABI reconstructed): the caller
+// passes pre-padded 64-byte blocks: input offset in WORDS, number of rounds in precompile_interpreted_data, two
+// Heap-type word reads per round at timestamp+1, one digest word written at timestamp+2 after the last round.
+__device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
+  const uint32_t in_word = __shfl_sync(ZK_FULL, abi, 0), out_word = __shfl_sync(ZK_FULL, abi, 2);
+  const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
+  const uint64_t rounds = (uint64_t)__shfl_sync(ZK_FULL, abi, 6) | (uint64_t)__shfl_sync(ZK_FULL, abi, 7) << 32;
+  const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
+  if (rounds == 0) return;
+  const uint32_t heap_page = L(L_BASE_PAGE) + 2;
+  // MemoryType::Heap queries address the current frame's heap; the reference checks the page number (memory.rs:447)
+  if (page_read != heap_page || page_write != heap_page) {
+    fail(ZKB_VM_REFERENCE_PANIC);
+    return;
+  }
+  const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
+  if (lane < 8) S.kbuf[lane] = c_sha256_iv[lane];
+  for (uint64_t r = 0; r < rounds; r++) {
+#pragma unroll
+    for (uint32_t k = 0; k < 2; k++) {
+      const uint32_t idx = in_word + 2u * (uint32_t)r + k;
+      u256l word = slab_read(src_slab, idx);
+      emit_mem(ts_read, page_read, idx, ZK_MEM_HEAP, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, word);
+      if (status != ZKB_VM_RUNNING) return;
+      if (lane < 8) S.kbuf[8 + 8 * k + (7 - lane)] = word;  // big-endian message words: M[j] = limb[7 - j]
+    }
+    sha256_compress_smem(S.kbuf, lane);
+  }
+  __syncwarp();
+  u256l digest = lane < 8 ? S.kbuf[7 - lane] : 0u;
   uint32_t s = cur_slab(0, true, out_word);
   if (status != ZKB_VM_RUNNING) return;
   slab_write(s, out_word, digest);

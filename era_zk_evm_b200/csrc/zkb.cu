@@ -14,7 +14,7 @@
 using namespace zkb;
 
 #ifndef ZKB_WARPS_PER_CTA
-#define ZKB_WARPS_PER_CTA 16
+#define ZKB_WARPS_PER_CTA 20
 #endif
 #ifndef ZKB_MIN_CTAS_PER_SM
 #define ZKB_MIN_CTAS_PER_SM 1
@@ -181,7 +181,12 @@ struct ZkbBatch {
   bool lockstep = false;
   uint8_t* d_pack = nullptr;
   uint64_t pack_capacity = 0;
-  uint64_t* d_offsets = nullptr;
+  uint64_t* d_offsets = nullptr;                  // [ZKB_N_STREAMS][n_vms + 1]
+  std::vector<uint64_t> h_offsets[ZKB_N_STREAMS];  // host copies that outlive the async uploads
+  uint8_t* d_stage = nullptr;                     // grow-only H2D staging buffer of the populate_* calls
+  uint64_t stage_capacity = 0;
+  cudaEvent_t ev_setup = nullptr;
+  bool launched = false;
   std::vector<void*> allocs;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   // checkpoint (VmLocalState: Clone, vm_state/mod.rs:53): device copies of every mutable per-VM array
@@ -235,6 +240,29 @@ static cudaError_t dalloc(ZkbBatch* b, T** p, size_t count, bool zero) {
   if (zero) e = cudaMemset(q, 0, bytes);
   *p = (T*)q;
   return e;
+}
+
+// device staging for host inputs: grow-only, so the steady state of a pipelined host loop never calls
+// cudaMalloc/cudaFree (both synchronise the whole device and would serialise against in-flight D2H copies)
+static int32_t stage_h2d(ZkbBatch* b, const void* src, size_t bytes, uint8_t** out) {
+  if (bytes > b->stage_capacity) {
+    if (b->d_stage) CUDA_OK(cudaFree(b->d_stage));
+    b->d_stage = nullptr;
+    b->stage_capacity = 0;
+    size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    CUDA_OK(cudaMalloc(&b->d_stage, cap));
+    b->stage_capacity = cap;
+  }
+  CUDA_OK(cudaMemcpy(b->d_stage, src, bytes, cudaMemcpyHostToDevice));
+  b->h2d_bytes += bytes;
+  *out = b->d_stage;
+  return ZKB_OK;
+}
+
+// wait for this batch's last launch only (not the device): other batches' kernels and copies keep running
+static int32_t wait_last_run(ZkbBatch* b) {
+  if (b->launched) CUDA_OK(cudaEventSynchronize(b->ev1));
+  return ZKB_OK;
 }
 
 static int32_t clear_cold_state(ZkbBatch* b) {
@@ -291,7 +319,7 @@ static int32_t upload(ZkbBatch* b) {
 static int32_t download_hot(ZkbBatch* b) {
   if (b->hot_stale) {
     CUDA_OK(cudaSetDevice(b->cfg.device));
-    CUDA_OK(cudaStreamSynchronize(b->last_stream));
+    if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;
     CUDA_OK(cudaMemcpy(b->h_hot.data(), b->d.hot, b->h_hot.size() * sizeof(VmHot), cudaMemcpyDeviceToHost));
     b->d2h_bytes += b->h_hot.size() * sizeof(VmHot);
     b->hot_stale = false;
@@ -360,7 +388,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
     for (int k = 0; k < ZKB_N_STREAMS; k++) ALLOC(d.streams[k], n * (size_t)c.cap_records[k] * REC_BYTES[k], false);
   ALLOC(d.queue, 4, true);
   ALLOC(b->d_fail, 4, true);
-  ALLOC(b->d_offsets, n + 1, false);
+  ALLOC(b->d_offsets, (n + 1) * ZKB_N_STREAMS, false);
 #undef ALLOC
   if (e != cudaSuccess) {
     std::string msg = std::string("cudaMalloc: ") + cudaGetErrorString(e);
@@ -380,6 +408,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   if (rc != ZKB_OK) return rc;
   CUDA_OK(cudaEventCreate(&b->ev0));
   CUDA_OK(cudaEventCreate(&b->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&b->ev_setup, cudaEventDisableTiming));
   int per_sm = 0, n_sm = 0;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, 0));
   CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -403,6 +432,8 @@ int32_t zkb_destroy(ZkbBatch* b) {
     if (r.saved) cudaFree(r.saved);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev_setup) cudaEventDestroy(b->ev_setup);
+  if (b->d_stage) cudaFree(b->d_stage);
   delete b;
   return ZKB_OK;
 }
@@ -410,7 +441,7 @@ int32_t zkb_destroy(ZkbBatch* b) {
 int32_t zkb_reset(ZkbBatch* b) {
   if (!b) return ZKB_ERR_INVALID_ARGUMENT;
   CUDA_OK(cudaSetDevice(b->cfg.device));
-  CUDA_OK(cudaDeviceSynchronize());
+  if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;
   for (auto& h : b->h_hot) init_hot(b, h);
   std::fill(b->h_root.begin(), b->h_root.end(), 0u);
   std::fill(b->h_bootrec.begin(), b->h_bootrec.end(), 0u);
@@ -453,16 +484,15 @@ int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const 
     be32_to_limbs(entries[i].key_be, h[i].key);
     be32_to_limbs(entries[i].value_be, h[i].value);
   }
-  DevStorageInit* d_e = nullptr;
-  CUDA_OK(cudaMalloc(&d_e, total * sizeof(DevStorageInit)));
-  CUDA_OK(cudaMemcpy(d_e, h.data(), total * sizeof(DevStorageInit), cudaMemcpyHostToDevice));
-  b->h2d_bytes += total * sizeof(DevStorageInit);
+  uint8_t* staged = nullptr;
+  int32_t src = stage_h2d(b, h.data(), total * sizeof(DevStorageInit), &staged);
+  if (src != ZKB_OK) return src;
+  DevStorageInit* d_e = reinterpret_cast<DevStorageInit*>(staged);
   CUDA_OK(cudaMemset(b->d_fail, 0, 4));
   zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
   CUDA_OK(cudaGetLastError());
   uint32_t fail = 0;
-  CUDA_OK(cudaMemcpy(&fail, b->d_fail, 4, cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaFree(d_e));
+  CUDA_OK(cudaMemcpy(&fail, b->d_fail, 4, cudaMemcpyDeviceToHost));  // also orders the kernel before the staging buffer is reused
   if (fail) return set_err(ZKB_ERR_INVALID_ARGUMENT, "storage table capacity exceeded while populating (raise ZkbConfig.storage_slots)");
   return ZKB_OK;
 }
@@ -544,13 +574,11 @@ int32_t zkb_populate_heap(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uin
   b->hot_dirty = true;
   size_t total = per_vm ? (size_t)(vm_hi - vm_lo) * n_bytes : n_bytes;
   uint8_t* d_bytes = nullptr;
-  CUDA_OK(cudaMalloc(&d_bytes, total));
-  CUDA_OK(cudaMemcpy(d_bytes, bytes, total, cudaMemcpyHostToDevice));
-  b->h2d_bytes += total;
+  int32_t src = stage_h2d(b, bytes, total, &d_bytes);
+  if (src != ZKB_OK) return src;
   zkb_populate_heap_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_bytes, n_bytes, per_vm, 1);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaFree(d_bytes));
+  CUDA_OK(cudaStreamSynchronize(0));  // the staging buffer is reused by the next populate_* call
   return ZKB_OK;
 }
 
@@ -590,6 +618,10 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   if (rc != ZKB_OK) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   b->last_stream = st;
+  if (st != nullptr) {  // populate_* / reset work runs on the default stream: order it before the launch on `st`
+    CUDA_OK(cudaEventRecord(b->ev_setup, 0));
+    CUDA_OK(cudaStreamWaitEvent(st, b->ev_setup, 0));
+  }
   CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 4, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_WARPS_PER_CTA - 1) / ZKB_WARPS_PER_CTA));
@@ -601,14 +633,14 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   CUDA_OK(cudaEventRecord(b->ev1, st));
   b->n_launches = 1;
   b->hot_stale = true;
+  b->launched = true;
   return ZKB_OK;
 }
 
 int32_t zkb_sync(ZkbBatch* b) {
   if (!b) return ZKB_ERR_INVALID_ARGUMENT;
   CUDA_OK(cudaSetDevice(b->cfg.device));
-  CUDA_OK(cudaStreamSynchronize(b->last_stream));
-  return ZKB_OK;
+  return wait_last_run(b);
 }
 
 int32_t zkb_last_run_ms(ZkbBatch* b, float* ms, uint32_t* n_kernel_launches) {
@@ -722,54 +754,91 @@ int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
   return ZKB_OK;
 }
 
-int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream) {
-  if (!b || kind >= ZKB_N_STREAMS || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
-  CUDA_OK(cudaSetDevice(b->cfg.device));
-  int32_t rc = download_hot(b);
-  if (rc != ZKB_OK) return rc;
+// offsets of stream `kind` (host copy kept in the batch so that the async upload may outlive this call)
+static uint64_t stream_offsets(ZkbBatch* b, uint32_t kind) {
   uint32_t n = b->cfg.n_vms;
-  std::vector<uint64_t> off(n + 1);
+  std::vector<uint64_t>& off = b->h_offsets[kind];
+  off.resize(n + 1);
   off[0] = 0;
   for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_hot[v].x[X_COUNT0 + kind] * REC_BYTES[kind];
-  uint64_t total = off[n];
-  if (total > b->pack_capacity) {
+  return off[n];
+}
+
+static int32_t ensure_pack_capacity(ZkbBatch* b) {
+  // one buffer per stream kind, laid out back to back, sized once for the current counts (grow-only)
+  uint64_t need = 0;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) need += (stream_offsets(b, k) + 255) / 256 * 256;
+  if (need > b->pack_capacity) {
+    CUDA_OK(cudaDeviceSynchronize());  // a previous async fetch may still read the old buffer
     if (b->d_pack) CUDA_OK(cudaFree(b->d_pack));
     b->d_pack = nullptr;
     b->pack_capacity = 0;
-    CUDA_OK(cudaMalloc(&b->d_pack, total));
-    b->pack_capacity = total;
+    uint64_t cap = need + need / 16;
+    CUDA_OK(cudaMalloc(&b->d_pack, cap));
+    b->pack_capacity = cap;
   }
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  CUDA_OK(cudaMemcpyAsync(b->d_offsets, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  return ZKB_OK;
+}
+
+static uint8_t* pack_region(ZkbBatch* b, uint32_t kind) {
+  uint64_t at = 0;
+  for (uint32_t k = 0; k < kind; k++) at += (b->h_offsets[k][b->cfg.n_vms] + 255) / 256 * 256;
+  return b->d_pack + at;
+}
+
+static int32_t pack_async(ZkbBatch* b, uint32_t kind, cudaStream_t st, uint8_t** dptr, uint64_t* n_bytes) {
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = download_hot(b);
+  if (rc != ZKB_OK) return rc;
+  rc = ensure_pack_capacity(b);
+  if (rc != ZKB_OK) return rc;
+  uint32_t n = b->cfg.n_vms;
+  uint64_t total = b->h_offsets[kind][n];
+  uint64_t* d_off = b->d_offsets + (size_t)kind * (n + 1);
+  uint8_t* dst = pack_region(b, kind);
+  CUDA_OK(cudaMemcpyAsync(d_off, b->h_offsets[kind].data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
   if (total) {
-    zkb_pack_kernel<<<n, 128, 0, st>>>(b->d.streams[kind], (uint64_t)b->cfg.cap_records[kind] * REC_BYTES[kind], b->d_offsets, b->d_pack, n);
+    zkb_pack_kernel<<<n, 128, 0, st>>>(b->d.streams[kind], (uint64_t)b->cfg.cap_records[kind] * REC_BYTES[kind], d_off, dst, n);
     CUDA_OK(cudaGetLastError());
   }
-  CUDA_OK(cudaStreamSynchronize(st));  // `off` is a host temporary
-  if (dptr) *dptr = b->d_pack;
+  *dptr = dst;
+  *n_bytes = total;
+  return ZKB_OK;
+}
+
+int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || kind >= ZKB_N_STREAMS || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
+  uint64_t total = 0;
+  int32_t rc = pack_async(b, kind, (cudaStream_t)cuda_stream, &p, &total);
+  if (rc != ZKB_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (dptr) *dptr = p;
   if (n_bytes) *n_bytes = total;
   return ZKB_OK;
 }
 
-int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity, uint64_t* offsets_out) {
-  if (!b || kind >= ZKB_N_STREAMS) return ZKB_ERR_INVALID_ARGUMENT;
-  void* dptr = nullptr;
+int32_t zkb_fetch_stream_packed_async(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity, uint64_t* offsets_out,
+                                      void* cuda_stream) {
+  if (!b || kind >= ZKB_N_STREAMS || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
   uint64_t total = 0;
-  int32_t rc = zkb_pack_stream_device(b, kind, &dptr, &total, nullptr);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int32_t rc = pack_async(b, kind, st, &p, &total);
   if (rc != ZKB_OK) return rc;
-  if (offsets_out) {
-    uint64_t acc = 0;
-    for (uint32_t v = 0; v < b->cfg.n_vms; v++) {
-      offsets_out[v] = acc;
-      acc += (uint64_t)b->h_hot[v].x[X_COUNT0 + kind] * REC_BYTES[kind];
-    }
-    offsets_out[b->cfg.n_vms] = acc;
-  }
+  if (offsets_out) memcpy(offsets_out, b->h_offsets[kind].data(), ((size_t)b->cfg.n_vms + 1) * 8);
   if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_stream_packed: host buffer too small");
   if (total && host_dst) {
-    CUDA_OK(cudaMemcpy(host_dst, dptr, total, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
     b->d2h_bytes += total;
   }
+  return ZKB_OK;
+}
+
+int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity, uint64_t* offsets_out) {
+  int32_t rc = zkb_fetch_stream_packed_async(b, kind, host_dst, host_capacity, offsets_out, nullptr);
+  if (rc != ZKB_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(nullptr));
   return ZKB_OK;
 }
 
@@ -872,6 +941,9 @@ int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   for (auto& r : b->snap) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaEventRecord(b->ev0, st));
+  CUDA_OK(cudaEventRecord(b->ev1, st));
+  b->launched = true;
   b->last_stream = st;
   b->hot_dirty = false;
   b->hot_stale = true;

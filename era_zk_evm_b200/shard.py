@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing: VM batches shard by VM index (every `VmState` owns its backends by value,
+/root/reference/src/vm_state/mod.rs:157-175, so no VM ever reads another's state) and the only exchange is the
+concatenation of the per-GPU witness / query streams.  One process per GPU; `torch.distributed` (NCCL over
+NVLink on the GPU box, gloo in the CPU tests) carries the bytes.  Nothing on the per-cycle path communicates.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """static VM-range partition [lo, hi) of rank `rank`; ranges differ by at most one VM"""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _DevicePtr:
+    """exposes a raw device pointer (a packed stream owned by the batch) to torch without a copy"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def device_bytes_as_tensor(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevicePtr(ptr, nbytes), device=device)
+
+
+def gather_varlen(local: torch.Tensor, dst: int = 0, group=None):
+    """Concatenates one variable-length uint8 tensor per rank on rank `dst`, in rank order.
+    Returns (concatenated tensor on dst | None elsewhere, byte offsets[world + 1] on every rank)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    if rank == dst:
+        out = torch.empty(int(offsets[-1]), dtype=torch.uint8, device=local.device)
+        out[offsets[rank]: offsets[rank + 1]].copy_(local)
+        ops = [dist.P2POp(dist.irecv, out[offsets[r]: offsets[r + 1]], r, group) for r in range(world) if r != dst and sizes[r]]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return out, offsets
+    if local.numel():
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
+            w.wait()
+    return None, offsets
+
+
+def all_gather_varlen(local: torch.Tensor, group=None):
+    """every rank gets the concatenation (one all_gather on max-padded chunks, then a compaction)"""
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    padded = torch.zeros(m, dtype=torch.uint8, device=local.device)
+    padded[: local.numel()].copy_(local)
+    chunks = [torch.empty(m, dtype=torch.uint8, device=local.device) for _ in range(world)]
+    dist.all_gather(chunks, padded, group=group)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return torch.cat([c[:s] for c, s in zip(chunks, sizes)]), offsets
+
+
+def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.device | None = None):
+    """Packs this rank's stream `kind` (VM-major, contiguous: the pack kernel writes the NCCL send buffer directly)
+    and concatenates the ranks' buffers on `dst`.  Returns (bytes tensor | None, rank byte offsets,
+    per-VM record counts of this rank)."""
+    counts = batch.stream_counts(kind)
+    if hasattr(batch, "pack_stream_device"):
+        ptr, nbytes = batch.pack_stream_device(kind)
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        local = device_bytes_as_tensor(ptr, nbytes, device)
+    else:   # host-resident batches (CPU tests over gloo)
+        parts = [batch.read_stream(vm, kind).view(np.uint8) for vm in range(batch.n_vms)]
+        flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+        local = torch.from_numpy(np.ascontiguousarray(flat))
+    out, offsets = gather_varlen(local, dst, group)
+    return out, offsets, counts

@@ -537,3 +537,369 @@ class StorageHeavy(Workload):
 
 
 WORKLOADS = {"alu_loop": AluLoop, "erc20": Erc20, "keccak": KeccakHeavy, "storage": StorageHeavy}
+
+
+# ---------------------------------------------------------------------------------------------
+# config 5: mixed-opcode synthetic block — a pool of RNG-generated programs over all 15 opcode families
+# (ALU 55 %, stack/UMA 25 %, jump/near-call/ret 10 %, log 7 %, far-call 2 %, precompile 1 %), ~512 cycles per VM.
+# Also the fuzzing corpus of the parity tests: every exception path the generator can reach (panicking near calls,
+# static violations, out-of-ergs frames, pointer-op panics, invalid opcodes, reverting callees) is exercised.
+# ---------------------------------------------------------------------------------------------
+class _Rng:
+    """splitmix64 stream (scalar) so program generation is reproducible and independent of numpy's generators"""
+
+    def __init__(self, seed: int):
+        self.s = seed & MASK64
+
+    def u64(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & MASK64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK64
+        return z ^ (z >> 31)
+
+    def below(self, n: int) -> int:
+        return self.u64() % n
+
+    def chance(self, p: float) -> bool:
+        return (self.u64() >> 11) / float(1 << 53) < p
+
+    def pick(self, seq):
+        return seq[self.below(len(seq))]
+
+    def u256(self) -> int:
+        bits = self.pick([8, 16, 32, 64, 128, 200, 256])
+        v = 0
+        for _ in range(4):
+            v = (v << 64) | self.u64()
+        return v & ((1 << bits) - 1)
+
+
+MIXED_CALLEE_BASE = 0x00A11CE000000000000000000000000000000100
+_CONDS = ["always", "always", "always", "gt", "lt", "eq", "ge", "le", "ne", "gtlt"]
+_GP = list(range(1, 11))        # general-purpose registers r1..r10; r11..r15 are reserved for control / pointers
+
+
+class _Gen:
+    """statement generator shared by the bootloader programs, their near-call subroutines and the callee contracts"""
+
+    def __init__(self, rng: _Rng, p: Program, kernel: bool):
+        self.r, self.p, self.kernel = rng, p, kernel
+        self.n_const = 0
+        self.n_label = 0
+
+    def const(self, v: int) -> str:
+        name = f"k{self.n_const}"
+        self.n_const += 1
+        self.p.const(name, v)
+        return name
+
+    def label(self) -> str:
+        self.n_label += 1
+        return f"L{self.n_label}"
+
+    def src(self):
+        k = self.r.below(10)
+        if k < 5:
+            return R(self.r.pick(_GP))
+        if k < 7:
+            return Imm(self.r.below(1 << 16) if self.r.chance(0.5) else self.r.below(40))
+        if k < 9:
+            return StackAbs(self.r.below(8))
+        return Code(self.const(self.r.u256()))
+
+    def dst(self):
+        return DStackAbs(self.r.below(8)) if self.r.chance(0.2) else self.r.pick(_GP)
+
+    def alu(self, cond=None):
+        r, p = self.r, self.p
+        cond = cond or r.pick(_CONDS)
+        k = r.below(20)
+        sf = r.chance(0.4)
+        if k < 5:
+            p.add(self.src(), r.pick(_GP), self.dst(), set_flags=sf, cond=cond)
+        elif k < 9:
+            p.sub(self.src(), r.pick(_GP), self.dst(), set_flags=sf, swap=r.chance(0.5), cond=cond)
+        elif k < 12:
+            p.mul(self.src(), r.pick(_GP), self.dst(), r.pick(_GP), set_flags=sf, cond=cond)
+        elif k < 14:
+            p.div(self.src(), r.pick(_GP), self.dst(), r.pick(_GP), set_flags=sf, swap=r.chance(0.5), cond=cond)
+        elif k < 17:
+            p.shift(r.below(4), self.src(), r.pick(_GP), self.dst(), set_flags=sf, swap=r.chance(0.5), cond=cond)
+        else:
+            p.binop(r.below(3), self.src(), r.pick(_GP), self.dst(), set_flags=sf, cond=cond)
+
+    def memory(self):
+        r, p = self.r, self.p
+        k = r.below(10)
+        if k < 2:       # balanced push / pop above the absolute window
+            p.add(R(r.pick(_GP)), 0, DStackPush(1))
+            p.add(StackPop(1), r.pick(_GP), r.pick(_GP))
+        elif k < 3:     # sp-relative read of the slot just below sp, context.sp
+            p.add(StackRel(1), 0, r.pick(_GP))
+            p.context(isa.CTX_SP, r.pick(_GP))
+        else:
+            off = r.below(32) * 32 + (r.below(32) if r.chance(0.3) else 0)
+            aux = r.chance(0.25)
+            use_reg = r.chance(0.4)
+            if use_reg:   # r11 = bounded offset derived from data
+                p.binop(isa.AND, Imm(0x3FF), r.pick(_GP), 11)
+            addr = R(11) if use_reg else Imm(off)
+            if r.chance(0.5):
+                (p.st_aux if aux else p.st)(addr, r.pick(_GP), 12 if r.chance(0.3) else 0, inc=r.chance(0.3))
+            else:
+                (p.ld_aux if aux else p.ld)(addr, r.pick(_GP), 12, inc=r.chance(0.3))
+
+    def storage(self, allow_write=True):
+        r, p = self.r, self.p
+        p.binop(isa.AND, Imm(0xF), r.pick(_GP), 11)        # 16 hot keys per contract
+        k = r.below(10)
+        if k < 5 or not allow_write:
+            p.sload(11, r.pick(_GP))
+        elif k < 9:
+            p.sstore(11, r.pick(_GP))
+        elif self.kernel:
+            (p.to_l1 if r.chance(0.3) else p.event)(11, r.pick(_GP), first=r.chance(0.5))
+        else:
+            p.sload(11, r.pick(_GP))
+
+    def context(self):
+        r, p = self.r, self.p
+        sub = r.pick([isa.CTX_THIS, isa.CTX_CALLER, isa.CTX_CODE_ADDRESS, isa.CTX_META, isa.CTX_ERGS_LEFT, isa.CTX_SP,
+                      isa.CTX_GET_U128] + ([isa.CTX_SET_U128, isa.CTX_INC_TX] if self.kernel else []))
+        if sub in (isa.CTX_SET_U128,):
+            p.context(sub, 0, r.pick(_GP))
+        elif sub == isa.CTX_INC_TX:
+            p.context(sub)
+        else:
+            p.context(sub, r.pick(_GP))
+
+    def safe_statement(self):
+        k = self.r.below(100)
+        if k < 62:
+            self.alu()
+        elif k < 90:
+            self.memory()
+        elif k < 97:
+            self.storage()
+        else:
+            self.context()
+
+    def risky_statement(self):
+        """may raise a pending exception / panic: only used inside near-call subroutines and callees"""
+        r, p = self.r, self.p
+        k = r.below(10)
+        if k < 3:       # pointer arithmetic on a register that may or may not hold a pointer
+            p.ptr(r.below(4), Imm(r.below(64)) if r.chance(0.6) else R(r.pick(_GP)), r.pick([1, 12, r.pick(_GP)]),
+                  r.pick(_GP), swap=True)
+        elif k < 5:     # fat-pointer read through r1 / r12 (non-pointer => panic)
+            p.ld_ptr(R(r.pick([1, 1, 12])), r.pick(_GP), 12, inc=r.chance(0.5))
+        elif k < 6:     # far heap offset: growth cost exceeds the frame's ergs
+            p.add(Code(self.const(r.pick([1 << 20, (1 << 32) - 33, (1 << 32) - 32, 1 << 40]))), 0, 11)
+            p.ld(R(11), r.pick(_GP))
+        elif k < 7:     # undecodable instruction (variant index beyond the valid range)
+            p.ins.append((isa.NOP, 0, R(0), 0, DR_ZERO, 0, 0, "always", None, None))
+            p.raw_patch = getattr(p, "raw_patch", {})
+            p.raw_patch[len(p.ins) - 1] = isa.N_VALID_VARIANTS + r.below(2048 - isa.N_VALID_VARIANTS)
+        elif k < 8 and not self.kernel:   # kernel-only opcode in user mode
+            p.event(r.pick(_GP), r.pick(_GP))
+        else:
+            self.storage()
+
+
+from .asm import DR as _DR, DStackPush, StackPop, StackRel  # noqa: E402
+DR_ZERO = _DR(0)
+
+
+def _patched_words(p: Program) -> bytes:
+    """Program.bytecode() with the undecodable-instruction patches of _Gen.risky_statement applied"""
+    patch = getattr(p, "raw_patch", {})
+    if not patch:
+        return p.bytecode()
+    ins = p.encode()
+    for i, variant in patch.items():
+        ins[i] = (ins[i] & ~((1 << isa.VARIANT_BITS) - 1)) | variant
+    ins += [0] * (-len(ins) % 4)
+    words = [(ins[i] << 192) | (ins[i + 1] << 128) | (ins[i + 2] << 64) | ins[i + 3] for i in range(0, len(ins), 4)]
+    words += [v for _, v in p.consts]
+    if len(words) % 2 == 0:
+        words.append(0)
+    return b"".join(w.to_bytes(32, "big") for w in words)
+
+
+def mixed_callee(rng: _Rng, kernel: bool) -> Program:
+    """a callee contract: reads calldata through r1, random statements, returns / reverts / panics"""
+    p = Program()
+    g = _Gen(rng, p, kernel)
+    p.ld_ptr(R(1), 2, 12, inc=True)              # r2 = calldata word 0 ; r12 = advanced pointer
+    p.ld_ptr(R(12), 3)
+    for _ in range(6 + rng.below(10)):
+        g.safe_statement() if rng.chance(0.8) else g.risky_statement()
+    p.st(Imm(0), rng.pick(_GP))
+    p.st(Imm(32), rng.pick(_GP))
+    k = rng.below(10)
+    abi = g.const(ret_abi(start=rng.below(2) * 16, length=rng.pick([0, 32, 64, 40])))
+    p.add(Code(abi), 0, 13)
+    if k < 7:
+        p.ret(isa.RET_OK, R(13))
+    elif k < 9:
+        p.ret(isa.RET_REVERT, R(13))
+    else:
+        p.ret(isa.RET_PANIC, R(0))
+    return p
+
+
+def mixed_bootloader(rng: _Rng, n_body: int, n_iters: int, callee_addresses) -> Program:
+    p = Program()
+    g = _Gen(rng, p, kernel=True)
+    subs = []                                     # (label, generator thunk) emitted after the main loop
+    p.nop(R(0), DStackPush(16))                   # sp = 16: slots 0..7 absolute window, 8..15 control
+    for i in range(8):
+        p.add(R(1 + i % 6), 0, DStackAbs(i))
+    p.add(Imm(0), 0, DStackAbs(8))                # loop counter
+    p.label("loop")
+    # every far-call return keeps its returndata page alive until the bootloader frame ends (memory.rs:702-712): the
+    # bounded slab pool of the device build (<= 32 per VM) caps the far calls of one VM
+    far_budget = max(0, 24 // n_iters)
+    for _ in range(n_body):
+        k = rng.below(100)
+        if k >= 96 and far_budget == 0:
+            k = 0
+        if k >= 96:
+            far_budget -= 1
+        if k < 88:
+            g.safe_statement()
+        elif k < 91:                              # forward conditional jump over 1..3 statements
+            lab = g.label()
+            p.jump(lab, cond=rng.pick(_CONDS[3:]))
+            for _ in range(1 + rng.below(3)):
+                g.alu(cond="always")
+            p.label(lab)
+        elif k < 96:                              # near call into a (possibly panicking) subroutine
+            sub, cont = g.label(), g.label()
+            ergs_limited = rng.chance(0.3)
+            if ergs_limited:
+                p.add(Imm(rng.pick([30, 60, 200, 1000])), 0, 13)
+            p.near_call(13 if ergs_limited else 0, sub, cont)
+            p.label(cont)
+            subs.append((sub, rng.below(1 << 30)))
+        elif k < 98:                              # far call (normal / delegate / mimic, sometimes static)
+            addr = rng.pick(callee_addresses + [0xDEAD0000 + rng.below(4)])       # unknown address => default AA
+            length = rng.pick([0, 32, 64, 100])
+            fwd_aux = rng.chance(0.2)
+            abi = g.const(far_call_abi(rng.pick([0xFFFFFFFF, 100000, 3000]), start=rng.below(3) * 32, length=length,
+                                       fwd=C.FWD_USE_AUX_HEAP if fwd_aux else C.FWD_USE_HEAP))
+            p.add(Code(abi), 0, 13)
+            p.add(Code(g.const(addr)), 0, 14)
+            cont = g.label()
+            p.far_call(R(13), 14, cont, sub=rng.pick([isa.FC_NORMAL, isa.FC_NORMAL, isa.FC_DELEGATE, isa.FC_MIMIC]),
+                       static=rng.chance(0.25))
+            p.label(cont)
+            p.ld_ptr(R(1), rng.pick(_GP), 12, inc=True, cond="always")   # returndata (r1 is a pointer after far ret)
+        else:                                     # keccak through the system contract
+            abi = g.const(far_call_abi(0xFFFFFFFF, start=rng.below(64), length=rng.pick([0, 1, 64, 135, 136, 200])))
+            p.add(Code(abi), 0, 13)
+            p.add(Imm(C.KECCAK256_PRECOMPILE_ADDRESS), 0, 14)
+            cont = g.label()
+            p.far_call(R(13), 14, cont)
+            p.label(cont)
+            p.ld_ptr(R(1), rng.pick(_GP))
+    p.add(StackAbs(8), 0, 13)
+    p.add(Imm(1), 13, 13)
+    p.add(R(13), 0, DStackAbs(8))
+    p.sub(Imm(n_iters), 13, 0, set_flags=True, swap=True)
+    p.jump("loop", cond="lt")
+    p.ret(isa.RET_OK, R(0))
+    for label, sub_seed in subs:
+        sr = _Rng(sub_seed)
+        sg = _Gen(sr, p, kernel=True)
+        sg.n_const, sg.n_label = g.n_const + 1000 * (1 + len(p.labels)), g.n_label + 1000 * (1 + len(p.labels))
+        p.label(label)
+        for _ in range(2 + sr.below(6)):
+            sg.safe_statement() if sr.chance(0.7) else sg.risky_statement()
+        k = sr.below(10)
+        if k < 6:
+            p.ret(isa.RET_OK, R(0))
+        elif k < 8:
+            p.ret(isa.RET_REVERT, R(0))
+        else:
+            p.ret(isa.RET_PANIC, R(0))
+    return p
+
+
+class Mixed(Workload):
+    name = "mixed"
+
+    def __init__(self, n_programs: int = 64, target_cycles: int = 512, vms_per_program: int = 32, seed: int = DEFAULT_SEED):
+        super().__init__(seed)
+        self.n_programs, self.vms_per_program = n_programs, vms_per_program
+        self.max_cycles_hint = 4 * target_cycles + 256
+        rng = _Rng(seed ^ 0xC0FFEE)
+        self.callees = []
+        for i in range(4):
+            addr = (MIXED_CALLEE_BASE + i) if i < 3 else 0x8123       # one callee lives in kernel space
+            prog = mixed_callee(_Rng(rng.u64()), kernel=addr < (1 << 16))
+            code = _patched_words(prog)
+            self.codes[f"callee{i}"] = (bytecode_hash(code), code)
+            self.callees.append(addr)
+        self._add_code("keccak", keccak_system_contract())
+        n_body = 24
+        n_iters = max(1, target_cycles // (n_body * 2))
+        self.boot_names = []
+        for i in range(n_programs):
+            prog = mixed_bootloader(_Rng(rng.u64()), n_body, n_iters, self.callees)
+            code = _patched_words(prog)
+            self.codes[f"boot{i}"] = (bytecode_hash(code), code)
+            self.boot_names.append(f"boot{i}")
+
+    def config(self, n_vms, device=0, witness=True):
+        cfg = super().config(n_vms, device, witness)
+        c = self.max_cycles_hint
+        cfg.cap_records[0] = c
+        cfg.cap_records[1] = 2 * c
+        cfg.cap_records[2] = c // 2
+        cfg.cap_records[3] = c // 8 + 8
+        cfg.cap_records[4] = c // 2
+        cfg.cap_records[5] = c // 4
+        cfg.stack_words = 64
+        cfg.heap_bytes = 2048
+        cfg.n_heap_slabs = 32
+        cfg.max_far_depth = 4
+        cfg.max_depth = 12
+        cfg.storage_slots = 128
+        cfg.journal_entries = c // 2
+        return cfg
+
+    def setup(self, batch, vm_ids):
+        vm_ids = np.asarray(vm_ids, dtype=np.uint64)
+        n = len(vm_ids)
+        for h, code in self.codes.values():
+            batch.load_bytecode(h, code)
+        batch.set_block_properties(self.codes["callee0"][0], False)      # default AA = callee0's code
+        prog_of = ((vm_ids // np.uint64(self.vms_per_program)) % np.uint64(self.n_programs)).astype(np.int64)
+        start = 0
+        while start < n:                                                 # one populate_code per run of equal programs
+            end = start + 1
+            while end < n and prog_of[end] == prog_of[start]:
+                end += 1
+            batch.populate_code(BOOT_BASE_PAGE, self.codes[self.boot_names[prog_of[start]]][0], vm_lo=start, vm_hi=end)
+            start = end
+        batch.set_local_field(FIELD_MEMORY_PAGE_COUNTER, INITIAL_MEMORY_PAGE_COUNTER)
+        batch.set_local_field(FIELD_ERGS_PER_PUBDATA, 1)
+        frame = make_frame(this_address=BOOTLOADER_ADDRESS, msg_sender=0, code_address=BOOTLOADER_ADDRESS,
+                           base_memory_page=BOOT_BASE_PAGE, code_page=BOOT_BASE_PAGE, ergs_remaining=1 << 31,
+                           heap_bound=2048, aux_heap_bound=2048)
+        batch.push_bootloader_context(frame)
+        entries = [(0, C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, addr, self.codes[f"callee{i}"][0]) for i, addr in enumerate(self.callees)]
+        entries.append((0, C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, C.KECCAK256_PRECOMPILE_ADDRESS, self.codes["keccak"][0]))
+        batch.populate_storage(storage_entries(entries))
+        rnd = vm_random_u64(self.seed, vm_ids, 6 * 4 + 32)
+        for r in range(6):
+            words = rnd[:, 4 * r: 4 * r + 4].copy()
+            if r % 2 == 1:
+                words[:, 0:3] = 0                                           # small values too (shift amounts, divisors)
+            batch.set_register(r, u64_to_be_bytes(words), per_vm=True)
+        batch.populate_heap(np.ascontiguousarray(u64_to_be_bytes(rnd[:, 24:56])), per_vm=True)
+
+
+WORKLOADS["mixed"] = Mixed

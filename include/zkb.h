@@ -190,6 +190,11 @@ int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
  * (must hold the stream's total bytes); offsets_out[n_vms + 1] receives the byte offset of each VM. */
 int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity,
                                 uint64_t* offsets_out);
+/* asynchronous variant: waits (on the host) only for THIS batch's last run, then enqueues pack + D2H on `cuda_stream`
+ * and returns; host_dst should be pinned. The copy engine then overlaps with other batches' kernels: this is how a
+ * host loop pipelines sub-batches (compute of k+1 under the witness download of k). Completion = stream sync. */
+int32_t zkb_fetch_stream_packed_async(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity,
+                                      uint64_t* offsets_out, void* cuda_stream);
 /* device-only variant: returns the packed device buffer (valid until the next run/fetch/destroy) */
 int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
 /* final storage value of one slot (== InMemoryStorage.inner lookup, storage.rs:9) */

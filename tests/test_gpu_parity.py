@@ -26,6 +26,9 @@ def _pair(w, vm_ids, oracle_mod):
     ("keccak", dict(n_calls=3), 40),
     ("keccak", dict(n_calls=2, preimage_bytes=200), 16),
     ("erc20", dict(n_transfers=4), 200),
+    ("mixed", dict(n_programs=24), 24 * 32),
+    ("mixed", dict(n_programs=16, seed=0xF00D), 16 * 32 + 5),
+    ("mixed", dict(n_programs=16, seed=0xBEEF, target_cycles=900), 16 * 32),
 ])
 def test_workload_parity(name, kwargs, n, oracle_mod):
     w = workloads.WORKLOADS[name](**kwargs)
@@ -52,3 +55,66 @@ def test_resumable_run_matches_single_run(oracle_mod):
     orc.run_threads(0, 0)
     problems = compare_batches(gpu, orc)
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_schedules_give_identical_results(schedule, oracle_mod):
+    """free-running and lockstep warp schedules are two launch shapes of the same interpreter"""
+    w = workloads.Mixed(n_programs=8, seed=0xABCD)
+    from era_zk_evm_b200 import GpuVmBatch
+    ids = list(range(8 * 32 + 3))
+    cfg = w.config(len(ids))
+    cfg.schedule = schedule
+    gpu, orc = GpuVmBatch(cfg), oracle_mod.OracleBatch(cfg)
+    w.setup(gpu, ids)
+    w.setup(orc, ids)
+    gpu.run()
+    orc.run_threads(0, 0)
+    problems = compare_batches(gpu, orc)
+    assert not problems, "\n".join(problems)
+
+
+def test_alu_golden_vectors_on_gpu():
+    """the CUDA U256 ALU against the committed Python-int golden vectors (no oracle involved)"""
+    import test_oracle_golden as G
+    from era_zk_evm_b200 import GpuVmBatch
+    allc = G.load("u256_vectors.json")
+    for op in sorted(G.OPS):
+        G.check_alu_vectors(GpuVmBatch, op, [c for c in allc if c["op"] == op])
+
+
+def test_keccak_golden_vectors_on_gpu():
+    """keccak256 precompile on the GPU against the committed digests: the reference's 8 live test shapes
+    (keccak256.rs:144-196) plus the 4 KiB / rate-boundary shapes, aligned and unaligned"""
+    import test_oracle_golden as G
+    import vm_harness as H
+    from era_zk_evm_b200 import GpuVmBatch, isa
+    from era_zk_evm_b200.asm import Code, Imm, Program, R, far_call_abi
+    from era_zk_evm_b200.isa import C
+    for v in G.load("hash_vectors.json")["keccak256"]:
+        data, un = G.keccak_input(v), v["unalignment"]
+        p = Program()
+        p.const("abi", far_call_abi(0xFFFFFFFF, start=un, length=len(data)))
+        p.add(Code("abi"), 0, 8)
+        p.add(Imm(C.KECCAK256_PRECOMPILE_ADDRESS), 0, 7)
+        p.far_call(R(8), 7, "fail")
+        p.ld_ptr(R(1), 2)
+        p.st(Imm(8000), 2)
+        p.ret(isa.RET_OK, R(0))
+        p.label("fail")
+        p.ret(isa.RET_PANIC, R(0))
+        heap = b"\xff" * un + data
+        b = H.launch(GpuVmBatch, p, 3, contracts={C.KECCAK256_PRECOMPILE_ADDRESS: workloads.keccak_system_contract()},
+                     heap=heap + b"\x00" * (-len(heap) % 32) if heap else None, heap_bound=8192,
+                     cfg_over=dict(heap_bytes=8192 + 64))
+        for vm in range(3):
+            r = H.rows(b, vm)
+            digest = [x for x in r if H.family_of(x) == "uma" and int(x["bits"]) & 0x40][0]
+            assert H.val(digest["dst0"]).to_bytes(32, "big").hex() == v["digest"], v
+        b.close()
+
+
+def test_sha256_golden_vectors_on_gpu():
+    import test_oracle_golden as G
+    from era_zk_evm_b200 import GpuVmBatch
+    G.check_sha256_precompile(GpuVmBatch)
