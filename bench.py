@@ -9,8 +9,9 @@ every VM runs from its bootloader entry to the end of execution, all witness str
 
 value     device throughput: inputs resident in HBM, each step = device-side restore of the initial batch state
           (zkb_restore, D2D) + ONE launch of the persistent interpreter kernel; CUDA events, max over ranks.
-e2e       the same metric through the public host API with HOST buffers: reset + populate (H2D) + run + packed
-          fetch of all six witness streams into pinned host memory (D2H), every step.
+e2e       the same metric through the public host API with HOST buffers: per sub-batch reset + populate (H2D) + run +
+          packed fetch of all six witness streams into pinned host memory (D2H), copies overlapped with the next
+          sub-batch's compute, every step.
 roofline  algorithmic bytes (exact byte length of the emitted streams) / average kernel duration, against the
           measured HBM copy bandwidth in MEASURED_PEAKS.json.
 --impl reference: the CPU restatement of the reference path (oracle/, "port": the Rust crate cannot be built in
@@ -92,30 +93,31 @@ class ClockSampler:
 def cpu_reference_run(workload, vm_ids, threads=0, repeats=1):
     """times the oracle (C++ restatement of the reference path) on `vm_ids`; returns (cycles/s, cycles, threads, seconds)."""
     import oracle
-    best = None
+    cfg = workload.config(len(vm_ids))
+    b = oracle.OracleBatch(cfg)
+    total_dt, cycles = 0.0, 0
     for _ in range(repeats):
-        cfg = workload.config(len(vm_ids))
-        b = oracle.OracleBatch(cfg)
+        b.reset()
         workload.setup(b, vm_ids)
         t0 = time.perf_counter()
         b.run_threads(0, threads)
-        dt = time.perf_counter() - t0
+        total_dt += time.perf_counter() - t0
         cycles, _ = b.totals()
         st = b.vm_status()
         assert (st[:, 0] == 1).all(), "oracle: not all VMs ended"
-        b.close()
-        if best is None or dt < best[1]:
-            best = (cycles, dt)
+    b.close()
+    dt = total_dt / repeats
     n_thr = threads or (os.cpu_count() or 1)
-    return best[0] / best[1], best[0], min(n_thr, len(vm_ids)), best[1]
+    return cycles / dt, cycles, min(n_thr, len(vm_ids)), dt
 
 
-def sized_cpu_sample(workload, target_seconds=6.0, max_vms=16384):
-    """bounded sample: calibrate on 512 VMs, then size the sample for ~target_seconds of wall time on all threads."""
-    rate, cycles, thr, dt = cpu_reference_run(workload, np.arange(512))
-    per_vm = cycles / 512
-    n = int(min(max_vms, max(1024, rate * target_seconds / per_vm)))
-    return n
+def sized_cpu_sample(workload, vms_cap, target_seconds=12.0):
+    """bounded sample: calibrate on 1024 VMs, then (n VMs, repeats) for ~target_seconds of CPU wall time on all threads."""
+    rate, cycles, thr, dt = cpu_reference_run(workload, np.arange(1024))
+    per_vm = cycles / 1024
+    n = int(min(vms_cap, max(1024, rate * target_seconds / per_vm)))
+    repeats = max(1, int(round(target_seconds / max(n * per_vm / rate, 1e-3))))
+    return n, min(repeats, 16)
 
 
 def main():
@@ -126,7 +128,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--vms", type=int, default=65536, help="VMs per GPU")
     ap.add_argument("--transfers", type=int, default=8)
-    ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage"])
+    ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
+    ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
+    ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -149,14 +153,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n = sized_cpu_sample(w)
+        import oracle
+        n = args.vms                      # one step = the whole configs[1] batch on the host cores (~1 s per step)
         ids = np.arange(n)
-        for _ in range(max(1, min(args.warmup, 1))):
-            cpu_reference_run(w, ids)
+        ob = oracle.OracleBatch(w.config(n))
         times, cyc = [], 0
-        for _ in range(args.steps):
-            rate, cyc, thr, dt = cpu_reference_run(w, ids)
-            times.append(dt)
+        thr = min(os.cpu_count() or 1, n)
+        for i in range(max(1, args.warmup) + args.steps):     # warm-up also faults in the witness buffers
+            ob.reset()
+            w.setup(ob, ids)
+            t0 = time.perf_counter()
+            ob.run_threads(0, 0)
+            dt = time.perf_counter() - t0
+            if i >= max(1, args.warmup):
+                times.append(dt)
+            cyc, _ = ob.totals()
+        ob.close()
         dt = float(np.mean(times))
         value = cyc / dt
         sample = f"{n} VMs of the same workload per step ({cyc} cycles), witness recording on"
@@ -172,7 +184,7 @@ def main():
     # ------------------------------------------------------------------ B200 arm --------------------------
     import torch
     import torch.distributed as dist
-    from era_zk_evm_b200 import GpuVmBatch
+    from era_zk_evm_b200 import GpuVmBatch, shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -184,6 +196,9 @@ def main():
     batch = GpuVmBatch(cfg)
     w.setup(batch, vm_ids)
     batch.snapshot()
+    concat_kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND] + \
+        ([records.STREAM_ROWS, records.STREAM_MEM] if args.gather_rows else [])
+    cur_stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -191,13 +206,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    pending = []
+
     def step():
+        """one pass of the hot path over the batch; at N > 1 followed by the only exchange on this path: the
+        concatenation of the per-GPU query-log streams on rank 0 (NCCL send/recv straight from the pack buffers),
+        left in flight so that it overlaps the next step's interpreter launch"""
         batch.restore()
         batch.run(sync=False)
+        if world > 1:
+            for pg in pending:     # stream-level wait: the pack buffers are reused below, AFTER this step's launch is queued
+                pg.wait()
+            pending.clear()
+            for kind in concat_kinds:
+                pg, _ = shard.gather_stream(batch, kind, dst=0, async_op=True, stream_ptr=cur_stream)
+                pending.append(pg)
+
+    def drain():
+        batch.sync()
+        for pg in pending:
+            pg.wait()
+        pending.clear()
 
     for _ in range(max(args.warmup, 0)):
         step()
-        batch.sync()
+        drain()
     cycles, sbytes = batch.totals()
     st = batch.vm_status()
     if not (st[:, 0] == 1).all():
@@ -211,8 +244,10 @@ def main():
         ev0.record()
         for _ in range(args.steps):
             step()
-            batch.sync()
+            if world == 1:
+                batch.sync()
             kernel_ms.append(batch.last_run_ms()[0])
+        drain()
         ev1.record()
         barrier()
         total_ms = ev0.elapsed_time(ev1)
@@ -228,57 +263,97 @@ def main():
     peak, peak_src = load_peak()
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = load_ncu_traffic(args.workload)
+    if isinstance(traffic, dict):      # ncu --set full capture at `vms` VMs: dram bytes scale linearly with the VM count
+        traffic = traffic["dram_bytes_per_launch"] * args.vms / traffic["vms"]
     roofline = {"bound": "hbm", "kernel": "zkb_run_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_ncu_traffic(args.workload), "peak_source": peak_src, "kernel_ms": k_ms,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_cycle": alg_bytes / cycles,
-                "note": "interpreter is integer-issue/latency bound; see profiles/ for pipe utilisation"}
+                "note": "interpreter is integer-issue/latency bound (no tensor-core work on this path); ncu issue-slot and ALU-pipe "
+                        "utilisation under profiles/; traffic = ncu dram read+write bytes scaled from the profiled VM count"}
 
     # ---- e2e through the public host API with host buffers (H2D inputs + D2H witness inside the timed region) ----
+    # The batch is processed as S sub-batches: inputs of sub-batch k go H2D, its interpreter launch runs on one stream,
+    # its six witness streams are packed and copied D2H into pinned host memory on another stream while sub-batch
+    # k+1 is populated and executed.  Every input byte and every witness byte crosses PCIe inside the timed region.
     e2e = None
     if not args.no_e2e:
-        caps = [int(cycles_k) for cycles_k in sbytes]
-        pinned = [torch.empty(max(nb, 8), dtype=torch.uint8, pin_memory=True) for nb in caps]
-        e2e_steps = max(1, min(args.steps, 2))
+        n_sub = max(1, min(args.sub_batches, args.vms // 1024))
+        bounds = [shard.partition(args.vms, n_sub, i) for i in range(n_sub)]
+        subs, sub_ids, pinned = [], [], []
+        for lo, hi in bounds:
+            scfg = w.config(hi - lo, device=local_rank)
+            subs.append(GpuVmBatch(scfg))
+            sub_ids.append(vm_ids[lo:hi])
+            w.prepared(vm_ids[lo:hi]) if hasattr(w, "prepared") and hasattr(w, "inputs") else None
+        run_stream, copy_stream = torch.cuda.Stream(), torch.cuda.Stream()
+        share = [(hi - lo) / args.vms for lo, hi in bounds]
+        for sh in share:   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
+            pinned.append([torch.empty(int(nb * sh * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) for nb in sbytes])
+        e2e_steps = max(1, min(args.steps, 3))
+        phase = {"setup_s": 0.0, "wait_run_s": 0.0}
 
         def e2e_step():
-            batch.reset()
-            w.setup(batch, vm_ids)
-            batch.run()
-            for k in range(records.N_STREAMS):
-                batch.fetch_stream_packed(k, pinned[k].data_ptr(), pinned[k].numel())
+            for i, sb in enumerate(subs):
+                t0 = time.perf_counter()
+                sb.reset()
+                w.setup(sb, sub_ids[i])
+                sb.run(stream=run_stream.cuda_stream, sync=False)
+                t1 = time.perf_counter()
+                for k in range(records.N_STREAMS):
+                    sb.fetch_stream_packed_async(k, pinned[i][k].data_ptr(), pinned[i][k].numel(), stream=copy_stream.cuda_stream)
+                t2 = time.perf_counter()
+                phase["setup_s"] += t1 - t0
+                phase["wait_run_s"] += t2 - t1
+            copy_stream.synchronize()
 
-        e2e_step()   # warm-up (also sizes the pack buffer)
-        batch.transfer_stats(reset=True)
+        e2e_step()   # warm-up (also sizes the pack buffers)
+        for sb in subs:
+            sb.transfer_stats(reset=True)
+        phase = {"setup_s": 0.0, "wait_run_s": 0.0}
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        h2d, d2h = batch.transfer_stats()
+        h2d = sum(sb.transfer_stats()[0] for sb in subs)
+        d2h = sum(sb.transfer_stats()[1] for sb in subs)
+        e2e_cycles = sum(sb.totals()[0] for sb in subs)
+        assert e2e_cycles == cycles, (e2e_cycles, cycles)
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
         e2e = {"value": total_cycles / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "path": "GpuVmBatch.reset + Workload.setup (populate_* from host arrays) + run + fetch_stream_packed x6 into pinned host"}
-        del pinned
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": n_sub,
+               "host_ms_per_step": {k: v * 1e3 / e2e_steps for k, v in phase.items()},
+               "pcie_floor_ms": d2h / e2e_steps / 54.5e9 * 1e3,
+               "path": "per sub-batch: GpuVmBatch.reset + Workload.setup (populate_* / set_register / push_bootloader_context from host "
+                       "arrays, H2D) + run + fetch_stream_packed_async x6 into pinned host (D2H), copy of k overlapped with compute of k+1"}
+        for sb in subs:
+            sb.close()
+        del pinned, subs
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n = sized_cpu_sample(w)
-        rate, cyc, thr, dt = cpu_reference_run(w, np.arange(n))
+        n, repeats = sized_cpu_sample(w, args.vms)
+        rate, cyc, thr, dt = cpu_reference_run(w, np.arange(n), repeats=repeats)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
-                        "sample": f"{n} VMs of the same workload ({cyc} cycles, {dt:.2f} s wall), witness recording on",
+                        "sample": f"{n} VMs of the same workload x {repeats} passes ({cyc} cycles and {dt:.2f} s wall per pass), witness recording on",
                         "note": "C++ restatement of the reference path (oracle/), not the Rust crate"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
-                "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "cycles_per_step": total_cycles, "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes))}
+                "e2e": e2e, "gpu_launches": args.steps * (1 + (len(concat_kinds) if world > 1 else 0)), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
+                "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
+                "multi_gpu": None if world == 1 else {
+                    "partition": "static VM ranges, one process per GPU", "collective": "NCCL send/recv concat on rank 0 inside the timed step",
+                    "concat_streams": [records.STREAM_NAMES[k] for k in concat_kinds],
+                    "concat_bytes_per_step": int(sum(sbytes[k] for k in concat_kinds)) * world}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

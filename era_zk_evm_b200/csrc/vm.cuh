@@ -87,6 +87,7 @@ struct DevBatch {
   uint32_t* j_val;      // [vm][journal][8]
   uint8_t* streams[ZKB_N_STREAMS];
   unsigned int* queue;
+  uint32_t* host_counts;  // [vm][8] in mapped pinned HOST memory: 6 stream counts, status, cycles (written once per run)
 };
 
 __device__ __forceinline__ uint32_t rec_bytes(int kind) {
@@ -239,12 +240,13 @@ struct Vm {
   }
 
   // start_new_execution_context (helpers.rs:237-241): the new frame must already be in S.F
-  __device__ __forceinline__ void emit_frame_start(uint32_t prev_ergs, uint32_t prev_pc, uint32_t prev_sp) {
+  __device__ __forceinline__ void emit_frame_start(uint32_t prev_ergs, uint32_t prev_pc, uint32_t prev_sp, uint32_t bound_kind,
+                                                   uint32_t bound_value) {
     ccount += 1u << 26;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
     if (p) {
-      uint32_t w = lane == 0 ? ZKB_FRAMEKIND_START : lane == 1 ? cycle : lane < 29 ? S.F[(lane - 2) & 31] : lane == 29 ? prev_ergs
-                   : lane == 30 ? (prev_pc | prev_sp << 16) : 0u;
+      uint32_t w = lane == 0 ? (ZKB_FRAMEKIND_START | bound_kind << 16) : lane == 1 ? cycle : lane < 29 ? S.F[(lane - 2) & 31]
+                   : lane == 29 ? prev_ergs : lane == 30 ? (prev_pc | prev_sp << 16) : bound_value;
       p[lane] = w;
     }
   }
@@ -480,7 +482,7 @@ struct Vm {
     __syncwarp();
   }
   // vm_state.start_frame (helpers.rs:225-246) for a frame already described in `nf` (lane i holds word i)
-  __device__ __forceinline__ void push_frame(uint32_t nf) {
+  __device__ __forceinline__ void push_frame(uint32_t nf, uint32_t bound_kind = 0, uint32_t bound_value = 0) {
     uint32_t depth = S.row[L_DEPTH];
     if (depth >= B.max_depth) {
       fail(ZKB_VM_CAP_DEPTH);
@@ -497,7 +499,7 @@ struct Vm {
       S.row[L_DEPTH] = depth + 1;
     }
     __syncwarp();
-    emit_frame_start(prev_ergs, prev_pc, prev_sp);
+    emit_frame_start(prev_ergs, prev_pc, prev_sp, bound_kind, bound_value);
     load_frame_from_F();
   }
   // vm_state.finish_frame (helpers.rs:248-264); leaves the finished frame in S.kbuf[0..31], the parent in S.F
@@ -1275,7 +1277,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   }
   if (ex) p_off = p_page = p_start = p_len = 0;
 
-  uint32_t growth = 0;
+  uint32_t growth = 0, bound_kind = 0, bound_value = 0;
   if (fwd != ZK_FWD_FORWARD_FAT_POINTER) {
     uint32_t upper = p_start + p_len;
     if (deref_beyond) upper = 0xFFFFFFFFu;
@@ -1285,7 +1287,10 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     if (upper >= bound) {
       growth = upper - bound;
       setL(w, upper);
+      bound = upper;
     }
+    bound_kind = fwd == ZK_FWD_USE_HEAP ? 1u : 2u;  // FrameRec.prev_bound_*: the caller's bound as the tracer sees it
+    bound_value = bound;
   }
   uint32_t ergs_after_growth;
   if (remaining_ergs >= growth) {
@@ -1399,7 +1404,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   __syncwarp();
   if (lane < 4) S.row[L_CTX + lane] = 0u;  // context_u128_register = 0 (far_call.rs:558)
   __syncwarp();
-  push_frame(nf);
+  push_frame(nf, bound_kind, bound_value);
   if (status != ZKB_VM_RUNNING) return;
   memory_start_global_frame(caller_level, cur_base, p_page);
 
@@ -1697,6 +1702,13 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
 #pragma unroll
   for (int k = 0; k < ZKB_N_STREAMS; k++) out = lane == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
   hot->x[lane] = out;
+  // the per-VM summary goes straight to mapped host memory (one 32-byte posted write per VM and run): the host can
+  // size and enqueue the witness download without a D2H copy of its own queueing behind the copies already in flight
+  const uint32_t st_out = (v.status == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : v.status;
+  uint32_t summary = lane == 6 ? st_out : v.cycle;
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.count[k] : summary;
+  if (lane < 8) v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
   __syncwarp();
 }
 

@@ -183,6 +183,8 @@ struct ZkbBatch {
   uint64_t pack_capacity = 0;
   uint64_t* d_offsets = nullptr;                  // [ZKB_N_STREAMS][n_vms + 1]
   std::vector<uint64_t> h_offsets[ZKB_N_STREAMS];  // host copies that outlive the async uploads
+  uint32_t* h_counts = nullptr;                   // mapped pinned mirror of DevBatch.host_counts
+  bool counts_valid = false;                      // h_counts reflects the device state (after upload / a finished run)
   uint8_t* d_stage = nullptr;                     // grow-only H2D staging buffer of the populate_* calls
   uint64_t stage_capacity = 0;
   cudaEvent_t ev_setup = nullptr;
@@ -196,6 +198,7 @@ struct ZkbBatch {
     size_t bytes;
   };
   std::vector<Region> snap;
+  std::vector<uint32_t> snap_counts;
   bool has_snapshot = false;
 };
 
@@ -304,6 +307,13 @@ static int32_t upload(ZkbBatch* b) {
     CUDA_OK(cudaMemcpy(b->d.hot, b->h_hot.data(), b->h_hot.size() * sizeof(VmHot), cudaMemcpyHostToDevice));
     b->h2d_bytes += b->h_hot.size() * sizeof(VmHot);
     b->hot_dirty = false;
+    for (size_t v = 0; v < b->h_hot.size(); v++) {
+      const VmHot& h = b->h_hot[v];
+      for (int k = 0; k < ZKB_N_STREAMS; k++) b->h_counts[v * 8 + k] = h.x[X_COUNT0 + k];
+      b->h_counts[v * 8 + 6] = h.x[X_STATUS];
+      b->h_counts[v * 8 + 7] = h.x[X_CYCLE];
+    }
+    b->counts_valid = true;
   }
   if (b->root_dirty) {
     CUDA_OK(cudaMemcpy2D(b->d.callstack, (size_t)b->cfg.max_depth * 128, b->h_root.data(), 128, 128, b->cfg.n_vms, cudaMemcpyHostToDevice));
@@ -324,6 +334,17 @@ static int32_t download_hot(ZkbBatch* b) {
     b->d2h_bytes += b->h_hot.size() * sizeof(VmHot);
     b->hot_stale = false;
   }
+  return ZKB_OK;
+}
+
+// per-VM summary (stream counts, status, cycles) without a device->host copy: valid after upload or a finished run
+static int32_t summary(ZkbBatch* b, const uint32_t** out) {
+  if (b->hot_dirty) {  // host-side edits not uploaded yet: the host mirror is authoritative
+    int32_t rc = upload(b);
+    if (rc != ZKB_OK) return rc;
+  }
+  if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  *out = b->h_counts;
   return ZKB_OK;
 }
 
@@ -397,6 +418,20 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
     cudaGetLastError();
     return set_err(ZKB_ERR_OUT_OF_MEMORY, msg);
   }
+  {
+    void* hp = nullptr;
+    cudaError_t he = cudaHostAlloc(&hp, n * 8 * sizeof(uint32_t), cudaHostAllocMapped);
+    void* dp = nullptr;
+    if (he == cudaSuccess) he = cudaHostGetDevicePointer(&dp, hp, 0);
+    if (he != cudaSuccess) {
+      for (void* p : b->allocs) cudaFree(p);
+      delete b;
+      return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("cudaHostAlloc: ") + cudaGetErrorString(he));
+    }
+    b->h_counts = (uint32_t*)hp;
+    d.host_counts = (uint32_t*)dp;
+    memset(hp, 0, n * 8 * sizeof(uint32_t));
+  }
   b->h_hot.resize(n);
   b->h_root.assign(n * 32, 0);
   b->h_bootrec.assign(n * 32, 0);
@@ -434,6 +469,7 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->ev_setup) cudaEventDestroy(b->ev_setup);
   if (b->d_stage) cudaFree(b->d_stage);
+  if (b->h_counts) cudaFreeHost(b->h_counts);
   delete b;
   return ZKB_OK;
 }
@@ -655,14 +691,12 @@ int32_t zkb_last_run_ms(ZkbBatch* b, float* ms, uint32_t* n_kernel_launches) {
 
 int32_t zkb_vm_status(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, ZkbVmStatus* out) {
   if (!range_ok(b, vm_lo, vm_hi) || !out) return ZKB_ERR_INVALID_ARGUMENT;
-  int32_t rc = download_hot(b);
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);
   if (rc != ZKB_OK) return rc;
   for (uint32_t v = vm_lo; v < vm_hi; v++) {
-    const VmHot& h = b->h_hot[v];
-    uint32_t code = h.x[X_STATUS];
-    if (code == ZKB_VM_RUNNING && h.live[L_DEPTH - 40] == 0 && h.x[X_CYCLE] > 0) code = ZKB_VM_ENDED;
-    out[v - vm_lo].code = code;
-    out[v - vm_lo].cycles = h.x[X_CYCLE];
+    out[v - vm_lo].code = c[(size_t)v * 8 + 6];
+    out[v - vm_lo].cycles = c[(size_t)v * 8 + 7];
   }
   return ZKB_OK;
 }
@@ -713,20 +747,22 @@ int32_t zkb_read_local_state(ZkbBatch* b, uint32_t vm, ZkbLocalState* out) {
 
 int32_t zkb_stream_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out) {
   if (!range_ok(b, vm_lo, vm_hi) || kind >= ZKB_N_STREAMS || !counts_out) return ZKB_ERR_INVALID_ARGUMENT;
-  int32_t rc = download_hot(b);
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);
   if (rc != ZKB_OK) return rc;
-  for (uint32_t v = vm_lo; v < vm_hi; v++) counts_out[v - vm_lo] = b->h_hot[v].x[X_COUNT0 + kind];
+  for (uint32_t v = vm_lo; v < vm_hi; v++) counts_out[v - vm_lo] = c[(size_t)v * 8 + kind];
   return ZKB_OK;
 }
 
 int32_t zkb_totals(ZkbBatch* b, uint64_t* total_cycles, uint64_t stream_bytes[ZKB_N_STREAMS]) {
   if (!b) return ZKB_ERR_INVALID_ARGUMENT;
-  int32_t rc = download_hot(b);
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);
   if (rc != ZKB_OK) return rc;
   uint64_t cyc = 0, sb[ZKB_N_STREAMS] = {0, 0, 0, 0, 0, 0};
-  for (const VmHot& h : b->h_hot) {
-    cyc += h.x[X_CYCLE];
-    for (int k = 0; k < ZKB_N_STREAMS; k++) sb[k] += (uint64_t)h.x[X_COUNT0 + k] * REC_BYTES[k];
+  for (size_t v = 0; v < b->cfg.n_vms; v++) {
+    cyc += c[v * 8 + 7];
+    for (int k = 0; k < ZKB_N_STREAMS; k++) sb[k] += (uint64_t)c[v * 8 + k] * REC_BYTES[k];
   }
   if (total_cycles) *total_cycles = cyc;
   if (stream_bytes) memcpy(stream_bytes, sb, sizeof(sb));
@@ -742,9 +778,10 @@ int32_t zkb_stream_device_view(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t
 
 int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
   if (!b || vm >= b->cfg.n_vms || kind >= ZKB_N_STREAMS) return ZKB_ERR_INVALID_ARGUMENT;
-  int32_t rc = download_hot(b);
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);
   if (rc != ZKB_OK) return rc;
-  uint64_t n = b->cfg.witness_mode ? (uint64_t)b->h_hot[vm].x[X_COUNT0 + kind] * REC_BYTES[kind] : 0;
+  uint64_t n = b->cfg.witness_mode ? (uint64_t)c[(size_t)vm * 8 + kind] * REC_BYTES[kind] : 0;
   if (n_bytes) *n_bytes = n;
   uint64_t take = std::min(n, max_bytes);
   if (dst && take) {
@@ -760,7 +797,7 @@ static uint64_t stream_offsets(ZkbBatch* b, uint32_t kind) {
   std::vector<uint64_t>& off = b->h_offsets[kind];
   off.resize(n + 1);
   off[0] = 0;
-  for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_hot[v].x[X_COUNT0 + kind] * REC_BYTES[kind];
+  for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_counts[(size_t)v * 8 + kind] * REC_BYTES[kind];
   return off[n];
 }
 
@@ -788,7 +825,8 @@ static uint8_t* pack_region(ZkbBatch* b, uint32_t kind) {
 
 static int32_t pack_async(ZkbBatch* b, uint32_t kind, cudaStream_t st, uint8_t** dptr, uint64_t* n_bytes) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
-  int32_t rc = download_hot(b);
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);  // waits for THIS batch's run only; no device->host copy
   if (rc != ZKB_OK) return rc;
   rc = ensure_pack_capacity(b);
   if (rc != ZKB_OK) return rc;
@@ -932,6 +970,7 @@ int32_t zkb_snapshot(ZkbBatch* b) {
   rc = download_hot(b);
   if (rc != ZKB_OK) return rc;
   for (auto& r : b->snap) CUDA_OK(cudaMemcpy(r.saved, r.live, r.bytes, cudaMemcpyDeviceToDevice));
+  b->snap_counts.assign(b->h_counts, b->h_counts + (size_t)b->cfg.n_vms * 8);
   b->has_snapshot = true;
   return ZKB_OK;
 }
@@ -940,6 +979,8 @@ int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
   if (!b || !b->has_snapshot) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_restore without zkb_snapshot");
   CUDA_OK(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;  // a running launch still owns the state and the host summary
+  memcpy(b->h_counts, b->snap_counts.data(), b->snap_counts.size() * sizeof(uint32_t));
   for (auto& r : b->snap) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   CUDA_OK(cudaEventRecord(b->ev1, st));

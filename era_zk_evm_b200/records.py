@@ -37,14 +37,14 @@ DECOMMIT_DTYPE = np.dtype([
     ("reserved0", "u1"), ("reserved1", "<u4"), ("hash", "<u4", 8),
 ])
 FRAME_DTYPE = np.dtype([
-    ("kind", "u1"), ("panicked", "u1"), ("reserved0", "<u2"), ("cycle", "<u4"),
+    ("kind", "u1"), ("panicked", "u1"), ("prev_bound_kind", "<u2"), ("cycle", "<u4"),
     ("this_address", "u1", 20), ("msg_sender", "u1", 20), ("code_address", "u1", 20),
     ("base_memory_page", "<u4"), ("code_page", "<u4"),
     ("sp", "<u2"), ("pc", "<u2"), ("exception_handler_location", "<u2"),
     ("this_shard_id", "u1"), ("caller_shard_id", "u1"), ("ergs_remaining", "<u4"),
     ("code_shard_id", "u1"), ("is_static", "u1"), ("is_local_frame", "u1"), ("reserved1", "u1"),
     ("context_u128_value", "<u4", 4), ("heap_bound", "<u4"), ("aux_heap_bound", "<u4"),
-    ("prev_ergs_remaining", "<u4"), ("prev_pc", "<u2"), ("prev_sp", "<u2"), ("reserved2", "<u4"),
+    ("prev_ergs_remaining", "<u4"), ("prev_pc", "<u2"), ("prev_sp", "<u2"), ("prev_bound_value", "<u4"),
 ])
 REFUND_DTYPE = np.dtype([("refund_type", "<u4"), ("refund_value", "<u4")])
 

@@ -30,9 +30,23 @@ def device_bytes_as_tensor(ptr: int, nbytes: int, device: torch.device) -> torch
     return torch.as_tensor(_DevicePtr(ptr, nbytes), device=device)
 
 
-def gather_varlen(local: torch.Tensor, dst: int = 0, group=None):
+class PendingGather:
+    """handle of an asynchronous gather: `wait()` returns (concatenated tensor on dst | None, rank byte offsets)"""
+
+    def __init__(self, out, offsets, works, keep=()):
+        self.out, self.offsets, self._works, self._keep = out, offsets, works, keep
+
+    def wait(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+        return self.out, self.offsets
+
+
+def gather_varlen(local: torch.Tensor, dst: int = 0, group=None, async_op: bool = False):
     """Concatenates one variable-length uint8 tensor per rank on rank `dst`, in rank order.
-    Returns (concatenated tensor on dst | None elsewhere, byte offsets[world + 1] on every rank)."""
+    Returns (concatenated tensor on dst | None elsewhere, byte offsets[world + 1] on every rank); with async_op a
+    PendingGather whose payload transfers (NCCL send/recv) are still in flight."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
@@ -43,14 +57,11 @@ def gather_varlen(local: torch.Tensor, dst: int = 0, group=None):
         out = torch.empty(int(offsets[-1]), dtype=torch.uint8, device=local.device)
         out[offsets[rank]: offsets[rank + 1]].copy_(local)
         ops = [dist.P2POp(dist.irecv, out[offsets[r]: offsets[r + 1]], r, group) for r in range(world) if r != dst and sizes[r]]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return out, offsets
-    if local.numel():
-        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
-            w.wait()
-    return None, offsets
+        pending = PendingGather(out, offsets, dist.batch_isend_irecv(ops) if ops else [], keep=(local,))
+    else:
+        works = dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]) if local.numel() else []
+        pending = PendingGather(None, offsets, works, keep=(local,))
+    return pending if async_op else pending.wait()
 
 
 def all_gather_varlen(local: torch.Tensor, group=None):
@@ -69,18 +80,21 @@ def all_gather_varlen(local: torch.Tensor, group=None):
     return torch.cat([c[:s] for c, s in zip(chunks, sizes)]), offsets
 
 
-def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.device | None = None):
+def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.device | None = None, async_op: bool = False,
+                  stream_ptr=None):
     """Packs this rank's stream `kind` (VM-major, contiguous: the pack kernel writes the NCCL send buffer directly)
     and concatenates the ranks' buffers on `dst`.  Returns (bytes tensor | None, rank byte offsets,
     per-VM record counts of this rank)."""
     counts = batch.stream_counts(kind)
     if hasattr(batch, "pack_stream_device"):
-        ptr, nbytes = batch.pack_stream_device(kind)
+        ptr, nbytes = batch.pack_stream_device(kind, stream_ptr)
         device = device or torch.device("cuda", torch.cuda.current_device())
         local = device_bytes_as_tensor(ptr, nbytes, device)
     else:   # host-resident batches (CPU tests over gloo)
         parts = [batch.read_stream(vm, kind).view(np.uint8) for vm in range(batch.n_vms)]
         flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
         local = torch.from_numpy(np.ascontiguousarray(flat))
+    if async_op:
+        return gather_varlen(local, dst, group, async_op=True), counts
     out, offsets = gather_varlen(local, dst, group)
     return out, offsets, counts

@@ -140,6 +140,14 @@ class Workload:
     def __init__(self, seed: int = DEFAULT_SEED):
         self.seed = seed
         self.codes = {}      # name -> (hash:int, code:bytes)
+        self._prepared = {}
+
+    def prepared(self, vm_ids):
+        """host-side input arrays of a VM range, generated once (workload GENERATION is not part of any timed region)"""
+        key = (int(vm_ids[0]) if len(vm_ids) else 0, len(vm_ids))
+        if key not in self._prepared:
+            self._prepared[key] = self.inputs(np.asarray(vm_ids, dtype=np.uint64))
+        return self._prepared[key]
 
     def _add_code(self, name: str, prog: Program):
         code = prog.bytecode()
@@ -372,7 +380,15 @@ class Erc20(Workload):
         pre[:, 0:32] = heap[:, 0:32]
         slot = keccak256_batch(pre)
         broke = (vm_ids % np.uint64(64)) == np.uint64(63)
-        return heap, slot, broke
+        from ._binding import STORAGE_INIT_DTYPE
+        ent = np.zeros(len(vm_ids), dtype=STORAGE_INIT_DTYPE)
+        ent["shard_id"] = 0
+        ent["address"] = np.frombuffer(TOKEN_ADDRESS.to_bytes(20, "big"), dtype=np.uint8)
+        ent["key_be"] = slot
+        bal = np.zeros((len(vm_ids), 32), dtype=np.uint8)
+        bal[~broke, 15] = 2                                  # 2^129
+        ent["value_be"] = bal
+        return heap, ent
 
     def setup(self, batch, vm_ids):
         vm_ids = np.asarray(vm_ids, dtype=np.uint64)
@@ -384,16 +400,8 @@ class Erc20(Workload):
             (0, C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, C.ADDRESS_EVENT_WRITER, self.codes["event_writer"][0]),
         ])
         batch.populate_storage(code_entries)
-        heap, slot, broke = self.inputs(vm_ids)
+        heap, ent = self.prepared(vm_ids)
         batch.populate_heap(heap, per_vm=True)
-        from ._binding import STORAGE_INIT_DTYPE
-        ent = np.zeros(len(vm_ids), dtype=STORAGE_INIT_DTYPE)
-        ent["shard_id"] = 0
-        ent["address"] = np.frombuffer(TOKEN_ADDRESS.to_bytes(20, "big"), dtype=np.uint8)
-        ent["key_be"] = slot
-        bal = np.zeros((len(vm_ids), 32), dtype=np.uint8)
-        bal[~broke, 15] = 2                                  # 2^129
-        ent["value_be"] = bal
         batch.populate_storage(ent, per_vm=True)
 
 

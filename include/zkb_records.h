@@ -138,7 +138,8 @@ typedef struct ZkbDecommitRec {
 typedef struct ZkbFrameRec {
   uint8_t kind;                /* ZKB_FRAMEKIND_* */
   uint8_t panicked;            /* finish only */
-  uint16_t reserved0;
+  uint16_t prev_bound_kind;    /* far_call only: 1 = previous context's heap_bound, 2 = its aux_heap_bound was (re)set to
+                                  prev_bound_value by this call's memory growth (far_call.rs:330-385); 0 = unchanged */
   uint32_t cycle;
   uint8_t this_address[20];    /* new context (start); zero for finish */
   uint8_t msg_sender[20];
@@ -161,7 +162,7 @@ typedef struct ZkbFrameRec {
   uint32_t prev_ergs_remaining; /* previous_context fields that changed this cycle (near_call.rs:49-55) */
   uint16_t prev_pc;
   uint16_t prev_sp;
-  uint32_t reserved2;
+  uint32_t prev_bound_value;
 } ZkbFrameRec;
 
 typedef struct ZkbRefundRec {

@@ -14,7 +14,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     path = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, f) for f in ("zkvm_oracle.cpp", "u256.hpp", "hashes.hpp")] + \
+    srcs = [os.path.join(_HERE, f) for f in ("zkvm_oracle.cpp", "u256.hpp", "hashes.hpp", "secp256k1.hpp")] + \
         [os.path.join(_HERE, "..", "include", "zkb.h"), os.path.join(_HERE, "..", "include", "zkb_records.h"),
          os.path.join(_HERE, "..", "era_zk_evm_b200", "csrc", "isa_tables.inc")]
     stale = force or not os.path.exists(path) or any(
@@ -83,3 +83,13 @@ def keccak_precompile_harness(data: bytes, unalignment: int):
     rc = fn(data, len(data), unalignment, out, C.byref(n))
     assert rc == 0
     return out.raw, n.value
+
+
+def ecrecover(digest: bytes, r: int, s: int, v_odd: bool):
+    """(ok, 20-byte address) — the oracle's restatement of the ecrecover precompile's recovery"""
+    fn = lib().orc_ecrecover
+    fn.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_char_p]
+    fn.restype = C.c_int32
+    out = C.create_string_buffer(20)
+    ok = fn(digest, r.to_bytes(32, "big"), s.to_bytes(32, "big"), int(v_odd), out)
+    return bool(ok), out.raw

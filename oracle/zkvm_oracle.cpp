@@ -40,6 +40,7 @@
 #include "../include/zkb.h"
 #include "../era_zk_evm_b200/csrc/isa_tables.inc"
 #include "hashes.hpp"
+#include "secp256k1.hpp"
 #include "u256.hpp"
 
 namespace {
@@ -233,10 +234,15 @@ struct Recorder {
     ZkbRefundRec r{type, value};
     push(ZKB_STREAM_REFUND, r);
   }
+  // set by the far_call handler right before start_frame: which bound of `prev` the call's memory growth touched
+  uint16_t far_call_bound_kind = 0;
   void start_new_execution_context(uint32_t cycle, const CallStackEntry& prev, const CallStackEntry& e) {
     ZkbFrameRec r;
     memset(&r, 0, sizeof(r));
     r.kind = ZKB_FRAMEKIND_START;
+    r.prev_bound_kind = far_call_bound_kind;
+    r.prev_bound_value = far_call_bound_kind == 1 ? prev.heap_bound : far_call_bound_kind == 2 ? prev.aux_heap_bound : 0;
+    far_call_bound_kind = 0;
     r.cycle = cycle;
     memcpy(r.this_address, e.this_address.b, 20);
     memcpy(r.msg_sender, e.msg_sender.b, 20);
@@ -668,6 +674,45 @@ static PrecompileResult sha256_precompile(const LogQuery& query, SimpleMemory& m
   return res;
 }
 
+// ecrecover precompile (external; memory ABI reconstructed): four Heap-type word reads at
+// input_memory_offset (digest, v in {0, 1}, r, s) at `timestamp`, two Heap-type word writes at output_memory_offset
+// (success marker, then the address right-aligned in the word; both zero on failure) at `timestamp + 1`.
+static bool ecrecover_address(const U256& hash, const U256& r, const U256& s, bool v_odd, U256* address) {
+  U256 qx, qy;
+  if (!orc_secp::recover(hash, r, s, v_odd, &qx, &qy)) return false;
+  uint8_t pk[64], digest[32];
+  qx.to_be(pk);
+  qy.to_be(pk + 32);
+  orc_hash::keccak_sponge256(pk, 64, 0x01, digest);
+  memset(digest, 0, 12);
+  *address = U256::from_be(digest);
+  return true;
+}
+
+static PrecompileResult ecrecover_precompile(const LogQuery& query, SimpleMemory& memory) {
+  PrecompileResult res;
+  res.executed = true;
+  PrecompileCallABI p = PrecompileCallABI::from_u256(query.key);
+  uint32_t ts_read = query.timestamp, ts_write = query.timestamp + 1;
+  U256 in[4];
+  for (uint32_t i = 0; i < 4; i++) {
+    MemoryQuery q{ts_read, ZK_MEM_HEAP, p.memory_page_to_read, p.input_memory_offset + i, U256::zero(), false, false};
+    q = memory.execute_partial_query(q);
+    res.mem_in.push_back(q);
+    in[i] = q.value;
+  }
+  const U256& v = in[1];
+  REF_ASSERT((v.w[1] | v.w[2] | v.w[3]) == 0 && v.w[0] <= 1, "ecrecover: v must be 0 or 1 (assert in the external precompile)");
+  U256 address = U256::zero();
+  bool ok = ecrecover_address(in[0], in[2], in[3], v.w[0] == 1, &address);
+  if (!ok) address = U256::zero();
+  MemoryQuery w0{ts_write, ZK_MEM_HEAP, p.memory_page_to_write, p.output_memory_offset, U256::from_u64(ok ? 1 : 0), false, true};
+  res.mem_out.push_back(memory.execute_partial_query(w0));
+  MemoryQuery w1{ts_write, ZK_MEM_HEAP, p.memory_page_to_write, p.output_memory_offset + 1, address, false, true};
+  res.mem_out.push_back(memory.execute_partial_query(w1));
+  return res;
+}
+
 static PrecompileResult execute_precompile(const LogQuery& query, SimpleMemory& memory) {
   uint16_t address_low = (uint16_t)(query.address.b[19] | (query.address.b[18] << 8));
   switch (address_low) {
@@ -676,7 +721,7 @@ static PrecompileResult execute_precompile(const LogQuery& query, SimpleMemory& 
     case ZK_SHA256_PRECOMPILE_ADDRESS:
       return sha256_precompile(query, memory);
     case ZK_ECRECOVER_PRECOMPILE_ADDRESS:
-      throw Unsupported("ecrecover precompile not implemented in this build");
+      return ecrecover_precompile(query, memory);
     default:
       return PrecompileResult{};
   }
@@ -1363,6 +1408,7 @@ void VmState::op_near_call(const DecodedOpcode& op, const PreState& pre) {
   ns.exception_handler_location = eh;
   ns.ergs_remaining = passed;
   ns.is_local_frame = true;
+  wt.far_call_bound_kind = 0;  // near calls never touch the heap bounds
   start_frame(ns);
 }
 
@@ -1568,6 +1614,7 @@ void VmState::op_far_call(const DecodedOpcode& op, const PreState& pre) {
       memory_growth_in_bytes = upper_bound - bound;
       bound = upper_bound;
     }
+    wt.far_call_bound_kind = forwarding_mode == ZK_FWD_USE_HEAP ? 1 : 2;
   }
   uint32_t cost_of_memory_growth = memory_growth_in_bytes * ZK_MEMORY_GROWTH_ERGS_PER_BYTE;
   uint32_t remaining_ergs_after_growth;
@@ -2191,6 +2238,15 @@ int32_t orc_read_heap(OrcBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n
 void orc_keccak256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::keccak_sponge256(data, len, 0x01, out); }
 void orc_sha3_256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::keccak_sponge256(data, len, 0x06, out); }
 void orc_sha256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::sha256(data, len, out); }
+int32_t orc_ecrecover(const uint8_t hash_be[32], const uint8_t r_be[32], const uint8_t s_be[32], uint32_t v_odd, uint8_t address_out[20]) {
+  U256 a;
+  bool ok = ecrecover_address(U256::from_be(hash_be), U256::from_be(r_be), U256::from_be(s_be), v_odd != 0, &a);
+  uint8_t buf[32];
+  a.to_be(buf);
+  memcpy(address_out, buf + 12, 20);
+  if (!ok) memset(address_out, 0, 20);
+  return ok ? 1 : 0;
+}
 
 // op: 0 add, 1 sub, 2 mul (out = low||high), 3 div (out = q||r), 4 shl, 5 shr ; operands as 32 BE bytes
 void orc_u256_op(uint32_t op, const uint8_t a_be[32], const uint8_t b_be[32], uint8_t out0_be[32], uint8_t out1_be[32], uint8_t* flag) {

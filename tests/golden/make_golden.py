@@ -11,6 +11,8 @@ can pin both:
                   digests from hashlib.sha256.
   * ecrecover   — the two known-answer vectors of src/testing/tests/precompiles/ecrecover.rs:127-143 (copied as DATA:
                   input words hash|v|r|s and the expected address).
+  * ecrecover_generated — signatures from the `cryptography` package + failure shapes, expected results from a
+                  Python-int secp256k1 (below).
   * u256        — ALU cases (add/sub/mul/div/shl/shr/rol/ror/xor/and/or) with results and flags from Python ints
                   following src/opcodes/execution/{add,sub,mul,div,shift,binop}.rs.
 """
@@ -116,6 +118,87 @@ def u256_case(op, a, b):
     return {"op": op, "a": hex(a), "b": hex(b), "out0": hex(out[0]), "out1": hex(out[1]), "flags": flags}
 
 
+# ---- secp256k1 in Python ints (independent of oracle/secp256k1.hpp and of the CUDA code) ---------------------------
+SP = 2**256 - 2**32 - 977
+SN = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+SG = (0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+      0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8)
+
+
+def ec_add(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    if a[0] == b[0]:
+        if (a[1] + b[1]) % SP == 0:
+            return None
+        lam = 3 * a[0] * a[0] * pow(2 * a[1], -1, SP) % SP
+    else:
+        lam = (b[1] - a[1]) * pow(b[0] - a[0], -1, SP) % SP
+    x = (lam * lam - a[0] - b[0]) % SP
+    return x, (lam * (a[0] - x) - a[1]) % SP
+
+
+def ec_mul(k, pt):
+    acc = None
+    while k:
+        if k & 1:
+            acc = ec_add(acc, pt)
+        pt = ec_add(pt, pt)
+        k >>= 1
+    return acc
+
+
+def py_ecrecover(z, r, s, v_odd):
+    if not (0 < r < SN and 0 < s < SN):
+        return None
+    rhs = (pow(r, 3, SP) + 7) % SP
+    y = pow(rhs, (SP + 1) // 4, SP)
+    if y * y % SP != rhs:
+        return None
+    if (y & 1) != int(v_odd):
+        y = SP - y
+    rinv = pow(r, -1, SN)
+    q = ec_add(ec_mul((-z * rinv) % SN, SG), ec_mul(s * rinv % SN, (r, y)))
+    if q is None:
+        return None
+    return keccak256(q[0].to_bytes(32, "big") + q[1].to_bytes(32, "big"))[12:]
+
+
+def ecrecover_cases():
+    """signatures made with the `cryptography` package (its own secp256k1), recovered with the Python-int code above;
+    plus the failure shapes: r = 0, s = 0, r >= n, s >= n, x = r not on the curve, wrong parity (a different key)."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec
+    from cryptography.hazmat.primitives.asymmetric.utils import Prehashed, decode_dss_signature
+    rng = random.Random(0xEC)
+    out = []
+    for i in range(6):
+        d = rng.randrange(1, SN)
+        key = ec.derive_private_key(d, ec.SECP256K1())
+        nums = key.public_key().public_numbers()
+        expected = keccak256(nums.x.to_bytes(32, "big") + nums.y.to_bytes(32, "big"))[12:]
+        digest = rng.randbytes(32) if i else b"\xff" * 32            # digest >= n exercises the reduction mod n
+        r, s = decode_dss_signature(key.sign(digest, ec.ECDSA(Prehashed(hashes.SHA256()))))
+        z = int.from_bytes(digest, "big")
+        hits = [v for v in (0, 1) if py_ecrecover(z, r, s, v) == expected]
+        assert len(hits) == 1
+        for v in (0, 1):
+            got = py_ecrecover(z, r, s, v)
+            out.append({"digest": digest.hex(), "r": hex(r), "s": hex(s), "v": v, "ok": got is not None,
+                        "address": got.hex() if got else "", "signer": v == hits[0]})
+    z = rng.getrandbits(256)
+    good_r = out[0]["r"]
+    for r, s in ((0, 5), (5, 0), (SN, 5), (int(good_r, 16), SN), (SN + 3, 7), (2**256 - 1, 2**256 - 1)):
+        out.append({"digest": z.to_bytes(32, "big").hex(), "r": hex(r), "s": hex(s), "v": 0, "ok": False, "address": "", "signer": False})
+    r = 1
+    while py_ecrecover(z, r, 12345, 0) is not None:    # smallest r whose x has no point on the curve
+        r += 1
+    out.append({"digest": z.to_bytes(32, "big").hex(), "r": hex(r), "s": hex(12345), "v": 0, "ok": False, "address": "", "signer": False})
+    return out
+
+
 def main():
     assert sponge256(b"", 0x06) == hashlib.sha3_256(b"").digest()
     for n in (1, 135, 136, 137, 271, 272, 1000):
@@ -151,6 +234,7 @@ def main():
          "address": bytes([88, 198, 174, 93, 17, 93, 119, 163, 216, 169, 239, 54, 214, 164, 45, 35, 105, 43, 170, 127]).hex(),
          "ref": "src/testing/tests/precompiles/ecrecover.rs:135-143"},
     ]
+    vec["ecrecover_generated"] = ecrecover_cases()
     with open(os.path.join(HERE, "hash_vectors.json"), "w") as f:
         json.dump(vec, f, indent=1)
 

@@ -118,3 +118,20 @@ def test_sha256_golden_vectors_on_gpu():
     import test_oracle_golden as G
     from era_zk_evm_b200 import GpuVmBatch
     G.check_sha256_precompile(GpuVmBatch)
+
+
+def test_host_replay_on_gpu_streams():
+    """include/zkb_host.hpp bound to libzkb.so: replay the GPU batch's streams through the C++ tracer mirror"""
+    import os
+    import test_host_replay as T
+    from era_zk_evm_b200 import GpuVmBatch
+    from era_zk_evm_b200.batch import LIB_PATH
+    shim = T.build_shim("zkb_", LIB_PATH)
+    w = workloads.Mixed(n_programs=8, seed=0x77)
+    n = 8 * 32
+    b = GpuVmBatch(w.config(n))
+    spy = T.InitialStateSpy(b)
+    w.setup(spy, np.arange(n))
+    b.run()
+    totals = T.replay_all(shim, b, spy, range(n))
+    assert totals[0] == b.totals()[0]
