@@ -87,7 +87,8 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
   if (vm >= vm_hi) return;
   Vm v(B, smem[warp], vm, lane);
   v.status = ZKB_VM_RUNNING;
-  v.journal_len = 0;
+  smem[warp].x[lane] = 0u;
+  __syncwarp();
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
@@ -95,7 +96,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
     u256l val = lane < 8 ? e[i].value[lane] : 0u;
     v.storage_access(e[i].shard, aw, key, true, val, false);
   }
-  if (v.status != ZKB_VM_RUNNING && lane == 0) atomicExch(fail_flag, v.status);
+  if (v.status != ZKB_VM_RUNNING && lane == 0) *fail_flag = v.status;
 }
 
 // K6c: SimpleMemory::populate_heap (memory.rs:287-291) into slab 0 (the bootloader frame's heap).
@@ -173,7 +174,8 @@ struct ZkbBatch {
   uint32_t* d_code_meta = nullptr;
   std::vector<int32_t> boot_code;  // per VM: code id bound by populate_code (page in boot_page)
   std::vector<uint32_t> boot_page;
-  uint32_t* d_fail = nullptr;
+  uint32_t* d_fail = nullptr;   // device pointer of h_fail (mapped pinned: reading it never queues behind D2H copies)
+  uint32_t* h_fail = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
   uint32_t n_launches = 0;
@@ -182,7 +184,9 @@ struct ZkbBatch {
   uint8_t* d_pack = nullptr;
   uint64_t pack_capacity = 0;
   uint64_t* d_offsets = nullptr;                  // [ZKB_N_STREAMS][n_vms + 1]
-  std::vector<uint64_t> h_offsets[ZKB_N_STREAMS];  // host copies that outlive the async uploads
+  uint64_t* h_offsets[ZKB_N_STREAMS] = {};         // PINNED host copies (a pageable source would make the "async" upload
+                                                  // wait for everything already queued on the stream)
+  bool offsets_valid = false;
   uint32_t* h_counts = nullptr;                   // mapped pinned mirror of DevBatch.host_counts
   bool counts_valid = false;                      // h_counts reflects the device state (after upload / a finished run)
   uint8_t* d_stage = nullptr;                     // grow-only H2D staging buffer of the populate_* calls
@@ -314,6 +318,7 @@ static int32_t upload(ZkbBatch* b) {
       b->h_counts[v * 8 + 7] = h.x[X_CYCLE];
     }
     b->counts_valid = true;
+    b->offsets_valid = false;
   }
   if (b->root_dirty) {
     CUDA_OK(cudaMemcpy2D(b->d.callstack, (size_t)b->cfg.max_depth * 128, b->h_root.data(), 128, 128, b->cfg.n_vms, cudaMemcpyHostToDevice));
@@ -408,7 +413,6 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   if (c.witness_mode)
     for (int k = 0; k < ZKB_N_STREAMS; k++) ALLOC(d.streams[k], n * (size_t)c.cap_records[k] * REC_BYTES[k], false);
   ALLOC(d.queue, 4, true);
-  ALLOC(b->d_fail, 4, true);
   ALLOC(b->d_offsets, (n + 1) * ZKB_N_STREAMS, false);
 #undef ALLOC
   if (e != cudaSuccess) {
@@ -428,9 +432,24 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
       delete b;
       return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("cudaHostAlloc: ") + cudaGetErrorString(he));
     }
+    void* fp = nullptr;
+    void* fdp = nullptr;
+    if (cudaHostAlloc(&fp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&fdp, fp, 0) == cudaSuccess) {
+      b->h_fail = (uint32_t*)fp;
+      b->d_fail = (uint32_t*)fdp;
+      *b->h_fail = 0;
+    }
     b->h_counts = (uint32_t*)hp;
     d.host_counts = (uint32_t*)dp;
     memset(hp, 0, n * 8 * sizeof(uint32_t));
+    void* op = nullptr;
+    if (cudaHostAlloc(&op, (n + 1) * ZKB_N_STREAMS * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
+      cudaFreeHost(hp);
+      for (void* p : b->allocs) cudaFree(p);
+      delete b;
+      return set_err(ZKB_ERR_OUT_OF_MEMORY, "cudaHostAlloc (stream offsets)");
+    }
+    for (int k = 0; k < ZKB_N_STREAMS; k++) b->h_offsets[k] = (uint64_t*)op + (size_t)k * (n + 1);
   }
   b->h_hot.resize(n);
   b->h_root.assign(n * 32, 0);
@@ -470,6 +489,8 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->ev_setup) cudaEventDestroy(b->ev_setup);
   if (b->d_stage) cudaFree(b->d_stage);
   if (b->h_counts) cudaFreeHost(b->h_counts);
+  if (b->h_fail) cudaFreeHost(b->h_fail);
+  if (b->h_offsets[0]) cudaFreeHost(b->h_offsets[0]);
   delete b;
   return ZKB_OK;
 }
@@ -524,11 +545,12 @@ int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const 
   int32_t src = stage_h2d(b, h.data(), total * sizeof(DevStorageInit), &staged);
   if (src != ZKB_OK) return src;
   DevStorageInit* d_e = reinterpret_cast<DevStorageInit*>(staged);
-  CUDA_OK(cudaMemset(b->d_fail, 0, 4));
+  if (!b->h_fail) return set_err(ZKB_ERR_OUT_OF_MEMORY, "no mapped host flag");
+  *b->h_fail = 0;
   zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
   CUDA_OK(cudaGetLastError());
-  uint32_t fail = 0;
-  CUDA_OK(cudaMemcpy(&fail, b->d_fail, 4, cudaMemcpyDeviceToHost));  // also orders the kernel before the staging buffer is reused
+  CUDA_OK(cudaStreamSynchronize(0));  // orders the kernel before the staging buffer is reused; the flag is host-mapped
+  uint32_t fail = *(volatile uint32_t*)b->h_fail;
   if (fail) return set_err(ZKB_ERR_INVALID_ARGUMENT, "storage table capacity exceeded while populating (raise ZkbConfig.storage_slots)");
   return ZKB_OK;
 }
@@ -670,6 +692,7 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   b->n_launches = 1;
   b->hot_stale = true;
   b->launched = true;
+  b->offsets_valid = false;
   return ZKB_OK;
 }
 
@@ -791,20 +814,23 @@ int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
   return ZKB_OK;
 }
 
-// offsets of stream `kind` (host copy kept in the batch so that the async upload may outlive this call)
-static uint64_t stream_offsets(ZkbBatch* b, uint32_t kind) {
+// byte offsets of every VM in every packed stream, computed once per finished run from the host-visible summary
+static void refresh_offsets(ZkbBatch* b) {
+  if (b->offsets_valid) return;
   uint32_t n = b->cfg.n_vms;
-  std::vector<uint64_t>& off = b->h_offsets[kind];
-  off.resize(n + 1);
-  off[0] = 0;
-  for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_counts[(size_t)v * 8 + kind] * REC_BYTES[kind];
-  return off[n];
+  for (uint32_t kind = 0; kind < ZKB_N_STREAMS; kind++) {
+    uint64_t* off = b->h_offsets[kind];
+    off[0] = 0;
+    for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_counts[(size_t)v * 8 + kind] * REC_BYTES[kind];
+  }
+  b->offsets_valid = true;
 }
 
 static int32_t ensure_pack_capacity(ZkbBatch* b) {
-  // one buffer per stream kind, laid out back to back, sized once for the current counts (grow-only)
+  // one buffer per stream kind, laid out back to back, sized for the current counts (grow-only)
+  refresh_offsets(b);
   uint64_t need = 0;
-  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) need += (stream_offsets(b, k) + 255) / 256 * 256;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) need += (b->h_offsets[k][b->cfg.n_vms] + 255) / 256 * 256;
   if (need > b->pack_capacity) {
     CUDA_OK(cudaDeviceSynchronize());  // a previous async fetch may still read the old buffer
     if (b->d_pack) CUDA_OK(cudaFree(b->d_pack));
@@ -834,7 +860,7 @@ static int32_t pack_async(ZkbBatch* b, uint32_t kind, cudaStream_t st, uint8_t**
   uint64_t total = b->h_offsets[kind][n];
   uint64_t* d_off = b->d_offsets + (size_t)kind * (n + 1);
   uint8_t* dst = pack_region(b, kind);
-  CUDA_OK(cudaMemcpyAsync(d_off, b->h_offsets[kind].data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_off, b->h_offsets[kind], (n + 1) * 8, cudaMemcpyHostToDevice, st));
   if (total) {
     zkb_pack_kernel<<<n, 128, 0, st>>>(b->d.streams[kind], (uint64_t)b->cfg.cap_records[kind] * REC_BYTES[kind], d_off, dst, n);
     CUDA_OK(cudaGetLastError());
@@ -864,7 +890,7 @@ int32_t zkb_fetch_stream_packed_async(ZkbBatch* b, uint32_t kind, void* host_dst
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int32_t rc = pack_async(b, kind, st, &p, &total);
   if (rc != ZKB_OK) return rc;
-  if (offsets_out) memcpy(offsets_out, b->h_offsets[kind].data(), ((size_t)b->cfg.n_vms + 1) * 8);
+  if (offsets_out) memcpy(offsets_out, b->h_offsets[kind], ((size_t)b->cfg.n_vms + 1) * 8);
   if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_stream_packed: host buffer too small");
   if (total && host_dst) {
     CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
@@ -981,6 +1007,7 @@ int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;  // a running launch still owns the state and the host summary
   memcpy(b->h_counts, b->snap_counts.data(), b->snap_counts.size() * sizeof(uint32_t));
+  b->offsets_valid = false;
   for (auto& r : b->snap) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   CUDA_OK(cudaEventRecord(b->ev1, st));

@@ -375,18 +375,18 @@ inline VmLocalState GpuVmBatch::replay(uint32_t vm, VmWitnessTracer& wt, const V
     for (uint32_t i = 0; i < std::max(n_refund, n_log); i++) {
       if (i < n_log) last_log = decode(logs[il + i]);
       if (i < n_refund) {
-        // the refund callback receives the partial query of the SSTORE it prices (helpers.rs:119-136)
-        LogQuery partial = last_log;
-        if (i >= n_log) {  // out-of-ergs SSTORE: refund recorded, query never executed (log.rs:136-144,196-199)
-          partial = LogQuery{};
-          partial.timestamp = row.timestamp + 1;
-          partial.tx_number_in_block = st.tx_number_in_block;
-          partial.shard_id = st.current.this_shard_id;
-          partial.address = st.current.this_address;
-          partial.key = U256::from_limbs32(row.src0);
-          partial.written_value = U256::from_limbs32(row.src1);
-          partial.rw_flag = true;
-        }
+        // the refund callback receives the PARTIAL query of the SSTORE it prices: key / written value from the operands,
+        // read_value = 0, is_service = false (log.rs:84-96, helpers.rs:119-136) -- also when the SSTORE then runs out of
+        // ergs and its query is never executed (log.rs:136-144,196-199)
+        LogQuery partial{};
+        partial.timestamp = row.timestamp + 1;
+        partial.tx_number_in_block = st.tx_number_in_block;
+        partial.aux_byte = ZK_STORAGE_AUX_BYTE;
+        partial.shard_id = st.current.this_shard_id;
+        partial.address = st.current.this_address;
+        partial.key = U256::from_limbs32(row.src0);
+        partial.written_value = U256::from_limbs32(row.src1);
+        partial.rw_flag = true;
         wt.record_refund_for_query(cyc, partial, RefundType{(RefundKind)refunds[ir + i].refund_type, refunds[ir + i].refund_value});
       }
       if (i < n_log) wt.add_log_query(cyc, last_log);

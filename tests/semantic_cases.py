@@ -1,0 +1,365 @@
+"""Hand-derived per-quirk programs.  Every expectation below is derived from the reference
+SOURCE (file:line cited), not from the oracle: the CPU suite runs them on the oracle (pinning the restatement), the
+`-m gpu` suite runs the same functions on the CUDA batch."""
+from era_zk_evm_b200 import isa, records
+from era_zk_evm_b200.asm import (Code, DStackAbs, DStackPush, Imm, Program, R, StackAbs, StackPop, far_call_abi, ret_abi)
+from era_zk_evm_b200.isa import C
+
+import vm_harness as H
+
+M256 = (1 << 256) - 1
+USER = 0x00000000000000000000000000000000DEADBEEF      # > 2^16: not a kernel address (execution_stack.rs:83-87)
+ROOT_ERGS = C.VM_INITIAL_FRAME_ERGS
+
+
+def case_ergs_charged_before_masking(B):
+    """cycle.rs:147-163,187-190: the raw variant's price is charged first; on shortfall ergs := 0, NOT_ENOUGH_ERGS,
+    the opcode becomes ret.panic; ret.rs:243 returns the (zero) remainder to the parent frame."""
+    p = Program()
+    p.add(R(1), 2, 3)
+    p.add(R(1), 2, 3)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, regs={1: 5, 2: 6}, ergs=10)
+    r = H.rows(b)
+    assert len(r) == 2
+    assert int(r[0]["ergs_after"]) == 10 - isa.OPCODE_PRICES[isa.VARIANT_INDEX[(isa.ADD, 0, isa.SRC_REG, isa.DST_REG, 0)]] == 2
+    assert H.val(r[0]["dst0"]) == 11
+    assert int(r[1]["error_flags"]) == 2 and int(r[1]["masked_variant"]) == isa.PANIC_VARIANT_IDX      # helpers.rs:344-352
+    assert int(r[1]["cond_resolved"]) == 1                                                            # panic encoding is "always"
+    assert int(r[1]["callstack_depth"]) == 0 and int(r[1]["ergs_after"]) == ROOT_ERGS - 10             # helpers.rs:295-303 + ret.rs:243
+    assert int(r[1]["flags_after"]) == 1                                                              # ret.rs:262-264
+    assert b.vm_status()[0, 0] == 1
+    b.close()
+
+
+def case_condition_false_is_nop_and_real_nop_moves_sp(B):
+    """cycle.rs:212-217: a false condition masks to NOP with zero operands (SP untouched, nothing written);
+    cycle.rs:298-301 + noop.rs:18-19: a real NOP with stack operands moves SP (pop then push, u16 wrapping,
+    mem_ops.rs:55-86) but reads and writes nothing."""
+    p = Program()
+    p.add(Imm(1), 0, DStackPush(1), cond="gt")              # flags are all clear -> masked
+    p.nop(StackPop(2), DStackPush(5))
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1)
+    r = H.rows(b)
+    assert int(r[0]["masked_variant"]) == isa.NOP_VARIANT_IDX and int(r[0]["cond_resolved"]) == 0 and int(r[0]["error_flags"]) == 0
+    assert int(r[0]["sp_after"]) == 0 and int(r[0]["n_mem"]) == 1        # only the instruction fetch
+    assert int(r[0]["bits"]) & 0xC0 == 0                                 # no dst written
+    assert int(r[1]["sp_after"]) == (0 - 2 + 5) & 0xFFFF and int(r[1]["n_mem"]) == 0
+    mem = b.read_stream(0, records.STREAM_MEM)
+    assert all(int(m["memory_type"]) == C.MEM_CODE for m in mem)
+    b.close()
+
+
+def case_pop_then_push_in_one_instruction(B):
+    """cycle.rs:278-297: src0 addressing mutates SP before dst0 addressing; mem_ops.rs:71-86 pop = subtract then
+    use the new SP, :55-70 push = use the old SP then add.  Reads at t+0, dst write at t+3 (mod.rs:220-231)."""
+    p = Program()
+    p.nop(R(0), DStackPush(3))                              # sp = 3
+    p.add(Imm(7), 0, DStackAbs(2))                          # stack[2] = 7
+    p.add(StackPop(1), 1, DStackPush(1))                    # reads stack[2], writes stack[2] = 7 + r1, sp back to 3
+    p.add(StackAbs(2), 0, 5)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, regs={1: 100})
+    r = H.rows(b)
+    assert int(r[2]["sp_after"]) == 3 and H.val(r[2]["src0"]) == 7 and H.val(r[2]["dst0"]) == 107
+    assert H.val(r[3]["dst0"]) == 107
+    mem = [m for m in b.read_stream(0, records.STREAM_MEM) if int(m["memory_type"]) == C.MEM_STACK]
+    ts = int(r[2]["timestamp"])
+    rd = [m for m in mem if int(m["timestamp"]) == ts]
+    wr = [m for m in mem if int(m["timestamp"]) == ts + 3]
+    assert len(rd) == 1 and int(rd[0]["index"]) == 2 and int(rd[0]["rw_flag"]) == 0 and H.val(rd[0]["value"]) == 7
+    assert len(wr) == 1 and int(wr[0]["index"]) == 2 and int(wr[0]["rw_flag"]) == 1 and H.val(wr[0]["value"]) == 107
+    assert int(wr[0]["page"]) == H.BOOT_PAGE + 1                          # stack page = base + 1 (execution_stack.rs:71-73)
+    b.close()
+
+
+def case_pointer_erasure_only_in_user_mode(B):
+    """cycle.rs:374-396: for opcodes that cannot take pointers the top 128 bits of a pointer operand are erased --
+    outside kernel mode only.  The row's SRC0_PTR bit is the pre-erasure marker (quirk 16)."""
+    ptr = (0xAAAA << 200) | (5 << 96) | (7 << 64) | (9 << 32) | 3
+    for this, expect in ((USER, ptr & ((1 << 128) - 1)), (H.BOOT_ADDRESS, ptr)):
+        p = Program()
+        p.add(R(1), 0, 3)
+        p.ret(isa.RET_OK, R(0))
+        b = H.launch(B, p, 1, regs={1: ptr}, ptr_regs=(1,), this_address=this)
+        r = H.rows(b)[0]
+        assert H.val(r["src0"]) == expect and H.val(r["dst0"]) == expect
+        assert int(r["bits"]) & records_bit("SRC0_PTR") and not int(r["bits"]) & records_bit("DST0_PTR")   # add.rs: result never a pointer
+        b.close()
+
+
+def records_bit(name):
+    return {"SRC0_PTR": 0x01, "SRC1_PTR": 0x02, "DST0_PTR": 0x04, "DST1_PTR": 0x08, "PENDING": 0x10, "SKIP": 0x20,
+            "DST0_VALID": 0x40, "DST1_VALID": 0x80}[name]
+
+
+def case_imm_zero_extended_and_r0(B):
+    """cycle.rs:331-335: imm16 operands are zero-extended; helpers.rs:318-334: r0 reads as zero, writes to it vanish."""
+    p = Program()
+    p.add(Imm(0xFFFF), 0, 3)
+    p.sub(Imm(0xFFFF), 0, 0, set_flags=True)                # result discarded, flags kept
+    p.add(R(0), 0, 4)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1)
+    r = H.rows(b)
+    assert H.val(r[0]["dst0"]) == 0xFFFF
+    assert H.val(r[1]["dst0"]) == 0xFFFF and int(r[1]["flags_after"]) == 4         # 0xFFFF - 0 > 0: GT (sub.rs:40-44)
+    assert H.val(r[2]["src0"]) == 0 and H.val(r[2]["dst0"]) == 0
+    b.close()
+
+
+def case_sload_reports_written_equals_read(B):
+    """helpers.rs:145-148: for reads the tracer sees written_value = read_value; log.rs:163-194 dst0 = value; t+1."""
+    p = Program()
+    p.add(Imm(0x42), 0, 1)
+    p.sload(1, 2)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, storage=[(0, H.BOOT_ADDRESS, 0x42, 0x1234)])
+    r = H.rows(b)
+    lg = b.read_stream(0, records.STREAM_LOG)
+    assert len(lg) == 1 and H.val(r[1]["dst0"]) == 0x1234
+    q = lg[0]
+    assert H.val(q["key"]) == 0x42 and H.val(q["read_value"]) == 0x1234 == H.val(q["written_value"])
+    assert int(q["rw_flag"]) == 0 and int(q["aux_byte"]) == C.STORAGE_AUX_BYTE and int(q["timestamp"]) == int(r[1]["timestamp"]) + 1
+    assert bytes(q["address"]) == H.BOOT_ADDRESS.to_bytes(20, "big")
+    b.close()
+
+
+def case_sstore_out_of_ergs_records_refund_only(B):
+    """log.rs:99-102 the refund is recorded first; :136-144 on shortfall ergs := 0 and spent_pubdata +=
+    min(ergs_available, pubdata cost); :196-199 the write itself is skipped (no log query, storage untouched)."""
+    price = isa.OPCODE_PRICES[isa.VARIANT_INDEX[(isa.LOG, isa.LOG_SSTORE, isa.SRC_REG, isa.DST_REG, 0)]]
+    epp = 3
+    cost = epp * C.INITIAL_STORAGE_WRITE_PUBDATA_BYTES
+    avail = 50
+    p = Program()
+    p.sstore(1, 2)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, regs={1: 7, 2: 9}, ergs=price + avail, ergs_per_pubdata=epp, storage=[(0, H.BOOT_ADDRESS, 7, 1)])
+    r = H.rows(b)
+    assert avail < cost
+    assert int(r[0]["ergs_after"]) == 0 and int(r[0]["spent_pubdata"]) == min(avail, cost)
+    assert len(b.read_stream(0, records.STREAM_REFUND)) == 1 and len(b.read_stream(0, records.STREAM_LOG)) == 0
+    assert b.read_storage(0, 0, H.BOOT_ADDRESS, 7) == 1
+    assert int(r[0]["bits"]) & records_bit("PENDING") == 0                  # "DO NOT set any pending" (log.rs:49-53)
+    b.close()
+    # with enough ergs: ergs -= cost, spent += cost, one refund + one log query (old value in read_value)
+    b = H.launch(B, p, 1, regs={1: 7, 2: 9}, ergs=price + cost + 100, ergs_per_pubdata=epp, storage=[(0, H.BOOT_ADDRESS, 7, 1)])
+    r = H.rows(b)
+    lg = b.read_stream(0, records.STREAM_LOG)
+    assert int(r[0]["ergs_after"]) == 100 and int(r[0]["spent_pubdata"]) == cost
+    assert len(lg) == 1 and H.val(lg[0]["read_value"]) == 1 and H.val(lg[0]["written_value"]) == 9 and int(lg[0]["rw_flag"]) == 1
+    assert b.read_storage(0, 0, H.BOOT_ADDRESS, 7) == 9
+    b.close()
+
+
+def case_near_call_panic_rolls_storage_back(B):
+    """near_call.rs:27-46 (pc = imm0, handler = imm1, ergs 0 => all); ret.rs:35-41,196-251 panic: frame finished with
+    panicked = true, pc := exception handler, LT flag; storage.rs:156-176 the frame's writes are undone in reverse."""
+    p = Program()
+    p.add(Imm(7), 0, 1)
+    p.add(Imm(99), 0, 2)
+    p.near_call(0, "body", "handler")
+    p.label("after")
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.sload(1, 5)
+    p.jump("after")
+    p.label("body")
+    p.sstore(1, 2)
+    p.add(Imm(100), 0, 2)
+    p.sstore(1, 2)
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 1, storage=[(0, H.BOOT_ADDRESS, 7, 5)], ergs=1 << 20)
+    r = H.rows(b)
+    fams = [H.family_of(x) for x in r]
+    assert fams == ["add", "add", "near_call", "log", "add", "log", "ret", "log", "jump", "ret"]
+    nc, panic_ret, sload = r[2], r[6], r[7]
+    assert int(nc["pc_after"]) == p.labels["body"] and int(nc["exception_handler"]) == p.labels["handler"]
+    assert int(nc["callstack_depth"]) == 2 and int(nc["frame_bits"]) & 0x02            # is_local_frame (near_call.rs:59-63)
+    assert int(panic_ret["pc_after"]) == p.labels["handler"] and int(panic_ret["flags_after"]) == 1
+    assert int(panic_ret["callstack_depth"]) == 1
+    assert H.val(sload["dst0"]) == 5                                                   # both writes rolled back
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    assert [(int(f["kind"]), int(f["panicked"])) for f in fr] == [(1, 0), (1, 0), (2, 1), (2, 0)]
+    assert b.read_storage(0, 0, H.BOOT_ADDRESS, 7) == 5
+    # all ergs passed on a zero ABI, remainder returned on ret (near_call.rs:32-46, ret.rs:243)
+    before = int(r[1]["ergs_after"])
+    spent_inside = sum(isa.OPCODE_PRICES[int(x["raw_opcode"]) & 0x7FF] for x in r[3:7])
+    nc_price = isa.OPCODE_PRICES[int(nc["raw_opcode"]) & 0x7FF]
+    assert int(nc["ergs_after"]) == before - nc_price
+    assert int(panic_ret["ergs_after"]) == before - nc_price - spent_inside
+    b.close()
+
+
+def callee_returning(value_word: int, sub=isa.RET_OK) -> Program:
+    c = Program()
+    c.const("v", value_word)
+    c.const("abi", ret_abi(start=0, length=32))
+    c.add(Code("v"), 0, 2)
+    c.st(Imm(0), 2)
+    c.add(Code("abi"), 0, 3)
+    c.ret(sub, R(3))
+    return c
+
+
+def case_far_call_ergs_and_decommit_refund(B):
+    """far_call.rs:468-487 callee ergs = min(requested, floor(e / 64) * 63); :423-433 decommit cost = 4 ergs per code
+    word, :450-453 refunded when the hash was already decommitted (decommitter.rs:38-47 => is_fresh = false, the tracer
+    is still told, quirk 14); :502-503 page counter += 8 per call; :573-610 r1 = calldata pointer, others cleared;
+    ret.rs:213-236 r1 = returndata pointer, r2.. = 0."""
+    callee = callee_returning(0xABCDEF)
+    n_words = len(callee.bytecode()) // 32
+    p = Program()
+    p.const("abi", far_call_abi(0xFFFFFFFF, start=0, length=32))
+    p.const("callee", USER)
+    for _ in range(2):
+        p.add(Code("abi"), 0, 8)
+        p.add(Code("callee"), 0, 7)
+        p.add(Imm(55), 0, 9)
+        p.far_call(R(8), 7, "fail")
+        p.ld_ptr(R(1), 4)
+    p.ret(isa.RET_OK, R(0))
+    p.label("fail")
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 1, contracts={USER: callee}, ergs=1 << 24, heap_bound=64)
+    r = H.rows(b)
+    calls = [i for i, x in enumerate(r) if H.family_of(x) == "far_call"]
+    assert len(calls) == 2
+    fc_price = isa.OPCODE_PRICES[isa.VARIANT_INDEX[(isa.FAR_CALL, isa.FC_NORMAL, isa.SRC_REG, isa.DST_REG, 0)]]
+    dec = b.read_stream(0, records.STREAM_DECOMMIT)
+    assert [int(d["is_fresh"]) for d in dec] == [1, 0] and int(dec[0]["memory_page"]) == int(dec[1]["memory_page"])
+    assert all(int(d["decommitted_length"]) == n_words for d in dec)
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    for k, i in enumerate(calls):
+        e_before = int(r[i - 1]["ergs_after"]) - fc_price
+        e_after_decommit = e_before - (C.ERGS_PER_CODE_WORD_DECOMMITTMENT * n_words if k == 0 else 0)
+        passed = (e_after_decommit // 64) * 63
+        new_frame = [f for f in fr if int(f["kind"]) == 1 and int(f["cycle"]) == int(r[i]["cycle"])][0]
+        assert int(new_frame["ergs_remaining"]) == passed == int(r[i]["ergs_after"])
+        assert int(new_frame["prev_ergs_remaining"]) == e_after_decommit - passed
+        assert int(r[i]["memory_page_counter"]) == 1024 + 8 * (k + 1) and int(new_frame["base_memory_page"]) == 1024 + 8 * k
+        assert int(new_frame["heap_bound"]) == C.NEW_FRAME_MEMORY_STIPEND and int(new_frame["is_local_frame"]) == 0
+        assert bytes(new_frame["msg_sender"]) == H.BOOT_ADDRESS.to_bytes(20, "big")
+        assert bytes(new_frame["this_address"]) == USER.to_bytes(20, "big")
+        assert int(r[i]["bits"]) & records_bit("DST0_PTR") and H.val(r[i]["dst0"]) == (32 << 96) | ((H.BOOT_PAGE + 2) << 32)
+        assert int(r[i]["pc_after"]) == 0 and int(r[i]["sp_after"]) == 0
+    rets = [x for x in r if H.family_of(x) == "ret" and int(x["callstack_depth"]) == 1]
+    assert len(rets) == 2 and all(int(x["bits"]) & records_bit("DST0_PTR") for x in rets)
+    loads = [x for x in r if H.family_of(x) == "uma" and int(x["callstack_depth"]) == 1]
+    assert [H.val(x["dst0"]) for x in loads] == [0xABCDEF, 0xABCDEF]
+    st = b.read_local_state(0)
+    b.close()
+
+
+def case_static_and_kernel_violations(B):
+    """cycle.rs:173-179: kernel-only opcode outside kernel mode => PRIVILAGED_ACCESS (4); writes in a static frame =>
+    WRITE_IN_STATIC_CONTEXT (8); both mask to panic.  far_call.rs:500: static is sticky for the callee."""
+    callee = Program()
+    callee.add(Imm(1), 0, 1)
+    callee.sstore(1, 1)
+    callee.ret(isa.RET_OK, R(0))
+    p = Program()
+    p.const("abi", far_call_abi(0xFFFFFFFF))
+    p.const("callee", USER)
+    p.add(Code("abi"), 0, 8)
+    p.add(Code("callee"), 0, 7)
+    p.far_call(R(8), 7, "handler", static=True)
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.add(Imm(77), 0, 6)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, contracts={USER: callee}, ergs=1 << 22)
+    r = H.rows(b)
+    bad = [x for x in r if int(x["error_flags"])]
+    assert len(bad) == 1 and int(bad[0]["error_flags"]) == 8 and int(bad[0]["masked_variant"]) == isa.PANIC_VARIANT_IDX
+    assert int(bad[0]["pc_after"]) == p.labels["handler"] and int(bad[0]["flags_after"]) == 1
+    assert len(b.read_stream(0, records.STREAM_LOG)) == 1                  # only the code-hash read (far_call.rs:131-145)
+    b.close()
+    q = Program()
+    q.event(1, 2)
+    q.ret(isa.RET_OK, R(0))
+    b = H.launch(B, q, 1, this_address=USER)
+    r = H.rows(b)
+    assert int(r[0]["error_flags"]) == 4 and int(r[0]["masked_variant"]) == isa.PANIC_VARIANT_IDX and len(r) == 1
+    b.close()
+
+
+def case_uma_unaligned_and_fat_pointer_tail(B):
+    """uma.rs:232-238,299-303 unaligned load = (w0 << 8u) | (w1 >> 8(32-u)); :349-400 unaligned store merges into both
+    words; :152-217 growth = max(0, offset + 32 - bound) at 1 erg/byte; :110-116 fat-pointer read past the slice
+    returns 0 without an exception; :305-320 bytes beyond `length` read as zero."""
+    w0 = int.from_bytes(bytes(range(1, 33)), "big")
+    w1 = int.from_bytes(bytes(range(33, 65)), "big")
+    p = Program()
+    p.ld(Imm(5), 1)                                           # unaligned heap load inside the bound
+    p.add(Imm(0), 0, 2)
+    p.sub(Imm(1), 2, 2, swap=True)                            # r2 = 0 - 1 = all ones
+    p.st(Imm(100), 2)                                         # unaligned store: grows the heap to 132
+    p.ld(Imm(96), 3)
+    p.ld(Imm(128), 4)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, heap=w0.to_bytes(32, "big") + w1.to_bytes(32, "big"), heap_bound=64, ergs=1 << 20)
+    r = H.rows(b)
+    whole = (w0 << 256) | w1
+    assert H.val(r[0]["dst0"]) == (whole >> (8 * (32 - 5))) & M256 and int(r[0]["n_mem"]) == 3        # fetch + 2 words
+    st_row = r[3]
+    st_price = isa.OPCODE_PRICES[int(st_row["raw_opcode"]) & 0x7FF]
+    assert int(st_row["heap_bound"]) == 132 and int(r[2]["ergs_after"]) - int(st_row["ergs_after"]) == st_price + (132 - 64)
+    assert int(st_row["n_mem"]) == 4                                                                # 2 reads + 2 writes
+    assert H.val(r[4]["dst0"]) == (1 << (8 * 28)) - 1                                              # bytes 100..127 set
+    assert H.val(r[5]["dst0"]) == ((1 << 32) - 1) << (8 * 28)                                        # bytes 128..131 set
+    b.close()
+    # fat pointer: slice [start 8, length 40) of the caller's heap, offset walking past the end
+    callee = Program()
+    callee.ld_ptr(R(1), 2, 1, inc=True)                       # bytes 8..39 ; r1.offset = 32
+    callee.ld_ptr(R(1), 3, 1, inc=True)                       # 8 bytes left: tail zeroed ; offset = 64
+    callee.ld_ptr(R(1), 4)                                    # offset >= length: reads 0, no exception
+    callee.ret(isa.RET_OK, R(0))
+    p = Program()
+    p.const("abi", far_call_abi(0xFFFFFFFF, start=8, length=40))
+    p.const("callee", USER)
+    p.add(Code("abi"), 0, 8)
+    p.add(Code("callee"), 0, 7)
+    p.far_call(R(8), 7, "fail")
+    p.ret(isa.RET_OK, R(0))
+    p.label("fail")
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 1, contracts={USER: callee}, heap=w0.to_bytes(32, "big") + w1.to_bytes(32, "big"), heap_bound=64,
+                 ergs=1 << 22)
+    r = [x for x in H.rows(b) if H.family_of(x) == "uma"]
+    assert H.val(r[0]["dst0"]) == (whole >> (8 * 24)) & M256
+    assert H.val(r[1]["dst0"]) == int.from_bytes(bytes(range(41, 49)) + bytes(24), "big")     # heap bytes 40..47, then zeros
+    assert H.val(r[2]["dst0"]) == 0 and int(r[2]["n_mem"]) == 0 and not int(r[2]["bits"]) & records_bit("PENDING")
+    assert H.val(r[0]["dst1"]) & 0xFFFFFFFF == 32 and int(r[0]["bits"]) & records_bit("DST1_PTR")      # uma.rs:335-344
+    assert not any(int(x["error_flags"]) for x in H.rows(b))
+    b.close()
+
+
+def case_context_and_cycle_bookkeeping(B):
+    """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
+    fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
+    p = Program()
+    p.context(isa.CTX_THIS, 1)
+    p.context(isa.CTX_CALLER, 2)
+    p.context(isa.CTX_ERGS_LEFT, 3)
+    p.context(isa.CTX_SP, 4)
+    p.jump("x")
+    p.add(Imm(1), 0, 9)                                     # skipped
+    p.label("x")
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=100000)
+    r = H.rows(b)
+    assert [int(x["timestamp"]) for x in r] == [C.STARTING_TIMESTAMP + C.TIME_DELTA_PER_CYCLE * i for i in range(len(r))]
+    assert [int(x["cycle"]) for x in r] == list(range(len(r)))
+    assert H.val(r[0]["dst0"]) == H.BOOT_ADDRESS and H.val(r[1]["dst0"]) == 0
+    ctx_price = isa.OPCODE_PRICES[int(r[0]["raw_opcode"]) & 0x7FF]
+    assert H.val(r[2]["dst0"]) == 100000 - 3 * ctx_price == int(r[2]["ergs_after"])       # ergs left AFTER paying for itself
+    assert H.val(r[3]["dst0"]) == 0
+    assert int(r[4]["pc_after"]) == p.labels["x"] == 6 and H.family_of(r[5]) == "ret" and len(r) == 6
+    assert [int(x["n_mem"]) for x in r] == [1, 0, 0, 0, 1, 0]                          # fetches at pc 0 and pc 4; pc 6 shares word 1
+    b.close()
+
+
+ALL = [v for k, v in sorted(globals().items()) if k.startswith("case_")]

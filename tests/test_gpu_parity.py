@@ -135,3 +135,21 @@ def test_host_replay_on_gpu_streams():
     b.run()
     totals = T.replay_all(shim, b, spy, range(n))
     assert totals[0] == b.totals()[0]
+
+
+def test_ecrecover_golden_vectors_on_gpu():
+    """warp-cooperative secp256k1 recovery on the GPU against the reference's known answers, signatures produced by the
+    `cryptography` package and the failure shapes (r/s out of range, x not on the curve)"""
+    import test_oracle_golden as G
+    from era_zk_evm_b200 import GpuVmBatch
+    G.check_ecrecover_precompile(GpuVmBatch)
+
+
+import semantic_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", semantic_cases.ALL, ids=lambda c: c.__name__)
+def test_semantic_case_on_gpu(case):
+    """the hand-derived quirk programs (expectations from the reference source) straight on the CUDA batch"""
+    from era_zk_evm_b200 import GpuVmBatch
+    case(GpuVmBatch)
