@@ -102,6 +102,7 @@ struct __align__(16) WarpSmem {
   uint32_t row[64];
   uint32_t F[32];
   uint32_t kbuf[64];
+  uint64_t base[8];  // per-VM global base pointers (Vm::PB_*)
   uint32_t x[32];  // cold warp-uniform scalars (VmHot.x layout): journal length, decommit count, slab mask, rare stream counts
 };
 
@@ -123,21 +124,33 @@ struct Vm {
   // decoded opcode (warp-uniform)
   uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
   uint32_t dst_loc_valid, dst_loc_index;
-  // per-VM global bases: recomputed from the launch constants where they are used (stack / heap / page-table accesses
-  // are the minority of cycles; keeping six 64-bit pointers alive costs 12 registers in every cycle)
-  __device__ __forceinline__ uint32_t* g_stack() const { return B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8; }
-  __device__ __forceinline__ uint8_t* g_stack_ptr() const { return B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words; }
-  __device__ __forceinline__ uint32_t* g_heap() const { return B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8; }
-  __device__ __forceinline__ uint32_t* g_lvl() const { return B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4; }
-  __device__ __forceinline__ uint32_t* g_slab_hwm() const { return B.slab_hwm + (size_t)vm * B.n_slabs; }
-  __device__ __forceinline__ uint32_t* g_pt() const { return B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2; }
-  uint8_t* row_base;  // this VM's slab of the ROWS / MEM streams (the two streams written every cycle)
-  uint8_t* mem_base;
-
-  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {
-    row_base = B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES;
-    mem_base = B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES;
+  // per-VM global bases live in shared memory (computed once per VM by vm_load): a use costs one broadcast LDS.64
+  // instead of a chain of 64-bit multiplies, and no registers are held across the cycle loop
+  enum { PB_STACK = 0, PB_STACK_PTR, PB_HEAP, PB_LVL, PB_SLAB_HWM, PB_PT, PB_ROWS, PB_MEM };
+  __device__ __forceinline__ uint32_t* g_stack() const { return reinterpret_cast<uint32_t*>(S.base[PB_STACK]); }
+  __device__ __forceinline__ uint8_t* g_stack_ptr() const { return reinterpret_cast<uint8_t*>(S.base[PB_STACK_PTR]); }
+  __device__ __forceinline__ uint32_t* g_heap() const { return reinterpret_cast<uint32_t*>(S.base[PB_HEAP]); }
+  __device__ __forceinline__ uint32_t* g_lvl() const { return reinterpret_cast<uint32_t*>(S.base[PB_LVL]); }
+  __device__ __forceinline__ uint32_t* g_slab_hwm() const { return reinterpret_cast<uint32_t*>(S.base[PB_SLAB_HWM]); }
+  __device__ __forceinline__ uint32_t* g_pt() const { return reinterpret_cast<uint32_t*>(S.base[PB_PT]); }
+  // record n of this VM's slab in the two streams written every cycle
+  __device__ __forceinline__ uint8_t* row_ptr(uint32_t n) const { return reinterpret_cast<uint8_t*>(S.base[PB_ROWS]) + (size_t)n * ZKB_ROW_BYTES; }
+  __device__ __forceinline__ uint8_t* mem_ptr(uint32_t n) const { return reinterpret_cast<uint8_t*>(S.base[PB_MEM]) + (size_t)n * ZKB_MEM_BYTES; }
+  __device__ __forceinline__ void init_bases() {
+    if (lane == 0) {
+      S.base[PB_STACK] = reinterpret_cast<uint64_t>(B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8);
+      S.base[PB_STACK_PTR] = reinterpret_cast<uint64_t>(B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words);
+      S.base[PB_HEAP] = reinterpret_cast<uint64_t>(B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8);
+      S.base[PB_LVL] = reinterpret_cast<uint64_t>(B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4);
+      S.base[PB_SLAB_HWM] = reinterpret_cast<uint64_t>(B.slab_hwm + (size_t)vm * B.n_slabs);
+      S.base[PB_PT] = reinterpret_cast<uint64_t>(B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2);
+      S.base[PB_ROWS] = reinterpret_cast<uint64_t>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
+      S.base[PB_MEM] = reinterpret_cast<uint64_t>(B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES);
+    }
+    __syncwarp();
   }
+
+  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {}
 
   // ---- small helpers -------------------------------------------------------------------------------
   __device__ __forceinline__ void fail(uint32_t code) {
@@ -201,7 +214,7 @@ struct Vm {
     }
     count_mem = n + 1;
     if (!B.witness) return;
-    uint32_t* p = reinterpret_cast<uint32_t*>(mem_base + (size_t)n * ZKB_MEM_BYTES);
+    uint32_t* p = reinterpret_cast<uint32_t*>(mem_ptr(n));
     if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, index, mtype | rw << 8 | is_ptr << 16 | origin << 24);
     if (lane < 8) p[4 + lane] = value;
   }
@@ -821,7 +834,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   __syncwarp();
   if (B.witness) {
     uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
-    *reinterpret_cast<uint2*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES + 8 * lane) = v;
+    *reinterpret_cast<uint2*>(row_ptr(n_rows) + 8 * lane) = v;
   }
 }
 
@@ -1715,6 +1728,7 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   v.ptr_mask = __shfl_sync(ZK_FULL, x, X_PTRMASK);
   v.prev_code_page = __shfl_sync(ZK_FULL, x, X_PREV_CODE_PAGE);
   S.x[lane] = x;
+  v.init_bases();
   v.count_rows = __shfl_sync(ZK_FULL, x, X_COUNT0 + ZKB_STREAM_ROWS);
   v.count_mem = __shfl_sync(ZK_FULL, x, X_COUNT0 + ZKB_STREAM_MEM);
   v.rowbits = 0;

@@ -89,6 +89,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
   v.status = ZKB_VM_RUNNING;
   smem[warp].x[lane] = 0u;
   __syncwarp();
+  v.init_bases();
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;

@@ -841,7 +841,7 @@ class Mixed(Workload):
     def __init__(self, n_programs: int = 64, target_cycles: int = 512, vms_per_program: int = 32, seed: int = DEFAULT_SEED):
         super().__init__(seed)
         self.n_programs, self.vms_per_program = n_programs, vms_per_program
-        self.max_cycles_hint = 4 * target_cycles + 256
+        self.max_cycles_hint = 2 * target_cycles + 256
         rng = _Rng(seed ^ 0xC0FFEE)
         self.callees = []
         for i in range(4):
