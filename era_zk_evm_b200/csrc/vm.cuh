@@ -55,6 +55,11 @@ struct VmHot {
 #ifndef ZKB_LOCKSTEP_PERIOD
 #define ZKB_LOCKSTEP_PERIOD 32
 #endif
+// internal status (never leaves the kernel): the VM finished a cycle whose ecrecover is still to be computed; the
+// schedulers park the VM state in HBM, run the recovery (DeferredEcrecover) and resume
+#define ZKB_VM_YIELD_ECRECOVER 0x100u
+// kbuf layout while an ecrecover is pending
+enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 61, KB_EC_SLAB = 62, KB_EC_OUT_WORD = 63 };  // 48..63: unused by keccak / sha256 / pop_frame
 #define ZKB_NO_SLAB 0xFFu
 #define ZKB_NO_CODE 0xFFFFFFFFu
 #define ZKB_PT_ENTRIES 32u   // one entry per lane
@@ -102,8 +107,6 @@ struct __align__(16) WarpSmem {
   uint32_t row[64];
   uint32_t F[32];
   uint32_t kbuf[64];
-  uint64_t base[8];  // per-VM global base pointers (Vm::PB_*)
-  uint32_t x[32];  // cold warp-uniform scalars (VmHot.x layout): journal length, decommit count, slab mask, rare stream counts
 };
 
 struct Vm {
@@ -113,8 +116,8 @@ struct Vm {
   const uint32_t lane;
   // warp-uniform registers
   uint32_t pc, sp, ergs, flags, timestamp, cycle, pending, ptr_mask, status;
-  uint32_t prev_code_page, far_depth;
-  uint32_t count_rows, count_mem;  // the two streams written every cycle; the other counts live in S.x
+  uint32_t prev_code_page, far_depth, journal_len, n_decommit, slab_free;
+  uint32_t count[ZKB_N_STREAMS];
   uint32_t rowbits;
   uint32_t ccount;  // per-cycle record counts, packed as CycleRow.n_mem | n_log << 16 | n_dfr << 24
   uint32_t forbid;  // ZK_E_* bits an opcode must not have in the current frame (kernel-only / not-in-static)
@@ -124,44 +127,30 @@ struct Vm {
   // decoded opcode (warp-uniform)
   uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
   uint32_t dst_loc_valid, dst_loc_index;
-  // per-VM global bases live in shared memory (computed once per VM by vm_load): a use costs one broadcast LDS.64
-  // instead of a chain of 64-bit multiplies, and no registers are held across the cycle loop
-  enum { PB_STACK = 0, PB_STACK_PTR, PB_HEAP, PB_LVL, PB_SLAB_HWM, PB_PT, PB_ROWS, PB_MEM };
-  __device__ __forceinline__ uint32_t* g_stack() const { return reinterpret_cast<uint32_t*>(S.base[PB_STACK]); }
-  __device__ __forceinline__ uint8_t* g_stack_ptr() const { return reinterpret_cast<uint8_t*>(S.base[PB_STACK_PTR]); }
-  __device__ __forceinline__ uint32_t* g_heap() const { return reinterpret_cast<uint32_t*>(S.base[PB_HEAP]); }
-  __device__ __forceinline__ uint32_t* g_lvl() const { return reinterpret_cast<uint32_t*>(S.base[PB_LVL]); }
-  __device__ __forceinline__ uint32_t* g_slab_hwm() const { return reinterpret_cast<uint32_t*>(S.base[PB_SLAB_HWM]); }
-  __device__ __forceinline__ uint32_t* g_pt() const { return reinterpret_cast<uint32_t*>(S.base[PB_PT]); }
-  // record n of this VM's slab in the two streams written every cycle
-  __device__ __forceinline__ uint8_t* row_ptr(uint32_t n) const { return reinterpret_cast<uint8_t*>(S.base[PB_ROWS]) + (size_t)n * ZKB_ROW_BYTES; }
-  __device__ __forceinline__ uint8_t* mem_ptr(uint32_t n) const { return reinterpret_cast<uint8_t*>(S.base[PB_MEM]) + (size_t)n * ZKB_MEM_BYTES; }
-  __device__ __forceinline__ void init_bases() {
-    if (lane == 0) {
-      S.base[PB_STACK] = reinterpret_cast<uint64_t>(B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8);
-      S.base[PB_STACK_PTR] = reinterpret_cast<uint64_t>(B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words);
-      S.base[PB_HEAP] = reinterpret_cast<uint64_t>(B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8);
-      S.base[PB_LVL] = reinterpret_cast<uint64_t>(B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4);
-      S.base[PB_SLAB_HWM] = reinterpret_cast<uint64_t>(B.slab_hwm + (size_t)vm * B.n_slabs);
-      S.base[PB_PT] = reinterpret_cast<uint64_t>(B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2);
-      S.base[PB_ROWS] = reinterpret_cast<uint64_t>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
-      S.base[PB_MEM] = reinterpret_cast<uint64_t>(B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES);
-    }
-    __syncwarp();
-  }
+  // per-VM global bases
+  uint32_t* g_stack;
+  uint8_t* g_stack_ptr;
+  uint32_t* g_heap;
+  uint32_t* g_lvl;
+  uint32_t* g_slab_hwm;
+  uint32_t* g_pt;
+  uint8_t* row_base;  // this VM's slab of the ROWS / MEM streams (the two streams written every cycle)
+  uint8_t* mem_base;
 
-  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {}
+  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {
+    g_stack = B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8;
+    g_stack_ptr = B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words;
+    g_heap = B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8;
+    g_lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
+    g_slab_hwm = B.slab_hwm + (size_t)vm * B.n_slabs;
+    g_pt = B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2;
+    row_base = B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES;
+    mem_base = B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES;
+  }
 
   // ---- small helpers -------------------------------------------------------------------------------
   __device__ __forceinline__ void fail(uint32_t code) {
     if (status == ZKB_VM_RUNNING) status = code;
-  }
-  // cold scalars in shared memory: read = broadcast load, write = lane 0 + warp sync
-  __device__ __forceinline__ uint32_t X(int i) const { return S.x[i]; }
-  __device__ __forceinline__ void setX(int i, uint32_t v) {
-    __syncwarp();
-    if (lane == 0) S.x[i] = v;
-    __syncwarp();
   }
   __device__ __forceinline__ uint32_t L(int w) const { return S.row[w]; }
   __device__ __forceinline__ void setL(int w, uint32_t v) {
@@ -193,12 +182,12 @@ struct Vm {
   // Every record is written straight from the registers that hold its fields: the scalar header by lane 0 as one
   // 8/16-byte vector store, each U256 by lanes 0..7 (one 32-byte segment) -- no shuffles, no lane-select chains.
   __device__ __forceinline__ uint8_t* stream_slot(int kind) {
-    uint32_t n = X(X_COUNT0 + kind);
+    uint32_t n = count[kind];
     if (n >= B.cap[kind]) {
       fail(ZKB_VM_CAP_STREAM);
       return nullptr;
     }
-    setX(X_COUNT0 + kind, n + 1);
+    count[kind] = n + 1;
     if (!B.witness) return nullptr;
     return B.streams[kind] + ((size_t)vm * B.cap[kind] + n) * rec_bytes(kind);
   }
@@ -207,14 +196,14 @@ struct Vm {
   __device__ __forceinline__ void emit_mem(uint32_t ts, uint32_t page, uint32_t index, uint32_t mtype, uint32_t rw, uint32_t is_ptr,
                                            uint32_t origin, u256l value) {
     ccount += 1u;
-    uint32_t n = count_mem;
+    uint32_t n = count[ZKB_STREAM_MEM];
     if (n >= B.cap[ZKB_STREAM_MEM]) {
       fail(ZKB_VM_CAP_STREAM);
       return;
     }
-    count_mem = n + 1;
+    count[ZKB_STREAM_MEM] = n + 1;
     if (!B.witness) return;
-    uint32_t* p = reinterpret_cast<uint32_t*>(mem_ptr(n));
+    uint32_t* p = reinterpret_cast<uint32_t*>(mem_base + (size_t)n * ZKB_MEM_BYTES);
     if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, index, mtype | rw << 8 | is_ptr << 16 | origin << 24);
     if (lane < 8) p[4 + lane] = value;
   }
@@ -279,8 +268,8 @@ struct Vm {
     is_ptr = 0;
     if (index >= B.stack_words) return 0u;  // never written (writes beyond the cap stop the VM) => still zero
     size_t off = (size_t)far_depth * B.stack_words + index;
-    is_ptr = g_stack_ptr()[off];
-    return lane < 8 ? g_stack()[off * 8 + lane] : 0u;
+    is_ptr = g_stack_ptr[off];
+    return lane < 8 ? g_stack[off * 8 + lane] : 0u;
   }
   __device__ __forceinline__ void stack_write(uint32_t index, u256l v, uint32_t is_ptr) {
     if (index >= B.stack_words) {
@@ -288,44 +277,44 @@ struct Vm {
       return;
     }
     size_t off = (size_t)far_depth * B.stack_words + index;
-    if (lane < 8) g_stack()[off * 8 + lane] = v;
-    if (lane == 8) g_stack_ptr()[off] = (uint8_t)is_ptr;
-    uint32_t hwm = g_lvl()[far_depth * 4 + 2];
-    if (index + 1 > hwm && lane == 0) g_lvl()[far_depth * 4 + 2] = index + 1;
+    if (lane < 8) g_stack[off * 8 + lane] = v;
+    if (lane == 8) g_stack_ptr[off] = (uint8_t)is_ptr;
+    uint32_t hwm = g_lvl[far_depth * 4 + 2];
+    if (index + 1 > hwm && lane == 0) g_lvl[far_depth * 4 + 2] = index + 1;
     __syncwarp();
   }
 
   // ---- heap slabs (SimpleMemory heaps / pages_with_extended_lifetime, memory.rs:439-521) ----------
   __device__ __forceinline__ uint32_t slab_alloc() {
-    uint32_t slab_free = X(X_SLAB_FREE);
     if (slab_free == 0) {
       fail(ZKB_VM_CAP_HEAP);
       return ZKB_NO_SLAB;
     }
     uint32_t s = __ffs(slab_free) - 1;
-    setX(X_SLAB_FREE, slab_free & ~(1u << s));
+    slab_free &= ~(1u << s);
     return s;
   }
   __device__ __forceinline__ void slab_release(uint32_t s) {
     if (s == ZKB_NO_SLAB) return;
-    uint32_t hwm = g_slab_hwm()[s];
-    uint32_t* base = g_heap() + (size_t)s * B.heap_words * 8;
+    uint32_t hwm = g_slab_hwm[s];
+    uint32_t* base = g_heap + (size_t)s * B.heap_words * 8;
     for (uint32_t i = lane; i < hwm * 8; i += 32) base[i] = 0u;  // == heap_on_return fill (memory.rs:181-183)
-    if (lane == 0) g_slab_hwm()[s] = 0;
-    setX(X_SLAB_FREE, X(X_SLAB_FREE) | 1u << s);
+    if (lane == 0) g_slab_hwm[s] = 0;
+    slab_free |= 1u << s;
+    __syncwarp();
   }
   __device__ __forceinline__ u256l slab_read(uint32_t s, uint32_t word) {
     if (s == ZKB_NO_SLAB || word >= B.heap_words) return 0u;
-    return lane < 8 ? g_heap()[((size_t)s * B.heap_words + word) * 8 + lane] : 0u;
+    return lane < 8 ? g_heap[((size_t)s * B.heap_words + word) * 8 + lane] : 0u;
   }
   __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
-    if (lane < 8) g_heap()[((size_t)s * B.heap_words + word) * 8 + lane] = v;
-    if (word + 1 > g_slab_hwm()[s] && lane == 0) g_slab_hwm()[s] = word + 1;
+    if (lane < 8) g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
+    if (word + 1 > g_slab_hwm[s] && lane == 0) g_slab_hwm[s] = word + 1;
     __syncwarp();
   }
   // slab of the current frame's heap (which = 0) / aux heap (which = 1); allocate lazily on first write
   __device__ __forceinline__ uint32_t cur_slab(uint32_t which, bool for_write, uint32_t word) {
-    uint32_t s = g_lvl()[far_depth * 4 + which];
+    uint32_t s = g_lvl[far_depth * 4 + which];
     if (for_write) {
       if (word >= B.heap_words) {
         fail(ZKB_VM_CAP_HEAP);
@@ -333,7 +322,7 @@ struct Vm {
       }
       if (s == ZKB_NO_SLAB) {
         s = slab_alloc();
-        if (lane == 0) g_lvl()[far_depth * 4 + which] = s;
+        if (lane == 0) g_lvl[far_depth * 4 + which] = s;
         __syncwarp();
       }
     }
@@ -342,7 +331,7 @@ struct Vm {
 
   // ---- page indirections (SimpleMemory.page_numbers_indirections, memory.rs:160-171,475-521) ------
   __device__ __forceinline__ int pt_find(uint32_t page) {
-    bool hit = lane < ZKB_PT_ENTRIES && g_pt()[lane * 2] == page;  // lanes beyond the table never match (not even "free")
+    bool hit = lane < ZKB_PT_ENTRIES && g_pt[lane * 2] == page;  // lanes beyond the table never match (not even "free")
     uint32_t m = __ballot_sync(ZK_FULL, hit);
     return m ? __ffs(m) - 1 : -1;
   }
@@ -354,8 +343,8 @@ struct Vm {
       return;
     }
     if (lane == 0) {
-      g_pt()[e * 2] = page;
-      g_pt()[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
+      g_pt[e * 2] = page;
+      g_pt[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
     }
     __syncwarp();
   }
@@ -368,9 +357,9 @@ struct Vm {
       ok = false;
       return 0u;
     }
-    uint32_t info = g_pt()[e * 2 + 1];
+    uint32_t info = g_pt[e * 2 + 1];
     uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
-    uint32_t s = kind == PT_EXT ? x : g_lvl()[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+    uint32_t s = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
     return slab_read(s, word);
   }
 
@@ -428,7 +417,6 @@ struct Vm {
       }
       if (lane < 8) vals[slot * 8 + lane] = nv;
       if (journal) {
-        const uint32_t journal_len = X(X_JOURNAL_LEN);
         if (journal_len >= B.journal_entries) {
           fail(ZKB_VM_CAP_STORAGE);
         } else {
@@ -436,7 +424,7 @@ struct Vm {
           uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
           if (lane < 8) jv[journal_len * 8 + lane] = old;
           if (lane == 8) js[journal_len] = (uint32_t)slot;
-          setX(X_JOURNAL_LEN, journal_len + 1);
+          journal_len++;
         }
       }
       __syncwarp();
@@ -448,14 +436,12 @@ struct Vm {
     uint32_t* vals = B.st_vals + (size_t)vm * B.storage_slots * 8;
     const uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
     const uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
-    uint32_t journal_len = X(X_JOURNAL_LEN);
     while (journal_len > mark) {
       journal_len--;
       uint32_t slot = js[journal_len];
       if (lane < 8) vals[slot * 8 + lane] = jv[journal_len * 8 + lane];
       __syncwarp();
     }
-    setX(X_JOURNAL_LEN, journal_len);
   }
 
   // ---- frames --------------------------------------------------------------------------------------
@@ -515,7 +501,7 @@ struct Vm {
     S.F[lane] = nf;
     __syncwarp();
     if (lane == 0) {
-      S.F[F_JOURNAL_MARK] = S.x[X_JOURNAL_LEN];  // storage.start_frame / event_sink.start_frame
+      S.F[F_JOURNAL_MARK] = journal_len;  // storage.start_frame / event_sink.start_frame
       S.row[L_DEPTH] = depth + 1;
     }
     __syncwarp();
@@ -825,17 +811,18 @@ __device__ __forceinline__ void Vm::cycle_once() {
                                                       sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
     S.row[L_COUNTS] = ccount;
   }
-  const uint32_t n_rows = count_rows;
+  const uint32_t n_rows = count[ZKB_STREAM_ROWS];
   if (n_rows >= B.cap[ZKB_STREAM_ROWS]) {
     fail(ZKB_VM_CAP_STREAM);
     return;
   }
-  count_rows = n_rows + 1;
+  count[ZKB_STREAM_ROWS] = n_rows + 1;
   __syncwarp();
   if (B.witness) {
     uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
-    *reinterpret_cast<uint2*>(row_ptr(n_rows) + 8 * lane) = v;
+    *reinterpret_cast<uint2*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES + 8 * lane) = v;
   }
+  if (family == ZK_OP_LOG && S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;  // the cycle is complete; its ecrecover is not
 }
 
 // context.rs:36-99
@@ -1014,11 +1001,7 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
       } else if (addr_low == ZK_SHA256_PRECOMPILE_ADDRESS) {
         sha256_precompile(abi);
       } else if (addr_low == ZK_ECRECOVER_PRECOMPILE_ADDRESS) {
-#ifndef ZKB_EXPERIMENT_NO_ECRECOVER
         ecrecover_precompile(abi);
-#else
-        fail(ZKB_VM_UNSUPPORTED);
-#endif
       }
       if (status != ZKB_VM_RUNNING) return;
       u256l one = lane == 0 ? 1u : 0u;
@@ -1043,9 +1026,9 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
       fail(ZKB_VM_REFERENCE_PANIC);
       return;
     }
-    uint32_t info = g_pt()[e * 2 + 1];
+    uint32_t info = g_pt[e * 2 + 1];
     uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
-    src_slab = kind == PT_EXT ? x : g_lvl()[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+    src_slab = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
   }
   const KeccakLanes kl = keccak_lanes(lane);
   uint64_t st = 0;
@@ -1117,7 +1100,7 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
-  const uint32_t src_slab = g_lvl()[far_depth * 4 + 0];
+  const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
   if (lane < 8) S.kbuf[lane] = c_sha256_iv[lane];
   for (uint64_t r = 0; r < rounds; r++) {
 #pragma unroll
@@ -1141,6 +1124,10 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
 // ecrecover precompile (external DefaultPrecompilesProcessor; memory ABI reconstructed): four
 // Heap-type word reads at input_memory_offset (digest, v in {0, 1}, r, s) at timestamp+1, two Heap-type word writes at
 // output_memory_offset (success marker, address; both zero on failure) at timestamp+2.
+// The cycle itself only moves data: it emits the six memory queries (the two writes with placeholder values), reserves
+// the output words and stashes the inputs; the ~6 000 modular multiplications of the recovery run AFTER the cycle, with
+// the VM state parked in HBM (run_deferred_ecrecover), and patch the two values in place.  Nothing inside the cycle
+// depends on them, and the interpreter's hot loop carries no live state across the call.
 __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
   const uint32_t in_word = __shfl_sync(ZK_FULL, abi, 0), out_word = __shfl_sync(ZK_FULL, abi, 2);
   const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
@@ -1150,41 +1137,45 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
-  const uint32_t src_slab = g_lvl()[far_depth * 4 + 0];
-  u256l in[4];
+  const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
+  u256l v_word = 0u;
 #pragma unroll
   for (uint32_t i = 0; i < 4; i++) {
-    in[i] = slab_read(src_slab, in_word + i);
-    emit_mem(ts_read, page_read, in_word + i, ZK_MEM_HEAP, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, in[i]);
+    u256l w = slab_read(src_slab, in_word + i);
+    emit_mem(ts_read, page_read, in_word + i, ZK_MEM_HEAP, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, w);
+    if (lane < 8) S.kbuf[KB_EC_INPUT + 8 * i + lane] = w;
+    if (i == 1) v_word = w;
   }
   if (status != ZKB_VM_RUNNING) return;
-  const uint32_t v_nz = __ballot_sync(ZK_FULL, in[1] != 0) & 0xFFu, v0 = __shfl_sync(ZK_FULL, in[1], 0);
-  if ((v_nz & 0xFEu) || v0 > 1u) {  // the external precompile asserts v == 0 || v == 1
+  const uint32_t v_nz = __ballot_sync(ZK_FULL, v_word != 0) & 0xFFu, v0 = __shfl_sync(ZK_FULL, v_word, 0);
+  if ((v_nz & 0xFEu) || v0 > 1u || page_write != heap_page) {  // the external precompile asserts v == 0 || v == 1
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
-  u256l address;
-  const bool ok = secp::ecrecover_warp(in[0], in[2], in[3], v0, lane, address);
-  if (page_write != heap_page) {
-    fail(ZKB_VM_REFERENCE_PANIC);
-    return;
-  }
-  const u256l marker = lane == 0 ? (ok ? 1u : 0u) : 0u;
   uint32_t s = cur_slab(0, true, out_word + 1);
   if (status != ZKB_VM_RUNNING) return;
-  slab_write(s, out_word, marker);
-  emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, marker);
-  slab_write(s, out_word + 1, address);
-  emit_mem(ts_write, page_write, out_word + 1, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, address);
+  const uint32_t first_record = count[ZKB_STREAM_MEM];
+  slab_write(s, out_word, 0u);
+  emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, 0u);
+  slab_write(s, out_word + 1, 0u);
+  emit_mem(ts_write, page_write, out_word + 1, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, 0u);
+  if (status != ZKB_VM_RUNNING) return;
+  if (lane == 0) {
+    S.kbuf[KB_EC_PENDING] = 1u;
+    S.kbuf[KB_EC_MEM_INDEX] = first_record;
+    S.kbuf[KB_EC_SLAB] = s;
+    S.kbuf[KB_EC_OUT_WORD] = out_word;
+  }
+  __syncwarp();
 }
 
 // SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth (already incremented)
 __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
   uint32_t level = far_depth;
   if (lane == 0) {
-    g_lvl()[level * 4 + 0] = ZKB_NO_SLAB;
-    g_lvl()[level * 4 + 1] = ZKB_NO_SLAB;
-    g_lvl()[level * 4 + 2] = 0;
+    g_lvl[level * 4 + 0] = ZKB_NO_SLAB;
+    g_lvl[level * 4 + 1] = ZKB_NO_SLAB;
+    g_lvl[level * 4 + 2] = 0;
   }
   __syncwarp();
   // the root "heaps" entry has page numbers 0/0 (memory.rs:230-233)
@@ -1200,7 +1191,7 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
       fail(ZKB_VM_REFERENCE_PANIC);  // "fat pointer must only point to reachable memory" (memory.rs:641)
       return;
     }
-    uint32_t kind = g_pt()[e * 2 + 1] & 0xFFu;
+    uint32_t kind = g_pt[e * 2 + 1] & 0xFFu;
     if (kind != PT_HEAP_LIVE && kind != PT_AUX_LIVE) fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:645
   }
 }
@@ -1208,12 +1199,12 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
 // SimpleMemory::finish_global_frame (memory.rs:660-758)
 __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
   // stack page goes back to the pool: clear what was touched (stack_on_return, memory.rs:185-188)
-  uint32_t hwm = g_lvl()[level * 4 + 2];
-  uint32_t* sbase = g_stack() + (size_t)level * B.stack_words * 8;
-  uint8_t* pbase = g_stack_ptr() + (size_t)level * B.stack_words;
+  uint32_t hwm = g_lvl[level * 4 + 2];
+  uint32_t* sbase = g_stack + (size_t)level * B.stack_words * 8;
+  uint8_t* pbase = g_stack_ptr + (size_t)level * B.stack_words;
   for (uint32_t i = lane; i < hwm * 8; i += 32) sbase[i] = 0u;
   for (uint32_t i = lane; i < hwm; i += 32) pbase[i] = 0;
-  uint32_t heap_slab = g_lvl()[level * 4 + 0], aux_slab = g_lvl()[level * 4 + 1];
+  uint32_t heap_slab = g_lvl[level * 4 + 0], aux_slab = g_lvl[level * 4 + 1];
   __syncwarp();
   uint32_t heap_page = base_page + 2, aux_page = base_page + 3;
   if (returndata_page == heap_page) {
@@ -1229,22 +1220,22 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
         fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:735
         return;
       }
-      if (lane == 0) g_pt()[e * 2 + 1] = (g_pt()[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
+      if (lane == 0) g_pt[e * 2 + 1] = (g_pt[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
       __syncwarp();
     }
     slab_release(heap_slab);
     slab_release(aux_slab);
   }
   // drop every indirection still owned by the finished level
-  uint32_t page = lane < ZKB_PT_ENTRIES ? g_pt()[lane * 2] : ZKB_PT_FREE;
-  uint32_t info = lane < ZKB_PT_ENTRIES ? g_pt()[lane * 2 + 1] : 0u;
+  uint32_t page = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2] : ZKB_PT_FREE;
+  uint32_t info = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2 + 1] : 0u;
   uint32_t drop = __ballot_sync(ZK_FULL, page != ZKB_PT_FREE && (info >> 16) == level);
   while (drop) {
     int e = __ffs(drop) - 1;
     drop &= drop - 1;
     uint32_t einfo = __shfl_sync(ZK_FULL, info, e);
     if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
-    if (lane == 0) g_pt()[e * 2] = ZKB_PT_FREE;
+    if (lane == 0) g_pt[e * 2] = ZKB_PT_FREE;
   }
   __syncwarp();
 }
@@ -1384,7 +1375,6 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
       if (u_eq(hw, code_hash)) id = (int)c;
     }
     uint32_t* dec = B.dec + (size_t)vm * ZKB_DEC_ENTRIES * 2;
-    const uint32_t n_decommit = X(X_N_DECOMMIT);
     uint32_t e_id = lane < n_decommit ? dec[lane * 2] : ZKB_NO_CODE;
     // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it
     uint32_t hist = id >= 0 ? __ballot_sync(ZK_FULL, e_id == (uint32_t)id) : (__ballot_sync(ZK_FULL, false));
@@ -1407,7 +1397,8 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
         dec[n_decommit * 2] = (uint32_t)id;
         dec[n_decommit * 2 + 1] = page_candidate;
       }
-      setX(X_N_DECOMMIT, n_decommit + 1);
+      n_decommit++;
+      __syncwarp();
       mapped_code_page = page_candidate;
       fresh_flag = 1;
       len16 = B.code_meta[id * 10 + 1] & 0xFFFFu;
@@ -1718,6 +1709,7 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   S.F[lane] = hot->F[lane];
   S.row[lane] = 0u;
   S.row[32 + lane] = lane >= 8 && lane < 24 ? hot->live[lane - 8] : 0u;
+  if (lane == 0) S.kbuf[KB_EC_PENDING] = 0u;
   v.prev_word = lane < 8 ? hot->prev_word[lane] : 0u;
   uint32_t x = hot->x[lane];
   v.timestamp = __shfl_sync(ZK_FULL, x, X_TIMESTAMP);
@@ -1727,10 +1719,11 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   v.status = ZKB_VM_RUNNING;
   v.ptr_mask = __shfl_sync(ZK_FULL, x, X_PTRMASK);
   v.prev_code_page = __shfl_sync(ZK_FULL, x, X_PREV_CODE_PAGE);
-  S.x[lane] = x;
-  v.init_bases();
-  v.count_rows = __shfl_sync(ZK_FULL, x, X_COUNT0 + ZKB_STREAM_ROWS);
-  v.count_mem = __shfl_sync(ZK_FULL, x, X_COUNT0 + ZKB_STREAM_MEM);
+  v.journal_len = __shfl_sync(ZK_FULL, x, X_JOURNAL_LEN);
+  v.n_decommit = __shfl_sync(ZK_FULL, x, X_N_DECOMMIT);
+  v.slab_free = __shfl_sync(ZK_FULL, x, X_SLAB_FREE);
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = __shfl_sync(ZK_FULL, x, X_COUNT0 + k);
   v.rowbits = 0;
   v.ccount = 0;
   v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
@@ -1751,7 +1744,7 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
   hot->F[lane] = S.F[lane];
   if (lane < 16) hot->live[lane] = S.row[40 + lane];
   if (lane < 8) hot->prev_word[lane] = v.prev_word;
-  uint32_t out = S.x[lane];  // cold scalars are already current in shared memory
+  uint32_t out = 0;
   out = lane == X_TIMESTAMP ? v.timestamp : out;
   out = lane == X_CYCLE ? v.cycle : out;
   out = lane == X_FLAGS ? v.flags : out;
@@ -1760,16 +1753,53 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
   out = lane == X_PTRMASK ? v.ptr_mask : out;
   out = lane == X_PREV_CODE_PAGE ? v.prev_code_page : out;
   out = lane == X_FAR_DEPTH ? v.far_depth : out;
-  out = lane == (uint32_t)(X_COUNT0 + ZKB_STREAM_ROWS) ? v.count_rows : out;
-  out = lane == (uint32_t)(X_COUNT0 + ZKB_STREAM_MEM) ? v.count_mem : out;
+  out = lane == X_JOURNAL_LEN ? v.journal_len : out;
+  out = lane == X_N_DECOMMIT ? v.n_decommit : out;
+  out = lane == X_SLAB_FREE ? v.slab_free : out;
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) out = lane == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
   hot->x[lane] = out;
   // the per-VM summary goes straight to mapped host memory (one 32-byte posted write per VM and run): the host can
   // size and enqueue the witness download without a D2H copy of its own queueing behind the copies already in flight
   const uint32_t st_out = (v.status == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : v.status;
   uint32_t summary = lane == 6 ? st_out : v.cycle;
-  if (lane < ZKB_N_STREAMS) summary = lane == ZKB_STREAM_ROWS ? v.count_rows : lane == ZKB_STREAM_MEM ? v.count_mem : S.x[X_COUNT0 + lane];
+#pragma unroll
+  for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.count[k] : summary;
   if (lane < 8) v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
   __syncwarp();
+}
+
+// the deferred half of the ecrecover precompile: runs between vm_store and vm_load, i.e. with no interpreter state in
+// registers; reads its inputs from the warp's scratch, patches the heap words and the two memory-query records
+// (plain scalar arguments: handing the launch-constant DevBatch to a non-inlined function by reference would force a
+// copy of the whole struct onto the local-memory stack of every thread)
+__device__ __noinline__ void run_deferred_ecrecover(uint32_t* kbuf, uint32_t* vm_heap, uint32_t heap_words, uint8_t* vm_mem_stream,
+                                                    uint32_t lane) {
+  __syncwarp();
+  u256l in[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) in[i] = lane < 8 ? kbuf[KB_EC_INPUT + 8 * i + lane] : 0u;
+  const uint32_t rec = kbuf[KB_EC_MEM_INDEX], slab = kbuf[KB_EC_SLAB], out_word = kbuf[KB_EC_OUT_WORD];
+  __syncwarp();
+  u256l address;
+  const bool ok = secp::ecrecover_warp(in[0], in[2], in[3], __shfl_sync(ZK_FULL, in[1], 0), lane, address);
+  const u256l marker = lane == 0 ? (ok ? 1u : 0u) : 0u;
+  uint32_t* heap = vm_heap + ((size_t)slab * heap_words + out_word) * 8;
+  if (lane < 8) {
+    heap[lane] = marker;
+    heap[8 + lane] = address;
+    if (vm_mem_stream) {
+      uint32_t* r = reinterpret_cast<uint32_t*>(vm_mem_stream + (size_t)rec * ZKB_MEM_BYTES);
+      r[4 + lane] = marker;
+      r[ZKB_MEM_BYTES / 4 + 4 + lane] = address;
+    }
+  }
+  if (lane == 0) kbuf[KB_EC_PENDING] = 0u;
+  __syncwarp();
+}
+__device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, WarpSmem& S, uint32_t vm, uint32_t lane) {
+  run_deferred_ecrecover(S.kbuf, B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8, B.heap_words,
+                         B.witness ? B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES : nullptr, lane);
 }
 
 // free-running schedule: one warp runs one VM to the end (or for max_cycles cycles)
@@ -1779,14 +1809,21 @@ __device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t 
   Vm v(B, S, vm_idx, lane);
   vm_load(v, hot);
   uint32_t n = 0;
-  while (v.status == ZKB_VM_RUNNING) {
-    if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
-      v.status = ZKB_VM_ENDED;
-      break;
+  for (;;) {
+    while (v.status == ZKB_VM_RUNNING) {
+      if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
+        v.status = ZKB_VM_ENDED;
+        break;
+      }
+      if (max_cycles && n >= max_cycles) break;
+      v.cycle_once();
+      n++;
     }
-    if (max_cycles && n >= max_cycles) break;
-    v.cycle_once();
-    n++;
+    if (v.status != ZKB_VM_YIELD_ECRECOVER) break;
+    v.status = ZKB_VM_RUNNING;  // park the VM, finish the pending recovery, resume
+    vm_store(v, hot);
+    deferred_ecrecover(B, S, vm_idx, lane);
+    vm_load(v, hot);
   }
   vm_store(v, hot);
 }
@@ -1819,6 +1856,13 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
         n++;
         active = v.status == ZKB_VM_RUNNING;
       }
+    }
+    if (valid && v.status == ZKB_VM_YIELD_ECRECOVER) {  // park the VM, finish the pending recovery, resume
+      v.status = ZKB_VM_RUNNING;
+      vm_store(v, hot);
+      deferred_ecrecover(B, S, v.vm, lane);
+      vm_load(v, hot);
+      active = true;
     }
     if (active && max_cycles && n >= max_cycles) active = false;
     if (!__syncthreads_or(active ? 1 : 0)) break;

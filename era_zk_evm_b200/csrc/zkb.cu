@@ -87,9 +87,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
   if (vm >= vm_hi) return;
   Vm v(B, smem[warp], vm, lane);
   v.status = ZKB_VM_RUNNING;
-  smem[warp].x[lane] = 0u;
-  __syncwarp();
-  v.init_bases();
+  v.journal_len = 0;
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;

@@ -386,7 +386,7 @@ class Erc20(Workload):
         ent["address"] = np.frombuffer(TOKEN_ADDRESS.to_bytes(20, "big"), dtype=np.uint8)
         ent["key_be"] = slot
         bal = np.zeros((len(vm_ids), 32), dtype=np.uint8)
-        bal[~broke, 15] = 2                                  # 2^129
+        bal[~broke, 15] = 16                                 # 2^132 > T * 2^128: every transfer of a funded VM succeeds
         ent["value_be"] = bal
         return heap, ent
 

@@ -77,7 +77,8 @@ def test_config2_erc20_65536_vms(oracle_mod):
     counts = check_stream_invariants(gpu)
     sample = sorted(set(np.linspace(0, n - 1, 48).astype(int).tolist() + [63, 127, 65535]))     # incl. reverting VMs (id % 64 == 63)
     check_sample_against_oracle(gpu, w, oracle_mod, sample)
-    # storage accounting: every successful transfer performs exactly two SSTOREs; broke VMs (balance 0) none
+    # storage accounting: every successful transfer performs exactly two SSTOREs; funded VMs (balance 2^132, amounts
+    # < 2^128) complete all 8, broke VMs (balance 0, id % 64 == 63) revert every transfer before any write
     lbuf, loffs = gpu.fetch_stream_packed(records.STREAM_LOG)
     lg = lbuf.view(records.LOG_DTYPE)
     vm_of = np.repeat(np.arange(n), counts[records.STREAM_LOG])
