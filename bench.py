@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--transfers", type=int, default=8)
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left free for the NCCL kernels of the concat")
+    ap.add_argument("--concat-mode", default="overlap", choices=["overlap", "simple"])
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -189,15 +191,21 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     vm_ids = np.arange(args.vms, dtype=np.uint64) + np.uint64(rank * args.vms)   # static VM-range partition
     cfg = w.config(args.vms, device=local_rank)
+    if world > 1:
+        cfg.reserved[0] = args.reserve_sms
     batch = GpuVmBatch(cfg)
     w.setup(batch, vm_ids)
     batch.snapshot()
-    concat_kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND] + \
-        ([records.STREAM_ROWS, records.STREAM_MEM] if args.gather_rows else [])
+    # the query logs a downstream consumer sorts / dedups globally; cycle rows, memory queries and frame records are
+    # per-VM witness and stay sharded unless --gather-rows asks for them
+    concat_kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_REFUND] + \
+        ([records.STREAM_ROWS, records.STREAM_MEM, records.STREAM_FRAME] if args.gather_rows else [])
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -207,26 +215,45 @@ def main():
         torch.cuda.synchronize()
 
     pending = []
+    state = {"ran": False}
+    dev = torch.device("cuda", local_rank)
+
+    def concat_previous():
+        """the only exchange on this path: the per-GPU query-log streams of the step that just finished are packed
+        (VM-major, straight into the NCCL send buffers) and concatenated on rank 0.  Only the pack kernels are ordered
+        before the next launch; the NCCL transfers stay in flight underneath it."""
+        for pg in pending:         # stream-level wait: the pack buffers are about to be reused
+            pg.wait()
+        pending.clear()
+        packed = [batch.pack_stream_device_async(kind, cur_stream) for kind in concat_kinds]   # waits for the run, enqueues the packs
+        return [shard.device_bytes_as_tensor(p, nb, dev) for p, nb in packed]
 
     def step():
-        """one pass of the hot path over the batch; at N > 1 followed by the only exchange on this path: the
-        concatenation of the per-GPU query-log streams on rank 0 (NCCL send/recv straight from the pack buffers),
-        left in flight so that it overlaps the next step's interpreter launch"""
+        """one pass of the hot path over the batch (+ at N > 1 the concat of the previous pass, overlapped)"""
+        if world > 1 and args.concat_mode == "simple":
+            batch.restore()
+            batch.run(sync=False)
+            state["ran"] = True
+            pending.extend(shard.gather_many(concat_previous(), dst=0))
+            state["ran"] = False
+            return
+        locals_ = concat_previous() if (world > 1 and state["ran"]) else None
         batch.restore()
+        if locals_ is not None:
+            pending.extend(shard.gather_many(locals_, dst=0))
         batch.run(sync=False)
-        if world > 1:
-            for pg in pending:     # stream-level wait: the pack buffers are reused below, AFTER this step's launch is queued
-                pg.wait()
-            pending.clear()
-            for kind in concat_kinds:
-                pg, _ = shard.gather_stream(batch, kind, dst=0, async_op=True, stream_ptr=cur_stream)
-                pending.append(pg)
+        state["ran"] = True
 
     def drain():
         batch.sync()
+        if world > 1 and state["ran"]:
+            locals_ = concat_previous()
+            pending.extend(shard.gather_many(locals_, dst=0))
+            state["ran"] = False
         for pg in pending:
             pg.wait()
         pending.clear()
+        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 0)):
         step()

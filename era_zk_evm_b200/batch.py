@@ -39,6 +39,8 @@ class GpuVmBatch(_binding.Batch):
         lib.zkb_stream_device_view.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
         lib.zkb_fetch_stream_packed.argtypes = [vp, u32, vp, u64, vp]
         lib.zkb_pack_stream_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp]
+        lib.zkb_pack_stream_device_async.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp]
+        lib.zkb_pack_stream_device_async.restype = C.c_int32
         lib.zkb_fetch_stream_packed_async.argtypes = [vp, u32, vp, u64, vp, vp]
         lib.zkb_fetch_stream_packed_async.restype = C.c_int32
         lib.zkb_snapshot.argtypes = [vp]
@@ -56,6 +58,12 @@ class GpuVmBatch(_binding.Batch):
     def pack_stream_device(self, kind: int, stream=None):
         p, n = C.c_void_p(), C.c_uint64()
         self._check(self._lib.zkb_pack_stream_device(self._h, kind, C.byref(p), C.byref(n), stream))
+        return p.value, n.value
+
+    def pack_stream_device_async(self, kind: int, stream=None):
+        """enqueue the pack of stream `kind` on `stream` (no synchronisation); returns (device pointer, bytes)"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.zkb_pack_stream_device_async(self._h, kind, C.byref(p), C.byref(n), stream))
         return p.value, n.value
 
     def fetch_stream_packed(self, kind: int, host_ptr: int | None = None, host_capacity: int = 0):

@@ -64,7 +64,10 @@ __device__ __forceinline__ KeccakLanes keccak_lanes(uint32_t lane) {
 __device__ __forceinline__ uint64_t keccak_f1600(uint64_t a, const KeccakLanes& k, uint32_t lane) {
 #pragma unroll 1
   for (int round = 0; round < 24; round++) {
-    uint64_t c = a ^ shfl64(a, k.c5) ^ shfl64(a, k.c10) ^ shfl64(a, k.c15) ^ shfl64(a, k.c20);
+    // column parity in three exchanges instead of four: rows {y, y+1}, then {y .. y+3}, then row y+4
+    uint64_t t2 = a ^ shfl64(a, k.c5);
+    t2 ^= shfl64(t2, k.c10);
+    uint64_t c = t2 ^ shfl64(a, k.c20);
     uint64_t d = shfl64(c, k.xm1) ^ rotl64(shfl64(c, k.xp1), 1);
     a ^= d;
     uint64_t b = rotl64(shfl64(a, k.pi_src), k.pi_rot);

@@ -162,10 +162,11 @@ struct Vm {
   __device__ __forceinline__ bool is_local() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_LOCAL; }
   __device__ __forceinline__ u256l reg_read(uint32_t idx) const { return lane < 8 ? S.regs[idx][lane] : 0u; }
   __device__ __forceinline__ void reg_write(uint32_t idx, u256l v, bool is_ptr) {
+    // limb l is written and read back by lane l only; the one cross-lane reader (limb 0 in operand addressing of a LATER
+    // cycle) sits behind the warp sync of the row emission, so no sync is needed here
     if (idx != 0) {
       if (lane < 8) S.regs[idx][lane] = v;
       ptr_mask = (ptr_mask & ~(1u << idx)) | ((is_ptr ? 1u : 0u) << idx);
-      __syncwarp();
     }
   }
   // address (5 LE-loaded words holding 20 BE bytes, in lanes 0..4) <-> U256 (address_to_u256, utils.rs:29-41)
@@ -822,7 +823,11 @@ __device__ __forceinline__ void Vm::cycle_once() {
     uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
     *reinterpret_cast<uint2*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES + 8 * lane) = v;
   }
-  if (family == ZK_OP_LOG && S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;  // the cycle is complete; its ecrecover is not
+  // rare end-of-cycle state changes, keyed on the opcode family so that ordinary cycles pay one compare:
+  if (family - ZK_OP_LOG <= 2u) {  // LOG, FAR_CALL, RET
+    if (family == ZK_OP_LOG && S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;  // the cycle is complete; its ecrecover is not
+    if (family == ZK_OP_RET && S.row[L_DEPTH] == 0) status = ZKB_VM_ENDED;              // execution_has_ended (mod.rs:96-98)
+  }
 }
 
 // context.rs:36-99
@@ -1809,12 +1814,9 @@ __device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t 
   Vm v(B, S, vm_idx, lane);
   vm_load(v, hot);
   uint32_t n = 0;
+  if (S.row[L_DEPTH] == 0) v.status = ZKB_VM_ENDED;  // nothing to run; later ends are detected by the RET that pops the last frame
   for (;;) {
     while (v.status == ZKB_VM_RUNNING) {
-      if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
-        v.status = ZKB_VM_ENDED;
-        break;
-      }
       if (max_cycles && n >= max_cycles) break;
       v.cycle_once();
       n++;
@@ -1838,7 +1840,10 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
   VmHot* hot = B.hot + (valid ? vm_idx : 0);
   Vm v(B, S, valid ? vm_idx : 0, lane);
   v.status = ZKB_VM_ENDED;
-  if (valid) vm_load(v, hot);
+  if (valid) {
+    vm_load(v, hot);
+    if (S.row[L_DEPTH] == 0) v.status = ZKB_VM_ENDED;  // nothing to run; later ends are detected by the RET that pops the last frame
+  }
   uint32_t n = 0;
   while (true) {
     // up to ZKB_LOCKSTEP_PERIOD cycles between two CTA barriers: the warps may drift by a few hundred instructions
@@ -1846,10 +1851,7 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
     bool active = valid && v.status == ZKB_VM_RUNNING;
 #pragma unroll 1
     for (int k = 0; k < ZKB_LOCKSTEP_PERIOD && active; k++) {
-      if (S.row[L_DEPTH] == 0) {  // execution_has_ended (mod.rs:96-98)
-        v.status = ZKB_VM_ENDED;
-        active = false;
-      } else if (max_cycles && n >= max_cycles) {
+      if (max_cycles && n >= max_cycles) {
         active = false;
       } else {
         v.cycle_once();

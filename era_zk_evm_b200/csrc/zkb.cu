@@ -466,6 +466,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, 0));
   CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   b->grid = std::max(1, per_sm * n_sm);  // persistent grid: a multiple of the SM count (148 on B200)
+  if (cfg->reserved[0] > 0 && (int)cfg->reserved[0] < n_sm) b->grid = per_sm * (n_sm - (int)cfg->reserved[0]);
   uint32_t sched = cfg->schedule;
   if (const char* env = getenv("ZKB_SCHEDULE")) sched = (uint32_t)atoi(env);  // experiment override
   b->lockstep = sched != ZKB_SCHED_FREE;
@@ -876,6 +877,17 @@ int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t
   int32_t rc = pack_async(b, kind, (cudaStream_t)cuda_stream, &p, &total);
   if (rc != ZKB_OK) return rc;
   CUDA_OK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (dptr) *dptr = p;
+  if (n_bytes) *n_bytes = total;
+  return ZKB_OK;
+}
+
+int32_t zkb_pack_stream_device_async(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || kind >= ZKB_N_STREAMS || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
+  uint64_t total = 0;
+  int32_t rc = pack_async(b, kind, (cudaStream_t)cuda_stream, &p, &total);
+  if (rc != ZKB_OK) return rc;
   if (dptr) *dptr = p;
   if (n_bytes) *n_bytes = total;
   return ZKB_OK;

@@ -98,3 +98,28 @@ def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.devi
         return gather_varlen(local, dst, group, async_op=True), counts
     out, offsets = gather_varlen(local, dst, group)
     return out, offsets, counts
+
+
+def gather_many(locals_: list, dst: int = 0, group=None):
+    """Concatenation of SEVERAL variable-length uint8 tensors per rank with ONE size exchange and one grouped batch of
+    NCCL send/recv: returns a list of PendingGather (payload transfers left in flight)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = locals_[0].device
+    n = torch.tensor([t.numel() for t in locals_], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = torch.stack(sizes).cpu().numpy()                       # [world, k]
+    ops, outs = [], []
+    for j, local in enumerate(locals_):
+        offsets = np.concatenate([[0], np.cumsum(sizes[:, j])]).astype(np.int64)
+        if rank == dst:
+            out = torch.empty(int(offsets[-1]), dtype=torch.uint8, device=dev)
+            out[offsets[rank]: offsets[rank + 1]].copy_(local)
+            ops += [dist.P2POp(dist.irecv, out[offsets[r]: offsets[r + 1]], r, group) for r in range(world) if r != dst and sizes[r, j]]
+        else:
+            out = None
+            if local.numel():
+                ops.append(dist.P2POp(dist.isend, local, dst, group))
+        outs.append((out, offsets))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    return [PendingGather(out, offsets, works if j == 0 else [], keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]

@@ -69,7 +69,8 @@ typedef struct ZkbConfig {
   uint32_t journal_entries;  /* per-VM storage rollback journal (storage.rs:98-120) */
   uint32_t host_mirror;      /* 1 = allocate pinned host mirrors for zkb_fetch_streams */
   uint32_t schedule;         /* ZkbSchedule: how warps are assigned to VMs (results are identical either way) */
-  uint32_t reserved[3];
+  uint32_t reserved[3];      /* reserved[0] = SMs left free by the persistent interpreter grid (0 = none): room for the
+                                NCCL send/recv kernels of the multi-GPU stream concat to run underneath the next launch */
 } ZkbConfig;
 
 /* mirror of CallStackEntry (execution_stack.rs:6-24) */
@@ -197,6 +198,10 @@ int32_t zkb_fetch_stream_packed_async(ZkbBatch* b, uint32_t kind, void* host_dst
                                       uint64_t* offsets_out, void* cuda_stream);
 /* device-only variant: returns the packed device buffer (valid until the next run/fetch/destroy) */
 int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
+/* as above without the final stream synchronisation: the pack kernel is only enqueued on `cuda_stream` (work queued
+ * later on that stream, or a collective that waits on it, sees the packed buffer; used to overlap the multi-GPU
+ * concatenation of step k with the interpreter launch of step k+1) */
+int32_t zkb_pack_stream_device_async(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
 /* final storage value of one slot (== InMemoryStorage.inner lookup, storage.rs:9) */
 int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8_t address[20],
                          const uint8_t key_be[32], uint8_t value_be_out[32]);

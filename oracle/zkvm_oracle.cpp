@@ -17,7 +17,8 @@
 // zkevm_opcode_defs / zk_evm_abstractions @ branch v1.4.1 are absent).  The interpreter logic is pinned by
 // source; the ISA data table (era_zk_evm_b200/isa.py -> isa_tables.inc), ABI bit layouts and the
 // sha256/ecrecover precompile memory ABIs are reconstructions => "parity unpinned" for those parts.
-// keccak256 is pinned by the reference's live tests (tests/test_oracle_kat.py replays them).
+// keccak256 is pinned by the reference's live tests, sha256 / ecrecover by its hash and known-answer vectors, the ALU by
+// Python-int vectors, handler quirks by hand-derived programs (tests/test_oracle_golden.py, tests/test_semantics.py).
 //
 // It is deliberately KINDER to the CPU than the reference: stack/heap pages are grown lazily and cleared by
 // high-water mark instead of the reference's 65 536-entry fill per far return (memory.rs:185-192), and code

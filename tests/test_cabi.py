@@ -44,7 +44,7 @@ def test_oracle_exports_the_same_surface(oracle_mod):
     """the checker mirrors the boundary (prefix orc_) so parity tests drive both through one code path"""
     lib = oracle_mod.lib()
     shared = [n for n in declared_functions() if n not in (
-        "zkb_stream_device_view", "zkb_fetch_stream_packed", "zkb_fetch_stream_packed_async", "zkb_pack_stream_device", "zkb_snapshot", "zkb_restore",
+        "zkb_stream_device_view", "zkb_fetch_stream_packed", "zkb_fetch_stream_packed_async", "zkb_pack_stream_device", "zkb_pack_stream_device_async", "zkb_snapshot", "zkb_restore",
         "zkb_transfer_stats", "zkb_gather_streams", "zkb_sort_log_queries")]
     missing = [n for n in shared if not hasattr(lib, n.replace("zkb_", "orc_", 1))]
     assert not missing, missing

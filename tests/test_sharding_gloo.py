@@ -54,6 +54,14 @@ def _worker(rank, world, port, n_total, out_dir):
                 result[kind] = (out.numpy().copy(), offsets)
             else:
                 assert out is None
+        # several streams with ONE size exchange (what bench.py does at N > 1)
+        from era_zk_evm_b200.shard import gather_many
+        locs = [torch.from_numpy(np.ascontiguousarray(np.concatenate(
+            [b.read_stream(vm, k).view(np.uint8) for vm in range(b.n_vms)]))) for k in (records.STREAM_LOG, records.STREAM_REFUND)]
+        many = [pg.wait() for pg in gather_many(locs, dst=0)]
+        if rank == 0:
+            assert np.array_equal(many[0][0].numpy(), result[records.STREAM_LOG][0])
+            assert np.array_equal(many[1][0].numpy(), result[records.STREAM_REFUND][0])
         # ragged edge: an empty contribution from one rank, and the all-gather flavour
         local = torch.arange(5 * rank, dtype=torch.uint8)
         cat, offs = all_gather_varlen(local)
