@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left free for the NCCL kernels of the concat")
-    ap.add_argument("--concat-mode", default="overlap", choices=["overlap", "simple"])
+    ap.add_argument("--concat-mode", default="simple", choices=["overlap", "simple"])
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

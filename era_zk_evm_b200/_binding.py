@@ -19,6 +19,7 @@ VM_RUNNING, VM_ENDED, VM_UNKNOWN_CODE_HASH, VM_REFERENCE_PANIC = 0, 1, 2, 3
 VM_CAP_STREAM, VM_CAP_STACK, VM_CAP_HEAP, VM_CAP_DEPTH, VM_CAP_STORAGE, VM_CAP_PAGES, VM_UNSUPPORTED = range(16, 23)
 
 SCHED_AUTO, SCHED_FREE, SCHED_LOCKSTEP = 0, 1, 2
+FLAT_STORAGE_HISTORY, FLAT_EVENT_HISTORY, FLAT_NET_EVENTS, FLAT_NET_L1_MESSAGES = range(4)
 FIELD_MEMORY_PAGE_COUNTER, FIELD_ERGS_PER_PUBDATA, FIELD_TX_NUMBER, FIELD_TIMESTAMP = range(4)
 
 
@@ -147,6 +148,8 @@ class Batch:
             "read_stream": [vp, u32, u32, vp, u64, C.POINTER(u64)],
             "read_storage": [vp, u32, C.c_uint8, C.c_char_p, C.c_char_p, vp],
             "read_heap": [vp, u32, u32, u32, vp],
+            "flatten_logs": [vp, vp], "flat_counts": [vp, u32, u32, u32, vp, vp],
+            "read_flat": [vp, u32, u32, vp, u64, C.POINTER(u64)],
         }
         for name, args in sigs.items():
             fn = self._f(name)
@@ -267,6 +270,24 @@ class Batch:
         if n.value:
             self._check(self._f("read_stream")(self._h, vm, kind, buf.ctypes.data, n.value, C.byref(n)))
         return buf.view(records.DTYPES[kind])
+
+    # -- post-processing: the backends' flattened histories (storage.rs:34-76, event_sink.rs:66-131) --------
+    def flatten_logs(self, stream=None):
+        self._check(self._f("flatten_logs")(self._h, stream))
+
+    def flat_counts(self, kind: int, vm_lo=0, vm_hi=None):
+        vm_hi = self.n_vms if vm_hi is None else vm_hi
+        counts, status = np.zeros(vm_hi - vm_lo, dtype=np.uint32), np.zeros(vm_hi - vm_lo, dtype=np.uint32)
+        self._check(self._f("flat_counts")(self._h, kind, vm_lo, vm_hi, counts.ctypes.data, status.ctypes.data))
+        return counts, status
+
+    def read_flat(self, vm: int, kind: int) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._f("read_flat")(self._h, vm, kind, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self._f("read_flat")(self._h, vm, kind, buf.ctypes.data, n.value, C.byref(n)))
+        return buf.view(records.LOG_DTYPE)
 
     def read_storage(self, vm: int, shard: int, address: int, key: int) -> int:
         out = (C.c_uint8 * 32)()

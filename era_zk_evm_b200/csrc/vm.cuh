@@ -60,6 +60,9 @@ struct VmHot {
 #define ZKB_VM_YIELD_ECRECOVER 0x100u
 // kbuf layout while an ecrecover is pending
 enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 61, KB_EC_SLAB = 62, KB_EC_OUT_WORD = 63 };  // 48..63: unused by keccak / sha256 / pop_frame
+// block-placement hint: keeps the per-cycle hot path contiguous in the instruction stream (the interpreter's first-order
+// cost is instruction fetch)
+#define ZK_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define ZKB_NO_SLAB 0xFFu
 #define ZKB_NO_CODE 0xFFFFFFFFu
 #define ZKB_PT_ENTRIES 32u   // one entry per lane
@@ -198,7 +201,7 @@ struct Vm {
                                            uint32_t origin, u256l value) {
     ccount += 1u;
     uint32_t n = count[ZKB_STREAM_MEM];
-    if (n >= B.cap[ZKB_STREAM_MEM]) {
+    if (ZK_UNLIKELY(n >= B.cap[ZKB_STREAM_MEM])) {
       fail(ZKB_VM_CAP_STREAM);
       return;
     }
@@ -572,7 +575,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   const uint32_t super_pc = pc >> 2, sub_pc = pc & 3u;
   uint32_t prev_super_pc = S.row[L_TX_PSP] >> 16;
   uint32_t raw_lo, raw_hi;
-  if (!pending) {
+  if (!ZK_UNLIKELY(pending)) {
     if (code_page != prev_code_page || prev_super_pc != super_pc) {
       u256l w = (lane < 8 && super_pc < code_len) ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
       prev_word = w;
@@ -594,15 +597,15 @@ __device__ __forceinline__ void Vm::cycle_once() {
   entry = ZK_OPCODE_TABLE[vidx];
   const uint32_t price = ZK_OPCODE_PRICES[vidx];
   uint32_t err = (entry & ZK_E_INVALID) ? 1u : 0u;
-  if (ergs < price) {
+  if (ZK_UNLIKELY(ergs < price)) {
     ergs = 0;
     err |= 2u;
   } else {
     ergs -= price;
   }
   const bool kernel_mode = !(forbid & ZK_E_KERNEL_ONLY);
-  if (entry & forbid) err |= ((entry & forbid & ZK_E_KERNEL_ONLY) ? 4u : 0u) | ((entry & forbid & ZK_E_STATIC_FORBIDDEN) ? 8u : 0u);
-  if (S.row[L_DEPTH] == ZK_VM_MAX_STACK_DEPTH) err |= 16u;
+  if (ZK_UNLIKELY(entry & forbid)) err |= ((entry & forbid & ZK_E_KERNEL_ONLY) ? 4u : 0u) | ((entry & forbid & ZK_E_STATIC_FORBIDDEN) ? 8u : 0u);
+  if (ZK_UNLIKELY(S.row[L_DEPTH] == ZK_VM_MAX_STACK_DEPTH)) err |= 16u;
   // flags: bit0 LT/OF, bit1 EQ, bit2 GT.  Byte `cond` of the table = the set of flag values that satisfy the condition
   // {Always, Gt, Lt, Eq, Ge, Le, Ne, GtOrLt} (cycle.rs:193-210)
   const uint32_t cond = (raw_lo >> ZK_COND_SHIFT) & 7u;
@@ -610,7 +613,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   bool resolved = (uint32_t)(kCondTable >> (cond * 8u + (flags & 7u))) & 1u;
   // mask_into_panic / mask_into_nop (cycle.rs:187-217): the masked opcode has all-zero operands
   uint32_t ops_lo = raw_lo, ops_hi = raw_hi;
-  if (err) {
+  if (ZK_UNLIKELY(err)) {
     vidx = ZK_PANIC_VARIANT_IDX;
     resolved = true;
   } else if (!resolved) {
@@ -799,7 +802,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
       break;
   }
   // the reference returns Err / panics before end_execution_cycle (cycle.rs:406): no row for a cycle that stopped the VM
-  if (status != ZKB_VM_RUNNING) return;
+  if (ZK_UNLIKELY(status != ZKB_VM_RUNNING)) return;
 
   timestamp += ZK_TIME_DELTA_PER_CYCLE;
   cycle += 1;
@@ -813,7 +816,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
     S.row[L_COUNTS] = ccount;
   }
   const uint32_t n_rows = count[ZKB_STREAM_ROWS];
-  if (n_rows >= B.cap[ZKB_STREAM_ROWS]) {
+  if (ZK_UNLIKELY(n_rows >= B.cap[ZKB_STREAM_ROWS])) {
     fail(ZKB_VM_CAP_STREAM);
     return;
   }

@@ -136,6 +136,150 @@ __global__ void zkb_pack_kernel(const uint8_t* __restrict__ src, uint64_t stride
   for (uint64_t i = threadIdx.x; i < n / 8; i += blockDim.x) d[i] = s[i];
 }
 
+
+// K7: per-VM flattening of the finished batch's storage / event logs: rebuilds what the reference's
+// backends hold after the run -- InMemoryStorage::flatten_and_net_history().0 (src/testing/storage.rs:34-76) and
+// InMemoryEventSink::flatten() (src/reference_impls/event_sink.rs:66-131) -- from the LOG + FRAME streams, i.e. the
+// chronological query history with the rollback queries that finish_frame(panicked) appends in reverse
+// (storage.rs:156-180, event_sink.rs:166-170), and the net (never rolled back) events / L1 messages in timestamp order.
+// One warp per VM: lanes scan 32 cycle rows at a time for their record counts, records are replayed in program order
+// against a stack of rollback marks (the same scheme as the interpreter's storage journal).
+struct FlatOut {
+  uint32_t* hist[2];   // [vm][cap_hist][32] storage history, event history (LogQueryRec words)
+  uint32_t* net[2];    // [vm][cap_net][32]  net events, net L1 messages
+  uint32_t* rb[2];     // [vm][cap_net]      indices of not-yet-rolled-back writes / events in hist[k]
+  uint32_t* counts;    // [vm][4] records in hist[0], hist[1], net[0], net[1]
+  uint32_t* status;    // [vm] 0 ok, 1 VM not ended, 2 capacity, 3 frame stack too deep
+  uint32_t cap_hist, cap_net;
+};
+#define ZKB_FLAT_MAX_DEPTH 256
+
+__global__ void __launch_bounds__(128) zkb_flatten_kernel(const DevBatch B, const FlatOut F) {
+  __shared__ uint32_t s_marks[4][ZKB_FLAT_MAX_DEPTH][2];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
+    const VmHot* hot = B.hot + vm;
+    const uint32_t n_rows = hot->x[X_COUNT0 + ZKB_STREAM_ROWS], n_frames = hot->x[X_COUNT0 + ZKB_STREAM_FRAME];
+    const bool ended = hot->x[X_STATUS] == ZKB_VM_ENDED || (hot->x[X_STATUS] == ZKB_VM_RUNNING && hot->live[L_DEPTH - 40] == 0 && hot->x[X_CYCLE] > 0);
+    uint32_t* cnt = F.counts + (size_t)vm * 4;
+    if (!ended) {
+      if (lane < 4) cnt[lane] = 0;
+      if (lane == 0) F.status[vm] = 1;
+      continue;
+    }
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
+    const uint32_t* logs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
+    const uint32_t* frames = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_FRAME] + (size_t)vm * B.cap[ZKB_STREAM_FRAME] * ZKB_FRAME_BYTES);
+    uint32_t* hist[2] = {F.hist[0] + (size_t)vm * F.cap_hist * 32, F.hist[1] + (size_t)vm * F.cap_hist * 32};
+    uint32_t* rb[2] = {F.rb[0] + (size_t)vm * F.cap_net, F.rb[1] + (size_t)vm * F.cap_net};
+    uint32_t n_hist[2] = {0, 0}, n_rb[2] = {0, 0};
+    uint32_t sp = 0, il = 0, ifr = 0, st = 0;
+    // frames recorded inside cycles; one more record = the bootloader push (helpers.rs:289-316), which opens frame 0
+    uint32_t in_rows = 0;
+    for (uint32_t base = 0; base < n_rows; base += 32) {
+      uint32_t w = base + lane < n_rows ? rows[(size_t)(base + lane) * 64 + 43] : 0u;
+      in_rows += (w >> 26) & 3u;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) in_rows += __shfl_xor_sync(0xffffffffu, in_rows, o);
+    if (n_frames == in_rows + 1) {
+      if (lane == 0) s_marks[warp][0][0] = s_marks[warp][0][1] = 0;
+      sp = 1;
+      ifr = 1;
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < n_rows && st == 0; base += 32) {
+      const uint32_t w = base + lane < n_rows ? rows[(size_t)(base + lane) * 64 + 43] : 0u;
+      const uint32_t nl = (w >> 16) & 0xFFu, nf = (w >> 26) & 3u;
+      uint32_t busy = __ballot_sync(0xffffffffu, (nl | nf) != 0);
+      while (busy && st == 0) {
+        const int r = __ffs(busy) - 1;
+        busy &= busy - 1;
+        const uint32_t nl_r = __shfl_sync(0xffffffffu, nl, r), nf_r = __shfl_sync(0xffffffffu, nf, r);
+        for (uint32_t j = 0; j < nl_r; j++, il++) {  // log queries of the cycle, in emission order
+          uint32_t word = logs[(size_t)il * 32 + lane];
+          const uint32_t aux = (__shfl_sync(0xffffffffu, word, 1) >> 16) & 0xFFu;
+          const uint32_t rw = __shfl_sync(0xffffffffu, word, 7) & 0xFFu;
+          if (aux == ZK_PRECOMPILE_AUX_BYTE) continue;  // precompile calls touch neither backend's log
+          const int k = aux == ZK_STORAGE_AUX_BYTE ? 0 : 1;
+          if (k == 0 && !rw && lane >= 24) word = 0u;   // the storage's own record of a read keeps written_value = 0 (storage.rs:134-135)
+          if (n_hist[k] >= F.cap_hist || (rw && n_rb[k] >= F.cap_net)) {
+            st = 2;
+            break;
+          }
+          hist[k][(size_t)n_hist[k] * 32 + lane] = word;
+          if (rw) {
+            if (lane == 0) rb[k][n_rb[k]] = n_hist[k];
+            n_rb[k]++;
+          }
+          n_hist[k]++;
+        }
+        for (uint32_t j = 0; j < nf_r && st == 0; j++, ifr++) {  // then the frame start / finish of the cycle
+          const uint32_t head = frames[(size_t)ifr * 32];
+          if ((head & 0xFFu) == ZKB_FRAMEKIND_START) {
+            if (sp >= ZKB_FLAT_MAX_DEPTH) {
+              st = 3;
+              break;
+            }
+            if (lane == 0) {
+              s_marks[warp][sp][0] = n_rb[0];
+              s_marks[warp][sp][1] = n_rb[1];
+            }
+            sp++;
+            __syncwarp();
+          } else {
+            const bool panicked = ((head >> 8) & 0xFFu) != 0;
+            if (sp == 0) {
+              st = 3;
+              break;
+            }
+            sp--;
+            __syncwarp();
+            if (panicked) {
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+                const uint32_t mark = s_marks[warp][sp][k];
+                __syncwarp();
+                while (n_rb[k] > mark && st == 0) {  // rollbacks.into_iter().rev() appended to the forward log
+                  n_rb[k]--;
+                  const uint32_t idx = rb[k][n_rb[k]];
+                  uint32_t word = hist[k][(size_t)idx * 32 + lane];
+                  if (lane == 7) word |= 1u << 8;  // LogQuery.rollback = true
+                  if (n_hist[k] >= F.cap_hist) {
+                    st = 2;
+                    break;
+                  }
+                  hist[k][(size_t)n_hist[k] * 32 + lane] = word;
+                  n_hist[k]++;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // net events / L1 messages = the events never rolled back, already in timestamp order (event_sink.rs:82-131)
+    uint32_t n_net[2] = {0, 0};
+    if (st == 0) {
+      __syncwarp();
+      for (uint32_t i = 0; i < n_rb[1]; i++) {
+        const uint32_t word = hist[1][(size_t)rb[1][i] * 32 + lane];
+        const int k = ((__shfl_sync(0xffffffffu, word, 1) >> 16) & 0xFFu) == ZK_EVENT_AUX_BYTE ? 0 : 1;
+        F.net[k][((size_t)vm * F.cap_net + n_net[k]) * 32 + lane] = word;
+        n_net[k]++;
+      }
+    }
+    if (lane == 0) {
+      cnt[0] = st ? 0 : n_hist[0];
+      cnt[1] = st ? 0 : n_hist[1];
+      cnt[2] = n_net[0];
+      cnt[3] = n_net[1];
+      F.status[vm] = st;
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -200,6 +344,9 @@ struct ZkbBatch {
     void* saved;
     size_t bytes;
   };
+  FlatOut flat{};
+  bool flat_allocated = false, flat_valid = false;
+  std::vector<uint32_t> h_flat_counts, h_flat_status;
   std::vector<Region> snap;
   std::vector<uint32_t> snap_counts;
   bool has_snapshot = false;
@@ -693,6 +840,7 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   b->hot_stale = true;
   b->launched = true;
   b->offsets_valid = false;
+  b->flat_valid = false;
   return ZKB_OK;
 }
 
@@ -914,6 +1062,67 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
   int32_t rc = zkb_fetch_stream_packed_async(b, kind, host_dst, host_capacity, offsets_out, nullptr);
   if (rc != ZKB_OK) return rc;
   CUDA_OK(cudaStreamSynchronize(nullptr));
+  return ZKB_OK;
+}
+
+int32_t zkb_flatten_logs(ZkbBatch* b, void* cuda_stream) {
+  if (!b || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = upload(b);
+  if (rc != ZKB_OK) return rc;
+  if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  size_t n = b->cfg.n_vms;
+  if (!b->flat_allocated) {
+    FlatOut& f = b->flat;
+    f.cap_net = std::max(1u, b->cfg.cap_records[ZKB_STREAM_LOG]);
+    f.cap_hist = 2 * f.cap_net;  // every write / event can be followed by at most one rollback query
+    cudaError_t e = cudaSuccess;
+#define ALLOC(ptr, count) if (e == cudaSuccess) e = dalloc(b, &(ptr), (count), false);
+    ALLOC(f.hist[0], n * f.cap_hist * 32);
+    ALLOC(f.hist[1], n * f.cap_hist * 32);
+    ALLOC(f.net[0], n * f.cap_net * 32);
+    ALLOC(f.net[1], n * f.cap_net * 32);
+    ALLOC(f.rb[0], n * f.cap_net);
+    ALLOC(f.rb[1], n * f.cap_net);
+    ALLOC(f.counts, n * 4);
+    ALLOC(f.status, n);
+#undef ALLOC
+    if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("flatten cudaMalloc: ") + cudaGetErrorString(e));
+    b->flat_allocated = true;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int grid = std::max(1, std::min<int>((int)((n + 3) / 4), 148 * 16));
+  zkb_flatten_kernel<<<grid, 128, 0, st>>>(b->d, b->flat);
+  CUDA_OK(cudaGetLastError());
+  b->h_flat_counts.resize(n * 4);
+  b->h_flat_status.resize(n);
+  CUDA_OK(cudaMemcpyAsync(b->h_flat_counts.data(), b->flat.counts, n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(b->h_flat_status.data(), b->flat.status, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  b->flat_valid = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_flat_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out) {
+  if (!range_ok(b, vm_lo, vm_hi) || kind >= 4 || !b->flat_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_flat_counts: call zkb_flatten_logs first");
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    if (counts_out) counts_out[v - vm_lo] = b->h_flat_counts[(size_t)v * 4 + kind];
+    if (status_out) status_out[v - vm_lo] = b->h_flat_status[v];
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_read_flat(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
+  if (!b || vm >= b->cfg.n_vms || kind >= 4 || !b->flat_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_read_flat: call zkb_flatten_logs first");
+  uint64_t n = (uint64_t)b->h_flat_counts[(size_t)vm * 4 + kind] * ZKB_LOG_BYTES;
+  if (n_bytes) *n_bytes = n;
+  uint64_t take = std::min(n, max_bytes);
+  if (dst && take) {
+    CUDA_OK(cudaSetDevice(b->cfg.device));
+    const FlatOut& f = b->flat;
+    const uint32_t* src = kind < 2 ? f.hist[kind] + (size_t)vm * f.cap_hist * 32 : f.net[kind - 2] + (size_t)vm * f.cap_net * 32;
+    CUDA_OK(cudaMemcpy(dst, src, take, cudaMemcpyDeviceToHost));
+  }
   return ZKB_OK;
 }
 

@@ -450,7 +450,7 @@ class KeccakHeavy(Workload):
         cfg.cap_records[5] = 8
         cfg.stack_words = 8
         cfg.heap_bytes = ((self.preimage_bytes + 31 + 96 + 31) // 32 + 1) * 32
-        cfg.n_heap_slabs = 6
+        cfg.n_heap_slabs = min(32, self.n_calls + 4)      # every returned digest page stays reachable until the end (memory.rs:702-712)
         cfg.max_far_depth = 3
         cfg.max_depth = 4
         cfg.storage_slots = 32

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-: > gpurun_out/n2_modes.jsonl
-for mode in "--concat-mode simple" "--concat-mode overlap" "--concat-mode overlap --reserve-sms 8" "--concat-mode simple --reserve-sms 8" "--concat-mode overlap --reserve-sms 16"; do
-  echo "{\"mode\": \"$mode\"}" >> gpurun_out/n2_modes.jsonl
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --no-e2e $mode 2>> gpurun_out/n2_modes.err | grep '^{' >> gpurun_out/n2_modes.jsonl
-done
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/pytest_gpu_a.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_a.log
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_a.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_a.log
+timeout 900 python bench.py > gpurun_out/bench_r01_final.json 2> gpurun_out/bench_r01_final.err
+timeout 600 python bench.py --workload keccak --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_keccak.json 2> gpurun_out/bench_keccak.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01_final.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_under_ncu.json 2>gpurun_out/ncu1.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:zkb_run_kernel -s 3 -c 1 -f -o gpurun_out/prof_r01_final python bench.py --vms 16384 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu2.json 2>gpurun_out/ncu2.err

@@ -208,6 +208,19 @@ int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8
 /* read back memory of the current frame's heap (debug / tests; = dump_page_content, memory.rs:300-313) */
 int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n_bytes, uint8_t* out);
 
+/* ---- post-processing (the step right after the path) ---------------------------------- */
+/* Rebuilds on the device, per VM, what the reference's backends hold after the run:
+ *   ZKB_FLAT_STORAGE_HISTORY  InMemoryStorage::flatten_and_net_history().0   (src/testing/storage.rs:34-76)
+ *   ZKB_FLAT_EVENT_HISTORY    InMemoryEventSink::flatten().0                 (src/reference_impls/event_sink.rs:66-131)
+ *   ZKB_FLAT_NET_EVENTS / ZKB_FLAT_NET_L1_MESSAGES   .1 / .2 of the same (as the LogQuery each EventMessage projects)
+ * i.e. the chronological query logs including the rollback queries finish_frame(panicked) appends in reverse
+ * (storage.rs:156-180), and the never-rolled-back events in timestamp order. Records are ZkbLogQueryRec.
+ * Only ended VMs are flattened (the reference asserts frames_stack.len() == 1); others report status 1. */
+enum ZkbFlatKind { ZKB_FLAT_STORAGE_HISTORY = 0, ZKB_FLAT_EVENT_HISTORY = 1, ZKB_FLAT_NET_EVENTS = 2, ZKB_FLAT_NET_L1_MESSAGES = 3 };
+int32_t zkb_flatten_logs(ZkbBatch* b, void* cuda_stream);
+int32_t zkb_flat_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out);
+int32_t zkb_read_flat(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
+
 /* ---- checkpoint / accounting ---------------------------------------------------------------------- */
 /* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a
  * device-side copy of every mutable per-VM array, restore puts it back (asynchronously on `cuda_stream`). */

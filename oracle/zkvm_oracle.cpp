@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -2211,6 +2212,82 @@ int32_t orc_read_stream(OrcBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
   uint64_t n = std::min<uint64_t>(max_bytes, s.size());
   if (dst && n) memcpy(dst, s.data(), n);
   if (n_bytes) *n_bytes = s.size();
+  return ZKB_OK;
+}
+
+// ---- flattened backend histories (the reference's own post-processing, restated) --------------------------------
+static ZkbLogQueryRec to_rec(const LogQuery& q) {
+  ZkbLogQueryRec r;
+  memset(&r, 0, sizeof(r));
+  r.timestamp = q.timestamp;
+  r.tx_number_in_block = q.tx_number_in_block;
+  r.aux_byte = q.aux_byte;
+  r.shard_id = q.shard_id;
+  memcpy(r.address, q.address.b, 20);
+  r.rw_flag = q.rw_flag;
+  r.rollback = q.rollback;
+  r.is_service = q.is_service;
+  q.key.to_limbs32(r.key);
+  q.read_value.to_limbs32(r.read_value);
+  q.written_value.to_limbs32(r.written_value);
+  return r;
+}
+
+// kind 0: InMemoryStorage::flatten_and_net_history().0 (storage.rs:34-76); kind 1: InMemoryEventSink::flatten().0;
+// kinds 2 / 3: the net events / L1 messages of flatten() (event_sink.rs:66-131: insert on forward, remove on rollback,
+// sort by timestamp), as the LogQuery each EventMessage is projected from.  false = the VM has not ended
+// (the reference asserts frames_stack.len() == 1).
+static bool flat_of(const VmState& vm, uint32_t kind, std::vector<ZkbLogQueryRec>* out) {
+  out->clear();
+  if (vm.storage.frames_stack.size() != 1 || vm.event_sink.frames_stack.size() != 1) return false;
+  if (kind == 0) {
+    for (const LogQuery& q : vm.storage.frames_stack[0].forward) out->push_back(to_rec(q));
+    return true;
+  }
+  const std::vector<LogQuery>& forward = vm.event_sink.frames_stack[0].forward;
+  if (kind == 1) {
+    for (const LogQuery& q : forward) out->push_back(to_rec(q));
+    return true;
+  }
+  std::map<uint32_t, LogQuery> tmp;
+  for (const LogQuery& q : forward) {
+    auto it = tmp.find(q.timestamp);
+    if (it != tmp.end()) {
+      REF_ASSERT(q.rollback, "event flatten: second query with the same timestamp must be a rollback (event_sink.rs:87)");
+      tmp.erase(it);
+    } else {
+      REF_ASSERT(!q.rollback, "event flatten: rollback without a forward query (event_sink.rs:90)");
+      tmp[q.timestamp] = q;
+    }
+  }
+  for (const auto& kv : tmp) {
+    bool is_event = kv.second.aux_byte == ZK_EVENT_AUX_BYTE;
+    if ((kind == 2) == is_event) out->push_back(to_rec(kv.second));
+  }
+  return true;
+}
+
+int32_t orc_flatten_logs(OrcBatch*, void*) { return ZKB_OK; }  // the backends already hold their histories
+
+int32_t orc_flat_counts(OrcBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out) {
+  if (vm_lo > vm_hi || vm_hi > b->cfg.n_vms || kind >= 4) return ZKB_ERR_INVALID_ARGUMENT;
+  std::vector<ZkbLogQueryRec> v;
+  for (uint32_t i = vm_lo; i < vm_hi; i++) {
+    bool ok = flat_of(*b->vms[i], kind, &v);
+    if (counts_out) counts_out[i - vm_lo] = (uint32_t)v.size();
+    if (status_out) status_out[i - vm_lo] = ok ? 0 : 1;
+  }
+  return ZKB_OK;
+}
+
+int32_t orc_read_flat(OrcBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
+  if (vm >= b->cfg.n_vms || kind >= 4) return ZKB_ERR_INVALID_ARGUMENT;
+  std::vector<ZkbLogQueryRec> v;
+  flat_of(*b->vms[vm], kind, &v);
+  uint64_t total = v.size() * sizeof(ZkbLogQueryRec);
+  uint64_t n = std::min<uint64_t>(max_bytes, total);
+  if (dst && n) memcpy(dst, v.data(), n);
+  if (n_bytes) *n_bytes = total;
   return ZKB_OK;
 }
 

@@ -363,3 +363,42 @@ def case_context_and_cycle_bookkeeping(B):
 
 
 ALL = [v for k, v in sorted(globals().items()) if k.startswith("case_")]
+
+
+def case_flattened_histories_after_a_panicking_near_call(B):
+    """The backends' own post-processing.  storage.rs:98-120 every write pushes a forward and a rollback
+    query; storage.rs:156-180 / event_sink.rs:166-170 finish_frame(panicked) appends the frame's forward log and then its
+    rollbacks IN REVERSE to the parent's forward log; event_sink.rs:82-131 net events = forward queries whose timestamp was
+    not cancelled by a rollback, in timestamp order."""
+    p = Program()
+    p.add(Imm(7), 0, 1)
+    p.add(Imm(99), 0, 2)
+    p.event(1, 2, first=True)                     # E0, in the bootloader frame: survives
+    p.near_call(0, "body", "handler")
+    p.label("after")
+    p.sload(1, 5)
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.jump("after")
+    p.label("body")
+    p.sstore(1, 2)                                # W1: 5 -> 99
+    p.event(1, 2)                                 # E1
+    p.add(Imm(100), 0, 2)
+    p.sstore(1, 2)                                # W2: 99 -> 100
+    p.to_l1(1, 2)                                 # M1
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 2, storage=[(0, H.BOOT_ADDRESS, 7, 5)], ergs=1 << 24)
+    b.flatten_logs()
+    for vm in range(2):
+        sh, eh = b.read_flat(vm, 0), b.read_flat(vm, 1)
+        got = [(int(q["rw_flag"]), int(q["rollback"]), H.val(q["read_value"]), H.val(q["written_value"])) for q in sh]
+        assert got == [(1, 0, 5, 99), (1, 0, 99, 100), (1, 1, 99, 100), (1, 1, 5, 99), (0, 0, 5, 0)]      # W1 W2 ~W2 ~W1 R
+        assert [(int(q["aux_byte"]), int(q["rollback"])) for q in eh] == [(1, 0), (1, 0), (2, 0), (2, 1), (1, 1)]   # E0 E1 M1 ~M1 ~E1
+        net_e, net_l1 = b.read_flat(vm, 2), b.read_flat(vm, 3)
+        assert len(net_e) == 1 and int(net_e[0]["is_service"]) == 1 and H.val(net_e[0]["written_value"]) == 99 and len(net_l1) == 0
+        assert int(sh[2]["timestamp"]) == int(sh[1]["timestamp"]) and int(eh[4]["timestamp"]) == int(eh[1]["timestamp"])
+    assert (b.flat_counts(0)[1] == 0).all()
+    b.close()
+
+
+ALL = [v for k, v in sorted(globals().items()) if k.startswith("case_")]

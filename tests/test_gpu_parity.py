@@ -153,3 +153,29 @@ def test_semantic_case_on_gpu(case):
     """the hand-derived quirk programs (expectations from the reference source) straight on the CUDA batch"""
     from era_zk_evm_b200 import GpuVmBatch
     case(GpuVmBatch)
+
+
+@pytest.mark.parametrize("name,kwargs,n", [
+    ("mixed", dict(n_programs=16, seed=0x51), 16 * 32),
+    ("storage", dict(), 64),
+    ("erc20", dict(n_transfers=3), 130),
+])
+def test_flattened_histories_match_the_oracle(name, kwargs, n, oracle_mod):
+    """zkb_flatten_logs (GPU) vs the oracle's InMemoryStorage / InMemoryEventSink forward logs and flatten()"""
+    w = workloads.WORKLOADS[name](**kwargs)
+    gpu, orc = _pair(w, list(range(n)), oracle_mod)
+    gpu.run()
+    orc.run_threads(0, 0)
+    gpu.flatten_logs()
+    orc.flatten_logs()
+    n_rollbacks = 0
+    for kind in range(4):
+        gc, gs = gpu.flat_counts(kind)
+        oc, os_ = orc.flat_counts(kind)
+        assert (gs == os_).all() and (gc == oc).all(), (kind, np.nonzero(gc != oc)[0][:5])
+        for vm in range(n):
+            a, b = gpu.read_flat(vm, kind), orc.read_flat(vm, kind)
+            assert a.tobytes() == b.tobytes(), (kind, vm)
+            n_rollbacks += int(a["rollback"].sum())
+    if name != "erc20":
+        assert n_rollbacks > 0
