@@ -1,5 +1,9 @@
-// Warp-cooperative keccak-f[1600]: lane i (0..24) holds state lane A[x + 5y] with i = x + 5y as one u64.
-// One round = 9 64-bit shuffles (theta 4+2, rho/pi 1, chi 2) + ~20 ALU ops; 24 rounds per permutation.
+// Octet-cooperative keccak-f[1600]: the 5 x 5 x 64 state of one VM lives in 5 of the 8 lanes of its octet -- octet lane
+// x (0..4) holds column x, a[y] = A[x][y] (five u64 = ten registers); lanes 5..7 carry zeros and only take part in the
+// octet's shuffles.  Per round: theta's column parity is lane-local (the column IS the lane), D needs two 64-bit
+// shuffles; rho + pi scatter the rotated lanes through a 25 x u64 shared-memory scratch of the VM, chi reads its three
+// inputs per output back from the same scratch (conflict-free), iota on lane 0.  ~90 warp instructions per round for
+// the four VMs of a warp.
 // Replaces the keccak256 round function of the external `DefaultPrecompilesProcessor`
 // (zk_evm_abstractions@v1.4.1, called from /root/reference/src/vm_state/helpers.rs:211-213; pinned by the live
 // tests at src/testing/tests/precompiles/keccak256.rs:144-196).
@@ -19,9 +23,9 @@ __constant__ uint64_t c_keccak_rc[24] = {
 // rho offsets r[x + 5y]
 __constant__ uint8_t c_keccak_rot[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
 
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-  uint32_t lo = __shfl_sync(ZK_FULL, (uint32_t)v, src);
-  uint32_t hi = __shfl_sync(ZK_FULL, (uint32_t)(v >> 32), src);
+__device__ __forceinline__ uint64_t oshfl64(uint64_t v, int src) {
+  uint32_t lo = oshfl((uint32_t)v, src);
+  uint32_t hi = oshfl((uint32_t)(v >> 32), src);
   return ((uint64_t)hi << 32) | lo;
 }
 
@@ -30,51 +34,63 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, uint32_t n) {
   return n ? (x << n) | (x >> (64u - n)) : x;
 }
 
+struct KeccakState {
+  uint64_t a[5];  // column `octet lane` of the state (zeros in lanes 5..7)
+};
+
 struct KeccakLanes {
-  int c5, c10, c15, c20;  // same column, other rows
-  int xm1, xp1, xp2;      // same row, x-1 / x+1 / x+2
-  int pi_src;             // lane whose value lands here after rho+pi
-  uint32_t pi_rot;        // rotation applied to that value
+  int xm1, xp1, xp2;  // octet lanes holding columns x-1 / x+1 / x+2 (own lane for lanes 5..7)
+  uint32_t rot;       // rho offsets of this column, 6 bits per y
+  uint32_t dst;       // scratch slot X + 5Y of pi's destination B[X = y][Y = 2x + 3y], 5 bits per y (31 = idle lane: slot 25+)
 };
 
 __device__ __forceinline__ KeccakLanes keccak_lanes(uint32_t lane) {
   KeccakLanes k;
-  if (lane < 25) {
-    int x = lane % 5, y = lane / 5;
-    k.c5 = (lane + 5) % 25;
-    k.c10 = (lane + 10) % 25;
-    k.c15 = (lane + 15) % 25;
-    k.c20 = (lane + 20) % 25;
-    k.xm1 = y * 5 + (x + 4) % 5;
-    k.xp1 = y * 5 + (x + 1) % 5;
-    k.xp2 = y * 5 + (x + 2) % 5;
-    // B[y'][2x'+3y'] = rot(A[x'][y']): this lane is (X, Y) with X = y', Y = (2x' + 3y') % 5  =>  y' = X, x' = (Y - 3X) / 2 mod 5
-    int yp = x;
-    int xp = ((y - 3 * x) % 5 + 5) % 5;
-    xp = (xp * 3) % 5;  // multiply by 2^-1 = 3 (mod 5)
-    k.pi_src = xp + 5 * yp;
-    k.pi_rot = c_keccak_rot[k.pi_src];
+  if (lane < 5) {
+    int x = (int)lane;
+    k.xm1 = (x + 4) % 5;
+    k.xp1 = (x + 1) % 5;
+    k.xp2 = (x + 2) % 5;
+    k.rot = 0;
+    k.dst = 0;
+#pragma unroll
+    for (int y = 0; y < 5; y++) {
+      k.rot |= (uint32_t)c_keccak_rot[x + 5 * y] << (6 * y);
+      k.dst |= (uint32_t)(y + 5 * ((2 * x + 3 * y) % 5)) << (5 * y);
+    }
   } else {
-    k.c5 = k.c10 = k.c15 = k.c20 = k.xm1 = k.xp1 = k.xp2 = k.pi_src = (int)lane;
-    k.pi_rot = 0;
+    k.xm1 = k.xp1 = k.xp2 = (int)lane;
+    k.rot = 0;
+    k.dst = 0;
   }
   return k;
 }
 
-__device__ __forceinline__ uint64_t keccak_f1600(uint64_t a, const KeccakLanes& k, uint32_t lane) {
+// ks: the VM's 25 x u64 shared-memory scratch.  All 8 lanes of the octet must call.
+__device__ __forceinline__ void keccak_f1600(KeccakState& s, const KeccakLanes& k, uint64_t* ks, uint32_t lane) {
+  const bool col = lane < 5;
 #pragma unroll 1
   for (int round = 0; round < 24; round++) {
-    // column parity in three exchanges instead of four: rows {y, y+1}, then {y .. y+3}, then row y+4
-    uint64_t t2 = a ^ shfl64(a, k.c5);
-    t2 ^= shfl64(t2, k.c10);
-    uint64_t c = t2 ^ shfl64(a, k.c20);
-    uint64_t d = shfl64(c, k.xm1) ^ rotl64(shfl64(c, k.xp1), 1);
-    a ^= d;
-    uint64_t b = rotl64(shfl64(a, k.pi_src), k.pi_rot);
-    a = b ^ (~shfl64(b, k.xp1) & shfl64(b, k.xp2));
-    if (lane == 0) a ^= c_keccak_rc[round];
+    // theta
+    uint64_t c = s.a[0] ^ s.a[1] ^ s.a[2] ^ s.a[3] ^ s.a[4];
+    uint64_t d = oshfl64(c, k.xm1) ^ rotl64(oshfl64(c, k.xp1), 1);
+    // rho + pi: B[y][2x + 3y] = rotl(A[x][y] ^ D[x], r[x][y])
+    if (col) {
+#pragma unroll
+      for (int y = 0; y < 5; y++) ks[(k.dst >> (5 * y)) & 31u] = rotl64(s.a[y] ^ d, (k.rot >> (6 * y)) & 63u);
+    }
+    osync();
+    // chi: A'[X][Y] = B[X][Y] ^ (~B[X+1][Y] & B[X+2][Y])
+    if (col) {
+#pragma unroll
+      for (int y = 0; y < 5; y++) {
+        uint64_t b0 = ks[lane + 5 * y], b1 = ks[k.xp1 + 5 * y], b2 = ks[k.xp2 + 5 * y];
+        s.a[y] = b0 ^ (~b1 & b2);
+      }
+      if (lane == 0) s.a[0] ^= c_keccak_rc[round];  // iota
+    }
+    osync();
   }
-  return a;
 }
 
 }  // namespace zkb

@@ -2,9 +2,10 @@
 // zk_evm_abstractions@v1.4.1, selected by address 0x02 from /root/reference/src/vm_state/helpers.rs:211-213;
 // hash vectors: src/testing/tests/precompiles/sha256.rs:119-136).
 //
-// One warp = one VM: the 8 working variables are warp-uniform registers, the rolling 16-word message schedule
-// lives in the warp's shared-memory scratch (broadcast reads, lane 0 writes) so the precompile adds no registers
-// to the interpreter's hot loop.  64 rounds per 64-byte block, one block = two VM heap words.
+// One octet (8 lanes) = one VM: the 8 working variables are octet-uniform registers, the rolling 16-word message
+// schedule lives in the VM's shared-memory scratch (broadcast reads, octet lane 0 writes) so the precompile adds no
+// registers to the interpreter's hot loop; the four VMs of a warp run their compressions in the same issue slots.
+// 64 rounds per 64-byte block, one block = two VM heap words.
 #pragma once
 #include <stdint.h>
 #include "u256.cuh"
@@ -24,11 +25,11 @@ __constant__ uint32_t c_sha256_iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t n) { return __funnelshift_r(x, x, n); }
 
-// hw: shared-memory scratch of the warp; hw[0..7] = chaining value (updated in place), hw[8..23] = the 16 message
-// words of the block (big-endian), clobbered.  All 32 lanes must call.
+// hw: shared-memory scratch of the VM; hw[0..7] = chaining value (updated in place), hw[8..23] = the 16 message
+// words of the block (big-endian), clobbered.  All 8 lanes of the octet must call.
 __device__ __noinline__ void sha256_compress_smem(uint32_t* hw, uint32_t lane) {
   uint32_t* w = hw + 8;
-  __syncwarp();
+  osync();
   uint32_t a = hw[0], b = hw[1], c = hw[2], d = hw[3], e = hw[4], f = hw[5], g = hw[6], h = hw[7];
 #pragma unroll 1
   for (int t = 0; t < 64; t++) {
@@ -40,9 +41,9 @@ __device__ __noinline__ void sha256_compress_smem(uint32_t* hw, uint32_t lane) {
       uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
       uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
       wt = w16 + s0 + w7 + s1;
-      __syncwarp();
+      osync();
       if (lane == 0) w[t & 15] = wt;
-      __syncwarp();
+      osync();
     }
     uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
     uint32_t ch = (e & f) ^ (~e & g);
@@ -52,11 +53,11 @@ __device__ __noinline__ void sha256_compress_smem(uint32_t* hw, uint32_t lane) {
     uint32_t t2 = S0 + mj;
     h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
-  __syncwarp();
+  osync();
   if (lane == 0) {
     hw[0] += a; hw[1] += b; hw[2] += c; hw[3] += d; hw[4] += e; hw[5] += f; hw[6] += g; hw[7] += h;
   }
-  __syncwarp();
+  osync();
 }
 
 }  // namespace zkb

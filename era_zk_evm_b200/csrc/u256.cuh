@@ -1,9 +1,12 @@
-// Warp-cooperative 256-bit integer arithmetic for sm_100a.
+// Octet-cooperative 256-bit integer arithmetic for sm_100a.
 //
-// Representation: a U256 is ONE 32-bit register per lane; lane l (0..7) holds limb l (little-endian,
-// limb 0 = least significant 32 bits), lanes 8..31 hold 0.  All 32 lanes of the warp call every function
-// (one VM per warp, warp-uniform control flow).  Carries are resolved with two __ballot_sync votes and one
-// integer add (generate/propagate trick) instead of an 8-step ripple, so ADD/SUB cost ~10 warp instructions.
+// Representation: a U256 is ONE 32-bit register per lane of an OCTET = 8 consecutive lanes of a warp; octet lane l
+// (0..7) holds limb l (little-endian, limb 0 = least significant 32 bits).  A warp carries FOUR independent U256
+// contexts (four VMs, one per octet); every cross-lane primitive below names only the calling octet in its member mask
+// (the cooperative-groups tile<8> pattern), so the four octets may execute the same instruction together (converged:
+// one issue slot serves four VMs) or different code (diverged: each octet syncs only with itself).
+// Carries are resolved with two octet votes and one integer add (generate/propagate trick) instead of an 8-step ripple,
+// so ADD/SUB cost ~10 warp instructions for four VMs.
 //
 // Semantics replaced (reference, ethereum_types::U256 as used in /root/reference/src/opcodes/execution/):
 //   u_add  -> overflowing_add  add.rs:35        u_sub -> overflowing_sub  sub.rs:35
@@ -13,109 +16,124 @@
 #include <stdint.h>
 
 #define ZK_FULL 0xffffffffu
+#define ZK_OCT 8u             // lanes per VM
+#define ZK_VMS_PER_WARP 4u
 
 namespace zkb {
 
-typedef uint32_t u256l;  // the per-lane limb of a warp-distributed U256
+typedef uint32_t u256l;  // the per-lane limb of an octet-distributed U256
 
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-__device__ __forceinline__ uint32_t bcast(uint32_t v, int src) { return __shfl_sync(ZK_FULL, v, src); }
+__device__ __forceinline__ uint32_t oct_lane() { return threadIdx.x & 7u; }
+__device__ __forceinline__ uint32_t oct_shift() { return threadIdx.x & 24u; }
+__device__ __forceinline__ uint32_t oct_mask() { return 0xFFu << oct_shift(); }
+__device__ __forceinline__ uint32_t oct_index() { return (threadIdx.x >> 3) & 3u; }  // octet within the warp
+// value of octet lane `src` (taken modulo 8)
+__device__ __forceinline__ uint32_t oshfl(uint32_t v, int src) { return __shfl_sync(oct_mask(), v, src, 8); }
+__device__ __forceinline__ uint32_t oshfl_xor(uint32_t v, int m) { return __shfl_xor_sync(oct_mask(), v, m, 8); }
+// 8-bit vote of the octet (bit l = octet lane l)
+__device__ __forceinline__ uint32_t oballot(bool p) { return __ballot_sync(oct_mask(), p) >> oct_shift(); }
+__device__ __forceinline__ bool oall(bool p) { return __all_sync(oct_mask(), p); }
+__device__ __forceinline__ void osync() { __syncwarp(oct_mask()); }
 
-__device__ __forceinline__ bool u_is_zero(u256l v) { return (__ballot_sync(ZK_FULL, v != 0) & 0xFFu) == 0; }
-__device__ __forceinline__ bool u_eq(u256l a, u256l b) { return (__ballot_sync(ZK_FULL, a != b) & 0xFFu) == 0; }
+__device__ __forceinline__ bool u_is_zero(u256l v) { return oballot(v != 0) == 0; }
+__device__ __forceinline__ bool u_eq(u256l a, u256l b) { return oballot(a != b) == 0; }
 
-// carry-in vector from generate/propagate votes: bit i = carry into limb i, bit n = carry out
-__device__ __forceinline__ uint32_t carry_chain(uint32_t G, uint32_t P) {
-  uint32_t Gs = G << 1;
+// carry-in vector from generate/propagate votes: bit i = carry into limb i (bit 0 = cin), bit 8 = carry out
+__device__ __forceinline__ uint32_t carry_chain(uint32_t G, uint32_t P, uint32_t cin = 0u) {
+  uint32_t Gs = (G << 1) | cin;
   return Gs | ((P + Gs) ^ P ^ Gs);
 }
 
-// a + b over `nl` limbs (8 or 16); returns the sum limb, sets carry-out
-__device__ __forceinline__ u256l u_add_n(u256l a, u256l b, uint32_t lane, uint32_t nl, bool& carry_out) {
-  uint32_t mask = (1u << nl) - 1u;
+// a + b + cin over the octet's 8 limbs; returns the sum limb, sets carry-out
+__device__ __forceinline__ u256l u_addc(u256l a, u256l b, uint32_t lane, uint32_t cin, bool& carry_out) {
   uint32_t s = a + b;
-  uint32_t G = __ballot_sync(ZK_FULL, s < a) & mask;
-  uint32_t P = __ballot_sync(ZK_FULL, s == 0xFFFFFFFFu) & mask;
-  uint32_t K = carry_chain(G, P);
-  carry_out = (K >> nl) & 1u;
-  return lane < nl ? s + ((K >> lane) & 1u) : 0u;
+  uint32_t G = oballot(s < a);
+  uint32_t P = oballot(s == 0xFFFFFFFFu);
+  uint32_t K = carry_chain(G, P, cin);
+  carry_out = (K >> 8) & 1u;
+  return s + ((K >> lane) & 1u);
 }
 
-__device__ __forceinline__ u256l u_add(u256l a, u256l b, uint32_t lane, bool& of) { return u_add_n(a, b, lane, 8, of); }
+__device__ __forceinline__ u256l u_add(u256l a, u256l b, uint32_t lane, bool& of) { return u_addc(a, b, lane, 0u, of); }
 
 __device__ __forceinline__ u256l u_sub(u256l a, u256l b, uint32_t lane, bool& borrow_out) {
   uint32_t d = a - b;
-  uint32_t G = __ballot_sync(ZK_FULL, a < b) & 0xFFu;
-  uint32_t P = __ballot_sync(ZK_FULL, a == b) & 0xFFu;
+  uint32_t G = oballot(a < b);
+  uint32_t P = oballot(a == b);
   uint32_t K = carry_chain(G, P);
   borrow_out = (K >> 8) & 1u;
-  return lane < 8 ? d - ((K >> lane) & 1u) : 0u;
+  return d - ((K >> lane) & 1u);
 }
 
 // unsigned compare: -1, 0, +1 (the most significant differing limb decides)
 __device__ __forceinline__ int u_cmp(u256l a, u256l b) {
-  uint32_t gt = __ballot_sync(ZK_FULL, a > b) & 0xFFu;
-  uint32_t lt = __ballot_sync(ZK_FULL, a < b) & 0xFFu;
+  uint32_t gt = oballot(a > b);
+  uint32_t lt = oballot(a < b);
   return gt > lt ? 1 : (gt < lt ? -1 : 0);
 }
 
-// 256 x 256 -> 512: lane k (0..15) accumulates column k of the schoolbook product in 96 bits, then two
-// 16-limb carry-resolved additions fold the columns.  lo/hi come back in lanes 0..7.
+// 256 x 256 -> 512 schoolbook product on 8 lanes: octet lane l accumulates column l (products a_i b_j with
+// i + j = l, i <= l) and column l + 8 (i + j = l + 8, i > l) -- both use the same b limb (j = (l - i) mod 8), so one
+// pair of shuffles feeds both columns.  The 96-bit column sums are then folded with four carry-resolved 8-limb adds.
 __device__ __forceinline__ void u_mul(u256l a, u256l b, uint32_t lane, u256l& lo, u256l& hi) {
-  uint64_t acc = 0;
-  uint32_t acc_top = 0;
+  uint64_t accL = 0, accH = 0;
+  uint32_t topL = 0, topH = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    uint32_t ai = __shfl_sync(ZK_FULL, a, i);
-    int j = (int)lane - i;
-    uint32_t bj = __shfl_sync(ZK_FULL, b, j & 7);
-    bj = (j >= 0 && j < 8) ? bj : 0u;
+    uint32_t ai = oshfl(a, i);
+    uint32_t bj = oshfl(b, ((int)lane - i) & 7);
     uint64_t prod = (uint64_t)ai * (uint64_t)bj;
-    acc += prod;
-    acc_top += (acc < prod) ? 1u : 0u;
+    bool low = (uint32_t)i <= lane;
+    uint64_t pl = low ? prod : 0ull, ph = low ? 0ull : prod;
+    accL += pl;
+    topL += (accL < pl) ? 1u : 0u;
+    accH += ph;
+    topH += (accH < ph) ? 1u : 0u;
   }
-  uint32_t c0 = (uint32_t)acc, c1 = (uint32_t)(acc >> 32), c2 = acc_top;
-  uint32_t y = __shfl_up_sync(ZK_FULL, c1, 1);
-  y = lane >= 1 ? y : 0u;
-  uint32_t z = __shfl_up_sync(ZK_FULL, c2, 2);
-  z = lane >= 2 ? z : 0u;
-  bool dummy;
-  uint32_t r = u_add_n(lane < 16 ? c0 : 0u, lane < 16 ? y : 0u, lane, 16, dummy);
-  r = u_add_n(r, lane < 16 ? z : 0u, lane, 16, dummy);
-  uint32_t up = __shfl_down_sync(ZK_FULL, r, 8);
-  lo = lane < 8 ? r : 0u;
-  hi = lane < 8 ? up : 0u;
+  // column k contributes c0 at limb k, c1 at limb k + 1, c2 at limb k + 2
+  const uint32_t c0L = (uint32_t)accL, c1L = (uint32_t)(accL >> 32), c0H = (uint32_t)accH, c1H = (uint32_t)(accH >> 32);
+  const uint32_t t1L = oshfl(c1L, ((int)lane - 1) & 7), t1H = oshfl(c1H, ((int)lane - 1) & 7);
+  const uint32_t t2L = oshfl(topL, ((int)lane - 2) & 7), t2H = oshfl(topH, ((int)lane - 2) & 7);
+  const uint32_t yL = lane >= 1 ? t1L : 0u, yH = lane >= 1 ? t1H : t1L;
+  const uint32_t zL = lane >= 2 ? t2L : 0u, zH = lane >= 2 ? t2H : t2L;
+  bool c, dummy;
+  uint32_t rL = u_addc(c0L, yL, lane, 0u, c);
+  uint32_t rH = u_addc(c0H, yH, lane, c ? 1u : 0u, dummy);
+  rL = u_addc(rL, zL, lane, 0u, c);
+  rH = u_addc(rH, zH, lane, c ? 1u : 0u, dummy);
+  lo = rL;
+  hi = rH;
 }
 
 // logical shifts by n bits; n >= 256 yields 0 (ethereum_types semantics)
 __device__ __forceinline__ u256l u_shl(u256l v, uint32_t n, uint32_t lane) {
   uint32_t k = n >> 5, b = n & 31u;
   int s0 = (int)lane - (int)k, s1 = s0 - 1;
-  uint32_t x0 = __shfl_sync(ZK_FULL, v, s0 & 31);
-  uint32_t x1 = __shfl_sync(ZK_FULL, v, s1 & 31);
+  uint32_t x0 = oshfl(v, s0 & 7);
+  uint32_t x1 = oshfl(v, s1 & 7);
   x0 = (s0 >= 0 && s0 < 8) ? x0 : 0u;
   x1 = (s1 >= 0 && s1 < 8) ? x1 : 0u;
   uint32_t r = __funnelshift_l(x1, x0, b);
-  return (lane < 8 && n < 256) ? r : 0u;
+  return n < 256 ? r : 0u;
 }
 
 __device__ __forceinline__ u256l u_shr(u256l v, uint32_t n, uint32_t lane) {
   uint32_t k = n >> 5, b = n & 31u;
   uint32_t s0 = lane + k, s1 = s0 + 1;
-  uint32_t x0 = __shfl_sync(ZK_FULL, v, s0 & 31);
-  uint32_t x1 = __shfl_sync(ZK_FULL, v, s1 & 31);
+  uint32_t x0 = oshfl(v, s0 & 7);
+  uint32_t x1 = oshfl(v, s1 & 7);
   x0 = s0 < 8 ? x0 : 0u;
   x1 = s1 < 8 ? x1 : 0u;
   uint32_t r = __funnelshift_r(x0, x1, b);
-  return (lane < 8 && n < 256) ? r : 0u;
+  return n < 256 ? r : 0u;
 }
 
 // number of significant bits (0 for zero)
 __device__ __forceinline__ uint32_t u_bits(u256l v) {
-  uint32_t nz = __ballot_sync(ZK_FULL, v != 0) & 0xFFu;
+  uint32_t nz = oballot(v != 0);
   if (nz == 0) return 0;
   int top = 31 - __clz(nz);
-  uint32_t tv = __shfl_sync(ZK_FULL, v, top);
+  uint32_t tv = oshfl(v, top);
   return (uint32_t)top * 32u + (32u - (uint32_t)__clz(tv));
 }
 
@@ -131,17 +149,17 @@ __device__ __forceinline__ void u_divmod(u256l a, u256l b, uint32_t lane, u256l&
   u256l d = u_shl(b, sh, lane);  // aligned divisor (fits: bits(d) == na <= 256)
   u256l rem = a;
   for (int i = (int)sh; i >= 0; i--) {
-    uint32_t gt = __ballot_sync(ZK_FULL, rem > d) & 0xFFu;
-    uint32_t lt = __ballot_sync(ZK_FULL, rem < d) & 0xFFu;
-    if (gt >= lt) {  // rem >= d (warp-uniform branch)
+    uint32_t gt = oballot(rem > d);
+    uint32_t lt = oballot(rem < d);
+    if (gt >= lt) {  // rem >= d (octet-uniform branch)
       bool bo;
       rem = u_sub(rem, d, lane, bo);
       if (lane == (uint32_t)(i >> 5)) q |= 1u << (i & 31);
     }
     // d >>= 1
-    uint32_t up = __shfl_down_sync(ZK_FULL, d, 1);
+    uint32_t up = oshfl(d, (lane + 1) & 7);
     up = lane < 7 ? up : 0u;
-    d = lane < 8 ? __funnelshift_r(d, up, 1) : 0u;
+    d = __funnelshift_r(d, up, 1);
   }
   r = rem;
 }

@@ -1,17 +1,21 @@
-// The batched EraVM interpreter: ONE WARP = ONE VM for the whole run.
+// The batched EraVM interpreter: ONE OCTET (8 lanes, a quarter warp) = ONE VM for the whole run, FOUR VMs per warp.
+// A U256 has eight 32-bit limbs, so eight lanes are what one VM can keep busy; the four octets of a warp run four VMs of
+// the batch side by side -- converged (one issue slot per instruction for all four) while they follow the same path
+// through the interpreter, which batches of transactions against the same contracts do, and diverged (each octet
+// syncs only with itself, u256.cuh) where they do not.
 //
 // Replaces (reference, /root/reference/src): vm_state/cycle.rs:19-429 (read_and_decode + cycle),
 // vm_state/mem_ops.rs:14-125, vm_state/helpers.rs:10-338, every handler in opcodes/execution/*.rs and the
 // backends reference_impls/{memory,decommitter}.rs + testing/storage.rs, re-designed for sm_100a:
-//   * opcode dispatch is warp-uniform; the 32 lanes are used for limb-parallel U256 arithmetic (u256.cuh),
-//     the 25-lane keccak state (keccak.cuh) and coalesced record stores;
+//   * opcode dispatch is octet-uniform; the 8 lanes of a VM are used for limb-parallel U256 arithmetic (u256.cuh),
+//     the column-per-lane keccak state (keccak.cuh) and vectorised record stores;
 //   * architectural state lives in shared memory (15 x 256-bit registers, current frame, the "live" tail of
-//     the cycle row) and warp-uniform registers (pc, sp, ergs, flags, timestamp ...);
+//     the cycle row) and octet-uniform registers (pc, sp, ergs, flags, timestamp ...);
 //   * SimpleMemory's growable pages become bounded per-VM slabs in HBM (stack per far-call level, a pool of heap
 //     slabs with a free mask, a 16-entry page-indirection table), InMemoryStorage becomes a per-VM open-addressed
 //     table + one rollback journal whose frame marks give the reference's rollback semantics;
 //   * every VmWitnessTracer callback becomes a packed record (include/zkb_records.h) appended to the VM's stream
-//     slab: the 256-byte cycle row is one 8-byte store per lane, a LogQuery/Frame record one 4-byte store per lane.
+//     slab: the 256-byte cycle row is two 16-byte stores per lane (two full 128-byte lines per VM and cycle).
 #pragma once
 #include <stdint.h>
 
@@ -65,7 +69,7 @@ enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 
 #define ZK_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define ZKB_NO_SLAB 0xFFu
 #define ZKB_NO_CODE 0xFFFFFFFFu
-#define ZKB_PT_ENTRIES 32u   // one entry per lane
+#define ZKB_PT_ENTRIES 32u   // four entries per octet lane
 #define ZKB_DEC_ENTRIES 16u
 #define ZKB_PT_FREE 0xFFFFFFFFu
 enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
@@ -104,20 +108,25 @@ __device__ __forceinline__ uint32_t rec_bytes(int kind) {
          : kind == ZKB_STREAM_DECOMMIT ? ZKB_DECOMMIT_BYTES : kind == ZKB_STREAM_FRAME ? ZKB_FRAME_BYTES : ZKB_REFUND_BYTES;
 }
 
-// shared memory per warp
-struct __align__(16) WarpSmem {
+// shared memory per VM.  Size = 360 words = 8 (mod 32): the four VMs of a warp sit 8 banks apart, so one 4-byte access
+// per lane by all four octets (same field, same limb index) is bank-conflict free.
+struct __align__(16) VmSmem {
   uint32_t regs[16][8];
   uint32_t row[64];
   uint32_t F[32];
   uint32_t kbuf[64];
+  uint64_t ks[26];     // keccak-f[1600] scratch (25 lanes)
+  uint32_t pad[20];
 };
+static_assert(sizeof(VmSmem) == 1440 && (sizeof(VmSmem) / 4) % 32 == 8, "VmSmem bank skew");
+typedef VmSmem WarpSmem;
 
 struct Vm {
   const DevBatch& B;
   WarpSmem& S;
   const uint32_t vm;
-  const uint32_t lane;
-  // warp-uniform registers
+  const uint32_t lane;  // lane within the VM's octet (0..7)
+  // octet-uniform registers
   uint32_t pc, sp, ergs, flags, timestamp, cycle, pending, ptr_mask, status;
   uint32_t prev_code_page, far_depth, journal_len, n_decommit, slab_free;
   uint32_t count[ZKB_N_STREAMS];
@@ -127,7 +136,7 @@ struct Vm {
   const uint32_t* code;
   uint32_t code_len;
   u256l prev_word;  // distributed
-  // decoded opcode (warp-uniform)
+  // decoded opcode (octet-uniform)
   uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
   uint32_t dst_loc_valid, dst_loc_index;
   // per-VM global bases
@@ -158,27 +167,27 @@ struct Vm {
   __device__ __forceinline__ uint32_t L(int w) const { return S.row[w]; }
   __device__ __forceinline__ void setL(int w, uint32_t v) {
     if (lane == 0) S.row[w] = v;
-    __syncwarp();
+    osync();
   }
   __device__ __forceinline__ bool is_kernel() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_KERNEL; }
   __device__ __forceinline__ bool is_static() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_STATIC; }
   __device__ __forceinline__ bool is_local() const { return (S.row[L_EH_BITS] >> 16) & ZKB_FRAMEBIT_LOCAL; }
-  __device__ __forceinline__ u256l reg_read(uint32_t idx) const { return lane < 8 ? S.regs[idx][lane] : 0u; }
+  __device__ __forceinline__ u256l reg_read(uint32_t idx) const { return S.regs[idx][lane]; }
   __device__ __forceinline__ void reg_write(uint32_t idx, u256l v, bool is_ptr) {
     // limb l is written and read back by lane l only; the one cross-lane reader (limb 0 in operand addressing of a LATER
-    // cycle) sits behind the warp sync of the row emission, so no sync is needed here
+    // cycle) sits behind the octet sync of the row emission, so no sync is needed here
     if (idx != 0) {
-      if (lane < 8) S.regs[idx][lane] = v;
+      S.regs[idx][lane] = v;
       ptr_mask = (ptr_mask & ~(1u << idx)) | ((is_ptr ? 1u : 0u) << idx);
     }
   }
   // address (5 LE-loaded words holding 20 BE bytes, in lanes 0..4) <-> U256 (address_to_u256, utils.rs:29-41)
   __device__ __forceinline__ u256l addr_words_to_u256(uint32_t aw) const {
-    uint32_t v = __shfl_sync(ZK_FULL, aw, (4 - (int)lane) & 31);
+    uint32_t v = oshfl(aw, (4 - (int)lane) & 7);
     return lane < 5 ? bswap32(v) : 0u;
   }
   __device__ __forceinline__ uint32_t u256_to_addr_words(u256l v) const {
-    uint32_t x = __shfl_sync(ZK_FULL, v, (4 - (int)lane) & 31);
+    uint32_t x = oshfl(v, (4 - (int)lane) & 7);
     return lane < 5 ? bswap32(x) : 0u;
   }
 
@@ -209,7 +218,7 @@ struct Vm {
     if (!B.witness) return;
     uint32_t* p = reinterpret_cast<uint32_t*>(mem_base + (size_t)n * ZKB_MEM_BYTES);
     if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, index, mtype | rw << 8 | is_ptr << 16 | origin << 24);
-    if (lane < 8) p[4 + lane] = value;
+    p[4 + lane] = value;
   }
 
   // witness_tracer.add_log_query (helpers.rs:151,161,208); aw = address words in lanes 0..4
@@ -224,11 +233,9 @@ struct Vm {
         p[7] = rw | is_service << 16;
       }
       if (lane < 5) p[2 + lane] = aw;
-      if (lane < 8) {
-        p[8 + lane] = key;
-        p[16 + lane] = read_value;
-        p[24 + lane] = written_value;
-      }
+      p[8 + lane] = key;
+      p[16 + lane] = read_value;
+      p[24 + lane] = written_value;
     }
   }
 
@@ -238,7 +245,7 @@ struct Vm {
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_DECOMMIT);
     if (p) {
       if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, (len & 0xFFFFu) | fresh << 16, 0u);
-      if (lane < 8) p[4 + lane] = hash;
+      p[4 + lane] = hash;
     }
   }
 
@@ -255,16 +262,26 @@ struct Vm {
     ccount += 1u << 26;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
     if (p) {
-      uint32_t w = lane == 0 ? (ZKB_FRAMEKIND_START | bound_kind << 16) : lane == 1 ? cycle : lane < 29 ? S.F[(lane - 2) & 31]
-                   : lane == 29 ? prev_ergs : lane == 30 ? (prev_pc | prev_sp << 16) : bound_value;
-      p[lane] = w;
+#pragma unroll
+      for (uint32_t q = 0; q < 4; q++) {
+        const uint32_t i = lane + 8u * q;
+        uint32_t w = i == 0 ? (ZKB_FRAMEKIND_START | bound_kind << 16) : i == 1 ? cycle : i < 29 ? S.F[(i - 2) & 31]
+                     : i == 29 ? prev_ergs : i == 30 ? (prev_pc | prev_sp << 16) : bound_value;
+        p[i] = w;
+      }
     }
   }
   // finish_execution_context (helpers.rs:258-259)
   __device__ __forceinline__ void emit_frame_finish(bool panicked) {
     ccount += 1u << 26;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_FRAME);
-    if (p) p[lane] = lane == 0 ? (ZKB_FRAMEKIND_FINISH | (panicked ? 1u : 0u) << 8) : lane == 1 ? cycle : 0u;
+    if (p) {
+      const uint32_t head = lane == 0 ? (ZKB_FRAMEKIND_FINISH | (panicked ? 1u : 0u) << 8) : lane == 1 ? cycle : 0u;
+      p[lane] = head;
+      p[8 + lane] = 0u;
+      p[16 + lane] = 0u;
+      p[24 + lane] = 0u;
+    }
   }
 
   // ---- stack page of the current far level (SimpleMemory stack_pages, memory.rs:412-437) ----------
@@ -273,7 +290,7 @@ struct Vm {
     if (index >= B.stack_words) return 0u;  // never written (writes beyond the cap stop the VM) => still zero
     size_t off = (size_t)far_depth * B.stack_words + index;
     is_ptr = g_stack_ptr[off];
-    return lane < 8 ? g_stack[off * 8 + lane] : 0u;
+    return g_stack[off * 8 + lane];
   }
   __device__ __forceinline__ void stack_write(uint32_t index, u256l v, uint32_t is_ptr) {
     if (index >= B.stack_words) {
@@ -281,11 +298,11 @@ struct Vm {
       return;
     }
     size_t off = (size_t)far_depth * B.stack_words + index;
-    if (lane < 8) g_stack[off * 8 + lane] = v;
-    if (lane == 8) g_stack_ptr[off] = (uint8_t)is_ptr;
+    g_stack[off * 8 + lane] = v;
+    if (lane == 1) g_stack_ptr[off] = (uint8_t)is_ptr;
     uint32_t hwm = g_lvl[far_depth * 4 + 2];
     if (index + 1 > hwm && lane == 0) g_lvl[far_depth * 4 + 2] = index + 1;
-    __syncwarp();
+    osync();
   }
 
   // ---- heap slabs (SimpleMemory heaps / pages_with_extended_lifetime, memory.rs:439-521) ----------
@@ -302,19 +319,20 @@ struct Vm {
     if (s == ZKB_NO_SLAB) return;
     uint32_t hwm = g_slab_hwm[s];
     uint32_t* base = g_heap + (size_t)s * B.heap_words * 8;
-    for (uint32_t i = lane; i < hwm * 8; i += 32) base[i] = 0u;  // == heap_on_return fill (memory.rs:181-183)
+    uint4* base4 = reinterpret_cast<uint4*>(base);
+    for (uint32_t i = lane; i < hwm * 2; i += 8) base4[i] = make_uint4(0u, 0u, 0u, 0u);  // == heap_on_return fill (memory.rs:181-183)
     if (lane == 0) g_slab_hwm[s] = 0;
     slab_free |= 1u << s;
-    __syncwarp();
+    osync();
   }
   __device__ __forceinline__ u256l slab_read(uint32_t s, uint32_t word) {
     if (s == ZKB_NO_SLAB || word >= B.heap_words) return 0u;
-    return lane < 8 ? g_heap[((size_t)s * B.heap_words + word) * 8 + lane] : 0u;
+    return g_heap[((size_t)s * B.heap_words + word) * 8 + lane];
   }
   __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
-    if (lane < 8) g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
+    g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
     if (word + 1 > g_slab_hwm[s] && lane == 0) g_slab_hwm[s] = word + 1;
-    __syncwarp();
+    osync();
   }
   // slab of the current frame's heap (which = 0) / aux heap (which = 1); allocate lazily on first write
   __device__ __forceinline__ uint32_t cur_slab(uint32_t which, bool for_write, uint32_t word) {
@@ -327,7 +345,7 @@ struct Vm {
       if (s == ZKB_NO_SLAB) {
         s = slab_alloc();
         if (lane == 0) g_lvl[far_depth * 4 + which] = s;
-        __syncwarp();
+        osync();
       }
     }
     return s;
@@ -335,9 +353,13 @@ struct Vm {
 
   // ---- page indirections (SimpleMemory.page_numbers_indirections, memory.rs:160-171,475-521) ------
   __device__ __forceinline__ int pt_find(uint32_t page) {
-    bool hit = lane < ZKB_PT_ENTRIES && g_pt[lane * 2] == page;  // lanes beyond the table never match (not even "free")
-    uint32_t m = __ballot_sync(ZK_FULL, hit);
-    return m ? __ffs(m) - 1 : -1;
+    // octet lane l looks at entries 4l .. 4l+3 (two 16-byte loads)
+    const uint4 a = reinterpret_cast<const uint4*>(g_pt)[lane * 2], b = reinterpret_cast<const uint4*>(g_pt)[lane * 2 + 1];
+    const uint32_t h = (a.x == page ? 1u : 0u) | (a.z == page ? 2u : 0u) | (b.x == page ? 4u : 0u) | (b.z == page ? 8u : 0u);
+    const uint32_t m = oballot(h != 0);
+    if (!m) return -1;
+    const int l = __ffs(m) - 1;
+    return l * 4 + (__ffs(oshfl(h, l)) - 1);
   }
   __device__ __forceinline__ void pt_upsert(uint32_t page, uint32_t kind, uint32_t slab_or_level, uint32_t cleanup_level) {
     int e = pt_find(page);
@@ -350,7 +372,7 @@ struct Vm {
       g_pt[e * 2] = page;
       g_pt[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
     }
-    __syncwarp();
+    osync();
   }
   // fat-pointer read of one word (memory.rs:475-521); ok = false => reference panic (unreachable page)
   __device__ __forceinline__ u256l fatptr_read(uint32_t page, uint32_t word, bool& ok) {
@@ -374,31 +396,32 @@ struct Vm {
     uint32_t* keys = B.st_keys + (size_t)vm * B.storage_slots * 8;
     uint32_t* addrs = B.st_addr + (size_t)vm * B.storage_slots * 8;
     uint32_t* vals = B.st_vals + (size_t)vm * B.storage_slots * 8;
-    // lanes 0..7 carry the key, lanes 8..12 the address, lane 13 the shard
-    uint32_t a_sh = __shfl_sync(ZK_FULL, aw, (lane - 8) & 31);
-    uint32_t ident = lane < 8 ? key : lane < 13 ? a_sh : lane == 13 ? shard : 0u;
-    uint32_t h = (ident + 0x9E3779B9u * (lane + 1u)) * 0x85EBCA6Bu;
+    // identity of a slot: key limb l in lane l, address word l in lanes 0..4, shard in lane 5
+    const uint32_t extra = lane < 5 ? aw : lane == 5 ? shard : 0u;
+    uint32_t h = (key + 0x9E3779B9u * (lane + 1u)) * 0x85EBCA6Bu;
     h ^= h >> 15;
-    h *= 0xC2B2AE35u;
+    h = (h ^ extra) * 0xC2B2AE35u;
+    h ^= h >> 13;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) h += __shfl_xor_sync(ZK_FULL, h, o) * 0x27D4EB2Fu + (h >> 13);
-    h = __shfl_sync(ZK_FULL, h, 0);
+    for (int o = 4; o >= 1; o >>= 1) h += oshfl_xor(h, o) * 0x27D4EB2Fu + (h >> 13);
+    h = oshfl(h, 0);
     uint32_t tag = h | 0x80000000u;
     uint32_t mask = B.storage_slots - 1;
     int found = -1, insert_at = -1;
-    for (uint32_t base = 0; base < B.storage_slots && found < 0 && insert_at < 0; base += 32) {
+    for (uint32_t base = 0; base < B.storage_slots && found < 0 && insert_at < 0; base += ZK_OCT) {
       uint32_t idx = (h + base + lane) & mask;
       uint32_t t = tags[idx];
-      uint32_t m_match = __ballot_sync(ZK_FULL, t == tag);
-      uint32_t m_empty = __ballot_sync(ZK_FULL, t == 0u);
+      uint32_t m_match = oballot(t == tag);
+      uint32_t m_empty = oballot(t == 0u);
       uint32_t before_empty = m_empty ? ((1u << (__ffs(m_empty) - 1)) - 1u) : 0xFFFFFFFFu;
       m_match &= before_empty;
       while (m_match) {
         int c = __ffs(m_match) - 1;
         m_match &= m_match - 1;
         uint32_t ci = (h + base + c) & mask;
-        uint32_t stored = lane < 8 ? keys[ci * 8 + lane] : lane < 14 ? addrs[ci * 8 + lane - 8] : 0u;
-        if (__all_sync(ZK_FULL, stored == ident)) {
+        bool same = keys[ci * 8 + lane] == key;
+        if (lane < 6) same = same && addrs[ci * 8 + lane] == extra;
+        if (oall(same)) {
           found = (int)ci;
           break;
         }
@@ -406,7 +429,7 @@ struct Vm {
       if (found < 0 && m_empty) insert_at = (int)((h + base + __ffs(m_empty) - 1) & mask);
     }
     u256l old = 0u;
-    if (found >= 0) old = lane < 8 ? vals[found * 8 + lane] : 0u;
+    if (found >= 0) old = vals[found * 8 + lane];
     if (is_write) {
       int slot = found;
       if (slot < 0) {
@@ -415,23 +438,23 @@ struct Vm {
           return 0u;
         }
         slot = insert_at;
-        if (lane < 8) keys[slot * 8 + lane] = ident;
-        else if (lane < 14) addrs[slot * 8 + lane - 8] = ident;
-        if (lane == 14) tags[slot] = tag;
+        keys[slot * 8 + lane] = key;
+        if (lane < 6) addrs[slot * 8 + lane] = extra;
+        if (lane == 6) tags[slot] = tag;
       }
-      if (lane < 8) vals[slot * 8 + lane] = nv;
+      vals[slot * 8 + lane] = nv;
       if (journal) {
         if (journal_len >= B.journal_entries) {
           fail(ZKB_VM_CAP_STORAGE);
         } else {
           uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
           uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
-          if (lane < 8) jv[journal_len * 8 + lane] = old;
-          if (lane == 8) js[journal_len] = (uint32_t)slot;
+          jv[journal_len * 8 + lane] = old;
+          if (lane == 0) js[journal_len] = (uint32_t)slot;
           journal_len++;
         }
       }
-      __syncwarp();
+      osync();
     }
     return old;
   }
@@ -443,8 +466,8 @@ struct Vm {
     while (journal_len > mark) {
       journal_len--;
       uint32_t slot = js[journal_len];
-      if (lane < 8) vals[slot * 8 + lane] = jv[journal_len * 8 + lane];
-      __syncwarp();
+      vals[slot * 8 + lane] = jv[journal_len * 8 + lane];
+      osync();
     }
   }
 
@@ -460,11 +483,11 @@ struct Vm {
       S.F[F_AUX_BOUND] = S.row[L_AUX_BOUND];
       S.F[F_EH_SHARDS] = (S.F[F_EH_SHARDS] & 0xFFFF0000u) | (S.row[L_EH_BITS] & 0xFFFFu);
     }
-    __syncwarp();
+    osync();
   }
   // derive the register/row-resident fields from S.F (after a push of a new frame or a pop)
   __device__ __forceinline__ void load_frame_from_F() {
-    __syncwarp();
+    osync();
     uint32_t sp_pc = S.F[F_SP_PC];
     sp = sp_pc & 0xFFFFu;
     pc = sp_pc >> 16;
@@ -489,46 +512,49 @@ struct Vm {
       code_len = B.code_meta[id * 10 + 1];
     }
     far_depth = S.F[F_FAR_LEVEL];
-    __syncwarp();
+    osync();
   }
-  // vm_state.start_frame (helpers.rs:225-246) for a frame already described in `nf` (lane i holds word i)
-  __device__ __forceinline__ void push_frame(uint32_t nf, uint32_t bound_kind = 0, uint32_t bound_value = 0) {
-    uint32_t depth = S.row[L_DEPTH];
+  // vm_state.start_frame (helpers.rs:225-246) in two halves.  push_begin saves the caller's frame (it stays readable
+  // in S.F); the handler then turns S.F into the callee's frame and calls push_end.
+  __device__ __forceinline__ bool push_begin() {
+    const uint32_t depth = S.row[L_DEPTH];
     if (depth >= B.max_depth) {
       fail(ZKB_VM_CAP_DEPTH);
-      return;
+      return false;
     }
     sync_frame_to_F();
-    uint32_t prev_ergs = ergs, prev_pc = pc, prev_sp = sp;
-    B.callstack[((size_t)vm * B.max_depth + depth) * 32 + lane] = S.F[lane];
-    __syncwarp();
-    S.F[lane] = nf;
-    __syncwarp();
+    reinterpret_cast<uint4*>(B.callstack + ((size_t)vm * B.max_depth + depth) * 32)[lane] = reinterpret_cast<const uint4*>(S.F)[lane];
+    osync();
+    return true;
+  }
+  // prev_*: the caller's ergs / pc / sp as the tracer sees the previous frame (after the call's own updates)
+  __device__ __forceinline__ void push_end(uint32_t prev_ergs, uint32_t prev_pc, uint32_t prev_sp, uint32_t bound_kind = 0,
+                                           uint32_t bound_value = 0) {
+    osync();
     if (lane == 0) {
       S.F[F_JOURNAL_MARK] = journal_len;  // storage.start_frame / event_sink.start_frame
-      S.row[L_DEPTH] = depth + 1;
+      S.row[L_DEPTH] = S.row[L_DEPTH] + 1;
     }
-    __syncwarp();
+    osync();
     emit_frame_start(prev_ergs, prev_pc, prev_sp, bound_kind, bound_value);
     load_frame_from_F();
   }
-  // vm_state.finish_frame (helpers.rs:248-264); leaves the finished frame in S.kbuf[0..31], the parent in S.F
+  // vm_state.finish_frame (helpers.rs:248-264); leaves the parent in S.F
   __device__ __forceinline__ void pop_frame(bool panicked) {
     sync_frame_to_F();
     if (panicked) storage_rollback(S.F[F_JOURNAL_MARK]);
     emit_frame_finish(panicked);
     uint32_t depth = S.row[L_DEPTH];
-    S.kbuf[lane] = S.F[lane];
-    __syncwarp();
-    S.F[lane] = B.callstack[((size_t)vm * B.max_depth + depth - 1) * 32 + lane];
+    osync();
+    reinterpret_cast<uint4*>(S.F)[lane] = reinterpret_cast<const uint4*>(B.callstack + ((size_t)vm * B.max_depth + depth - 1) * 32)[lane];
     if (lane == 0) S.row[L_DEPTH] = depth - 1;
-    __syncwarp();
+    osync();
     load_frame_from_F();
   }
 
   // ---- operand write-back (helpers.rs:266-287) ------------------------------------------------------
   __device__ __forceinline__ void dst0_update(u256l v, bool is_ptr) {
-    if (lane < 8) S.row[24 + lane] = v;
+    S.row[24 + lane] = v;
     rowbits |= ZKB_ROWBIT_DST0_VALID | (is_ptr ? ZKB_ROWBIT_DST0_PTR : 0u);
     if (dst_loc_valid) {
       stack_write(dst_loc_index, v, is_ptr ? 1u : 0u);
@@ -538,7 +564,7 @@ struct Vm {
     }
   }
   __device__ __forceinline__ void dst1_update(u256l v, bool is_ptr) {
-    if (lane < 8) S.row[32 + lane] = v;
+    S.row[32 + lane] = v;
     rowbits |= ZKB_ROWBIT_DST1_VALID | (is_ptr ? ZKB_ROWBIT_DST1_PTR : 0u);
     reg_write(dst1_reg, v, is_ptr);
   }
@@ -565,7 +591,7 @@ struct Vm {
 // ===================================================================================================
 __device__ __forceinline__ void Vm::cycle_once() {
   const uint32_t row_cycle = cycle, row_ts = timestamp, pc_before = pc;
-  if (lane < 16) S.row[24 + lane] = 0u;  // dst0 / dst1 fields default to zero
+  *reinterpret_cast<uint2*>(&S.row[24 + 2 * lane]) = make_uint2(0u, 0u);  // dst0 / dst1 fields default to zero
   rowbits = 0;
   ccount = 0;
   dst_loc_valid = 0;
@@ -577,13 +603,13 @@ __device__ __forceinline__ void Vm::cycle_once() {
   uint32_t raw_lo, raw_hi;
   if (!ZK_UNLIKELY(pending)) {
     if (code_page != prev_code_page || prev_super_pc != super_pc) {
-      u256l w = (lane < 8 && super_pc < code_len) ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
+      u256l w = super_pc < code_len ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
       prev_word = w;
       prev_super_pc = super_pc;
       emit_mem(timestamp, code_page, super_pc, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, w);
     }
-    raw_lo = __shfl_sync(ZK_FULL, prev_word, 6 - 2 * (int)sub_pc);
-    raw_hi = __shfl_sync(ZK_FULL, prev_word, 7 - 2 * (int)sub_pc);
+    raw_lo = oshfl(prev_word, 6 - 2 * (int)sub_pc);
+    raw_hi = oshfl(prev_word, 7 - 2 * (int)sub_pc);
   } else {
     pending = 0;
     prev_super_pc = super_pc;
@@ -629,7 +655,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   imm0 = ops_hi & 0xFFFFu;
   imm1 = ops_hi >> 16;
   // delayed changes (mod.rs:134-153): previous_super_pc lives in the row tail
-  __syncwarp();
+  osync();
   if (lane == 0) S.row[L_TX_PSP] = (S.row[L_TX_PSP] & 0xFFFFu) | prev_super_pc << 16;
 
   // ---- operand addressing (mem_ops.rs:14-125, cycle.rs:275-345) ----
@@ -638,7 +664,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   u256l src0 = reg_read(src0_reg);
   uint32_t src0_ptr = (ptr_mask >> src0_reg) & 1u;
   if (src_mode != ZK_SRC_REG) {
-    uint32_t vaddr = (__shfl_sync(ZK_FULL, src0, 0) + imm0) & 0xFFFFu;
+    uint32_t vaddr = (oshfl(src0, 0) + imm0) & 0xFFFFu;
     if (src_mode == ZK_SRC_IMM) {
       src0 = lane == 0 ? imm0 : 0u;
       src0_ptr = 0;
@@ -656,7 +682,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
         src0 = 0u;  // NOP moves SP but never reads (cycle.rs:298-301)
         src0_ptr = 0;
       } else if (src_mode == ZK_SRC_CODE) {
-        src0 = (lane < 8 && index < code_len) ? __ldg(code + (size_t)index * 8 + lane) : 0u;
+        src0 = index < code_len ? __ldg(code + (size_t)index * 8 + lane) : 0u;
         src0_ptr = 0;
         emit_mem(timestamp, code_page, index, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, src0);
       } else {
@@ -698,10 +724,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
     src1 = lane < 4 ? src1 : 0u;
     src1_ptr = 0;
   }
-  if (lane < 8) {
-    S.row[8 + lane] = src0;
-    S.row[16 + lane] = src1;
-  }
+  S.row[8 + lane] = src0;
+  S.row[16 + lane] = src1;
   const bool set_flags = entry & ZK_E_FLAG0;
 
   // ---- dispatch (parsing.rs:47-79) ----
@@ -759,7 +783,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
       break;
     }
     case ZK_OP_JUMP:  // jump.rs:24-25
-      pc = __shfl_sync(ZK_FULL, src0, 0) & 0xFFFFu;
+      pc = oshfl(src0, 0) & 0xFFFFu;
       break;
     case ZK_OP_CONTEXT:
       pc = new_pc;
@@ -807,7 +831,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   timestamp += ZK_TIME_DELTA_PER_CYCLE;
   cycle += 1;
 
-  // ---- end_execution_cycle: emit the 256-byte row, one 8-byte store per lane ----
+  // ---- end_execution_cycle: emit the 256-byte row, two 16-byte stores per lane (each a full 128-byte line per VM) ----
   // lane 0 drops the scalar head of the row next to the operand values already staged in shared memory
   if (lane == 0) {
     *reinterpret_cast<uint4*>(&S.row[0]) = make_uint4(row_cycle, row_ts, raw_lo, raw_hi);
@@ -821,10 +845,12 @@ __device__ __forceinline__ void Vm::cycle_once() {
     return;
   }
   count[ZKB_STREAM_ROWS] = n_rows + 1;
-  __syncwarp();
+  osync();
   if (B.witness) {
-    uint2 v = *reinterpret_cast<const uint2*>(&S.row[2 * lane]);
-    *reinterpret_cast<uint2*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES + 8 * lane) = v;
+    const uint4 v0 = reinterpret_cast<const uint4*>(S.row)[lane], v1 = reinterpret_cast<const uint4*>(S.row)[8 + lane];
+    uint4* dst = reinterpret_cast<uint4*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES);
+    dst[lane] = v0;
+    dst[8 + lane] = v1;
   }
   // rare end-of-cycle state changes, keyed on the opcode family so that ordinary cycles pay one compare:
   if (family - ZK_OP_LOG <= 2u) {  // LOG, FAR_CALL, RET
@@ -837,16 +863,16 @@ __device__ __forceinline__ void Vm::cycle_once() {
 __device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
   if (sub == ZK_CTX_SET_U128) {
     if (lane < 4) S.row[L_CTX + lane] = src0;
-    __syncwarp();
+    osync();
     return;
   }
   if (sub == ZK_CTX_SET_ERGS_PER_PUBDATA) {
-    setL(L_EPP, __shfl_sync(ZK_FULL, src0, 0));
+    setL(L_EPP, oshfl(src0, 0));
     return;
   }
   if (sub == ZK_CTX_INC_TX) {
     uint32_t t = S.row[L_TX_PSP];
-    __syncwarp();
+    osync();
     setL(L_TX_PSP, (t & 0xFFFF0000u) | ((t + 1u) & 0xFFFFu));
     return;
   }
@@ -872,7 +898,7 @@ __device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
 
 // shift.rs:44-67
 __device__ __forceinline__ void Vm::op_shift(uint32_t sub, u256l src0, u256l src1) {
-  uint32_t n = __shfl_sync(ZK_FULL, src1, 0) & 0xFFu;
+  uint32_t n = oshfl(src1, 0) & 0xFFu;
   bool cyclic = sub == ZK_ROL || sub == ZK_ROR, right = sub == ZK_SHR || sub == ZK_ROR;
   u256l r;
   if (right) {
@@ -892,14 +918,14 @@ __device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1,
     pending = 1;
     return;
   }
-  uint32_t s1_nz = __ballot_sync(ZK_FULL, src1 != 0) & 0xFFu;
-  uint32_t off1 = __shfl_sync(ZK_FULL, src1, 0);
+  uint32_t s1_nz = oballot(src1 != 0);
+  uint32_t off1 = oshfl(src1, 0);
   if (sub == ZK_PTR_ADD || sub == ZK_PTR_SUB) {
     if (s1_nz & 0xFEu) {  // src1 >= 2^32 (MAX_OFFSET_FOR_ADD_SUB, ptr.rs:47)
       pending = 1;
       return;
     }
-    uint32_t off0 = __shfl_sync(ZK_FULL, src0, 0);
+    uint32_t off0 = oshfl(src0, 0);
     uint32_t r = sub == ZK_PTR_ADD ? off0 + off1 : off0 - off1;
     bool of = sub == ZK_PTR_ADD ? r < off0 : off0 < off1;
     if (of) {
@@ -914,7 +940,7 @@ __device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1,
     }
     dst0_update(lane < 4 ? src0 : src1, true);
   } else {  // Shrink (ptr.rs:140-192)
-    uint32_t len = __shfl_sync(ZK_FULL, src0, 3);
+    uint32_t len = oshfl(src0, 3);
     if (len < off1) {
       pending = 1;
       return;
@@ -926,7 +952,7 @@ __device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1,
 // near_call.rs:6-68
 __device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
   flags = 0;
-  uint32_t abi_ergs = __shfl_sync(ZK_FULL, src0, 0);
+  uint32_t abi_ergs = oshfl(src0, 0);
   uint32_t passed, remaining;
   if (abi_ergs == 0 || ergs < abi_ergs) {
     passed = ergs;
@@ -937,13 +963,15 @@ __device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
   }
   ergs = remaining;
   pc = new_pc;
-  sync_frame_to_F();
-  uint32_t nf = S.F[lane];
-  if (lane == F_SP_PC) nf = sp | imm0 << 16;
-  if (lane == F_EH_SHARDS) nf = (nf & 0xFFFF0000u) | imm1;
-  if (lane == F_ERGS) nf = passed;
-  if (lane == F_MISC) nf |= 1u << 16;
-  push_frame(nf);
+  if (!push_begin()) return;
+  // the callee's frame is a clone of the caller's with is_local_frame set (near_call.rs:59-63)
+  if (lane == 0) {
+    S.F[F_SP_PC] = sp | imm0 << 16;
+    S.F[F_EH_SHARDS] = (S.F[F_EH_SHARDS] & 0xFFFF0000u) | imm1;
+    S.F[F_ERGS] = passed;
+    S.F[F_MISC] |= 1u << 16;
+  }
+  push_end(ergs, pc, sp);
 }
 
 // log.rs:11-330
@@ -962,11 +990,11 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
   } else if (sub == ZK_LOG_TO_L1) {
     ergs_on_pubdata = epp * ZK_L1_MESSAGE_PUBDATA_BYTES;
   }
-  uint32_t extra = sub == ZK_LOG_PRECOMPILE ? __shfl_sync(ZK_FULL, src1, 0) : 0u;
+  uint32_t extra = sub == ZK_LOG_PRECOMPILE ? oshfl(src1, 0) : 0u;
   uint32_t total = extra + ergs_on_pubdata;
   bool not_enough = ergs_available < total;
   uint32_t spent = S.row[L_SPENT_PUBDATA];
-  __syncwarp();
+  osync();
   if (not_enough) {
     ergs = 0;
     setL(L_SPENT_PUBDATA, spent + min(ergs_available, ergs_on_pubdata));
@@ -1022,9 +1050,9 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
 // keccak256 precompile (external DefaultPrecompilesProcessor; memory ABI pinned by keccak256.rs:100-139):
 // byte offset/length in, one output word (word index) out; one FatPointer-type read per distinct input word.
 __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
-  const uint32_t in_off = __shfl_sync(ZK_FULL, abi, 0), in_len = __shfl_sync(ZK_FULL, abi, 1);
-  const uint32_t out_word = __shfl_sync(ZK_FULL, abi, 2);
-  const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
+  const uint32_t in_off = oshfl(abi, 0), in_len = oshfl(abi, 1);
+  const uint32_t out_word = oshfl(abi, 2);
+  const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
   const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
   // resolve the source page once (fat-pointer indirection, memory.rs:475-521)
   uint32_t src_slab = ZKB_NO_SLAB;
@@ -1039,7 +1067,9 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
     src_slab = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
   }
   const KeccakLanes kl = keccak_lanes(lane);
-  uint64_t st = 0;
+  KeccakState st;
+#pragma unroll
+  for (int y = 0; y < 5; y++) st.a[y] = 0;
   const uint64_t end = (uint64_t)in_off + in_len;
   uint64_t next_emit_word = in_off / 32;
   const uint32_t n_blocks = in_len / 136 + 1;
@@ -1055,33 +1085,39 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
           emit_mem(ts_read, page_read, (uint32_t)w, ZK_MEM_FAT_PTR, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, word);
           next_emit_word = w + 1;
         }
-        if (lane < 8) S.kbuf[(uint32_t)(w - w0) * 8 + (7 - lane)] = bswap32(word);  // byte stream order
+        S.kbuf[(uint32_t)(w - w0) * 8 + (7 - lane)] = bswap32(word);  // byte stream order
       }
     }
-    __syncwarp();
-    uint64_t v = 0;
-    if (lane < 17) {
-      uint32_t o = (uint32_t)(a0 - w0 * 32) + 8 * lane;  // byte offset into kbuf
-      uint32_t i = o >> 2, sh = (o & 3u) * 8;
-      uint32_t x0 = S.kbuf[i], x1 = S.kbuf[i + 1], x2 = S.kbuf[(i + 2) & 63];
-      uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
-      v = ((uint64_t)hi << 32) | lo;
-      uint32_t b0 = 8 * lane;
-      if (b0 >= nb) v = 0;
-      else if (b0 + 8 > nb) v &= (1ull << (8 * (nb - b0))) - 1ull;
-      if (nb < 136) {  // final block: pad10*1 with the keccak domain byte 0x01
-        if (lane == nb / 8) v ^= 1ull << (8 * (nb % 8));
-        if (lane == 16) v ^= 0x80ull << 56;
+    osync();
+    // absorb: rate word i (bytes [8 i, 8 i + 8) of the block, little-endian) belongs to column i % 5, row i / 5
+    if (lane < 5) {
+#pragma unroll
+      for (int y = 0; y < 4; y++) {
+        const uint32_t wi = lane + 5u * (uint32_t)y;
+        if (wi < 17) {
+          uint32_t o = (uint32_t)(a0 - w0 * 32) + 8 * wi;  // byte offset into kbuf
+          uint32_t i = o >> 2, sh = (o & 3u) * 8;
+          uint32_t x0 = S.kbuf[i], x1 = S.kbuf[i + 1], x2 = S.kbuf[(i + 2) & 63];
+          uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+          uint64_t v = ((uint64_t)hi << 32) | lo;
+          uint32_t b0 = 8 * wi;
+          if (b0 >= nb) v = 0;
+          else if (b0 + 8 > nb) v &= (1ull << (8 * (nb - b0))) - 1ull;
+          if (nb < 136) {  // final block: pad10*1 with the keccak domain byte 0x01
+            if (wi == nb / 8) v ^= 1ull << (8 * (nb % 8));
+            if (wi == 16) v ^= 0x80ull << 56;
+          }
+          st.a[y] ^= v;
+        }
       }
     }
-    __syncwarp();
-    st ^= v;
-    st = keccak_f1600(st, kl, lane);
+    osync();
+    keccak_f1600(st, kl, S.ks, lane);
   }
-  // digest = first 32 bytes of the state (little-endian lanes) read as one big-endian word
+  // digest = first 32 bytes of the state (row 0 of columns 0..3, little-endian lanes) read as one big-endian word
   int t = 7 - (int)lane;
-  uint32_t lo = __shfl_sync(ZK_FULL, (uint32_t)st, (t >> 1) & 31), hi = __shfl_sync(ZK_FULL, (uint32_t)(st >> 32), (t >> 1) & 31);
-  u256l digest = lane < 8 ? bswap32((t & 1) ? hi : lo) : 0u;
+  uint32_t lo = oshfl((uint32_t)st.a[0], (t >> 1) & 7), hi = oshfl((uint32_t)(st.a[0] >> 32), (t >> 1) & 7);
+  u256l digest = bswap32((t & 1) ? hi : lo);
   // the write goes through MemoryType::Heap: the reference checks the page only by debug_assert (memory.rs:447)
   if (page_write != L(L_BASE_PAGE) + 2) {
     fail(ZKB_VM_REFERENCE_PANIC);
@@ -1097,9 +1133,9 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
 // passes pre-padded 64-byte blocks: input offset in WORDS, number of rounds in precompile_interpreted_data, two
 // Heap-type word reads per round at timestamp+1, one digest word written at timestamp+2 after the last round.
 __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
-  const uint32_t in_word = __shfl_sync(ZK_FULL, abi, 0), out_word = __shfl_sync(ZK_FULL, abi, 2);
-  const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
-  const uint64_t rounds = (uint64_t)__shfl_sync(ZK_FULL, abi, 6) | (uint64_t)__shfl_sync(ZK_FULL, abi, 7) << 32;
+  const uint32_t in_word = oshfl(abi, 0), out_word = oshfl(abi, 2);
+  const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
+  const uint64_t rounds = (uint64_t)oshfl(abi, 6) | (uint64_t)oshfl(abi, 7) << 32;
   const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
   if (rounds == 0) return;
   const uint32_t heap_page = L(L_BASE_PAGE) + 2;
@@ -1109,7 +1145,7 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
     return;
   }
   const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
-  if (lane < 8) S.kbuf[lane] = c_sha256_iv[lane];
+  S.kbuf[lane] = c_sha256_iv[lane];
   for (uint64_t r = 0; r < rounds; r++) {
 #pragma unroll
     for (uint32_t k = 0; k < 2; k++) {
@@ -1117,12 +1153,12 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
       u256l word = slab_read(src_slab, idx);
       emit_mem(ts_read, page_read, idx, ZK_MEM_HEAP, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, word);
       if (status != ZKB_VM_RUNNING) return;
-      if (lane < 8) S.kbuf[8 + 8 * k + (7 - lane)] = word;  // big-endian message words: M[j] = limb[7 - j]
+      S.kbuf[8 + 8 * k + (7 - lane)] = word;  // big-endian message words: M[j] = limb[7 - j]
     }
     sha256_compress_smem(S.kbuf, lane);
   }
-  __syncwarp();
-  u256l digest = lane < 8 ? S.kbuf[7 - lane] : 0u;
+  osync();
+  u256l digest = S.kbuf[7 - lane];
   uint32_t s = cur_slab(0, true, out_word);
   if (status != ZKB_VM_RUNNING) return;
   slab_write(s, out_word, digest);
@@ -1137,8 +1173,8 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
 // the VM state parked in HBM (run_deferred_ecrecover), and patch the two values in place.  Nothing inside the cycle
 // depends on them, and the interpreter's hot loop carries no live state across the call.
 __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
-  const uint32_t in_word = __shfl_sync(ZK_FULL, abi, 0), out_word = __shfl_sync(ZK_FULL, abi, 2);
-  const uint32_t page_read = __shfl_sync(ZK_FULL, abi, 4), page_write = __shfl_sync(ZK_FULL, abi, 5);
+  const uint32_t in_word = oshfl(abi, 0), out_word = oshfl(abi, 2);
+  const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
   const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
   const uint32_t heap_page = L(L_BASE_PAGE) + 2;
   if (page_read != heap_page) {  // MemoryType::Heap queries address the current frame's heap (memory.rs:447)
@@ -1151,11 +1187,11 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
   for (uint32_t i = 0; i < 4; i++) {
     u256l w = slab_read(src_slab, in_word + i);
     emit_mem(ts_read, page_read, in_word + i, ZK_MEM_HEAP, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, w);
-    if (lane < 8) S.kbuf[KB_EC_INPUT + 8 * i + lane] = w;
+    S.kbuf[KB_EC_INPUT + 8 * i + lane] = w;
     if (i == 1) v_word = w;
   }
   if (status != ZKB_VM_RUNNING) return;
-  const uint32_t v_nz = __ballot_sync(ZK_FULL, v_word != 0) & 0xFFu, v0 = __shfl_sync(ZK_FULL, v_word, 0);
+  const uint32_t v_nz = oballot(v_word != 0), v0 = oshfl(v_word, 0);
   if ((v_nz & 0xFEu) || v0 > 1u || page_write != heap_page) {  // the external precompile asserts v == 0 || v == 1
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
@@ -1174,7 +1210,7 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
     S.kbuf[KB_EC_SLAB] = s;
     S.kbuf[KB_EC_OUT_WORD] = out_word;
   }
-  __syncwarp();
+  osync();
 }
 
 // SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth (already incremented)
@@ -1185,7 +1221,7 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
     g_lvl[level * 4 + 1] = ZKB_NO_SLAB;
     g_lvl[level * 4 + 2] = 0;
   }
-  __syncwarp();
+  osync();
   // the root "heaps" entry has page numbers 0/0 (memory.rs:230-233)
   uint32_t cur_heap = caller_level == 0 ? 0u : caller_base + 2, cur_aux = caller_level == 0 ? 0u : caller_base + 3;
   if (calldata_page == 0) {
@@ -1210,10 +1246,11 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
   uint32_t hwm = g_lvl[level * 4 + 2];
   uint32_t* sbase = g_stack + (size_t)level * B.stack_words * 8;
   uint8_t* pbase = g_stack_ptr + (size_t)level * B.stack_words;
-  for (uint32_t i = lane; i < hwm * 8; i += 32) sbase[i] = 0u;
-  for (uint32_t i = lane; i < hwm; i += 32) pbase[i] = 0;
+  uint4* sbase4 = reinterpret_cast<uint4*>(sbase);
+  for (uint32_t i = lane; i < hwm * 2; i += 8) sbase4[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = lane; i < hwm; i += 8) pbase[i] = 0;
   uint32_t heap_slab = g_lvl[level * 4 + 0], aux_slab = g_lvl[level * 4 + 1];
-  __syncwarp();
+  osync();
   uint32_t heap_page = base_page + 2, aux_page = base_page + 3;
   if (returndata_page == heap_page) {
     pt_upsert(heap_page, PT_EXT, heap_slab, level - 1);
@@ -1229,23 +1266,26 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
         return;
       }
       if (lane == 0) g_pt[e * 2 + 1] = (g_pt[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
-      __syncwarp();
+      osync();
     }
     slab_release(heap_slab);
     slab_release(aux_slab);
   }
-  // drop every indirection still owned by the finished level
-  uint32_t page = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2] : ZKB_PT_FREE;
-  uint32_t info = lane < ZKB_PT_ENTRIES ? g_pt[lane * 2 + 1] : 0u;
-  uint32_t drop = __ballot_sync(ZK_FULL, page != ZKB_PT_FREE && (info >> 16) == level);
-  while (drop) {
-    int e = __ffs(drop) - 1;
-    drop &= drop - 1;
-    uint32_t einfo = __shfl_sync(ZK_FULL, info, e);
-    if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
-    if (lane == 0) g_pt[e * 2] = ZKB_PT_FREE;
+  // drop every indirection still owned by the finished level (octet lane l holds entries l, l + 8, l + 16, l + 24)
+#pragma unroll 1
+  for (uint32_t q = 0; q < ZKB_PT_ENTRIES / ZK_OCT; q++) {
+    const uint32_t e0 = lane + ZK_OCT * q;
+    const uint32_t page = g_pt[e0 * 2], info = g_pt[e0 * 2 + 1];
+    uint32_t drop = oballot(page != ZKB_PT_FREE && (info >> 16) == level);
+    while (drop) {
+      int l = __ffs(drop) - 1;
+      drop &= drop - 1;
+      uint32_t einfo = oshfl(info, l);
+      if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
+      if (lane == 0) g_pt[(l + ZK_OCT * q) * 2] = ZKB_PT_FREE;
+    }
   }
-  __syncwarp();
+  osync();
 }
 
 // far_call.rs:35-613
@@ -1255,14 +1295,14 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   const bool is_call_shard = entry & ZK_E_FLAG0, is_static_call = entry & ZK_E_FLAG1;
   const uint32_t eh = imm0;
   // called address / kernel test
-  const uint32_t dest_nz = __ballot_sync(ZK_FULL, src1 != 0) & 0x1Fu;  // limbs 0..4 = low 160 bits
-  const bool dst_is_kernel = (dest_nz & 0x1Eu) == 0 && __shfl_sync(ZK_FULL, src1, 0) < 65536u;
+  const uint32_t dest_nz = oballot(src1 != 0) & 0x1Fu;  // limbs 0..4 = low 160 bits
+  const bool dst_is_kernel = (dest_nz & 0x1Eu) == 0 && oshfl(src1, 0) < 65536u;
   const u256l dest_key = lane < 5 ? src1 : 0u;             // value & U256_TO_ADDRESS_MASK
   const uint32_t dest_aw = u256_to_addr_words(src1);       // lanes 0..4
   // FarCallABI::from_u256
-  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
-  uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
-  const uint32_t abi_ergs = __shfl_sync(ZK_FULL, src0, 6), top = __shfl_sync(ZK_FULL, src0, 7);
+  uint32_t p_off = oshfl(src0, 0), p_page = oshfl(src0, 1);
+  uint32_t p_start = oshfl(src0, 2), p_len = oshfl(src0, 3);
+  const uint32_t abi_ergs = oshfl(src0, 6), top = oshfl(src0, 7);
   const uint32_t fwd_byte = top & 0xFFu, abi_shard = (top >> 8) & 0xFFu;
   const uint32_t fwd = fwd_byte == ZK_FWD_FORWARD_FAT_POINTER ? ZK_FWD_FORWARD_FAT_POINTER : fwd_byte == ZK_FWD_USE_AUX_HEAP ? ZK_FWD_USE_AUX_HEAP : ZK_FWD_USE_HEAP;
   const bool constructor_call = ((top >> 16) & 0xFFu) != 0 && kernel_mode;
@@ -1291,7 +1331,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     u256l v = storage_access(new_code_shard, deployer_aw, dest_key, false, 0u, false);
     emit_log(ts1, ZK_STORAGE_AUX_BYTE, new_code_shard, deployer_aw, 0, 0, dest_key, v, v);
     bool mask_aa = u_is_zero(v) && !dst_is_kernel;
-    code_hash = mask_aa ? (lane < 8 ? B.default_aa[lane] : 0u) : v;
+    code_hash = mask_aa ? B.default_aa[lane] : v;
     map_to_trivial = false;
   }
   const uint32_t page_candidate = map_to_trivial ? ZK_UNMAPPED_PAGE : new_base;
@@ -1299,7 +1339,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   uint32_t ex = 0;
   uint32_t code_len_words = 0;
   {
-    uint32_t top_limb = __shfl_sync(ZK_FULL, code_hash, 7);
+    uint32_t top_limb = oshfl(code_hash, 7);
     uint32_t version = top_limb >> 24, marker = (top_limb >> 16) & 0xFFu;
     if (version == ZK_CODE_HASH_VERSION_BYTE) {
       bool at_rest = marker == ZK_CODE_AT_REST_MARKER, constructed_now = marker == ZK_YET_CONSTRUCTED_MARKER;
@@ -1315,7 +1355,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
           fail(ZKB_VM_REFERENCE_PANIC);  // far_call.rs:222-227
           return;
         }
-        code_hash = lane < 8 ? B.default_aa[lane] : 0u;
+        code_hash = B.default_aa[lane];
         code_len_words = aa_top & 0xFFFFu;
       } else {
         ex |= EX_CONSTRUCTED_SYSTEM;
@@ -1347,7 +1387,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     if (deref_beyond) upper = 0xFFFFFFFFu;
     int w = fwd == ZK_FWD_USE_HEAP ? L_HEAP_BOUND : L_AUX_BOUND;
     uint32_t bound = S.row[w];
-    __syncwarp();
+    osync();
     if (upper >= bound) {
       growth = upper - bound;
       setL(w, upper);
@@ -1379,13 +1419,15 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     // SimpleDecommitter::decommit_into_memory (decommitter.rs:32-99)
     int id = -1;
     for (uint32_t c = 0; c < B.n_codes && id < 0; c++) {
-      uint32_t hw = lane < 8 ? B.code_meta[c * 10 + 2 + lane] : 0u;
+      uint32_t hw = B.code_meta[c * 10 + 2 + lane];
       if (u_eq(hw, code_hash)) id = (int)c;
     }
     uint32_t* dec = B.dec + (size_t)vm * ZKB_DEC_ENTRIES * 2;
-    uint32_t e_id = lane < n_decommit ? dec[lane * 2] : ZKB_NO_CODE;
-    // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it
-    uint32_t hist = id >= 0 ? __ballot_sync(ZK_FULL, e_id == (uint32_t)id) : (__ballot_sync(ZK_FULL, false));
+    // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it.
+    // Octet lane l looks at entries l and l + 8 (ZKB_DEC_ENTRIES = 16).
+    const uint32_t e_lo = lane < n_decommit ? dec[lane * 2] : ZKB_NO_CODE, e_hi = lane + 8 < n_decommit ? dec[(lane + 8) * 2] : ZKB_NO_CODE;
+    const bool have_id = id >= 0;
+    uint32_t hist = oballot(have_id && e_lo == (uint32_t)id) | oballot(have_id && e_hi == (uint32_t)id) << 8;
     uint32_t fresh_flag, len16;
     if (hist) {
       mapped_code_page = dec[(__ffs(hist) - 1) * 2 + 1];
@@ -1406,7 +1448,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
         dec[n_decommit * 2 + 1] = page_candidate;
       }
       n_decommit++;
-      __syncwarp();
+      osync();
       mapped_code_page = page_candidate;
       fresh_flag = 1;
       len16 = B.code_meta[id * 10 + 1] & 0xFFFFu;
@@ -1429,7 +1471,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   pc = new_pc;
   const bool new_static = is_static() || is_static_call;
   uint32_t page_counter = S.row[L_PAGE_COUNTER];
-  __syncwarp();
+  osync();
   setL(L_PAGE_COUNTER, page_counter + ZK_NEW_MEMORY_PAGES_PER_FAR_CALL);
 
   // new frame, lane i = word i
@@ -1439,55 +1481,60 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     fail(ZKB_VM_CAP_DEPTH);
     return;
   }
-  sync_frame_to_F();
-  uint32_t nf = 0;
+  if (!push_begin()) return;  // the caller's frame is saved and still readable in S.F
   {
-    uint32_t this_w = lane < 5 ? S.F[F_THIS + lane] : 0u;          // lanes 0..4
-    uint32_t sender_w = lane < 5 ? S.F[F_SENDER + lane] : 0u;
-    uint32_t next_this = sub == ZK_FC_DELEGATE ? this_w : dest_aw;
-    uint32_t next_sender = sub == ZK_FC_NORMAL ? this_w : sub == ZK_FC_DELEGATE ? sender_w : r15_aw;
-    uint32_t a = __shfl_sync(ZK_FULL, next_this, lane & 7);
-    uint32_t b = __shfl_sync(ZK_FULL, next_sender, (lane - 5) & 7);
-    uint32_t c = __shfl_sync(ZK_FULL, dest_aw, (lane - 10) & 7);
-    uint32_t ctx_frame = lane >= F_CTX && lane < F_CTX + 4 ? S.F[lane] : 0u;
-    uint32_t ctx_reg = lane >= F_CTX && lane < F_CTX + 4 ? S.row[L_CTX + lane - F_CTX] : 0u;
-    if (lane < 5) nf = a;
-    else if (lane < 10) nf = b;
-    else if (lane < 15) nf = c;
-    else if (lane == F_BASE_PAGE) nf = new_base;
-    else if (lane == F_CODE_PAGE) nf = mapped_code_page;
-    else if (lane == F_SP_PC) nf = ZK_INITIAL_SP_ON_FAR_CALL;
-    else if (lane == F_EH_SHARDS) nf = eh | new_this_shard << 16 | caller_shard << 24;
-    else if (lane == F_ERGS) nf = passed;
-    else if (lane == F_MISC) nf = new_code_shard | (new_static ? 1u : 0u) << 8;
-    else if (lane >= F_CTX && lane < F_CTX + 4) nf = sub == ZK_FC_DELEGATE ? ctx_frame : ctx_reg;
-    else if (lane == F_HEAP_BOUND || lane == F_AUX_BOUND) nf = ZK_NEW_FRAME_MEMORY_STIPEND;
-    else if (lane == F_CODE_ID) nf = new_code_id;
-    else if (lane == F_FAR_LEVEL) nf = caller_level + 1;
+    const uint32_t prev_ergs = ergs, prev_pc = pc, prev_sp = sp;
+    const uint32_t this_w = lane < 5 ? S.F[F_THIS + lane] : 0u;  // lanes 0..4
+    const uint32_t sender_w = lane < 5 ? S.F[F_SENDER + lane] : 0u;
+    const uint32_t next_this = sub == ZK_FC_DELEGATE ? this_w : dest_aw;
+    const uint32_t next_sender = sub == ZK_FC_NORMAL ? this_w : sub == ZK_FC_DELEGATE ? sender_w : r15_aw;
+    const uint32_t ctx = lane < 4 ? (sub == ZK_FC_DELEGATE ? S.F[F_CTX + lane] : S.row[L_CTX + lane]) : 0u;
+    osync();
+    if (lane < 5) {
+      S.F[F_THIS + lane] = next_this;
+      S.F[F_SENDER + lane] = next_sender;
+      S.F[F_CODE_ADDR + lane] = dest_aw;
+    }
+    if (lane < 4) {
+      S.F[F_CTX + lane] = ctx;
+      S.row[L_CTX + lane] = 0u;  // context_u128_register = 0 (far_call.rs:558)
+    }
+    if (lane == 5) {
+      S.F[F_BASE_PAGE] = new_base;
+      S.F[F_CODE_PAGE] = mapped_code_page;
+      S.F[F_SP_PC] = ZK_INITIAL_SP_ON_FAR_CALL;
+      S.F[F_EH_SHARDS] = eh | new_this_shard << 16 | caller_shard << 24;
+      S.F[F_ERGS] = passed;
+      S.F[F_MISC] = new_code_shard | (new_static ? 1u : 0u) << 8;
+    }
+    if (lane == 6) {
+      S.F[F_HEAP_BOUND] = ZK_NEW_FRAME_MEMORY_STIPEND;
+      S.F[F_AUX_BOUND] = ZK_NEW_FRAME_MEMORY_STIPEND;
+      S.F[F_CODE_ID] = new_code_id;
+      S.F[F_JOURNAL_MARK] = 0u;
+      S.F[F_FAR_LEVEL] = caller_level + 1;
+      S.F[30] = 0u;
+      S.F[31] = 0u;
+    }
+    push_end(prev_ergs, prev_pc, prev_sp, bound_kind, bound_value);
   }
-  __syncwarp();
-  if (lane < 4) S.row[L_CTX + lane] = 0u;  // context_u128_register = 0 (far_call.rs:558)
-  __syncwarp();
-  push_frame(nf, bound_kind, bound_value);
   if (status != ZKB_VM_RUNNING) return;
   memory_start_global_frame(caller_level, cur_base, p_page);
 
   // register ABI (far_call.rs:573-610)
   u256l r1 = lane == 0 ? p_off : lane == 1 ? p_page : lane == 2 ? p_start : lane == 3 ? p_len : 0u;
   u256l r2 = lane == 0 ? ((constructor_call ? 1u : 0u) | (to_system ? 2u : 0u)) : 0u;
-  if (lane < 8) {
-    S.regs[1][lane] = r1;
-    S.regs[2][lane] = r2;
-    S.row[24 + lane] = r1;
-    S.row[32 + lane] = r2;
-  }
+  S.regs[1][lane] = r1;
+  S.regs[2][lane] = r2;
+  S.row[24 + lane] = r1;
+  S.row[32 + lane] = r2;
   // registers[] index i <-> r(i+1): system ABI regs r3..r12, reserved r13,r14, implicit r15
   uint32_t clear_mask = 0xE000u | (to_system ? 0u : 0x1FF8u);
   for (uint32_t r = 3; r < 16; r++)
-    if (((clear_mask >> r) & 1u) && lane < 8) S.regs[r][lane] = 0u;
+    if ((clear_mask >> r) & 1u) S.regs[r][lane] = 0u;
   ptr_mask = 0x0002u;  // only r1 is a pointer: r2 plain, r3..r12 markers removed or zeroed, r13..r15 zeroed
   rowbits |= ZKB_ROWBIT_DST0_VALID | ZKB_ROWBIT_DST0_PTR | ZKB_ROWBIT_DST1_VALID;
-  __syncwarp();
+  osync();
 }
 
 // ret.rs:9-265
@@ -1498,9 +1545,9 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
     src0 = 0u;
     src0_ptr = false;
   }
-  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
-  uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
-  const uint32_t fwd_byte = __shfl_sync(ZK_FULL, src0, 7) & 0xFFu;
+  uint32_t p_off = oshfl(src0, 0), p_page = oshfl(src0, 1);
+  uint32_t p_start = oshfl(src0, 2), p_len = oshfl(src0, 3);
+  const uint32_t fwd_byte = oshfl(src0, 7) & 0xFFu;
   const uint32_t fwd = fwd_byte == ZK_FWD_FORWARD_FAT_POINTER ? ZK_FWD_FORWARD_FAT_POINTER : fwd_byte == ZK_FWD_USE_AUX_HEAP ? ZK_FWD_USE_AUX_HEAP : ZK_FWD_USE_HEAP;
   bool to_label = entry & ZK_E_FLAG0;
   const uint32_t label_pc = imm0;
@@ -1552,22 +1599,20 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
     fail(ZKB_VM_REFERENCE_PANIC);  // pop of the root frame (execution_stack.rs:113 unwrap)
     return;
   }
-  __syncwarp();
+  osync();
   pop_frame(panicked);
   to_label = to_label && local;
   if (!local) {
     memory_finish_global_frame(finished_level, base, p_page);
     u256l r1 = lane == 0 ? p_off : lane == 1 ? p_page : lane == 2 ? p_start : lane == 3 ? p_len : 0u;
-    if (lane < 8) {
-      S.regs[1][lane] = r1;
-      S.row[24 + lane] = r1;
+    S.regs[1][lane] = r1;
+    S.row[24 + lane] = r1;
 #pragma unroll
-      for (int r = 2; r < 16; r++) S.regs[r][lane] = 0u;
-    }
+    for (int r = 2; r < 16; r++) S.regs[r][lane] = 0u;
     if (lane < 4) S.row[L_CTX + lane] = 0u;
     ptr_mask = 0x0002u;
     rowbits |= ZKB_ROWBIT_DST0_VALID | ZKB_ROWBIT_DST0_PTR;
-    __syncwarp();
+    osync();
   }
   ergs += ergs_remaining;  // ret.rs:243
   if (to_label) pc = label_pc;
@@ -1577,12 +1622,12 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
       fail(ZKB_VM_REFERENCE_PANIC);  // ret.rs:255-256
       return;
     }
-    __syncwarp();
+    osync();
     if (lane == 0) {
       S.row[L_HEAP_BOUND] = fin_heap_bound;
       S.row[L_AUX_BOUND] = fin_aux_bound;
     }
-    __syncwarp();
+    osync();
   }
   if (variant == ZK_RET_PANIC) flags = 1u;
 }
@@ -1590,8 +1635,8 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
 // uma.rs:26-425
 __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr) {
   const bool inc = entry & ZK_E_FLAG0;
-  uint32_t p_off = __shfl_sync(ZK_FULL, src0, 0), p_page = __shfl_sync(ZK_FULL, src0, 1);
-  const uint32_t p_start = __shfl_sync(ZK_FULL, src0, 2), p_len = __shfl_sync(ZK_FULL, src0, 3);
+  uint32_t p_off = oshfl(src0, 0), p_page = oshfl(src0, 1);
+  const uint32_t p_start = oshfl(src0, 2), p_len = oshfl(src0, 3);
   const bool is_ptr_read = sub == ZK_UMA_PTR_READ;
   const bool is_heap = sub == ZK_UMA_HEAP_READ || sub == ZK_UMA_HEAP_WRITE;
   const bool is_write = sub == ZK_UMA_HEAP_WRITE || sub == ZK_UMA_AUX_WRITE;
@@ -1609,7 +1654,7 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
     if (!(p_off < p_len)) skip = true;
     src_offset = p_start + p_off;
   } else {
-    uint32_t hi_nz = __ballot_sync(ZK_FULL, src0 != 0) & 0xFEu;
+    uint32_t hi_nz = oballot(src0 != 0) & 0xFEu;
     if (hi_nz || p_off > (uint32_t)ZK_MAX_OFFSET_TO_DEREF) {
       ex = ex_deref = true;
       skip = true;
@@ -1622,7 +1667,7 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
   if (!is_ptr_read) {
     int w = is_heap ? L_HEAP_BOUND : L_AUX_BOUND;
     uint32_t bound = S.row[w];
-    __syncwarp();
+    osync();
     if (incremented >= bound) {
       growth = incremented - bound;
       setL(w, incremented);
@@ -1706,139 +1751,130 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
 // ===================================================================================================
 // load / run / store one VM
 // ===================================================================================================
-// load VM `v.vm`'s hot state from HBM into shared memory / warp-uniform registers
+// load VM `v.vm`'s hot state from HBM into shared memory / octet-uniform registers
 __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
-  WarpSmem& S = v.S;
+  VmSmem& S = v.S;
   const uint32_t lane = v.lane;
-  uint32_t* sregs = &S.regs[0][0];
-  const uint32_t* hregs = &hot->regs[0][0];
+  uint4* sregs = reinterpret_cast<uint4*>(&S.regs[0][0]);
+  const uint4* hregs = reinterpret_cast<const uint4*>(&hot->regs[0][0]);
 #pragma unroll
-  for (int i = 0; i < 4; i++) sregs[i * 32 + lane] = hregs[i * 32 + lane];
-  S.F[lane] = hot->F[lane];
-  S.row[lane] = 0u;
-  S.row[32 + lane] = lane >= 8 && lane < 24 ? hot->live[lane - 8] : 0u;
+  for (int i = 0; i < 4; i++) sregs[i * 8 + lane] = hregs[i * 8 + lane];
+  reinterpret_cast<uint4*>(S.F)[lane] = reinterpret_cast<const uint4*>(hot->F)[lane];
+  // row words 0..39 start as zero, words 40..55 are the live tail, 56..63 reserved (zero)
+  uint4* srow = reinterpret_cast<uint4*>(S.row);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  srow[lane] = zero4;
+  srow[8 + lane] = (lane >= 2 && lane < 6) ? reinterpret_cast<const uint4*>(hot->live)[lane - 2] : zero4;
   if (lane == 0) S.kbuf[KB_EC_PENDING] = 0u;
-  v.prev_word = lane < 8 ? hot->prev_word[lane] : 0u;
-  uint32_t x = hot->x[lane];
-  v.timestamp = __shfl_sync(ZK_FULL, x, X_TIMESTAMP);
-  v.cycle = __shfl_sync(ZK_FULL, x, X_CYCLE);
-  v.flags = __shfl_sync(ZK_FULL, x, X_FLAGS);
-  v.pending = __shfl_sync(ZK_FULL, x, X_PENDING);
+  v.prev_word = hot->prev_word[lane];
+  const uint32_t* x = hot->x;
+  v.timestamp = x[X_TIMESTAMP];
+  v.cycle = x[X_CYCLE];
+  v.flags = x[X_FLAGS];
+  v.pending = x[X_PENDING];
   v.status = ZKB_VM_RUNNING;
-  v.ptr_mask = __shfl_sync(ZK_FULL, x, X_PTRMASK);
-  v.prev_code_page = __shfl_sync(ZK_FULL, x, X_PREV_CODE_PAGE);
-  v.journal_len = __shfl_sync(ZK_FULL, x, X_JOURNAL_LEN);
-  v.n_decommit = __shfl_sync(ZK_FULL, x, X_N_DECOMMIT);
-  v.slab_free = __shfl_sync(ZK_FULL, x, X_SLAB_FREE);
+  v.ptr_mask = x[X_PTRMASK];
+  v.prev_code_page = x[X_PREV_CODE_PAGE];
+  v.journal_len = x[X_JOURNAL_LEN];
+  v.n_decommit = x[X_N_DECOMMIT];
+  v.slab_free = x[X_SLAB_FREE];
 #pragma unroll
-  for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = __shfl_sync(ZK_FULL, x, X_COUNT0 + k);
+  for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = x[X_COUNT0 + k];
   v.rowbits = 0;
   v.ccount = 0;
   v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
-  __syncwarp();
+  osync();
   v.load_frame_from_F();
 }
 
 // write the hot state back to HBM (the batch is resumable: zkb_run may be called again)
 __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
-  WarpSmem& S = v.S;
+  VmSmem& S = v.S;
   const uint32_t lane = v.lane;
-  __syncwarp();
+  osync();
   v.sync_frame_to_F();
-  uint32_t* sregs = &S.regs[0][0];
-  uint32_t* gregs = &hot->regs[0][0];
+  const uint4* sregs = reinterpret_cast<const uint4*>(&S.regs[0][0]);
+  uint4* gregs = reinterpret_cast<uint4*>(&hot->regs[0][0]);
 #pragma unroll
-  for (int i = 0; i < 4; i++) gregs[i * 32 + lane] = sregs[i * 32 + lane];
-  hot->F[lane] = S.F[lane];
-  if (lane < 16) hot->live[lane] = S.row[40 + lane];
-  if (lane < 8) hot->prev_word[lane] = v.prev_word;
-  uint32_t out = 0;
-  out = lane == X_TIMESTAMP ? v.timestamp : out;
-  out = lane == X_CYCLE ? v.cycle : out;
-  out = lane == X_FLAGS ? v.flags : out;
-  out = lane == X_PENDING ? v.pending : out;
-  out = lane == X_STATUS ? v.status : out;
-  out = lane == X_PTRMASK ? v.ptr_mask : out;
-  out = lane == X_PREV_CODE_PAGE ? v.prev_code_page : out;
-  out = lane == X_FAR_DEPTH ? v.far_depth : out;
-  out = lane == X_JOURNAL_LEN ? v.journal_len : out;
-  out = lane == X_N_DECOMMIT ? v.n_decommit : out;
-  out = lane == X_SLAB_FREE ? v.slab_free : out;
+  for (int i = 0; i < 4; i++) gregs[i * 8 + lane] = sregs[i * 8 + lane];
+  reinterpret_cast<uint4*>(hot->F)[lane] = reinterpret_cast<const uint4*>(S.F)[lane];
+  if (lane < 4) reinterpret_cast<uint4*>(hot->live)[lane] = reinterpret_cast<const uint4*>(S.row)[10 + lane];
+  hot->prev_word[lane] = v.prev_word;
+  // x[]: octet lane l writes words 4l .. 4l+3
+  {
+    uint32_t w[4];
 #pragma unroll
-  for (int k = 0; k < ZKB_N_STREAMS; k++) out = lane == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
-  hot->x[lane] = out;
+    for (int q = 0; q < 4; q++) {
+      const uint32_t i = lane * 4 + q;
+      uint32_t out = 0;
+      out = i == X_TIMESTAMP ? v.timestamp : out;
+      out = i == X_CYCLE ? v.cycle : out;
+      out = i == X_FLAGS ? v.flags : out;
+      out = i == X_PENDING ? v.pending : out;
+      out = i == X_STATUS ? v.status : out;
+      out = i == X_PTRMASK ? v.ptr_mask : out;
+      out = i == X_PREV_CODE_PAGE ? v.prev_code_page : out;
+      out = i == X_FAR_DEPTH ? v.far_depth : out;
+      out = i == X_JOURNAL_LEN ? v.journal_len : out;
+      out = i == X_N_DECOMMIT ? v.n_decommit : out;
+      out = i == X_SLAB_FREE ? v.slab_free : out;
+#pragma unroll
+      for (int k = 0; k < ZKB_N_STREAMS; k++) out = i == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
+      w[q] = out;
+    }
+    reinterpret_cast<uint4*>(hot->x)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   // the per-VM summary goes straight to mapped host memory (one 32-byte posted write per VM and run): the host can
   // size and enqueue the witness download without a D2H copy of its own queueing behind the copies already in flight
   const uint32_t st_out = (v.status == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : v.status;
   uint32_t summary = lane == 6 ? st_out : v.cycle;
 #pragma unroll
   for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.count[k] : summary;
-  if (lane < 8) v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
-  __syncwarp();
+  v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
+  osync();
 }
 
 // the deferred half of the ecrecover precompile: runs between vm_store and vm_load, i.e. with no interpreter state in
-// registers; reads its inputs from the warp's scratch, patches the heap words and the two memory-query records
+// registers; reads its inputs from the VM's scratch, patches the heap words and the two memory-query records
 // (plain scalar arguments: handing the launch-constant DevBatch to a non-inlined function by reference would force a
 // copy of the whole struct onto the local-memory stack of every thread)
-__device__ __noinline__ void run_deferred_ecrecover(uint32_t* kbuf, uint32_t* vm_heap, uint32_t heap_words, uint8_t* vm_mem_stream,
+__device__ __noinline__ void run_deferred_ecrecover(uint32_t* kbuf, uint64_t* ks, uint32_t* vm_heap, uint32_t heap_words, uint8_t* vm_mem_stream,
                                                     uint32_t lane) {
-  __syncwarp();
+  osync();
   u256l in[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) in[i] = lane < 8 ? kbuf[KB_EC_INPUT + 8 * i + lane] : 0u;
+  for (int i = 0; i < 4; i++) in[i] = kbuf[KB_EC_INPUT + 8 * i + lane];
   const uint32_t rec = kbuf[KB_EC_MEM_INDEX], slab = kbuf[KB_EC_SLAB], out_word = kbuf[KB_EC_OUT_WORD];
-  __syncwarp();
+  osync();
   u256l address;
-  const bool ok = secp::ecrecover_warp(in[0], in[2], in[3], __shfl_sync(ZK_FULL, in[1], 0), lane, address);
+  const bool ok = secp::ecrecover_octet(in[0], in[2], in[3], oshfl(in[1], 0), lane, ks, address);
   const u256l marker = lane == 0 ? (ok ? 1u : 0u) : 0u;
   uint32_t* heap = vm_heap + ((size_t)slab * heap_words + out_word) * 8;
-  if (lane < 8) {
-    heap[lane] = marker;
-    heap[8 + lane] = address;
-    if (vm_mem_stream) {
-      uint32_t* r = reinterpret_cast<uint32_t*>(vm_mem_stream + (size_t)rec * ZKB_MEM_BYTES);
-      r[4 + lane] = marker;
-      r[ZKB_MEM_BYTES / 4 + 4 + lane] = address;
-    }
+  heap[lane] = marker;
+  heap[8 + lane] = address;
+  if (vm_mem_stream) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(vm_mem_stream + (size_t)rec * ZKB_MEM_BYTES);
+    r[4 + lane] = marker;
+    r[ZKB_MEM_BYTES / 4 + 4 + lane] = address;
   }
   if (lane == 0) kbuf[KB_EC_PENDING] = 0u;
-  __syncwarp();
+  osync();
 }
-__device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, WarpSmem& S, uint32_t vm, uint32_t lane) {
-  run_deferred_ecrecover(S.kbuf, B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8, B.heap_words,
+__device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, VmSmem& S, uint32_t vm, uint32_t lane) {
+  run_deferred_ecrecover(S.kbuf, S.ks, B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8, B.heap_words,
                          B.witness ? B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES : nullptr, lane);
 }
 
-// free-running schedule: one warp runs one VM to the end (or for max_cycles cycles)
-__device__ __forceinline__ void run_vm(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
-  VmHot* hot = B.hot + vm_idx;
-  if (hot->x[X_STATUS] != ZKB_VM_RUNNING) return;
-  Vm v(B, S, vm_idx, lane);
-  vm_load(v, hot);
-  uint32_t n = 0;
-  if (S.row[L_DEPTH] == 0) v.status = ZKB_VM_ENDED;  // nothing to run; later ends are detected by the RET that pops the last frame
-  for (;;) {
-    while (v.status == ZKB_VM_RUNNING) {
-      if (max_cycles && n >= max_cycles) break;
-      v.cycle_once();
-      n++;
-    }
-    if (v.status != ZKB_VM_YIELD_ECRECOVER) break;
-    v.status = ZKB_VM_RUNNING;  // park the VM, finish the pending recovery, resume
-    vm_store(v, hot);
-    deferred_ecrecover(B, S, vm_idx, lane);
-    vm_load(v, hot);
-  }
-  vm_store(v, hot);
-}
-
-// lockstep schedule: the W warps of a CTA run W consecutive VMs cycle by cycle with one CTA barrier per VM
-// cycle.  Batches of transactions against the same contracts follow (nearly) the same path through the
-// interpreter, so the warps of a CTA execute the same handler at the same time and share its instruction-cache
-// lines (the interpreter is ~190 KB of SASS against a 32 KB L1.5 I-cache; the free-running schedule spends most
-// of its issue slots waiting for instruction fetch).
-__device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
+// Runs the four VMs of one warp (VM `vm_idx` on the calling octet) to the end, or for max_cycles cycles each.
+//
+// Inside the warp the four octets re-converge at one warp vote per VM cycle, so VMs that follow the same path through
+// the interpreter share every issue slot.  LOCKSTEP additionally lines up the W warps of the CTA: they meet at a CTA
+// barrier every ZKB_LOCKSTEP_PERIOD cycles, so batches of transactions against the same contracts execute the same
+// handler at the same time and share its instruction-cache lines (the interpreter is ~170 KB of SASS against a 32 KB
+// L1.5 instruction cache; free-running warps spend most of their issue slots waiting for instruction fetch).
+// All threads of the warp (LOCKSTEP: of the CTA) must call, also for vm_idx >= n_vms.
+template <bool LOCKSTEP>
+__device__ __forceinline__ void run_vm_group(const DevBatch& B, VmSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
   const bool valid = vm_idx < B.n_vms && B.hot[vm_idx < B.n_vms ? vm_idx : 0].x[X_STATUS] == ZKB_VM_RUNNING;
   VmHot* hot = B.hot + (valid ? vm_idx : 0);
   Vm v(B, S, valid ? vm_idx : 0, lane);
@@ -1851,15 +1887,14 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
   while (true) {
     // up to ZKB_LOCKSTEP_PERIOD cycles between two CTA barriers: the warps may drift by a few hundred instructions
     // (still inside the I-cache window) and the barrier waits for the slowest SUM of cycles, not the slowest cycle
-    bool active = valid && v.status == ZKB_VM_RUNNING;
+    bool active = valid && v.status == ZKB_VM_RUNNING && !(max_cycles && n >= max_cycles);
 #pragma unroll 1
-    for (int k = 0; k < ZKB_LOCKSTEP_PERIOD && active; k++) {
-      if (max_cycles && n >= max_cycles) {
-        active = false;
-      } else {
+    for (int k = 0; k < ZKB_LOCKSTEP_PERIOD; k++) {
+      if (!__any_sync(ZK_FULL, active)) break;  // warp-uniform; also the per-cycle re-convergence point of the four octets
+      if (active) {
         v.cycle_once();
         n++;
-        active = v.status == ZKB_VM_RUNNING;
+        active = v.status == ZKB_VM_RUNNING && !(max_cycles && n >= max_cycles);
       }
     }
     if (valid && v.status == ZKB_VM_YIELD_ECRECOVER) {  // park the VM, finish the pending recovery, resume
@@ -1867,10 +1902,13 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, WarpSmem& S, uin
       vm_store(v, hot);
       deferred_ecrecover(B, S, v.vm, lane);
       vm_load(v, hot);
-      active = true;
+      active = !(max_cycles && n >= max_cycles);
     }
-    if (active && max_cycles && n >= max_cycles) active = false;
-    if (!__syncthreads_or(active ? 1 : 0)) break;
+    if (LOCKSTEP) {
+      if (!__syncthreads_or(active ? 1 : 0)) break;
+    } else {
+      if (!__any_sync(ZK_FULL, active)) break;
+    }
   }
   if (valid) vm_store(v, hot);
 }

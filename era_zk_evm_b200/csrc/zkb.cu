@@ -24,32 +24,37 @@ using namespace zkb;
 // kernels
 // ---------------------------------------------------------------------------------------------------
 // K1: persistent interpreter.  Replaces the caller loop `while !vm.execution_has_ended() { vm.cycle() }`.
-// LOCKSTEP = false: each warp pulls VM indices from an atomic queue and runs its VM to completion.
-// LOCKSTEP = true : each CTA pulls groups of W consecutive VMs and steps them together (run_vm_group).
+// One VM per octet (8 lanes), four VMs per warp, ZKB_VMS_PER_CTA per CTA (vm.cuh).
+// LOCKSTEP = false: each warp pulls four consecutive VM indices from an atomic queue and runs them to completion.
+// LOCKSTEP = true : each CTA pulls ZKB_VMS_PER_CTA consecutive VMs and steps them together (run_vm_group).
+#define ZKB_VMS_PER_CTA (ZKB_WARPS_PER_CTA * ZK_VMS_PER_WARP)
+#define ZKB_RUN_SMEM_BYTES (ZKB_VMS_PER_CTA * sizeof(VmSmem))
 template <bool LOCKSTEP>
 __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) zkb_run_kernel(const DevBatch B, uint32_t max_cycles) {
-  __shared__ WarpSmem smem[ZKB_WARPS_PER_CTA];
+  extern __shared__ uint4 smem_raw[];
   __shared__ uint32_t s_base;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  WarpSmem& S = smem[warp];
+  VmSmem* smem = reinterpret_cast<VmSmem*>(smem_raw);
+  const uint32_t lane = oct_lane(), warp = threadIdx.x >> 5, oct = threadIdx.x >> 3;  // oct = VM slot within the CTA
+  VmSmem& S = smem[oct];
   if (!LOCKSTEP) {
     while (true) {
-      uint32_t vm_idx = 0;
-      if (lane == 0) vm_idx = atomicAdd(B.queue, 1u);
-      vm_idx = __shfl_sync(ZK_FULL, vm_idx, 0);
-      if (vm_idx >= B.n_vms) break;
-      run_vm(B, S, vm_idx, lane, max_cycles);
+      uint32_t vm_base = 0;
+      if ((threadIdx.x & 31u) == 0) vm_base = atomicAdd(B.queue, (uint32_t)ZK_VMS_PER_WARP);
+      vm_base = __shfl_sync(ZK_FULL, vm_base, 0);
+      if (vm_base >= B.n_vms) break;
+      run_vm_group<false>(B, S, vm_base + oct_index(), lane, max_cycles);
     }
   } else {
     while (true) {
-      if (threadIdx.x == 0) s_base = atomicAdd(B.queue, (uint32_t)ZKB_WARPS_PER_CTA);
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue, (uint32_t)ZKB_VMS_PER_CTA);
       __syncthreads();
       const uint32_t base = s_base;
       if (base >= B.n_vms) break;
-      run_vm_group(B, S, base + warp, lane, max_cycles);
+      run_vm_group<true>(B, S, base + oct, lane, max_cycles);
       __syncthreads();
     }
   }
+  (void)warp;
 }
 
 // K6a: per-VM cold-state initialisation (level table, page indirections)
@@ -77,22 +82,22 @@ struct DevStorageInit {
   uint32_t value[8];
 };
 
-// K6b: InMemoryStorage::populate (storage.rs:26-32): one warp per VM inserts n entries through the same
+// K6b: InMemoryStorage::populate (storage.rs:26-32): one octet per VM inserts n entries through the same
 // open-addressed insert the interpreter uses (no journal).
 __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, uint32_t vm_hi, const DevStorageInit* entries, uint32_t n,
                                             uint32_t per_vm, uint32_t* fail_flag) {
-  __shared__ WarpSmem smem[4];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t vm = vm_lo + blockIdx.x * 4 + warp;
-  if (vm >= vm_hi) return;
-  Vm v(B, smem[warp], vm, lane);
+  __shared__ VmSmem smem[16];  // not touched by storage_access; the Vm object only wants a reference
+  const uint32_t lane = oct_lane(), oct = threadIdx.x >> 3;
+  uint32_t vm = vm_lo + blockIdx.x * 16 + oct;
+  if (vm >= vm_hi) return;  // octet-uniform: whole octets leave together
+  Vm v(B, smem[oct], vm, lane);
   v.status = ZKB_VM_RUNNING;
   v.journal_len = 0;
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
-    u256l key = lane < 8 ? e[i].key[lane] : 0u;
-    u256l val = lane < 8 ? e[i].value[lane] : 0u;
+    u256l key = e[i].key[lane];
+    u256l val = e[i].value[lane];
     v.storage_access(e[i].shard, aw, key, true, val, false);
   }
   if (v.status != ZKB_VM_RUNNING && lane == 0) *fail_flag = v.status;
@@ -610,7 +615,9 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   CUDA_OK(cudaEventCreate(&b->ev1));
   CUDA_OK(cudaEventCreateWithFlags(&b->ev_setup, cudaEventDisableTiming));
   int per_sm = 0, n_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, 0));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES));
   CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   b->grid = std::max(1, per_sm * n_sm);  // persistent grid: a multiple of the SM count (148 on B200)
   if (cfg->reserved[0] > 0 && (int)cfg->reserved[0] < n_sm) b->grid = per_sm * (n_sm - (int)cfg->reserved[0]);
@@ -694,7 +701,7 @@ int32_t zkb_populate_storage(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const 
   DevStorageInit* d_e = reinterpret_cast<DevStorageInit*>(staged);
   if (!b->h_fail) return set_err(ZKB_ERR_OUT_OF_MEMORY, "no mapped host flag");
   *b->h_fail = 0;
-  zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 3) / 4, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
+  zkb_populate_storage_kernel<<<(vm_hi - vm_lo + 15) / 16, 128>>>(b->d, vm_lo, vm_hi, d_e, n, per_vm, b->d_fail);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(0));  // orders the kernel before the staging buffer is reused; the flag is host-mapped
   uint32_t fail = *(volatile uint32_t*)b->h_fail;
@@ -829,11 +836,11 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   }
   CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 4, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
-  int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_WARPS_PER_CTA - 1) / ZKB_WARPS_PER_CTA));
+  int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_VMS_PER_CTA - 1) / ZKB_VMS_PER_CTA));
   if (b->lockstep)
-    zkb_run_kernel<true><<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
+    zkb_run_kernel<true><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
   else
-    zkb_run_kernel<false><<<grid, ZKB_WARPS_PER_CTA * 32, 0, st>>>(b->d, max_cycles_per_vm);
+    zkb_run_kernel<false><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(b->ev1, st));
   b->n_launches = 1;
