@@ -116,9 +116,13 @@ struct __align__(16) VmSmem {
   uint32_t F[32];
   uint32_t kbuf[64];
   uint64_t ks[26];     // keccak-f[1600] scratch (25 lanes)
-  uint32_t pad[20];
+  uint32_t pw[8];      // previous_code_word (cycle.rs:59-100): the 4 opcodes of the current code word
+  uint32_t pt[ZKB_PT_ENTRIES * 2];  // page indirections (page, kind | slab << 8 | cleanup_level << 16); HBM copy: DevBatch.pt
+  uint32_t hwm[32];    // words touched per heap slab; HBM copy: DevBatch.slab_hwm
+  uint32_t lv[4];      // the current far level's entry of DevBatch.lvl: heap slab, aux slab, stack high-water mark, -
+  uint32_t pad[8];
 };
-static_assert(sizeof(VmSmem) == 1440 && (sizeof(VmSmem) / 4) % 32 == 8, "VmSmem bank skew");
+static_assert(sizeof(VmSmem) == 1824 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
 typedef VmSmem WarpSmem;
 
 struct Vm {
@@ -135,7 +139,7 @@ struct Vm {
   uint32_t forbid;  // ZK_E_* bits an opcode must not have in the current frame (kernel-only / not-in-static)
   const uint32_t* code;
   uint32_t code_len;
-  u256l prev_word;  // distributed
+  uint32_t tx_psp;  // tx_number_in_block | previous_super_pc << 16 (row word L_TX_PSP, written back at row emission)
   // decoded opcode (octet-uniform)
   uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
   uint32_t dst_loc_valid, dst_loc_index;
@@ -144,8 +148,6 @@ struct Vm {
   uint8_t* g_stack_ptr;
   uint32_t* g_heap;
   uint32_t* g_lvl;
-  uint32_t* g_slab_hwm;
-  uint32_t* g_pt;
   uint8_t* row_base;  // this VM's slab of the ROWS / MEM streams (the two streams written every cycle)
   uint8_t* mem_base;
 
@@ -154,8 +156,6 @@ struct Vm {
     g_stack_ptr = B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words;
     g_heap = B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8;
     g_lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
-    g_slab_hwm = B.slab_hwm + (size_t)vm * B.n_slabs;
-    g_pt = B.pt + (size_t)vm * ZKB_PT_ENTRIES * 2;
     row_base = B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES;
     mem_base = B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES;
   }
@@ -226,7 +226,7 @@ struct Vm {
                                            u256l key, u256l read_value, u256l written_value) {
     ccount += 1u << 16;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_LOG);
-    uint32_t tx = S.row[L_TX_PSP] & 0xFFFFu;
+    uint32_t tx = tx_psp & 0xFFFFu;
     if (p) {
       if (lane == 0) {
         *reinterpret_cast<uint2*>(p) = make_uint2(ts, tx | aux << 16 | shard << 24);
@@ -300,9 +300,9 @@ struct Vm {
     size_t off = (size_t)far_depth * B.stack_words + index;
     g_stack[off * 8 + lane] = v;
     if (lane == 1) g_stack_ptr[off] = (uint8_t)is_ptr;
-    uint32_t hwm = g_lvl[far_depth * 4 + 2];
-    if (index + 1 > hwm && lane == 0) g_lvl[far_depth * 4 + 2] = index + 1;
-    osync();
+    if (lane == 0 && index + 1 > S.lv[2]) S.lv[2] = index + 1;
+    // no octet sync: limb l is read back by lane l; the pointer byte and the high-water mark are read by other lanes only
+    // in later cycles, i.e. behind the sync of the row emission
   }
 
   // ---- heap slabs (SimpleMemory heaps / pages_with_extended_lifetime, memory.rs:439-521) ----------
@@ -317,11 +317,11 @@ struct Vm {
   }
   __device__ __forceinline__ void slab_release(uint32_t s) {
     if (s == ZKB_NO_SLAB) return;
-    uint32_t hwm = g_slab_hwm[s];
+    uint32_t hwm = S.hwm[s];
     uint32_t* base = g_heap + (size_t)s * B.heap_words * 8;
     uint4* base4 = reinterpret_cast<uint4*>(base);
     for (uint32_t i = lane; i < hwm * 2; i += 8) base4[i] = make_uint4(0u, 0u, 0u, 0u);  // == heap_on_return fill (memory.rs:181-183)
-    if (lane == 0) g_slab_hwm[s] = 0;
+    if (lane == 0) S.hwm[s] = 0;
     slab_free |= 1u << s;
     osync();
   }
@@ -331,12 +331,14 @@ struct Vm {
   }
   __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
     g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
-    if (word + 1 > g_slab_hwm[s] && lane == 0) g_slab_hwm[s] = word + 1;
-    osync();
+    if (word + 1 > S.hwm[s] && lane == 0) S.hwm[s] = word + 1;  // (as in stack_write: no octet sync needed)
   }
+  // heap (which = 0) / aux heap (which = 1) slab of far level x: the current level's entry lives in shared memory, the
+  // callers' entries are current in HBM (written back when the callee's level started)
+  __device__ __forceinline__ uint32_t level_slab(uint32_t x, uint32_t which) const { return x == far_depth ? S.lv[which] : g_lvl[x * 4 + which]; }
   // slab of the current frame's heap (which = 0) / aux heap (which = 1); allocate lazily on first write
   __device__ __forceinline__ uint32_t cur_slab(uint32_t which, bool for_write, uint32_t word) {
-    uint32_t s = g_lvl[far_depth * 4 + which];
+    uint32_t s = S.lv[which];
     if (for_write) {
       if (word >= B.heap_words) {
         fail(ZKB_VM_CAP_HEAP);
@@ -344,7 +346,7 @@ struct Vm {
       }
       if (s == ZKB_NO_SLAB) {
         s = slab_alloc();
-        if (lane == 0) g_lvl[far_depth * 4 + which] = s;
+        if (lane == 0) S.lv[which] = s;
         osync();
       }
     }
@@ -354,7 +356,7 @@ struct Vm {
   // ---- page indirections (SimpleMemory.page_numbers_indirections, memory.rs:160-171,475-521) ------
   __device__ __forceinline__ int pt_find(uint32_t page) {
     // octet lane l looks at entries 4l .. 4l+3 (two 16-byte loads)
-    const uint4 a = reinterpret_cast<const uint4*>(g_pt)[lane * 2], b = reinterpret_cast<const uint4*>(g_pt)[lane * 2 + 1];
+    const uint4 a = reinterpret_cast<const uint4*>(S.pt)[lane * 2], b = reinterpret_cast<const uint4*>(S.pt)[lane * 2 + 1];
     const uint32_t h = (a.x == page ? 1u : 0u) | (a.z == page ? 2u : 0u) | (b.x == page ? 4u : 0u) | (b.z == page ? 8u : 0u);
     const uint32_t m = oballot(h != 0);
     if (!m) return -1;
@@ -369,8 +371,8 @@ struct Vm {
       return;
     }
     if (lane == 0) {
-      g_pt[e * 2] = page;
-      g_pt[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
+      S.pt[e * 2] = page;
+      S.pt[e * 2 + 1] = kind | slab_or_level << 8 | cleanup_level << 16;
     }
     osync();
   }
@@ -383,9 +385,9 @@ struct Vm {
       ok = false;
       return 0u;
     }
-    uint32_t info = g_pt[e * 2 + 1];
+    uint32_t info = S.pt[e * 2 + 1];
     uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
-    uint32_t s = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+    uint32_t s = kind == PT_EXT ? x : level_slab(x, kind == PT_AUX_LIVE ? 1 : 0);
     return slab_read(s, word);
   }
 
@@ -408,6 +410,7 @@ struct Vm {
     uint32_t tag = h | 0x80000000u;
     uint32_t mask = B.storage_slots - 1;
     int found = -1, insert_at = -1;
+    u256l old = 0u;
     for (uint32_t base = 0; base < B.storage_slots && found < 0 && insert_at < 0; base += ZK_OCT) {
       uint32_t idx = (h + base + lane) & mask;
       uint32_t t = tags[idx];
@@ -419,17 +422,16 @@ struct Vm {
         int c = __ffs(m_match) - 1;
         m_match &= m_match - 1;
         uint32_t ci = (h + base + c) & mask;
-        bool same = keys[ci * 8 + lane] == key;
-        if (lane < 6) same = same && addrs[ci * 8 + lane] == extra;
-        if (oall(same)) {
+        // key, address and value of the candidate are fetched together (one HBM round trip instead of two)
+        const uint32_t k = keys[ci * 8 + lane], a = lane < 6 ? addrs[ci * 8 + lane] : 0u, val = vals[ci * 8 + lane];
+        if (oall(k == key && a == extra)) {
           found = (int)ci;
+          old = val;
           break;
         }
       }
       if (found < 0 && m_empty) insert_at = (int)((h + base + __ffs(m_empty) - 1) & mask);
     }
-    u256l old = 0u;
-    if (found >= 0) old = vals[found * 8 + lane];
     if (is_write) {
       int slot = found;
       if (slot < 0) {
@@ -599,17 +601,19 @@ __device__ __forceinline__ void Vm::cycle_once() {
   // ---- fetch (cycle.rs:46-130) ----
   const uint32_t code_page = S.row[L_CODE_PAGE];
   const uint32_t super_pc = pc >> 2, sub_pc = pc & 3u;
-  uint32_t prev_super_pc = S.row[L_TX_PSP] >> 16;
+  uint32_t prev_super_pc = tx_psp >> 16;
   uint32_t raw_lo, raw_hi;
   if (!ZK_UNLIKELY(pending)) {
     if (code_page != prev_code_page || prev_super_pc != super_pc) {
       u256l w = super_pc < code_len ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
-      prev_word = w;
+      S.pw[lane] = w;
+      osync();
       prev_super_pc = super_pc;
       emit_mem(timestamp, code_page, super_pc, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, w);
     }
-    raw_lo = oshfl(prev_word, 6 - 2 * (int)sub_pc);
-    raw_hi = oshfl(prev_word, 7 - 2 * (int)sub_pc);
+    const uint2 raw = *reinterpret_cast<const uint2*>(&S.pw[6 - 2 * (int)sub_pc]);  // broadcast read
+    raw_lo = raw.x;
+    raw_hi = raw.y;
   } else {
     pending = 0;
     prev_super_pc = super_pc;
@@ -654,9 +658,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
   dst1_reg = ops_lo >> 28;
   imm0 = ops_hi & 0xFFFFu;
   imm1 = ops_hi >> 16;
-  // delayed changes (mod.rs:134-153): previous_super_pc lives in the row tail
-  osync();
-  if (lane == 0) S.row[L_TX_PSP] = (S.row[L_TX_PSP] & 0xFFFFu) | prev_super_pc << 16;
+  // delayed changes (mod.rs:134-153): previous_super_pc goes back to the row tail with the row head
+  tx_psp = (tx_psp & 0xFFFFu) | prev_super_pc << 16;
 
   // ---- operand addressing (mem_ops.rs:14-125, cycle.rs:275-345) ----
   const uint32_t family = entry & 15u, sub = (entry >> ZK_E_SUB_SHIFT) & 15u;
@@ -664,7 +667,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   u256l src0 = reg_read(src0_reg);
   uint32_t src0_ptr = (ptr_mask >> src0_reg) & 1u;
   if (src_mode != ZK_SRC_REG) {
-    uint32_t vaddr = (oshfl(src0, 0) + imm0) & 0xFFFFu;
+    uint32_t vaddr = (S.regs[src0_reg][0] + imm0) & 0xFFFFu;
     if (src_mode == ZK_SRC_IMM) {
       src0 = lane == 0 ? imm0 : 0u;
       src0_ptr = 0;
@@ -838,6 +841,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
     *reinterpret_cast<uint4*>(&S.row[4]) = make_uint4(vidx | (resolved ? 1u : 0u) << 16 | err << 24, pc_before | pc << 16,
                                                       sp | flags << 16 | (rowbits | (pending ? ZKB_ROWBIT_PENDING : 0u)) << 24, ergs);
     S.row[L_COUNTS] = ccount;
+    S.row[L_TX_PSP] = tx_psp;
   }
   const uint32_t n_rows = count[ZKB_STREAM_ROWS];
   if (ZK_UNLIKELY(n_rows >= B.cap[ZKB_STREAM_ROWS])) {
@@ -871,9 +875,7 @@ __device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
     return;
   }
   if (sub == ZK_CTX_INC_TX) {
-    uint32_t t = S.row[L_TX_PSP];
-    osync();
-    setL(L_TX_PSP, (t & 0xFFFF0000u) | ((t + 1u) & 0xFFFFu));
+    tx_psp = (tx_psp & 0xFFFF0000u) | ((tx_psp + 1u) & 0xFFFFu);
     return;
   }
   u256l v = 0u;
@@ -1062,9 +1064,9 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
       fail(ZKB_VM_REFERENCE_PANIC);
       return;
     }
-    uint32_t info = g_pt[e * 2 + 1];
+    uint32_t info = S.pt[e * 2 + 1];
     uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
-    src_slab = kind == PT_EXT ? x : g_lvl[x * 4 + (kind == PT_AUX_LIVE ? 1 : 0)];
+    src_slab = kind == PT_EXT ? x : level_slab(x, kind == PT_AUX_LIVE ? 1 : 0);
   }
   const KeccakLanes kl = keccak_lanes(lane);
   KeccakState st;
@@ -1144,7 +1146,7 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
-  const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
+  const uint32_t src_slab = S.lv[0];
   S.kbuf[lane] = c_sha256_iv[lane];
   for (uint64_t r = 0; r < rounds; r++) {
 #pragma unroll
@@ -1181,7 +1183,7 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
     fail(ZKB_VM_REFERENCE_PANIC);
     return;
   }
-  const uint32_t src_slab = g_lvl[far_depth * 4 + 0];
+  const uint32_t src_slab = S.lv[0];
   u256l v_word = 0u;
 #pragma unroll
   for (uint32_t i = 0; i < 4; i++) {
@@ -1216,10 +1218,10 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
 // SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth (already incremented)
 __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
   uint32_t level = far_depth;
-  if (lane == 0) {
-    g_lvl[level * 4 + 0] = ZKB_NO_SLAB;
-    g_lvl[level * 4 + 1] = ZKB_NO_SLAB;
-    g_lvl[level * 4 + 2] = 0;
+  // the caller's level entry goes back to HBM, the callee starts with no heaps and an untouched stack page
+  if (lane < 4) {
+    g_lvl[caller_level * 4 + lane] = S.lv[lane];
+    S.lv[lane] = lane < 2 ? ZKB_NO_SLAB : 0u;
   }
   osync();
   // the root "heaps" entry has page numbers 0/0 (memory.rs:230-233)
@@ -1235,7 +1237,7 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
       fail(ZKB_VM_REFERENCE_PANIC);  // "fat pointer must only point to reachable memory" (memory.rs:641)
       return;
     }
-    uint32_t kind = g_pt[e * 2 + 1] & 0xFFu;
+    uint32_t kind = S.pt[e * 2 + 1] & 0xFFu;
     if (kind != PT_HEAP_LIVE && kind != PT_AUX_LIVE) fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:645
   }
 }
@@ -1243,13 +1245,13 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
 // SimpleMemory::finish_global_frame (memory.rs:660-758)
 __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
   // stack page goes back to the pool: clear what was touched (stack_on_return, memory.rs:185-188)
-  uint32_t hwm = g_lvl[level * 4 + 2];
+  uint32_t hwm = S.lv[2];  // S.lv still holds the finished level's entry (the parent's is reloaded at the end)
   uint32_t* sbase = g_stack + (size_t)level * B.stack_words * 8;
   uint8_t* pbase = g_stack_ptr + (size_t)level * B.stack_words;
   uint4* sbase4 = reinterpret_cast<uint4*>(sbase);
   for (uint32_t i = lane; i < hwm * 2; i += 8) sbase4[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = lane; i < hwm; i += 8) pbase[i] = 0;
-  uint32_t heap_slab = g_lvl[level * 4 + 0], aux_slab = g_lvl[level * 4 + 1];
+  uint32_t heap_slab = S.lv[0], aux_slab = S.lv[1];
   osync();
   uint32_t heap_page = base_page + 2, aux_page = base_page + 3;
   if (returndata_page == heap_page) {
@@ -1265,7 +1267,7 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
         fail(ZKB_VM_REFERENCE_PANIC);  // memory.rs:735
         return;
       }
-      if (lane == 0) g_pt[e * 2 + 1] = (g_pt[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
+      if (lane == 0) S.pt[e * 2 + 1] = (S.pt[e * 2 + 1] & 0xFFFFu) | (level - 1) << 16;
       osync();
     }
     slab_release(heap_slab);
@@ -1275,16 +1277,18 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
 #pragma unroll 1
   for (uint32_t q = 0; q < ZKB_PT_ENTRIES / ZK_OCT; q++) {
     const uint32_t e0 = lane + ZK_OCT * q;
-    const uint32_t page = g_pt[e0 * 2], info = g_pt[e0 * 2 + 1];
+    const uint32_t page = S.pt[e0 * 2], info = S.pt[e0 * 2 + 1];
     uint32_t drop = oballot(page != ZKB_PT_FREE && (info >> 16) == level);
     while (drop) {
       int l = __ffs(drop) - 1;
       drop &= drop - 1;
       uint32_t einfo = oshfl(info, l);
       if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
-      if (lane == 0) g_pt[(l + ZK_OCT * q) * 2] = ZKB_PT_FREE;
+      if (lane == 0) S.pt[(l + ZK_OCT * q) * 2] = ZKB_PT_FREE;
     }
   }
+  osync();
+  if (lane < 4) S.lv[lane] = g_lvl[far_depth * 4 + lane];  // back in the caller's far level
   osync();
 }
 
@@ -1766,7 +1770,8 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   srow[lane] = zero4;
   srow[8 + lane] = (lane >= 2 && lane < 6) ? reinterpret_cast<const uint4*>(hot->live)[lane - 2] : zero4;
   if (lane == 0) S.kbuf[KB_EC_PENDING] = 0u;
-  v.prev_word = hot->prev_word[lane];
+  S.pw[lane] = hot->prev_word[lane];
+  v.tx_psp = hot->live[L_TX_PSP - 40];
   const uint32_t* x = hot->x;
   v.timestamp = x[X_TIMESTAMP];
   v.cycle = x[X_CYCLE];
@@ -1785,6 +1790,17 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
   osync();
   v.load_frame_from_F();
+  // cold per-VM tables that the interpreter keeps in shared memory while the VM runs
+  {
+    const uint4* gpt = reinterpret_cast<const uint4*>(v.B.pt + (size_t)v.vm * ZKB_PT_ENTRIES * 2);
+    uint4* spt = reinterpret_cast<uint4*>(S.pt);
+    spt[lane] = gpt[lane];
+    spt[8 + lane] = gpt[8 + lane];
+    const uint32_t* ghwm = v.B.slab_hwm + (size_t)v.vm * v.B.n_slabs;
+    for (uint32_t i = lane; i < v.B.n_slabs; i += ZK_OCT) S.hwm[i] = ghwm[i];
+    if (lane < 4) S.lv[lane] = v.g_lvl[v.far_depth * 4 + lane];
+  }
+  osync();
 }
 
 // write the hot state back to HBM (the batch is resumable: zkb_run may be called again)
@@ -1799,7 +1815,7 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
   for (int i = 0; i < 4; i++) gregs[i * 8 + lane] = sregs[i * 8 + lane];
   reinterpret_cast<uint4*>(hot->F)[lane] = reinterpret_cast<const uint4*>(S.F)[lane];
   if (lane < 4) reinterpret_cast<uint4*>(hot->live)[lane] = reinterpret_cast<const uint4*>(S.row)[10 + lane];
-  hot->prev_word[lane] = v.prev_word;
+  hot->prev_word[lane] = S.pw[lane];
   // x[]: octet lane l writes words 4l .. 4l+3
   {
     uint32_t w[4];
@@ -1831,6 +1847,15 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
 #pragma unroll
   for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.count[k] : summary;
   v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
+  {
+    uint4* gpt = reinterpret_cast<uint4*>(v.B.pt + (size_t)v.vm * ZKB_PT_ENTRIES * 2);
+    const uint4* spt = reinterpret_cast<const uint4*>(S.pt);
+    gpt[lane] = spt[lane];
+    gpt[8 + lane] = spt[8 + lane];
+    uint32_t* ghwm = v.B.slab_hwm + (size_t)v.vm * v.B.n_slabs;
+    for (uint32_t i = lane; i < v.B.n_slabs; i += ZK_OCT) ghwm[i] = S.hwm[i];
+    if (lane < 4) v.g_lvl[v.far_depth * 4 + lane] = S.lv[lane];
+  }
   osync();
 }
 
