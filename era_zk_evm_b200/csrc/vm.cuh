@@ -120,9 +120,15 @@ struct __align__(16) VmSmem {
   uint32_t pt[ZKB_PT_ENTRIES * 2];  // page indirections (page, kind | slab << 8 | cleanup_level << 16); HBM copy: DevBatch.pt
   uint32_t hwm[32];    // words touched per heap slab; HBM copy: DevBatch.slab_hwm
   uint32_t lv[4];      // the current far level's entry of DevBatch.lvl: heap slab, aux slab, stack high-water mark, -
-  uint32_t pad[8];
+  // octet-uniform cold state.  Every lane of the octet stores the same value and a lane reads back at least its own
+  // store, so these need no octet sync; they live here to keep the interpreter's register file for the hot state.
+  uint32_t u[12];      // U_* below
+  uint64_t gp[6];      // GP_* below: per-VM base pointers into the HBM slabs
+  uint32_t pad[16];
 };
-static_assert(sizeof(VmSmem) == 1824 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
+enum { U_FAR_DEPTH = 0, U_JOURNAL_LEN, U_N_DECOMMIT, U_SLAB_FREE, U_COUNT2 /* LOG, DECOMMIT, FRAME, REFUND */, U_CODE_LEN = 8 };
+enum { GP_STACK = 0 /* stack page of the current far level */, GP_STACK_PTR, GP_HEAP, GP_LVL, GP_CODE };
+static_assert(sizeof(VmSmem) == 1952 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
 typedef VmSmem WarpSmem;
 
 struct Vm {
@@ -130,34 +136,47 @@ struct Vm {
   WarpSmem& S;
   const uint32_t vm;
   const uint32_t lane;  // lane within the VM's octet (0..7)
-  // octet-uniform registers
+  // octet-uniform registers (the hot state; the cold state sits in S.u / S.gp)
   uint32_t pc, sp, ergs, flags, timestamp, cycle, pending, ptr_mask, status;
-  uint32_t prev_code_page, far_depth, journal_len, n_decommit, slab_free;
-  uint32_t count[ZKB_N_STREAMS];
+  uint32_t prev_code_page;
+  uint32_t n_rows, n_mem;   // records in the ROWS / MEM streams (the two streams written every cycle)
+  uint8_t* row_ptr;         // next free slot of this VM's ROWS / MEM slab
+  uint8_t* mem_ptr;
   uint32_t rowbits;
   uint32_t ccount;  // per-cycle record counts, packed as CycleRow.n_mem | n_log << 16 | n_dfr << 24
   uint32_t forbid;  // ZK_E_* bits an opcode must not have in the current frame (kernel-only / not-in-static)
-  const uint32_t* code;
-  uint32_t code_len;
   uint32_t tx_psp;  // tx_number_in_block | previous_super_pc << 16 (row word L_TX_PSP, written back at row emission)
-  // decoded opcode (octet-uniform)
-  uint32_t entry, dst0_reg, dst1_reg, imm0, imm1;
-  uint32_t dst_loc_valid, dst_loc_index;
-  // per-VM global bases
-  uint32_t* g_stack;
-  uint8_t* g_stack_ptr;
-  uint32_t* g_heap;
-  uint32_t* g_lvl;
-  uint8_t* row_base;  // this VM's slab of the ROWS / MEM streams (the two streams written every cycle)
-  uint8_t* mem_base;
+  // decoded opcode (octet-uniform): table entry + the operand fields of the (masked) instruction
+  uint32_t entry, ops_lo, ops_hi;
+  uint32_t dst_loc;  // stack destination of dst0: index | 1 << 16 when valid
 
-  __device__ Vm(const DevBatch& b, WarpSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {
-    g_stack = B.stack_mem + (size_t)vm * (B.max_far_depth + 1) * B.stack_words * 8;
-    g_stack_ptr = B.stack_ptr + (size_t)vm * (B.max_far_depth + 1) * B.stack_words;
-    g_heap = B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8;
-    g_lvl = B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4;
-    row_base = B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES;
-    mem_base = B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES;
+  __device__ Vm(const DevBatch& b, VmSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {}
+  // cold state accessors
+  __device__ __forceinline__ uint32_t& far_depth() const { return S.u[U_FAR_DEPTH]; }
+  __device__ __forceinline__ uint32_t& journal_len() const { return S.u[U_JOURNAL_LEN]; }
+  __device__ __forceinline__ uint32_t& n_decommit() const { return S.u[U_N_DECOMMIT]; }
+  __device__ __forceinline__ uint32_t& slab_free() const { return S.u[U_SLAB_FREE]; }
+  __device__ __forceinline__ uint32_t& count(int kind) const { return S.u[U_COUNT2 + kind - 2]; }  // kind >= ZKB_STREAM_LOG
+  __device__ __forceinline__ uint32_t stream_count(int kind) const { return kind == ZKB_STREAM_ROWS ? n_rows : kind == ZKB_STREAM_MEM ? n_mem : S.u[U_COUNT2 + kind - 2]; }
+  __device__ __forceinline__ uint32_t code_len() const { return S.u[U_CODE_LEN]; }
+  __device__ __forceinline__ const uint32_t* code() const { return reinterpret_cast<const uint32_t*>(S.gp[GP_CODE]); }
+  __device__ __forceinline__ uint32_t* g_stack() const { return reinterpret_cast<uint32_t*>(S.gp[GP_STACK]); }
+  __device__ __forceinline__ uint8_t* g_stack_ptr() const { return reinterpret_cast<uint8_t*>(S.gp[GP_STACK_PTR]); }
+  __device__ __forceinline__ uint32_t* g_heap() const { return reinterpret_cast<uint32_t*>(S.gp[GP_HEAP]); }
+  __device__ __forceinline__ uint32_t* g_lvl() const { return reinterpret_cast<uint32_t*>(S.gp[GP_LVL]); }
+  __device__ __forceinline__ uint32_t dst0_reg() const { return (ops_lo >> 24) & 15u; }
+  __device__ __forceinline__ uint32_t dst1_reg() const { return ops_lo >> 28; }
+  __device__ __forceinline__ uint32_t imm0() const { return ops_hi & 0xFFFFu; }
+  __device__ __forceinline__ uint32_t imm1() const { return ops_hi >> 16; }
+  // per-VM bases (vm_load); the stack bases are re-pointed at the current far level by load_frame_from_F
+  __device__ __forceinline__ void set_vm_pointers() {
+    S.gp[GP_HEAP] = reinterpret_cast<uint64_t>(B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8);
+    S.gp[GP_LVL] = reinterpret_cast<uint64_t>(B.lvl + (size_t)vm * (B.max_far_depth + 1) * 4);
+  }
+  __device__ __forceinline__ void set_level_pointers(uint32_t level) {
+    const size_t page = (size_t)vm * (B.max_far_depth + 1) + level;
+    S.gp[GP_STACK] = reinterpret_cast<uint64_t>(B.stack_mem + page * B.stack_words * 8);
+    S.gp[GP_STACK_PTR] = reinterpret_cast<uint64_t>(B.stack_ptr + page * B.stack_words);
   }
 
   // ---- small helpers -------------------------------------------------------------------------------
@@ -195,12 +214,12 @@ struct Vm {
   // Every record is written straight from the registers that hold its fields: the scalar header by lane 0 as one
   // 8/16-byte vector store, each U256 by lanes 0..7 (one 32-byte segment) -- no shuffles, no lane-select chains.
   __device__ __forceinline__ uint8_t* stream_slot(int kind) {
-    uint32_t n = count[kind];
+    uint32_t n = count(kind);
     if (n >= B.cap[kind]) {
       fail(ZKB_VM_CAP_STREAM);
       return nullptr;
     }
-    count[kind] = n + 1;
+    count(kind) = n + 1;
     if (!B.witness) return nullptr;
     return B.streams[kind] + ((size_t)vm * B.cap[kind] + n) * rec_bytes(kind);
   }
@@ -209,14 +228,14 @@ struct Vm {
   __device__ __forceinline__ void emit_mem(uint32_t ts, uint32_t page, uint32_t index, uint32_t mtype, uint32_t rw, uint32_t is_ptr,
                                            uint32_t origin, u256l value) {
     ccount += 1u;
-    uint32_t n = count[ZKB_STREAM_MEM];
-    if (ZK_UNLIKELY(n >= B.cap[ZKB_STREAM_MEM])) {
+    if (ZK_UNLIKELY(n_mem >= B.cap[ZKB_STREAM_MEM])) {
       fail(ZKB_VM_CAP_STREAM);
       return;
     }
-    count[ZKB_STREAM_MEM] = n + 1;
+    n_mem++;
+    uint32_t* p = reinterpret_cast<uint32_t*>(mem_ptr);
+    mem_ptr += ZKB_MEM_BYTES;
     if (!B.witness) return;
-    uint32_t* p = reinterpret_cast<uint32_t*>(mem_base + (size_t)n * ZKB_MEM_BYTES);
     if (lane == 0) *reinterpret_cast<uint4*>(p) = make_uint4(ts, page, index, mtype | rw << 8 | is_ptr << 16 | origin << 24);
     p[4 + lane] = value;
   }
@@ -288,18 +307,18 @@ struct Vm {
   __device__ __forceinline__ u256l stack_read(uint32_t index, uint32_t& is_ptr) {
     is_ptr = 0;
     if (index >= B.stack_words) return 0u;  // never written (writes beyond the cap stop the VM) => still zero
-    size_t off = (size_t)far_depth * B.stack_words + index;
-    is_ptr = g_stack_ptr[off];
-    return g_stack[off * 8 + lane];
+    const uint32_t off = index;  // g_stack() / g_stack_ptr() point at the current far level's page
+    is_ptr = g_stack_ptr()[off];
+    return g_stack()[off * 8 + lane];
   }
   __device__ __forceinline__ void stack_write(uint32_t index, u256l v, uint32_t is_ptr) {
     if (index >= B.stack_words) {
       fail(ZKB_VM_CAP_STACK);
       return;
     }
-    size_t off = (size_t)far_depth * B.stack_words + index;
-    g_stack[off * 8 + lane] = v;
-    if (lane == 1) g_stack_ptr[off] = (uint8_t)is_ptr;
+    const uint32_t off = index;  // g_stack() / g_stack_ptr() point at the current far level's page
+    g_stack()[off * 8 + lane] = v;
+    if (lane == 1) g_stack_ptr()[off] = (uint8_t)is_ptr;
     if (lane == 0 && index + 1 > S.lv[2]) S.lv[2] = index + 1;
     // no octet sync: limb l is read back by lane l; the pointer byte and the high-water mark are read by other lanes only
     // in later cycles, i.e. behind the sync of the row emission
@@ -307,35 +326,35 @@ struct Vm {
 
   // ---- heap slabs (SimpleMemory heaps / pages_with_extended_lifetime, memory.rs:439-521) ----------
   __device__ __forceinline__ uint32_t slab_alloc() {
-    if (slab_free == 0) {
+    if (slab_free() == 0) {
       fail(ZKB_VM_CAP_HEAP);
       return ZKB_NO_SLAB;
     }
-    uint32_t s = __ffs(slab_free) - 1;
-    slab_free &= ~(1u << s);
+    uint32_t s = __ffs(slab_free()) - 1;
+    slab_free() &= ~(1u << s);
     return s;
   }
   __device__ __forceinline__ void slab_release(uint32_t s) {
     if (s == ZKB_NO_SLAB) return;
     uint32_t hwm = S.hwm[s];
-    uint32_t* base = g_heap + (size_t)s * B.heap_words * 8;
+    uint32_t* base = g_heap() + (size_t)s * B.heap_words * 8;
     uint4* base4 = reinterpret_cast<uint4*>(base);
     for (uint32_t i = lane; i < hwm * 2; i += 8) base4[i] = make_uint4(0u, 0u, 0u, 0u);  // == heap_on_return fill (memory.rs:181-183)
     if (lane == 0) S.hwm[s] = 0;
-    slab_free |= 1u << s;
+    slab_free() |= 1u << s;
     osync();
   }
   __device__ __forceinline__ u256l slab_read(uint32_t s, uint32_t word) {
     if (s == ZKB_NO_SLAB || word >= B.heap_words) return 0u;
-    return g_heap[((size_t)s * B.heap_words + word) * 8 + lane];
+    return g_heap()[((size_t)s * B.heap_words + word) * 8 + lane];
   }
   __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
-    g_heap[((size_t)s * B.heap_words + word) * 8 + lane] = v;
+    g_heap()[((size_t)s * B.heap_words + word) * 8 + lane] = v;
     if (word + 1 > S.hwm[s] && lane == 0) S.hwm[s] = word + 1;  // (as in stack_write: no octet sync needed)
   }
   // heap (which = 0) / aux heap (which = 1) slab of far level x: the current level's entry lives in shared memory, the
   // callers' entries are current in HBM (written back when the callee's level started)
-  __device__ __forceinline__ uint32_t level_slab(uint32_t x, uint32_t which) const { return x == far_depth ? S.lv[which] : g_lvl[x * 4 + which]; }
+  __device__ __forceinline__ uint32_t level_slab(uint32_t x, uint32_t which) const { return x == far_depth() ? S.lv[which] : g_lvl()[x * 4 + which]; }
   // slab of the current frame's heap (which = 0) / aux heap (which = 1); allocate lazily on first write
   __device__ __forceinline__ uint32_t cur_slab(uint32_t which, bool for_write, uint32_t word) {
     uint32_t s = S.lv[which];
@@ -446,14 +465,14 @@ struct Vm {
       }
       vals[slot * 8 + lane] = nv;
       if (journal) {
-        if (journal_len >= B.journal_entries) {
+        if (journal_len() >= B.journal_entries) {
           fail(ZKB_VM_CAP_STORAGE);
         } else {
           uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
           uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
-          jv[journal_len * 8 + lane] = old;
-          if (lane == 0) js[journal_len] = (uint32_t)slot;
-          journal_len++;
+          jv[journal_len() * 8 + lane] = old;
+          if (lane == 0) js[journal_len()] = (uint32_t)slot;
+          journal_len()++;
         }
       }
       osync();
@@ -465,10 +484,10 @@ struct Vm {
     uint32_t* vals = B.st_vals + (size_t)vm * B.storage_slots * 8;
     const uint32_t* js = B.j_slot + (size_t)vm * B.journal_entries;
     const uint32_t* jv = B.j_val + (size_t)vm * B.journal_entries * 8;
-    while (journal_len > mark) {
-      journal_len--;
-      uint32_t slot = js[journal_len];
-      vals[slot * 8 + lane] = jv[journal_len * 8 + lane];
+    while (journal_len() > mark) {
+      journal_len()--;
+      uint32_t slot = js[journal_len()];
+      vals[slot * 8 + lane] = jv[journal_len() * 8 + lane];
       osync();
     }
   }
@@ -507,13 +526,15 @@ struct Vm {
     }
     uint32_t id = S.F[F_CODE_ID];
     if (id == ZKB_NO_CODE) {
-      code = nullptr;
-      code_len = 0;
+      S.gp[GP_CODE] = 0;
+      S.u[U_CODE_LEN] = 0;
     } else {
-      code = B.code_words + (size_t)B.code_meta[id * 10] * 8;
-      code_len = B.code_meta[id * 10 + 1];
+      S.gp[GP_CODE] = reinterpret_cast<uint64_t>(B.code_words + (size_t)B.code_meta[id * 10] * 8);
+      S.u[U_CODE_LEN] = B.code_meta[id * 10 + 1];
     }
-    far_depth = S.F[F_FAR_LEVEL];
+    const uint32_t level = S.F[F_FAR_LEVEL];
+    far_depth() = level;
+    set_level_pointers(level);
     osync();
   }
   // vm_state.start_frame (helpers.rs:225-246) in two halves.  push_begin saves the caller's frame (it stays readable
@@ -534,7 +555,7 @@ struct Vm {
                                            uint32_t bound_value = 0) {
     osync();
     if (lane == 0) {
-      S.F[F_JOURNAL_MARK] = journal_len;  // storage.start_frame / event_sink.start_frame
+      S.F[F_JOURNAL_MARK] = journal_len();  // storage.start_frame / event_sink.start_frame
       S.row[L_DEPTH] = S.row[L_DEPTH] + 1;
     }
     osync();
@@ -558,17 +579,18 @@ struct Vm {
   __device__ __forceinline__ void dst0_update(u256l v, bool is_ptr) {
     S.row[24 + lane] = v;
     rowbits |= ZKB_ROWBIT_DST0_VALID | (is_ptr ? ZKB_ROWBIT_DST0_PTR : 0u);
-    if (dst_loc_valid) {
+    if (dst_loc) {
+      const uint32_t dst_loc_index = dst_loc & 0xFFFFu;
       stack_write(dst_loc_index, v, is_ptr ? 1u : 0u);
       emit_mem(timestamp + 3, L(L_BASE_PAGE) + 1, dst_loc_index, ZK_MEM_STACK, 1, is_ptr ? 1u : 0u, ZKB_MEMORIGIN_VM, v);
     } else {
-      reg_write(dst0_reg, v, is_ptr);
+      reg_write(dst0_reg(), v, is_ptr);
     }
   }
   __device__ __forceinline__ void dst1_update(u256l v, bool is_ptr) {
     S.row[32 + lane] = v;
     rowbits |= ZKB_ROWBIT_DST1_VALID | (is_ptr ? ZKB_ROWBIT_DST1_PTR : 0u);
-    reg_write(dst1_reg, v, is_ptr);
+    reg_write(dst1_reg(), v, is_ptr);
   }
 
   // handlers
@@ -596,7 +618,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   *reinterpret_cast<uint2*>(&S.row[24 + 2 * lane]) = make_uint2(0u, 0u);  // dst0 / dst1 fields default to zero
   rowbits = 0;
   ccount = 0;
-  dst_loc_valid = 0;
+  dst_loc = 0;
 
   // ---- fetch (cycle.rs:46-130) ----
   const uint32_t code_page = S.row[L_CODE_PAGE];
@@ -605,7 +627,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
   uint32_t raw_lo, raw_hi;
   if (!ZK_UNLIKELY(pending)) {
     if (code_page != prev_code_page || prev_super_pc != super_pc) {
-      u256l w = super_pc < code_len ? __ldg(code + (size_t)super_pc * 8 + lane) : 0u;
+      u256l w = super_pc < code_len() ? __ldg(code() + (size_t)super_pc * 8 + lane) : 0u;
       S.pw[lane] = w;
       osync();
       prev_super_pc = super_pc;
@@ -642,7 +664,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
   const uint64_t kCondTable = 0xFA33EEFCCCAAF0FFull;
   bool resolved = (uint32_t)(kCondTable >> (cond * 8u + (flags & 7u))) & 1u;
   // mask_into_panic / mask_into_nop (cycle.rs:187-217): the masked opcode has all-zero operands
-  uint32_t ops_lo = raw_lo, ops_hi = raw_hi;
+  ops_lo = raw_lo;
+  ops_hi = raw_hi;
   if (ZK_UNLIKELY(err)) {
     vidx = ZK_PANIC_VARIANT_IDX;
     resolved = true;
@@ -653,11 +676,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
     entry = ZK_OPCODE_TABLE[vidx];
     ops_lo = ops_hi = 0u;
   }
-  uint32_t src0_reg = (ops_lo >> 16) & 15u, src1_reg = (ops_lo >> 20) & 15u;
-  dst0_reg = (ops_lo >> 24) & 15u;
-  dst1_reg = ops_lo >> 28;
-  imm0 = ops_hi & 0xFFFFu;
-  imm1 = ops_hi >> 16;
+  const uint32_t src0_reg = (ops_lo >> 16) & 15u, src1_reg = (ops_lo >> 20) & 15u;
   // delayed changes (mod.rs:134-153): previous_super_pc goes back to the row tail with the row head
   tx_psp = (tx_psp & 0xFFFFu) | prev_super_pc << 16;
 
@@ -667,9 +686,9 @@ __device__ __forceinline__ void Vm::cycle_once() {
   u256l src0 = reg_read(src0_reg);
   uint32_t src0_ptr = (ptr_mask >> src0_reg) & 1u;
   if (src_mode != ZK_SRC_REG) {
-    uint32_t vaddr = (S.regs[src0_reg][0] + imm0) & 0xFFFFu;
+    uint32_t vaddr = (S.regs[src0_reg][0] + imm0()) & 0xFFFFu;
     if (src_mode == ZK_SRC_IMM) {
-      src0 = lane == 0 ? imm0 : 0u;
+      src0 = lane == 0 ? imm0() : 0u;
       src0_ptr = 0;
     } else {
       uint32_t index;
@@ -685,7 +704,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
         src0 = 0u;  // NOP moves SP but never reads (cycle.rs:298-301)
         src0_ptr = 0;
       } else if (src_mode == ZK_SRC_CODE) {
-        src0 = index < code_len ? __ldg(code + (size_t)index * 8 + lane) : 0u;
+        src0 = index < code_len() ? __ldg(code() + (size_t)index * 8 + lane) : 0u;
         src0_ptr = 0;
         emit_mem(timestamp, code_page, index, ZK_MEM_CODE, 0, 0, ZKB_MEMORIGIN_VM, src0);
       } else {
@@ -695,7 +714,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
     }
   }
   if (dst_mode != ZK_DST_REG) {
-    uint32_t vaddr = (S.regs[dst0_reg][0] + imm1) & 0xFFFFu;
+    uint32_t vaddr = (S.regs[dst0_reg()][0] + imm1()) & 0xFFFFu;
+    uint32_t dst_loc_index;
     if (dst_mode == ZK_DST_STACK_PUSH) {
       dst_loc_index = sp;
       sp = (sp + vaddr) & 0xFFFFu;
@@ -704,7 +724,7 @@ __device__ __forceinline__ void Vm::cycle_once() {
     } else {
       dst_loc_index = vaddr;
     }
-    dst_loc_valid = 1;
+    dst_loc = dst_loc_index | 1u << 16;
   }
   u256l src1 = reg_read(src1_reg);
   uint32_t src1_ptr = (ptr_mask >> src1_reg) & 1u;
@@ -843,19 +863,19 @@ __device__ __forceinline__ void Vm::cycle_once() {
     S.row[L_COUNTS] = ccount;
     S.row[L_TX_PSP] = tx_psp;
   }
-  const uint32_t n_rows = count[ZKB_STREAM_ROWS];
   if (ZK_UNLIKELY(n_rows >= B.cap[ZKB_STREAM_ROWS])) {
     fail(ZKB_VM_CAP_STREAM);
     return;
   }
-  count[ZKB_STREAM_ROWS] = n_rows + 1;
+  n_rows++;
   osync();
   if (B.witness) {
     const uint4 v0 = reinterpret_cast<const uint4*>(S.row)[lane], v1 = reinterpret_cast<const uint4*>(S.row)[8 + lane];
-    uint4* dst = reinterpret_cast<uint4*>(row_base + (size_t)n_rows * ZKB_ROW_BYTES);
+    uint4* dst = reinterpret_cast<uint4*>(row_ptr);
     dst[lane] = v0;
     dst[8 + lane] = v1;
   }
+  row_ptr += ZKB_ROW_BYTES;
   // rare end-of-cycle state changes, keyed on the opcode family so that ordinary cycles pay one compare:
   if (family - ZK_OP_LOG <= 2u) {  // LOG, FAR_CALL, RET
     if (family == ZK_OP_LOG && S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;  // the cycle is complete; its ecrecover is not
@@ -968,8 +988,8 @@ __device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
   if (!push_begin()) return;
   // the callee's frame is a clone of the caller's with is_local_frame set (near_call.rs:59-63)
   if (lane == 0) {
-    S.F[F_SP_PC] = sp | imm0 << 16;
-    S.F[F_EH_SHARDS] = (S.F[F_EH_SHARDS] & 0xFFFF0000u) | imm1;
+    S.F[F_SP_PC] = sp | imm0() << 16;
+    S.F[F_EH_SHARDS] = (S.F[F_EH_SHARDS] & 0xFFFF0000u) | imm1();
     S.F[F_ERGS] = passed;
     S.F[F_MISC] |= 1u << 16;
   }
@@ -1200,7 +1220,7 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
   }
   uint32_t s = cur_slab(0, true, out_word + 1);
   if (status != ZKB_VM_RUNNING) return;
-  const uint32_t first_record = count[ZKB_STREAM_MEM];
+  const uint32_t first_record = n_mem;
   slab_write(s, out_word, 0u);
   emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, 0u);
   slab_write(s, out_word + 1, 0u);
@@ -1215,12 +1235,12 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
   osync();
 }
 
-// SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth (already incremented)
+// SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth() (already incremented)
 __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
-  uint32_t level = far_depth;
+  uint32_t level = far_depth();
   // the caller's level entry goes back to HBM, the callee starts with no heaps and an untouched stack page
   if (lane < 4) {
-    g_lvl[caller_level * 4 + lane] = S.lv[lane];
+    g_lvl()[caller_level * 4 + lane] = S.lv[lane];
     S.lv[lane] = lane < 2 ? ZKB_NO_SLAB : 0u;
   }
   osync();
@@ -1246,8 +1266,9 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
 __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
   // stack page goes back to the pool: clear what was touched (stack_on_return, memory.rs:185-188)
   uint32_t hwm = S.lv[2];  // S.lv still holds the finished level's entry (the parent's is reloaded at the end)
-  uint32_t* sbase = g_stack + (size_t)level * B.stack_words * 8;
-  uint8_t* pbase = g_stack_ptr + (size_t)level * B.stack_words;
+  const size_t fpage = (size_t)vm * (B.max_far_depth + 1) + level;  // g_stack() already points at the caller's page
+  uint32_t* sbase = B.stack_mem + fpage * B.stack_words * 8;
+  uint8_t* pbase = B.stack_ptr + fpage * B.stack_words;
   uint4* sbase4 = reinterpret_cast<uint4*>(sbase);
   for (uint32_t i = lane; i < hwm * 2; i += 8) sbase4[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = lane; i < hwm; i += 8) pbase[i] = 0;
@@ -1288,7 +1309,7 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
     }
   }
   osync();
-  if (lane < 4) S.lv[lane] = g_lvl[far_depth * 4 + lane];  // back in the caller's far level
+  if (lane < 4) S.lv[lane] = g_lvl()[far_depth() * 4 + lane];  // back in the caller's far level
   osync();
 }
 
@@ -1297,7 +1318,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
   enum { EX_NOT_PTR = 1, EX_HASH_FORMAT = 2, EX_ERGS_DECOMMIT = 4, EX_ERGS_GROW = 8, EX_MALFORMED_PTR = 16, EX_CONSTRUCTED_SYSTEM = 32 };
   flags = 0;
   const bool is_call_shard = entry & ZK_E_FLAG0, is_static_call = entry & ZK_E_FLAG1;
-  const uint32_t eh = imm0;
+  const uint32_t eh = imm0();
   // called address / kernel test
   const uint32_t dest_nz = oballot(src1 != 0) & 0x1Fu;  // limbs 0..4 = low 160 bits
   const bool dst_is_kernel = (dest_nz & 0x1Eu) == 0 && oshfl(src1, 0) < 65536u;
@@ -1429,7 +1450,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
     uint32_t* dec = B.dec + (size_t)vm * ZKB_DEC_ENTRIES * 2;
     // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it.
     // Octet lane l looks at entries l and l + 8 (ZKB_DEC_ENTRIES = 16).
-    const uint32_t e_lo = lane < n_decommit ? dec[lane * 2] : ZKB_NO_CODE, e_hi = lane + 8 < n_decommit ? dec[(lane + 8) * 2] : ZKB_NO_CODE;
+    const uint32_t e_lo = lane < n_decommit() ? dec[lane * 2] : ZKB_NO_CODE, e_hi = lane + 8 < n_decommit() ? dec[(lane + 8) * 2] : ZKB_NO_CODE;
     const bool have_id = id >= 0;
     uint32_t hist = oballot(have_id && e_lo == (uint32_t)id) | oballot(have_id && e_hi == (uint32_t)id) << 8;
     uint32_t fresh_flag, len16;
@@ -1443,15 +1464,15 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
         status = ZKB_VM_UNKNOWN_CODE_HASH;  // anyhow::Err (decommitter.rs:50-56)
         return;
       }
-      if (n_decommit >= ZKB_DEC_ENTRIES) {
+      if (n_decommit() >= ZKB_DEC_ENTRIES) {
         fail(ZKB_VM_CAP_PAGES);
         return;
       }
       if (lane == 0) {
-        dec[n_decommit * 2] = (uint32_t)id;
-        dec[n_decommit * 2 + 1] = page_candidate;
+        dec[n_decommit() * 2] = (uint32_t)id;
+        dec[n_decommit() * 2 + 1] = page_candidate;
       }
-      n_decommit++;
+      n_decommit()++;
       osync();
       mapped_code_page = page_candidate;
       fresh_flag = 1;
@@ -1480,8 +1501,8 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
 
   // new frame, lane i = word i
   const uint32_t r15_aw = u256_to_addr_words(reg_read(ZK_CALL_IMPLICIT_PARAMETER_REG_IDX + 1));
-  const uint32_t caller_level = far_depth;
-  if (far_depth + 1 > B.max_far_depth) {
+  const uint32_t caller_level = far_depth();
+  if (far_depth() + 1 > B.max_far_depth) {
     fail(ZKB_VM_CAP_DEPTH);
     return;
   }
@@ -1554,7 +1575,7 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
   const uint32_t fwd_byte = oshfl(src0, 7) & 0xFFu;
   const uint32_t fwd = fwd_byte == ZK_FWD_FORWARD_FAT_POINTER ? ZK_FWD_FORWARD_FAT_POINTER : fwd_byte == ZK_FWD_USE_AUX_HEAP ? ZK_FWD_USE_AUX_HEAP : ZK_FWD_USE_HEAP;
   bool to_label = entry & ZK_E_FLAG0;
-  const uint32_t label_pc = imm0;
+  const uint32_t label_pc = imm0();
   const bool local = is_local();
   const uint32_t base = L(L_BASE_PAGE);
   bool deref_beyond = false;
@@ -1596,7 +1617,7 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
     }
   }
   const bool panicked = variant == ZK_RET_REVERT || variant == ZK_RET_PANIC;
-  const uint32_t finished_level = far_depth;
+  const uint32_t finished_level = far_depth();
   const uint32_t finished_eh = L(L_EH_BITS) & 0xFFFFu;
   const uint32_t fin_heap_bound = L(L_HEAP_BOUND), fin_aux_bound = L(L_AUX_BOUND);
   if (S.row[L_DEPTH] == 0) {
@@ -1780,14 +1801,19 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   v.status = ZKB_VM_RUNNING;
   v.ptr_mask = x[X_PTRMASK];
   v.prev_code_page = x[X_PREV_CODE_PAGE];
-  v.journal_len = x[X_JOURNAL_LEN];
-  v.n_decommit = x[X_N_DECOMMIT];
-  v.slab_free = x[X_SLAB_FREE];
+  v.journal_len() = x[X_JOURNAL_LEN];
+  v.n_decommit() = x[X_N_DECOMMIT];
+  v.slab_free() = x[X_SLAB_FREE];
+  v.n_rows = x[X_COUNT0 + ZKB_STREAM_ROWS];
+  v.n_mem = x[X_COUNT0 + ZKB_STREAM_MEM];
 #pragma unroll
-  for (int k = 0; k < ZKB_N_STREAMS; k++) v.count[k] = x[X_COUNT0 + k];
+  for (int k = ZKB_STREAM_LOG; k < ZKB_N_STREAMS; k++) v.count(k) = x[X_COUNT0 + k];
+  v.row_ptr = v.B.streams[ZKB_STREAM_ROWS] + ((size_t)v.vm * v.B.cap[ZKB_STREAM_ROWS] + v.n_rows) * ZKB_ROW_BYTES;
+  v.mem_ptr = v.B.streams[ZKB_STREAM_MEM] + ((size_t)v.vm * v.B.cap[ZKB_STREAM_MEM] + v.n_mem) * ZKB_MEM_BYTES;
   v.rowbits = 0;
   v.ccount = 0;
-  v.entry = v.dst0_reg = v.dst1_reg = v.imm0 = v.imm1 = v.dst_loc_valid = v.dst_loc_index = 0;
+  v.entry = v.ops_lo = v.ops_hi = v.dst_loc = 0;
+  v.set_vm_pointers();
   osync();
   v.load_frame_from_F();
   // cold per-VM tables that the interpreter keeps in shared memory while the VM runs
@@ -1798,7 +1824,7 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
     spt[8 + lane] = gpt[8 + lane];
     const uint32_t* ghwm = v.B.slab_hwm + (size_t)v.vm * v.B.n_slabs;
     for (uint32_t i = lane; i < v.B.n_slabs; i += ZK_OCT) S.hwm[i] = ghwm[i];
-    if (lane < 4) S.lv[lane] = v.g_lvl[v.far_depth * 4 + lane];
+    if (lane < 4) S.lv[lane] = v.g_lvl()[v.far_depth() * 4 + lane];
   }
   osync();
 }
@@ -1830,12 +1856,12 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
       out = i == X_STATUS ? v.status : out;
       out = i == X_PTRMASK ? v.ptr_mask : out;
       out = i == X_PREV_CODE_PAGE ? v.prev_code_page : out;
-      out = i == X_FAR_DEPTH ? v.far_depth : out;
-      out = i == X_JOURNAL_LEN ? v.journal_len : out;
-      out = i == X_N_DECOMMIT ? v.n_decommit : out;
-      out = i == X_SLAB_FREE ? v.slab_free : out;
+      out = i == X_FAR_DEPTH ? v.far_depth() : out;
+      out = i == X_JOURNAL_LEN ? v.journal_len() : out;
+      out = i == X_N_DECOMMIT ? v.n_decommit() : out;
+      out = i == X_SLAB_FREE ? v.slab_free() : out;
 #pragma unroll
-      for (int k = 0; k < ZKB_N_STREAMS; k++) out = i == (uint32_t)(X_COUNT0 + k) ? v.count[k] : out;
+      for (int k = 0; k < ZKB_N_STREAMS; k++) out = i == (uint32_t)(X_COUNT0 + k) ? v.stream_count(k) : out;
       w[q] = out;
     }
     reinterpret_cast<uint4*>(hot->x)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1845,7 +1871,7 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
   const uint32_t st_out = (v.status == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : v.status;
   uint32_t summary = lane == 6 ? st_out : v.cycle;
 #pragma unroll
-  for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.count[k] : summary;
+  for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.stream_count(k) : summary;
   v.B.host_counts[(size_t)v.vm * 8 + lane] = summary;
   {
     uint4* gpt = reinterpret_cast<uint4*>(v.B.pt + (size_t)v.vm * ZKB_PT_ENTRIES * 2);
@@ -1854,7 +1880,7 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
     gpt[8 + lane] = spt[8 + lane];
     uint32_t* ghwm = v.B.slab_hwm + (size_t)v.vm * v.B.n_slabs;
     for (uint32_t i = lane; i < v.B.n_slabs; i += ZK_OCT) ghwm[i] = S.hwm[i];
-    if (lane < 4) v.g_lvl[v.far_depth * 4 + lane] = S.lv[lane];
+    if (lane < 4) v.g_lvl()[v.far_depth() * 4 + lane] = S.lv[lane];
   }
   osync();
 }

@@ -14,7 +14,7 @@
 using namespace zkb;
 
 #ifndef ZKB_WARPS_PER_CTA
-#define ZKB_WARPS_PER_CTA 20
+#define ZKB_WARPS_PER_CTA 24
 #endif
 #ifndef ZKB_MIN_CTAS_PER_SM
 #define ZKB_MIN_CTAS_PER_SM 1
@@ -92,7 +92,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
   if (vm >= vm_hi) return;  // octet-uniform: whole octets leave together
   Vm v(B, smem[oct], vm, lane);
   v.status = ZKB_VM_RUNNING;
-  v.journal_len = 0;
+  v.journal_len() = 0;
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
