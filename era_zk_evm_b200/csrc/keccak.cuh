@@ -72,19 +72,20 @@ __device__ __forceinline__ void keccak_f1600(KeccakState& s, const KeccakLanes& 
 #pragma unroll 1
   for (int round = 0; round < 24; round++) {
     // theta
+    uint64_t* kb = ks;
     uint64_t c = s.a[0] ^ s.a[1] ^ s.a[2] ^ s.a[3] ^ s.a[4];
     uint64_t d = oshfl64(c, k.xm1) ^ rotl64(oshfl64(c, k.xp1), 1);
     // rho + pi: B[y][2x + 3y] = rotl(A[x][y] ^ D[x], r[x][y])
     if (col) {
 #pragma unroll
-      for (int y = 0; y < 5; y++) ks[(k.dst >> (5 * y)) & 31u] = rotl64(s.a[y] ^ d, (k.rot >> (6 * y)) & 63u);
+      for (int y = 0; y < 5; y++) kb[(k.dst >> (5 * y)) & 31u] = rotl64(s.a[y] ^ d, (k.rot >> (6 * y)) & 63u);
     }
     osync();
     // chi: A'[X][Y] = B[X][Y] ^ (~B[X+1][Y] & B[X+2][Y])
     if (col) {
 #pragma unroll
       for (int y = 0; y < 5; y++) {
-        uint64_t b0 = ks[lane + 5 * y], b1 = ks[k.xp1 + 5 * y], b2 = ks[k.xp2 + 5 * y];
+        uint64_t b0 = kb[lane + 5 * y], b1 = kb[k.xp1 + 5 * y], b2 = kb[k.xp2 + 5 * y];
         s.a[y] = b0 ^ (~b1 & b2);
       }
       if (lane == 0) s.a[0] ^= c_keccak_rc[round];  // iota

@@ -114,8 +114,8 @@ struct __align__(16) VmSmem {
   uint32_t regs[16][8];
   uint32_t row[64];
   uint32_t F[32];
-  uint32_t kbuf[64];
-  uint64_t ks[26];     // keccak-f[1600] scratch (25 lanes)
+  uint32_t kbuf[64];   // precompile scratch: message staging / sha256 schedule / ecrecover stash; the keccak-f[1600] lane scratch
+                       // (25 x u64, ks()) aliases its first 200 bytes -- staging is consumed before the permutation starts
   uint32_t pw[8];      // previous_code_word (cycle.rs:59-100): the 4 opcodes of the current code word
   uint32_t pt[ZKB_PT_ENTRIES * 2];  // page indirections (page, kind | slab << 8 | cleanup_level << 16); HBM copy: DevBatch.pt
   uint32_t hwm[32];    // words touched per heap slab; HBM copy: DevBatch.slab_hwm
@@ -124,11 +124,12 @@ struct __align__(16) VmSmem {
   // store, so these need no octet sync; they live here to keep the interpreter's register file for the hot state.
   uint32_t u[12];      // U_* below
   uint64_t gp[6];      // GP_* below: per-VM base pointers into the HBM slabs
-  uint32_t pad[16];
+  uint32_t pad[4];
+  __device__ __forceinline__ uint64_t* ks() { return reinterpret_cast<uint64_t*>(kbuf); }
 };
 enum { U_FAR_DEPTH = 0, U_JOURNAL_LEN, U_N_DECOMMIT, U_SLAB_FREE, U_COUNT2 /* LOG, DECOMMIT, FRAME, REFUND */, U_CODE_LEN = 8 };
 enum { GP_STACK = 0 /* stack page of the current far level */, GP_STACK_PTR, GP_HEAP, GP_LVL, GP_CODE };
-static_assert(sizeof(VmSmem) == 1952 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
+static_assert(sizeof(VmSmem) == 1696 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
 typedef VmSmem WarpSmem;
 
 struct Vm {
@@ -1134,7 +1135,7 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
       }
     }
     osync();
-    keccak_f1600(st, kl, S.ks, lane);
+    keccak_f1600(st, kl, S.ks(), lane);
   }
   // digest = first 32 bytes of the state (row 0 of columns 0..3, little-endian lanes) read as one big-endian word
   int t = 7 - (int)lane;
@@ -1912,7 +1913,7 @@ __device__ __noinline__ void run_deferred_ecrecover(uint32_t* kbuf, uint64_t* ks
   osync();
 }
 __device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, VmSmem& S, uint32_t vm, uint32_t lane) {
-  run_deferred_ecrecover(S.kbuf, S.ks, B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8, B.heap_words,
+  run_deferred_ecrecover(S.kbuf, S.ks(), B.heap_mem + (size_t)vm * B.n_slabs * B.heap_words * 8, B.heap_words,
                          B.witness ? B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES : nullptr, lane);
 }
 

@@ -7,6 +7,8 @@ counter-based RNG splitmix64(seed ^ vm_index) (default seed 0x5EED0001).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import isa
@@ -379,7 +381,8 @@ class Erc20(Workload):
         pre = np.zeros((n, 64), dtype=np.uint8)
         pre[:, 0:32] = heap[:, 0:32]
         slot = keccak256_batch(pre)
-        broke = (vm_ids % np.uint64(64)) == np.uint64(63)
+        broke_mod = int(os.environ.get("ZKB_ERC20_BROKE_MOD", "64"))       # experiment knob; 0 = every VM funded
+        broke = (vm_ids % np.uint64(broke_mod)) == np.uint64(broke_mod - 1) if broke_mod else np.zeros(len(vm_ids), dtype=bool)
         from ._binding import STORAGE_INIT_DTYPE
         ent = np.zeros(len(vm_ids), dtype=STORAGE_INIT_DTYPE)
         ent["shard_id"] = 0

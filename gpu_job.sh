@@ -1,7 +1,4 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/pytest_parity.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_parity.log
-tail -5 gpurun_out/pytest_parity.log
 B="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
-for v in w16 w20 w24 w28; do for w in erc20 alu_loop; do
+for v in w24plain w24plainnoz; do for w in erc20 alu_loop keccak; do
   echo "== $v $w"; ZKB_LIB_PATH=build/variants/libzkb_$v.so timeout 300 $B --workload $w 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value']/1e6, d['roofline']['kernel_ms'])"
 done; done
