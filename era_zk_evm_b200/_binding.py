@@ -110,6 +110,28 @@ class ZkbError(RuntimeError):
     pass
 
 
+def pack_bytecodes(codes):
+    """[bytes] -> (all code words back to back, uint64 word offsets[n + 1])"""
+    for c in codes:
+        assert len(c) % 32 == 0
+    offsets = np.zeros(len(codes) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(c) // 32 for c in codes], dtype=np.uint64)
+    return b"".join(codes), offsets
+
+
+def hash_bytecodes(lib, prefix: str, codes, marker: int = 0, device: int = 0) -> list:
+    """versioned code hashes of `codes` through <prefix>hash_bytecodes (zkb_: the GPU kernel; orc_: the CPU oracle)"""
+    fn = getattr(lib, prefix + "hash_bytecodes")
+    fn.argtypes = [C.c_int32, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_void_p]
+    fn.restype = C.c_int32
+    words, offsets = pack_bytecodes(codes)
+    out = np.zeros((len(codes), 32), dtype=np.uint8)
+    rc = fn(device, words, offsets.ctypes.data, len(codes), marker, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"{prefix}hash_bytecodes failed with status {rc}")
+    return [int.from_bytes(out[i].tobytes(), "big") for i in range(len(codes))]
+
+
 class Batch:
     """Thin object wrapper over the C ABI; method names follow the reference's own
     (`populate`, `push_bootloader_context`, `execution_has_ended`, ...)."""
@@ -148,6 +170,7 @@ class Batch:
             "read_stream": [vp, u32, u32, vp, u64, C.POINTER(u64)],
             "read_storage": [vp, u32, C.c_uint8, C.c_char_p, C.c_char_p, vp],
             "read_heap": [vp, u32, u32, u32, vp],
+            "ingest_bytecodes": [vp, C.c_char_p, vp, u32, vp],
             "flatten_logs": [vp, vp], "flat_counts": [vp, u32, u32, u32, vp, vp],
             "read_flat": [vp, u32, u32, vp, u64, C.POINTER(u64)],
         }
@@ -183,6 +206,15 @@ class Batch:
             return
         self._check(self._f("load_bytecode")(self._h, int_to_be32(code_hash), code, len(code) // 32))
         self._loaded.add(code_hash)
+
+    def ingest_bytecodes(self, codes) -> list:
+        """hash (GPU, row f-4) + populate: returns the versioned code hashes as ints (= zkb_ingest_bytecodes)"""
+        words, offsets = pack_bytecodes(codes)
+        out = np.zeros((len(codes), 32), dtype=np.uint8)
+        self._check(self._f("ingest_bytecodes")(self._h, words, offsets.ctypes.data, len(codes), out.ctypes.data))
+        hashes = [int.from_bytes(out[i].tobytes(), "big") for i in range(len(codes))]
+        self._loaded.update(hashes)
+        return hashes
 
     def set_block_properties(self, default_aa_code_hash: int, zkporter_is_available: bool = False):
         self._check(self._f("set_block_properties")(self._h, int_to_be32(default_aa_code_hash), int(zkporter_is_available)))

@@ -32,6 +32,12 @@ def load_library() -> C.CDLL:
     return _LIB
 
 
+def hash_bytecodes(codes, marker: int = 0, device: int = 0) -> list:
+    """versioned code hashes (ContractCodeSha256 layout, far_call.rs:169-252) of `codes`, computed by the GPU kernel
+    behind zkb_hash_bytecodes (SURVEY §8 row f-4: the ingest step before SimpleDecommitter::populate)"""
+    return _binding.hash_bytecodes(load_library(), "zkb_", codes, marker, device)
+
+
 class GpuVmBatch(_binding.Batch):
     def __init__(self, cfg: ZkbConfig):
         super().__init__(load_library(), "zkb_", cfg)

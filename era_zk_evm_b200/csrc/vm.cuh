@@ -76,6 +76,7 @@ enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
 
 struct DevBatch {
   uint32_t n_vms, witness;
+  uint32_t warm_refund_bytes;  // ZkbConfig.reserved[1]: 0 = RefundType::None always (storage.rs:80-86), else the f-3 oracle
   uint32_t cap[ZKB_N_STREAMS];
   uint32_t stack_words, heap_words, n_slabs, max_far_depth, max_depth, storage_slots, journal_entries;
   const uint32_t* code_words;  // 8 u32 (LE limbs) per 256-bit code word, all bytecodes back to back
@@ -269,11 +270,11 @@ struct Vm {
     }
   }
 
-  // witness_tracer.record_refund_for_query (helpers.rs:130-134); InMemoryStorage => RefundType::None (storage.rs:80-86)
-  __device__ __forceinline__ void emit_refund() {
+  // witness_tracer.record_refund_for_query (helpers.rs:130-134): type 0 = RefundType::None, 1 = RepeatedWrite(value)
+  __device__ __forceinline__ void emit_refund(uint32_t type, uint32_t value) {
     ccount += 1u << 28;
     uint32_t* p = (uint32_t*)stream_slot(ZKB_STREAM_REFUND);
-    if (p && lane < 2) p[lane] = 0u;
+    if (p && lane < 2) p[lane] = lane == 0 ? type : value;
   }
 
   // start_new_execution_context (helpers.rs:237-241): the new frame must already be in S.F
@@ -413,7 +414,16 @@ struct Vm {
 
   // ---- storage (InMemoryStorage, storage.rs:88-186) ----------------------------------------------
   // aw: address words in lanes 0..4.  Returns the previous value; on writes stores `nv` and journals.
-  __device__ __forceinline__ u256l storage_access(uint32_t shard, uint32_t aw, u256l key, bool is_write, u256l nv, bool journal) {
+  // mode (always a literal at the call site):
+  //   ST_READ / ST_WRITE  execute_partial_query (storage.rs:88-139); with the refund-aware oracle enabled they also set
+  //                       the slot's cold/warm marker (storage.rs:105-110,126-131; word 6 of the slot's address row --
+  //                       a read of an absent key then claims a slot with value 0 to carry its marker)
+  //   ST_POPULATE         InMemoryStorage::populate (storage.rs:26-32): no marker, no journal
+  //   ST_IS_WARM          the probe behind estimate_refunds_for_write: returns the marker (0 / 1), changes nothing
+  enum { ST_READ = 0, ST_WRITE = 1, ST_POPULATE = 2, ST_IS_WARM = 3 };
+  __device__ __forceinline__ u256l storage_access(uint32_t shard, uint32_t aw, u256l key, const uint32_t mode, u256l nv) {
+    const bool is_write = mode == ST_WRITE || mode == ST_POPULATE, journal = mode == ST_WRITE;
+    const bool track_warm = B.warm_refund_bytes != 0u;
     uint32_t* tags = B.st_tags + (size_t)vm * B.storage_slots;
     uint32_t* keys = B.st_keys + (size_t)vm * B.storage_slots * 8;
     uint32_t* addrs = B.st_addr + (size_t)vm * B.storage_slots * 8;
@@ -431,6 +441,7 @@ struct Vm {
     uint32_t mask = B.storage_slots - 1;
     int found = -1, insert_at = -1;
     u256l old = 0u;
+    uint32_t marker_w = 0u;
     for (uint32_t base = 0; base < B.storage_slots && found < 0 && insert_at < 0; base += ZK_OCT) {
       uint32_t idx = (h + base + lane) & mask;
       uint32_t t = tags[idx];
@@ -443,16 +454,19 @@ struct Vm {
         m_match &= m_match - 1;
         uint32_t ci = (h + base + c) & mask;
         // key, address and value of the candidate are fetched together (one HBM round trip instead of two)
-        const uint32_t k = keys[ci * 8 + lane], a = lane < 6 ? addrs[ci * 8 + lane] : 0u, val = vals[ci * 8 + lane];
-        if (oall(k == key && a == extra)) {
+        const uint32_t k = keys[ci * 8 + lane], a = lane < 7 ? addrs[ci * 8 + lane] : 0u, val = vals[ci * 8 + lane];
+        if (oall(k == key && (lane >= 6 || a == extra))) {
           found = (int)ci;
           old = val;
+          marker_w = a;  // lane 6: the slot's cold/warm marker
           break;
         }
       }
       if (found < 0 && m_empty) insert_at = (int)((h + base + __ffs(m_empty) - 1) & mask);
     }
-    if (is_write) {
+    if (mode == ST_IS_WARM) return found >= 0 ? oshfl(marker_w, 6) : 0u;
+    const uint32_t new_marker = (track_warm && mode != ST_POPULATE) ? 1u : 0u;
+    if (is_write || (track_warm && found < 0)) {  // claim a slot: a new key, or (refund-aware oracle) the marker of an absent key
       int slot = found;
       if (slot < 0) {
         if (insert_at < 0) {
@@ -462,8 +476,17 @@ struct Vm {
         slot = insert_at;
         keys[slot * 8 + lane] = key;
         if (lane < 6) addrs[slot * 8 + lane] = extra;
-        if (lane == 6) tags[slot] = tag;
+        if (lane == 6) addrs[slot * 8 + 6] = new_marker;
+        if (lane == 7) tags[slot] = tag;
+        if (!is_write) vals[slot * 8 + lane] = 0u;
+      } else if (new_marker && lane == 6) {
+        addrs[slot * 8 + 6] = 1u;
       }
+    } else if (new_marker && lane == 6) {
+      addrs[found * 8 + 6] = 1u;  // read of a present key
+    }
+    if (is_write) {
+      const int slot = found >= 0 ? found : insert_at;
       vals[slot * 8 + lane] = nv;
       if (journal) {
         if (journal_len() >= B.journal_entries) {
@@ -1007,8 +1030,15 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
   const uint32_t epp = L(L_EPP);
   uint32_t ergs_on_pubdata = 0;
   if (sub == ZK_LOG_SSTORE) {
-    emit_refund();  // refund_for_partial_query (log.rs:99-102)
-    uint32_t net = shard == 0 ? ZK_INITIAL_STORAGE_WRITE_PUBDATA_BYTES : 0u;
+    // refund_for_partial_query (log.rs:99-102): Storage::estimate_refunds_for_write, asked BEFORE the write executes.
+    // The reference's InMemoryStorage answers None (storage.rs:80-86); the refund-aware oracle (row f-3) answers
+    // RepeatedWrite for a slot of the rollup shard whose cold/warm marker is already set.
+    uint32_t refund = 0;
+    if (ZK_UNLIKELY(B.warm_refund_bytes != 0u) && shard == 0) {
+      if (oshfl(storage_access(shard, aw, src0, ST_IS_WARM, 0u), 0)) refund = B.warm_refund_bytes;
+    }
+    emit_refund(refund ? 1u : 0u, refund);
+    uint32_t net = shard == 0 ? ZK_INITIAL_STORAGE_WRITE_PUBDATA_BYTES - refund : 0u;
     ergs_on_pubdata = epp * net;
   } else if (sub == ZK_LOG_TO_L1) {
     ergs_on_pubdata = epp * ZK_L1_MESSAGE_PUBDATA_BYTES;
@@ -1027,14 +1057,14 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
   }
   switch (sub) {
     case ZK_LOG_SLOAD: {
-      u256l v = storage_access(shard, aw, src0, false, 0u, false);
+      u256l v = storage_access(shard, aw, src0, ST_READ, 0u);
       emit_log(ts_log, ZK_STORAGE_AUX_BYTE, shard, aw, 0, is_first, src0, v, v);  // written := read (helpers.rs:145-148)
       dst0_update(v, false);
       break;
     }
     case ZK_LOG_SSTORE: {
       if (not_enough) return;
-      u256l old = storage_access(shard, aw, src0, true, src1, true);
+      u256l old = storage_access(shard, aw, src0, ST_WRITE, src1);
       emit_log(ts_log, ZK_STORAGE_AUX_BYTE, shard, aw, 1, is_first, src0, old, src1);
       break;
     }
@@ -1354,7 +1384,7 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
       return;
     }
     const uint32_t deployer_aw = lane == 4 ? bswap32(ZK_DEPLOYER_SYSTEM_CONTRACT_ADDRESS) : 0u;
-    u256l v = storage_access(new_code_shard, deployer_aw, dest_key, false, 0u, false);
+    u256l v = storage_access(new_code_shard, deployer_aw, dest_key, ST_READ, 0u);
     emit_log(ts1, ZK_STORAGE_AUX_BYTE, new_code_shard, deployer_aw, 0, 0, dest_key, v, v);
     bool mask_aa = u_is_zero(v) && !dst_is_kernel;
     code_hash = mask_aa ? B.default_aa[lane] : v;

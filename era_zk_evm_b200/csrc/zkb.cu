@@ -98,7 +98,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
     u256l key = e[i].key[lane];
     u256l val = e[i].value[lane];
-    v.storage_access(e[i].shard, aw, key, true, val, false);
+    v.storage_access(e[i].shard, aw, key, Vm::ST_POPULATE, val);
   }
   if (v.status != ZKB_VM_RUNNING && lane == 0) *fail_flag = v.status;
 }
@@ -288,6 +288,71 @@ __global__ void __launch_bounds__(128) zkb_flatten_kernel(const DevBatch B, cons
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// K8: versioned bytecode hashes (row f-4; ContractCodeSha256 layout parsed at far_call.rs:169-252).  One thread per
+// bytecode: sha256 is a serial chain per message, so the parallelism of an ingest batch is across contracts; each thread
+// streams its own code as 16-byte loads and keeps the 16-word schedule in registers.  Integer-ALU bound (~1 300
+// instructions per 64-byte block), not HBM bound.
+__device__ __forceinline__ void sha256_block_regs(uint32_t h[8], uint32_t w[16]) {
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+  for (int t = 0; t < 64; t++) {
+    if (t >= 16) {
+      uint32_t w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
+      uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      w[t & 15] = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+    }
+    uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+    uint32_t ch = (e & f) ^ (~e & g);
+    uint32_t t1 = hh + S1 + ch + c_sha256_k[t] + w[t & 15];
+    uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+__global__ void __launch_bounds__(128) zkb_hash_bytecodes_kernel(const uint8_t* __restrict__ words_be, const uint64_t* __restrict__ offsets_words,
+                                                                 uint32_t n, uint32_t marker, uint8_t* __restrict__ hashes_be) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t w0 = offsets_words[i], n_words = offsets_words[i + 1] - w0, n_bytes = n_words * 32;
+  const uint4* src = reinterpret_cast<const uint4*>(words_be + w0 * 32);
+  uint32_t h[8], w[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) h[k] = c_sha256_iv[k];
+  const uint64_t full = n_bytes / 64;
+  for (uint64_t blk = 0; blk < full; blk++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint4 v = __ldg(src + blk * 4 + q);
+      w[4 * q + 0] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+    }
+    sha256_block_regs(h, w);
+  }
+  // padding: the code is a whole number of 32-byte words, so the tail is 0 or 32 bytes and always fits one block
+#pragma unroll
+  for (int k = 0; k < 16; k++) w[k] = 0u;
+  if (n_bytes % 64) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const uint4 v = __ldg(src + full * 4 + q);
+      w[4 * q + 0] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+    }
+    w[8] = 0x80000000u;
+  } else {
+    w[0] = 0x80000000u;
+  }
+  const uint64_t n_bits = n_bytes * 8;
+  w[14] = (uint32_t)(n_bits >> 32);
+  w[15] = (uint32_t)n_bits;
+  sha256_block_regs(h, w);
+  uint32_t* out = reinterpret_cast<uint32_t*>(hashes_be + (size_t)i * 32);
+  out[0] = bswap32((uint32_t)ZK_CODE_HASH_VERSION_BYTE << 24 | (marker & 0xFFu) << 16 | ((uint32_t)n_words & 0xFFFFu));
+#pragma unroll
+  for (int k = 1; k < 8; k++) out[k] = bswap32(h[k]);
+}
+
 static thread_local std::string g_err;
 static int32_t set_err(int32_t code, const std::string& msg) {
   g_err = msg;
@@ -524,6 +589,8 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
       (cfg->storage_slots & (cfg->storage_slots - 1)) || cfg->max_far_depth == 0 || cfg->max_depth < 2 || cfg->stack_words == 0 ||
       cfg->max_far_depth > 250)
     return set_err(ZKB_ERR_INVALID_ARGUMENT, "bad capacity in ZkbConfig");
+  if (cfg->reserved[1] > ZK_INITIAL_STORAGE_WRITE_PUBDATA_BYTES)
+    return set_err(ZKB_ERR_INVALID_ARGUMENT, "warm_write_refund_bytes above INITIAL_STORAGE_WRITE_PUBDATA_BYTES (log.rs:110 asserts refund <= net cost)");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return set_err(ZKB_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
   CUDA_OK(cudaSetDevice(cfg->device));
@@ -538,6 +605,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   d.stack_words = c.stack_words;
   d.heap_words = c.heap_bytes / 32;
   d.n_slabs = c.n_heap_slabs;
+  d.warm_refund_bytes = c.reserved[1];
   d.max_far_depth = c.max_far_depth;
   d.max_depth = c.max_depth;
   d.storage_slots = c.storage_slots;
@@ -1174,6 +1242,51 @@ int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n
     if (w >= hw) break;
     uint32_t limb = slab[(size_t)w * 8 + (31 - k) / 4];
     out[i] = (uint8_t)(limb >> (8 * ((31 - k) % 4)));
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_hash_bytecodes(int32_t device, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t marker,
+                           uint8_t* hashes_be_out) {
+  if (!offsets_words || (n && !hashes_be_out)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return ZKB_OK;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return set_err(ZKB_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= n_dev) return ZKB_ERR_INVALID_ARGUMENT;
+  const uint64_t total_words = offsets_words[n];
+  if (total_words && !words_be) return ZKB_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets_words[i + 1] < offsets_words[i]) return ZKB_ERR_INVALID_ARGUMENT;
+    if (offsets_words[i + 1] - offsets_words[i] > 0xFFFFu)
+      return set_err(ZKB_ERR_INVALID_ARGUMENT, "bytecode longer than 65535 words (MAX_CODE_PAGE_SIZE_IN_WORDS)");
+  }
+  CUDA_OK(cudaSetDevice(device));
+  uint8_t *d_words = nullptr, *d_hashes = nullptr;
+  uint64_t* d_off = nullptr;
+  cudaError_t e = cudaMalloc(&d_words, std::max<uint64_t>(total_words * 32, 32));
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, (size_t)(n + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_hashes, (size_t)n * 32);
+  if (e == cudaSuccess && total_words) e = cudaMemcpy(d_words, words_be, total_words * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets_words, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    zkb_hash_bytecodes_kernel<<<(n + 127) / 128, 128>>>(d_words, d_off, n, marker, d_hashes);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(hashes_be_out, d_hashes, (size_t)n * 32, cudaMemcpyDeviceToHost);
+  cudaFree(d_words);
+  cudaFree(d_off);
+  cudaFree(d_hashes);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_CUDA, cudaGetErrorString(e));
+  return ZKB_OK;
+}
+
+int32_t zkb_ingest_bytecodes(ZkbBatch* b, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t* hashes_be_out) {
+  if (!b || !offsets_words || (n && !hashes_be_out)) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = zkb_hash_bytecodes(b->cfg.device, words_be, offsets_words, n, (uint8_t)ZK_CODE_AT_REST_MARKER, hashes_be_out);
+  if (rc != ZKB_OK) return rc;
+  for (uint32_t i = 0; i < n; i++) {
+    rc = zkb_load_bytecode(b, hashes_be_out + 32 * (size_t)i, words_be + 32 * offsets_words[i], (uint32_t)(offsets_words[i + 1] - offsets_words[i]));
+    if (rc != ZKB_OK) return rc;
   }
   return ZKB_OK;
 }

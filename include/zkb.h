@@ -70,7 +70,13 @@ typedef struct ZkbConfig {
   uint32_t host_mirror;      /* 1 = allocate pinned host mirrors for zkb_fetch_streams */
   uint32_t schedule;         /* ZkbSchedule: how warps are assigned to VMs (results are identical either way) */
   uint32_t reserved[3];      /* reserved[0] = SMs left free by the persistent interpreter grid (0 = none): room for the
-                                NCCL send/recv kernels of the multi-GPU stream concat to run underneath the next launch */
+                                NCCL send/recv kernels of the multi-GPU stream concat to run underneath the next launch.
+                                reserved[1] = warm_write_refund_bytes (the refund-aware storage oracle):
+                                0 = the reference's InMemoryStorage, estimate_refunds_for_write() == RefundType::None
+                                (storage.rs:80-86); 1..64 = a storage write to a slot whose cold/warm marker
+                                (storage.rs:10,105-110,126-131) is already set is answered with
+                                RefundType::RepeatedWrite{pubdata_bytes = this value} on the rollup shard, which
+                                log.rs:99-119 subtracts from INITIAL_STORAGE_WRITE_PUBDATA_BYTES. */
 } ZkbConfig;
 
 /* mirror of CallStackEntry (execution_stack.rs:6-24) */
@@ -220,6 +226,18 @@ enum ZkbFlatKind { ZKB_FLAT_STORAGE_HISTORY = 0, ZKB_FLAT_EVENT_HISTORY = 1, ZKB
 int32_t zkb_flatten_logs(ZkbBatch* b, void* cuda_stream);
 int32_t zkb_flat_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out);
 int32_t zkb_read_flat(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
+
+/* ---- bytecode ingestion: the step right BEFORE the path ----------------------------- */
+/* Versioned code hashes of n bytecodes, computed on the GPU: byte 0 = version (1), byte 1 = marker (0 at rest,
+ * 1 being constructed), bytes 2..3 = length in 32-byte words (big-endian u16), bytes 4..31 = sha256(code)[4..32] --
+ * the ContractCodeSha256 layout far_call parses (src/opcodes/execution/far_call.rs:169-252) and the key under which
+ * SimpleDecommitter::populate files the code (src/reference_impls/decommitter.rs:23-28).
+ * words_be: all bytecodes back to back, 32-byte big-endian words; offsets_words[n + 1]: word offset of each bytecode
+ * (offsets_words[n] = total); hashes_be_out: n x 32 bytes.  Lengths above 65 535 words are rejected. */
+int32_t zkb_hash_bytecodes(int32_t device, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t marker,
+                           uint8_t* hashes_be_out);
+/* hash (at-rest marker) + zkb_load_bytecode of every bytecode: populate() for callers that hold code, not hashes */
+int32_t zkb_ingest_bytecodes(ZkbBatch* b, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t* hashes_be_out);
 
 /* ---- checkpoint / accounting ---------------------------------------------------------------------- */
 /* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a

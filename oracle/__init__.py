@@ -41,6 +41,11 @@ class OracleBatch(_binding.Batch):
         self._check(self._lib.orc_run_threads(self._h, max_cycles_per_vm, n_threads))
 
 
+def hash_bytecodes(codes, marker: int = 0) -> list:
+    """versioned code hashes through the oracle's restatement (orc_hash_bytecodes)"""
+    return _binding.hash_bytecodes(lib(), "orc_", codes, marker)
+
+
 def _hash_fn(name):
     fn = getattr(lib(), name)
     fn.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]

@@ -477,8 +477,21 @@ struct ApplicationData {
 
 struct InMemoryStorage {
   std::unordered_map<SlotKey, U256, SlotKeyHash> inner;
+  std::unordered_set<SlotKey, SlotKeyHash> cold_warm_markers;  // storage.rs:10: set on every executed read / write, never rolled back
   std::vector<ApplicationData> frames_stack;
+  // row f-3 (refund-aware oracle): 0 = the reference's test storage (always RefundType::None, storage.rs:80-86);
+  // 1..64 = RepeatedWrite refund, in pubdata bytes, for a write to an already warm slot of the rollup shard
+  uint32_t warm_write_refund_bytes = 0;
   InMemoryStorage() { frames_stack.emplace_back(); }  // storage.rs:18-24
+
+  // Storage::estimate_refunds_for_write (storage.rs:80-86 answers None; the policy above is this build's f-3 oracle).
+  // Returns (refund type, pubdata bytes); called BEFORE the write executes (log.rs:99-102).
+  std::pair<uint32_t, uint32_t> estimate_refunds_for_write(const LogQuery& q) const {
+    if (warm_write_refund_bytes == 0 || q.shard_id != 0) return {0u, 0u};
+    SlotKey k{q.shard_id, q.address, q.key};
+    if (!cold_warm_markers.count(k)) return {0u, 0u};
+    return {1u, warm_write_refund_bytes};
+  }
 
   // storage.rs:88-139
   LogQuery execute_partial_query(LogQuery q) {
@@ -489,6 +502,7 @@ struct InMemoryStorage {
     SlotKey k{q.shard_id, q.address, q.key};
     auto it = inner.find(k);
     U256 current = it == inner.end() ? U256::zero() : it->second;
+    cold_warm_markers.insert(k);  // storage.rs:105-110 (writes), :126-131 (reads)
     if (q.rw_flag) {
       inner[k] = q.written_value;
       q.read_value = current;
@@ -852,11 +866,12 @@ struct VmState {
     wt.add_memory_query(q, ZKB_MEMORIGIN_VM);
     return q;
   }
-  // helpers.rs:119-136 + storage.rs:80-86 (InMemoryStorage always answers RefundType::None)
+  // helpers.rs:119-136: ask the storage oracle, hand the answer to the tracer, return RefundType::pubdata_refund()
   uint32_t refund_for_partial_query(const LogQuery& q) {
     REF_ASSERT(q.rw_flag, "refund for read");
-    wt.record_refund(0, 0);
-    return 0;
+    auto refund = storage.estimate_refunds_for_write(q);
+    wt.record_refund(refund.first, refund.second);
+    return refund.second;
   }
   // helpers.rs:138-155
   LogQuery access_storage(LogQuery q) {
@@ -1955,6 +1970,7 @@ static VmState* new_vm(OrcBatch* b) {
   vm->decommitter.known_hashes = &b->known_hashes;
   vm->block_properties = b->block_properties;
   vm->wt.enabled = b->cfg.witness_mode != 0;
+  vm->storage.warm_write_refund_bytes = b->cfg.reserved[1];
   return vm;
 }
 
@@ -1970,6 +1986,7 @@ extern "C" {
 
 int32_t orc_create(const ZkbConfig* cfg, OrcBatch** out) {
   if (!cfg || !out || cfg->n_vms == 0) return ZKB_ERR_INVALID_ARGUMENT;
+  if (cfg->reserved[1] > ZK_INITIAL_STORAGE_WRITE_PUBDATA_BYTES) return ZKB_ERR_INVALID_ARGUMENT;  // log.rs:110
   OrcBatch* b = new OrcBatch();
   b->cfg = *cfg;
   b->vms.resize(cfg->n_vms);
@@ -2313,6 +2330,33 @@ int32_t orc_read_heap(OrcBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n
 }
 
 // ---- standalone primitives exposed for the oracle's own pinning tests (tests/test_oracle_*.py) ----
+// versioned code hash (row f-4): ContractCodeSha256 layout as parsed at /root/reference/src/opcodes/execution/far_call.rs:169-252
+// (version byte, marker byte, big-endian u16 length in words, sha256(code)[4..32]) = the key of
+// SimpleDecommitter::populate (/root/reference/src/reference_impls/decommitter.rs:23-28)
+int32_t orc_hash_bytecodes(int32_t /*device*/, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t marker,
+                           uint8_t* hashes_be_out) {
+  if (!offsets_words || (n && !hashes_be_out)) return ZKB_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets_words[i + 1] < offsets_words[i]) return ZKB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_words = offsets_words[i + 1] - offsets_words[i];
+    if (n_words > 0xFFFFu) return ZKB_ERR_INVALID_ARGUMENT;
+    uint8_t* out = hashes_be_out + 32 * (size_t)i;
+    orc_hash::sha256(words_be + 32 * offsets_words[i], n_words * 32, out);
+    out[0] = (uint8_t)ZK_CODE_HASH_VERSION_BYTE;
+    out[1] = marker;
+    out[2] = (uint8_t)(n_words >> 8);
+    out[3] = (uint8_t)n_words;
+  }
+  return ZKB_OK;
+}
+int32_t orc_ingest_bytecodes(OrcBatch* b, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t* hashes_be_out) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  int32_t rc = orc_hash_bytecodes(0, words_be, offsets_words, n, (uint8_t)ZK_CODE_AT_REST_MARKER, hashes_be_out);
+  for (uint32_t i = 0; i < n && rc == ZKB_OK; i++)
+    rc = orc_load_bytecode(b, hashes_be_out + 32 * (size_t)i, words_be + 32 * offsets_words[i], (uint32_t)(offsets_words[i + 1] - offsets_words[i]));
+  return rc;
+}
+
 void orc_keccak256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::keccak_sponge256(data, len, 0x01, out); }
 void orc_sha3_256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::keccak_sponge256(data, len, 0x06, out); }
 void orc_sha256(const uint8_t* data, uint64_t len, uint8_t out[32]) { orc_hash::sha256(data, len, out); }

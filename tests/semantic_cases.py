@@ -193,6 +193,58 @@ def case_near_call_panic_rolls_storage_back(B):
     b.close()
 
 
+def case_refund_aware_storage_oracle(B):
+    """SURVEY §8 row f-3.  log.rs:99-119: estimate_refunds_for_write is asked BEFORE the write executes, its answer goes
+    to the tracer (helpers.rs:130-134) and its pubdata_refund() is subtracted from INITIAL_STORAGE_WRITE_PUBDATA_BYTES on
+    the rollup shard.  The oracle behind ZkbConfig.reserved[1] answers RepeatedWrite(n) for a slot whose cold/warm marker
+    is set; the markers are set by every executed read and write (storage.rs:105-110,126-131) and finish_frame never
+    touches them (storage.rs:144-186), so a rolled-back write leaves its slot warm."""
+    refund, epp = 24, 2
+    full, net = epp * C.INITIAL_STORAGE_WRITE_PUBDATA_BYTES, epp * (C.INITIAL_STORAGE_WRITE_PUBDATA_BYTES - refund)
+    p = Program()
+    p.add(Imm(7), 0, 1)
+    p.add(Imm(11), 0, 4)
+    p.add(Imm(13), 0, 6)
+    p.add(Imm(99), 0, 2)
+    p.sstore(1, 2)                       # W1  key 7 cold            -> None, full price
+    p.sstore(1, 4)                       # W2  key 7 warm (W1)       -> RepeatedWrite
+    p.sload(4, 5)                        #     key 11 absent: the read sets its marker
+    p.sstore(4, 2)                       # W3  key 11 warm (read)    -> RepeatedWrite
+    p.near_call(0, "body", "handler")
+    p.label("after")
+    p.sstore(6, 4)                       # W5  key 13 warm (W4, rolled back: the marker stays) -> RepeatedWrite
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.jump("after")
+    p.label("body")
+    p.sstore(6, 2)                       # W4  key 13 cold           -> None
+    p.ret(isa.RET_PANIC, R(0))
+    for policy in (refund, 0):
+        b = H.launch(B, p, 1, ergs=1 << 20, ergs_per_pubdata=epp, cfg_over=dict(warm_write_refund_bytes=policy))
+        r = H.rows(b)
+        assert [H.family_of(x) for x in r] == ["add"] * 4 + ["log", "log", "log", "log", "near_call", "log", "ret", "jump", "log", "ret"]
+        rf = b.read_stream(0, records.STREAM_REFUND)
+        want = [(0, 0), (1, refund), (1, refund), (0, 0), (1, refund)] if policy else [(0, 0)] * 5
+        assert [(int(x["refund_type"]), int(x["refund_value"])) for x in rf] == want
+        # ergs: every SSTORE pays its opcode price + ergs_per_pubdata * net bytes; spent_pubdata accumulates the same
+        price = isa.OPCODE_PRICES[isa.VARIANT_INDEX[(isa.LOG, isa.LOG_SSTORE, isa.SRC_REG, isa.DST_REG, 0)]]
+        writes = [r[4], r[5], r[7], r[9], r[12]]
+        prev = [r[3], r[4], r[6], r[8], r[11]]
+        costs = [full, net, net, full, net] if policy else [full] * 5
+        spent = 0
+        for w, pv, c, i in zip(writes, prev, costs, range(5)):
+            if i not in (3, 4):                         # W4 / W5 sit next to frame switches: checked through spent_pubdata below
+                assert int(pv["ergs_after"]) - int(w["ergs_after"]) == price + c
+            spent += c
+            assert int(w["spent_pubdata"]) == spent    # spent_pubdata_counter is never rolled back (log.rs:136-147)
+        assert b.read_storage(0, 0, H.BOOT_ADDRESS, 7) == 11 and b.read_storage(0, 0, H.BOOT_ADDRESS, 11) == 99
+        assert b.read_storage(0, 0, H.BOOT_ADDRESS, 13) == 11       # W4 rolled back, W5 applied
+        lg = b.read_stream(0, records.STREAM_LOG)
+        assert [int(x["rw_flag"]) for x in lg] == [1, 1, 0, 1, 1, 1]
+        assert H.val(lg[5]["read_value"]) == 0                      # W5 saw the rolled-back slot
+        b.close()
+
+
 def callee_returning(value_word: int, sub=isa.RET_OK) -> Program:
     c = Program()
     c.const("v", value_word)

@@ -45,6 +45,31 @@ def test_workload_parity(name, kwargs, n, oracle_mod):
     assert (gc, gb) == (oc, ob)
 
 
+@pytest.mark.parametrize("name,kwargs,n", [
+    ("storage", dict(), 70),
+    ("erc20", dict(n_transfers=3), 130),
+    ("mixed", dict(n_programs=24), 24 * 32),
+])
+def test_refund_aware_storage_oracle_parity(name, kwargs, n, oracle_mod):
+    """with the refund-aware oracle on (ZkbConfig.reserved[1]) every SSTORE probes the slot's
+    cold/warm marker first; streams (incl. the RefundRec type / value and the ergs they change) must match the oracle"""
+    from era_zk_evm_b200 import GpuVmBatch
+    w = workloads.WORKLOADS[name](**kwargs)
+    vm_ids = list(range(n))
+    cfg = w.config(n)
+    cfg.reserved[1] = 40
+    cfg.storage_slots = max(cfg.storage_slots, 128)      # reads of absent keys claim a slot for their marker
+    gpu, orc = GpuVmBatch(cfg), oracle_mod.OracleBatch(cfg)
+    w.setup(gpu, vm_ids)
+    w.setup(orc, vm_ids)
+    gpu.run()
+    orc.run_threads(0, 0)
+    problems = compare_batches(gpu, orc)
+    assert not problems, "\n".join(problems)
+    refunds = [r for vm in vm_ids[:40] for r in gpu.read_stream(vm, records.STREAM_REFUND)]
+    assert any(int(r["refund_type"]) == 1 and int(r["refund_value"]) == 40 for r in refunds), "no repeated write in the sample"
+
+
 def test_resumable_run_matches_single_run(oracle_mod):
     w = workloads.Erc20(n_transfers=2)
     gpu, orc = _pair(w, list(range(33)), oracle_mod)

@@ -27,7 +27,10 @@ def small_config(n_vms, max_cycles=256, **over):
     cfg.storage_slots = 64
     cfg.journal_entries = 64
     for k, v in over.items():
-        setattr(cfg, k, v)
+        if k == "warm_write_refund_bytes":      # ZkbConfig.reserved[1]: the refund-aware storage oracle (row f-3)
+            cfg.reserved[1] = v
+        else:
+            setattr(cfg, k, v)
     return cfg
 
 
