@@ -121,16 +121,20 @@ struct __align__(16) VmSmem {
   uint32_t pt[ZKB_PT_ENTRIES * 2];  // page indirections (page, kind | slab << 8 | cleanup_level << 16); HBM copy: DevBatch.pt
   uint32_t hwm[32];    // words touched per heap slab; HBM copy: DevBatch.slab_hwm
   uint32_t lv[4];      // the current far level's entry of DevBatch.lvl: heap slab, aux slab, stack high-water mark, -
-  // octet-uniform cold state.  Every lane of the octet stores the same value and a lane reads back at least its own
-  // store, so these need no octet sync; they live here to keep the interpreter's register file for the hot state.
-  uint32_t u[12];      // U_* below
+  // Octet-uniform cold state, kept here to leave the interpreter's register file to the hot state.
+  // u[] / gp[]: written by every lane (same value) only inside load_frame_from_F / vm_load, i.e. between two octet syncs.
+  // ul[k][l]: scalars that are read-modify-written in the middle of a cycle (stream counts, journal length, ...) --
+  // every lane keeps a PRIVATE copy (lane l only ever touches ul[k][l]), so they need no sync and cannot race.
+  uint32_t u[4];       // U_* below
   uint64_t gp[6];      // GP_* below: per-VM base pointers into the HBM slabs
-  uint32_t pad[4];
+  uint32_t ul[8][8];   // UL_* below
+  uint32_t pad[12];
   __device__ __forceinline__ uint64_t* ks() { return reinterpret_cast<uint64_t*>(kbuf); }
 };
-enum { U_FAR_DEPTH = 0, U_JOURNAL_LEN, U_N_DECOMMIT, U_SLAB_FREE, U_COUNT2 /* LOG, DECOMMIT, FRAME, REFUND */, U_CODE_LEN = 8 };
+enum { U_FAR_DEPTH = 0, U_CODE_LEN = 1 };
+enum { UL_JOURNAL_LEN = 0, UL_N_DECOMMIT, UL_SLAB_FREE, UL_COUNT2 /* LOG, DECOMMIT, FRAME, REFUND */ };
 enum { GP_STACK = 0 /* stack page of the current far level */, GP_STACK_PTR, GP_HEAP, GP_LVL, GP_CODE };
-static_assert(sizeof(VmSmem) == 1696 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
+static_assert(sizeof(VmSmem) == 1952 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
 typedef VmSmem WarpSmem;
 
 struct Vm {
@@ -155,11 +159,11 @@ struct Vm {
   __device__ Vm(const DevBatch& b, VmSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {}
   // cold state accessors
   __device__ __forceinline__ uint32_t& far_depth() const { return S.u[U_FAR_DEPTH]; }
-  __device__ __forceinline__ uint32_t& journal_len() const { return S.u[U_JOURNAL_LEN]; }
-  __device__ __forceinline__ uint32_t& n_decommit() const { return S.u[U_N_DECOMMIT]; }
-  __device__ __forceinline__ uint32_t& slab_free() const { return S.u[U_SLAB_FREE]; }
-  __device__ __forceinline__ uint32_t& count(int kind) const { return S.u[U_COUNT2 + kind - 2]; }  // kind >= ZKB_STREAM_LOG
-  __device__ __forceinline__ uint32_t stream_count(int kind) const { return kind == ZKB_STREAM_ROWS ? n_rows : kind == ZKB_STREAM_MEM ? n_mem : S.u[U_COUNT2 + kind - 2]; }
+  __device__ __forceinline__ uint32_t& journal_len() const { return S.ul[UL_JOURNAL_LEN][lane]; }
+  __device__ __forceinline__ uint32_t& n_decommit() const { return S.ul[UL_N_DECOMMIT][lane]; }
+  __device__ __forceinline__ uint32_t& slab_free() const { return S.ul[UL_SLAB_FREE][lane]; }
+  __device__ __forceinline__ uint32_t& count(int kind) const { return S.ul[UL_COUNT2 + kind - 2][lane]; }  // kind >= ZKB_STREAM_LOG
+  __device__ __forceinline__ uint32_t stream_count(int kind) const { return kind == ZKB_STREAM_ROWS ? n_rows : kind == ZKB_STREAM_MEM ? n_mem : S.ul[UL_COUNT2 + kind - 2][lane]; }
   __device__ __forceinline__ uint32_t code_len() const { return S.u[U_CODE_LEN]; }
   __device__ __forceinline__ const uint32_t* code() const { return reinterpret_cast<const uint32_t*>(S.gp[GP_CODE]); }
   __device__ __forceinline__ uint32_t* g_stack() const { return reinterpret_cast<uint32_t*>(S.gp[GP_STACK]); }
@@ -342,6 +346,7 @@ struct Vm {
     uint32_t* base = g_heap() + (size_t)s * B.heap_words * 8;
     uint4* base4 = reinterpret_cast<uint4*>(base);
     for (uint32_t i = lane; i < hwm * 2; i += 8) base4[i] = make_uint4(0u, 0u, 0u, 0u);  // == heap_on_return fill (memory.rs:181-183)
+    osync();  // every lane has read the mark (loop bound above) before lane 0 resets it
     if (lane == 0) S.hwm[s] = 0;
     slab_free() |= 1u << s;
     osync();
@@ -352,7 +357,7 @@ struct Vm {
   }
   __device__ __forceinline__ void slab_write(uint32_t s, uint32_t word, u256l v) {
     g_heap()[((size_t)s * B.heap_words + word) * 8 + lane] = v;
-    if (word + 1 > S.hwm[s] && lane == 0) S.hwm[s] = word + 1;  // (as in stack_write: no octet sync needed)
+    if (lane == 0 && word + 1 > S.hwm[s]) S.hwm[s] = word + 1;  // lane 0 owns the mark (as in stack_write: no octet sync needed)
   }
   // heap (which = 0) / aux heap (which = 1) slab of far level x: the current level's entry lives in shared memory, the
   // callers' entries are current in HBM (written back when the callee's level started)
@@ -367,6 +372,7 @@ struct Vm {
       }
       if (s == ZKB_NO_SLAB) {
         s = slab_alloc();
+        osync();  // every lane has read the old entry
         if (lane == 0) S.lv[which] = s;
         osync();
       }
@@ -639,7 +645,8 @@ struct Vm {
 // ===================================================================================================
 __device__ __forceinline__ void Vm::cycle_once() {
   const uint32_t row_cycle = cycle, row_ts = timestamp, pc_before = pc;
-  *reinterpret_cast<uint2*>(&S.row[24 + 2 * lane]) = make_uint2(0u, 0u);  // dst0 / dst1 fields default to zero
+  S.row[24 + lane] = 0u;  // dst0 / dst1 fields default to zero (lane l owns limb l of both, here and in dst*_update)
+  S.row[32 + lane] = 0u;
   rowbits = 0;
   ccount = 0;
   dst_loc = 0;
