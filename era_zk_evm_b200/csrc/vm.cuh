@@ -1343,7 +1343,7 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
       drop &= drop - 1;
       uint32_t einfo = oshfl(info, l);
       if ((einfo & 0xFFu) == PT_EXT) slab_release((einfo >> 8) & 0xFFu);
-      if (lane == 0) S.pt[(l + ZK_OCT * q) * 2] = ZKB_PT_FREE;
+      if ((int)lane == l) S.pt[e0 * 2] = ZKB_PT_FREE;  // the lane that read the entry frees it (no cross-lane write)
     }
   }
   osync();

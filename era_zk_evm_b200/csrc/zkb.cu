@@ -34,8 +34,19 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
   extern __shared__ uint4 smem_raw[];
   __shared__ uint32_t s_base;
   VmSmem* smem = reinterpret_cast<VmSmem*>(smem_raw);
-  const uint32_t lane = oct_lane(), warp = threadIdx.x >> 5, oct = threadIdx.x >> 3;  // oct = VM slot within the CTA
+  uint32_t lane = oct_lane();
+  const uint32_t warp = threadIdx.x >> 5, oct = threadIdx.x >> 3;  // oct = VM slot within the CTA
+#ifdef ZKB_PINNED_BASE
+  // Experiment (off by default): the VM's shared-memory window and the lane index are used by almost every instruction;
+  // left to itself ptxas re-derives them from %tid / the shared window base again and again (7 % of the executed
+  // instructions).  Passing them through an empty volatile asm pins them in registers: +3.5 % on the register-only ALU
+  // loop, -2.7 % on ERC-20 (two more registers of pressure in the far-call / UMA handlers -> spills).
+  uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(&smem[oct]);
+  asm volatile("" : "+r"(s_addr), "+r"(lane));
+  VmSmem& S = *reinterpret_cast<VmSmem*>(__cvta_shared_to_generic(s_addr));
+#else
   VmSmem& S = smem[oct];
+#endif
   if (!LOCKSTEP) {
     while (true) {
       uint32_t vm_base = 0;
