@@ -131,7 +131,9 @@ def main():
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left free for the NCCL kernels of the concat")
-    ap.add_argument("--concat-mode", default="simple", choices=["overlap", "simple"])
+    ap.add_argument("--concat-mode", default="simple", choices=["async", "overlap", "simple"],
+                    help="N > 1: simple (default, fastest measured) = launch, pack, exchange; async = pack, launch the next "
+                         "pass, then exchange sizes + payload on a side stream; overlap = exchange between restore and launch")
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -228,8 +230,29 @@ def main():
         packed = [batch.pack_stream_device_async(kind, cur_stream) for kind in concat_kinds]   # waits for the run, enqueues the packs
         return [shard.device_bytes_as_tensor(p, nb, dev) for p, nb in packed]
 
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    packed_ev = torch.cuda.Event() if world > 1 else None
+
+    def exchange_on_side_stream(locals_):
+        """size exchange + NCCL send/recv of the packed buffers on a side stream: the host-side wait for the sizes and the
+        transfers themselves run underneath the interpreter launch that is already queued on the main stream"""
+        packed_ev.record()                      # main stream: the pack kernels of the finished pass
+        with torch.cuda.stream(side):
+            side.wait_event(packed_ev)
+            pending.extend(shard.gather_many(locals_, dst=0))
+
     def step():
         """one pass of the hot path over the batch (+ at N > 1 the concat of the previous pass, overlapped)"""
+        if world > 1 and args.concat_mode == "async":
+            # pass k-1 is still running: wait for it (the pack needs its record counts), pack its query-log streams,
+            # queue restore + launch of pass k right behind the packs, THEN do the exchange of pass k-1 on the side stream
+            locals_ = concat_previous() if state["ran"] else None
+            batch.restore()
+            batch.run(sync=False)
+            state["ran"] = True
+            if locals_ is not None:
+                exchange_on_side_stream(locals_)
+            return
         if world > 1 and args.concat_mode == "simple":
             batch.restore()
             batch.run(sync=False)
@@ -248,7 +271,10 @@ def main():
         batch.sync()
         if world > 1 and state["ran"]:
             locals_ = concat_previous()
-            pending.extend(shard.gather_many(locals_, dst=0))
+            if args.concat_mode == "async":
+                exchange_on_side_stream(locals_)
+            else:
+                pending.extend(shard.gather_many(locals_, dst=0))
             state["ran"] = False
         for pg in pending:
             pg.wait()

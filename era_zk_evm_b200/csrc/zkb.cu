@@ -364,6 +364,42 @@ __global__ void __launch_bounds__(128) zkb_hash_bytecodes_kernel(const uint8_t* 
   for (int k = 1; k < 8; k++) out[k] = bswap32(h[k]);
 }
 
+// K9: sparse part of zkb_restore.  The stack pages and heap slabs are 80 % of a batch's mutable state but a VM touches
+// only a prefix of each: [0, high-water mark) -- everything beyond it is zero in the live arrays AND in the snapshot
+// (slabs / pages are cleared up to their mark when they are released, memory.rs:181-188).  So restoring
+// max(live mark, snapshot mark) words per page is a full restore; the marks themselves (DevBatch.lvl / slab_hwm) are
+// restored by the dense copies that follow on the same stream.  One warp per VM, 16-byte copies.
+struct SnapView {
+  const uint32_t* stack_mem;
+  const uint8_t* stack_ptr;
+  const uint32_t* heap_mem;
+  const uint32_t* lvl;
+  const uint32_t* slab_hwm;
+};
+__global__ void __launch_bounds__(128) zkb_restore_sparse_kernel(const DevBatch B, const SnapView Sn) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t levels = B.max_far_depth + 1;
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
+    for (uint32_t l = 0; l < levels; l++) {
+      const size_t page = (size_t)vm * levels + l;
+      const uint32_t n = min(B.stack_words, max(B.lvl[page * 4 + 2], Sn.lvl[page * 4 + 2]));
+      const uint4* src = reinterpret_cast<const uint4*>(Sn.stack_mem + page * B.stack_words * 8);
+      uint4* dst = reinterpret_cast<uint4*>(B.stack_mem + page * B.stack_words * 8);
+      for (uint32_t i = lane; i < n * 2; i += 32) dst[i] = src[i];
+      const uint8_t* psrc = Sn.stack_ptr + page * B.stack_words;
+      uint8_t* pdst = B.stack_ptr + page * B.stack_words;
+      for (uint32_t i = lane; i < n; i += 32) pdst[i] = psrc[i];
+    }
+    for (uint32_t sl = 0; sl < B.n_slabs; sl++) {
+      const size_t slab = (size_t)vm * B.n_slabs + sl;
+      const uint32_t n = min(B.heap_words, max(B.slab_hwm[slab], Sn.slab_hwm[slab]));
+      const uint4* src = reinterpret_cast<const uint4*>(Sn.heap_mem + slab * B.heap_words * 8);
+      uint4* dst = reinterpret_cast<uint4*>(B.heap_mem + slab * B.heap_words * 8);
+      for (uint32_t i = lane; i < n * 2; i += 32) dst[i] = src[i];
+    }
+  }
+}
+
 static thread_local std::string g_err;
 static int32_t set_err(int32_t code, const std::string& msg) {
   g_err = msg;
@@ -424,6 +460,7 @@ struct ZkbBatch {
     void* live;
     void* saved;
     size_t bytes;
+    bool sparse;  // stack pages / heap slabs: restored by zkb_restore_sparse_kernel (touched prefixes only)
   };
   FlatOut flat{};
   bool flat_allocated = false, flat_valid = false;
@@ -1320,12 +1357,12 @@ int32_t zkb_snapshot(ZkbBatch* b) {
   const DevBatch& d = b->d;
   size_t n = c.n_vms, levels = c.max_far_depth + 1;
   if (b->snap.empty()) {
-    auto add = [&](void* live, size_t bytes) { b->snap.push_back(ZkbBatch::Region{live, nullptr, bytes}); };
+    auto add = [&](void* live, size_t bytes, bool sparse = false) { b->snap.push_back(ZkbBatch::Region{live, nullptr, bytes, sparse}); };
     add(d.hot, n * sizeof(VmHot));
     add(d.callstack, n * c.max_depth * 128);
-    add(d.stack_mem, n * levels * c.stack_words * 32);
-    add(d.stack_ptr, n * levels * c.stack_words);
-    add(d.heap_mem, n * c.n_heap_slabs * (size_t)c.heap_bytes);
+    add(d.stack_mem, n * levels * c.stack_words * 32, true);   // regions 2..6: SnapView of zkb_restore (order matters)
+    add(d.stack_ptr, n * levels * c.stack_words, true);
+    add(d.heap_mem, n * c.n_heap_slabs * (size_t)c.heap_bytes, true);
     add(d.lvl, n * levels * 16);
     add(d.slab_hwm, n * c.n_heap_slabs * 4);
     add(d.pt, n * ZKB_PT_ENTRIES * 8);
@@ -1359,7 +1396,19 @@ int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
   if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;  // a running launch still owns the state and the host summary
   memcpy(b->h_counts, b->snap_counts.data(), b->snap_counts.size() * sizeof(uint32_t));
   b->offsets_valid = false;
-  for (auto& r : b->snap) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
+  // stack pages and heap slabs first, by their high-water marks (which the dense copies below then restore as well)
+  static const bool dense_only = getenv("ZKB_RESTORE_DENSE") != nullptr;   // experiment / cross-check knob
+  if (!dense_only) {
+    SnapView sv{(const uint32_t*)b->snap[2].saved, (const uint8_t*)b->snap[3].saved, (const uint32_t*)b->snap[4].saved,
+                (const uint32_t*)b->snap[5].saved, (const uint32_t*)b->snap[6].saved};
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
+    const int grid = (int)std::min<uint32_t>((b->cfg.n_vms + 3) / 4, (uint32_t)n_sm * 16);
+    zkb_restore_sparse_kernel<<<grid, 128, 0, st>>>(b->d, sv);
+    CUDA_OK(cudaGetLastError());
+  }
+  for (auto& r : b->snap)
+    if (dense_only || !r.sparse) CUDA_OK(cudaMemcpyAsync(r.live, r.saved, r.bytes, cudaMemcpyDeviceToDevice, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   CUDA_OK(cudaEventRecord(b->ev1, st));
   b->launched = true;

@@ -70,6 +70,32 @@ def test_refund_aware_storage_oracle_parity(name, kwargs, n, oracle_mod):
     assert any(int(r["refund_type"]) == 1 and int(r["refund_value"]) == 40 for r in refunds), "no repeated write in the sample"
 
 
+@pytest.mark.parametrize("name,kwargs,n", [
+    ("erc20", dict(n_transfers=3), 130),
+    ("keccak", dict(n_calls=2, preimage_bytes=200), 16),
+    ("mixed", dict(n_programs=16, seed=0xF00D), 16 * 32 + 5),
+])
+@pytest.mark.parametrize("cycles_before_snapshot", [0, 53])
+def test_snapshot_restore_reruns_identically(name, kwargs, n, cycles_before_snapshot, oracle_mod):
+    """zkb_snapshot / zkb_restore (VmLocalState + backends are plain Clone values in the reference, vm_state/mod.rs:53):
+    the restore copies stack pages and heap slabs only up to their high-water marks, so a batch restored to a snapshot --
+    taken before the run or in the middle of it -- must re-run to exactly the streams of the first run, i.e. the oracle's"""
+    w = workloads.WORKLOADS[name](**kwargs)
+    gpu, orc = _pair(w, list(range(n)), oracle_mod)
+    if cycles_before_snapshot:
+        gpu.run(max_cycles_per_vm=cycles_before_snapshot)
+    gpu.snapshot()
+    orc.run_threads(0, 0)
+    for attempt in range(3):
+        gpu.run()
+        problems = compare_batches(gpu, orc)
+        assert not problems, f"run {attempt}: " + "\n".join(problems)
+        gpu.restore()
+        if cycles_before_snapshot:
+            st = gpu.vm_status()
+            assert (st[:, 1] <= cycles_before_snapshot).all()       # back at the snapshot's cycle counts
+
+
 def test_resumable_run_matches_single_run(oracle_mod):
     w = workloads.Erc20(n_transfers=2)
     gpu, orc = _pair(w, list(range(33)), oracle_mod)
