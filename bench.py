@@ -227,6 +227,8 @@ def main():
         for pg in pending:         # stream-level wait: the pack buffers are about to be reused
             pg.wait()
         pending.clear()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)   # rank 0's own share is copied out of the pack buffer there
         packed = [batch.pack_stream_device_async(kind, cur_stream) for kind in concat_kinds]   # waits for the run, enqueues the packs
         return [shard.device_bytes_as_tensor(p, nb, dev) for p, nb in packed]
 
@@ -257,7 +259,7 @@ def main():
             batch.restore()
             batch.run(sync=False)
             state["ran"] = True
-            pending.extend(shard.gather_many(concat_previous(), dst=0))
+            pending.extend(shard.gather_many(concat_previous(), dst=0, copy_stream=side))
             state["ran"] = False
             return
         locals_ = concat_previous() if (world > 1 and state["ran"]) else None
@@ -284,6 +286,18 @@ def main():
     for _ in range(max(args.warmup, 0)):
         step()
         drain()
+    if world > 1 and os.environ.get("ZKB_BENCH_PHASES"):      # diagnostic: the concat's phases, serialised
+        def timed(fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, (time.perf_counter() - t0) * 1e3
+        batch.restore(); batch.run(sync=True)
+        locals_, t_pack = timed(concat_previous)
+        pend, t_x = timed(lambda: shard.gather_many(locals_, dst=0))
+        _, t_wait = timed(lambda: [pg.wait() for pg in pend])
+        _, t_restore = timed(batch.restore)
+        print(f"[rank {rank}] phases ms: pack {t_pack:.2f} exchange(enqueue+sizes) {t_x:.2f} wait {t_wait:.2f} restore {t_restore:.2f} "
+              f"bytes {sum(int(t.numel()) for t in locals_)}", file=sys.stderr)
+        batch.run(sync=True)
+        state["ran"] = False
     cycles, sbytes = batch.totals()
     st = batch.vm_status()
     if not (st[:, 0] == 1).all():

@@ -147,9 +147,16 @@ __global__ void zkb_pack_kernel(const uint8_t* __restrict__ src, uint64_t stride
   uint32_t vm = blockIdx.x;
   if (vm >= n_vms) return;
   uint64_t begin = offsets[vm], n = offsets[vm + 1] - begin;
-  const uint2* s = reinterpret_cast<const uint2*>(src + (size_t)vm * stride);
-  uint2* d = reinterpret_cast<uint2*>(dst + begin);
-  for (uint64_t i = threadIdx.x; i < n / 8; i += blockDim.x) d[i] = s[i];
+  const uint8_t* sp = src + (size_t)vm * stride;
+  if (((stride | begin | n) & 15u) == 0) {  // every record kind but the 8-byte RefundRec: 16-byte copies
+    const uint4* s = reinterpret_cast<const uint4*>(sp);
+    uint4* d = reinterpret_cast<uint4*>(dst + begin);
+    for (uint64_t i = threadIdx.x; i < n / 16; i += blockDim.x) d[i] = s[i];
+  } else {
+    const uint2* s = reinterpret_cast<const uint2*>(sp);
+    uint2* d = reinterpret_cast<uint2*>(dst + begin);
+    for (uint64_t i = threadIdx.x; i < n / 8; i += blockDim.x) d[i] = s[i];
+  }
 }
 
 

@@ -100,7 +100,7 @@ def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.devi
     return out, offsets, counts
 
 
-def gather_many(locals_: list, dst: int = 0, group=None):
+def gather_many(locals_: list, dst: int = 0, group=None, copy_stream=None):
     """Concatenation of SEVERAL variable-length uint8 tensors per rank with ONE size exchange and one grouped batch of
     NCCL send/recv: returns a list of PendingGather (payload transfers left in flight)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -114,7 +114,13 @@ def gather_many(locals_: list, dst: int = 0, group=None):
         offsets = np.concatenate([[0], np.cumsum(sizes[:, j])]).astype(np.int64)
         if rank == dst:
             out = torch.empty(int(offsets[-1]), dtype=torch.uint8, device=dev)
-            out[offsets[rank]: offsets[rank + 1]].copy_(local)
+            if copy_stream is None:
+                out[offsets[rank]: offsets[rank + 1]].copy_(local)
+            else:   # dst's own share: off the caller's stream (it only has to finish before the pack buffers are reused)
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    out[offsets[rank]: offsets[rank + 1]].copy_(local)
+                out.record_stream(copy_stream)
             ops += [dist.P2POp(dist.irecv, out[offsets[r]: offsets[r + 1]], r, group) for r in range(world) if r != dst and sizes[r, j]]
         else:
             out = None
