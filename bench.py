@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--concat-mode", default="simple", choices=["async", "overlap", "simple"],
                     help="N > 1: simple (default, fastest measured) = launch, pack, exchange; async = pack, launch the next "
                          "pass, then exchange sizes + payload on a side stream; overlap = exchange between restore and launch")
+    ap.add_argument("--concat-transport", default="nccl", choices=["peer", "nccl"],
+                    help="N > 1: nccl (default) = grouped NCCL send/recv; peer = ranks copy their packed streams into rank 0's "
+                         "IPC-mapped buffer with the copy engines (measured 37 GB/s per link on this pool: tools/peer_copy_bw.py)")
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -233,6 +236,7 @@ def main():
         return [shard.device_bytes_as_tensor(p, nb, dev) for p, nb in packed]
 
     side = torch.cuda.Stream(device=dev) if world > 1 else None
+    sink = {"obj": None}
     packed_ev = torch.cuda.Event() if world > 1 else None
 
     def exchange_on_side_stream(locals_):
@@ -259,7 +263,14 @@ def main():
             batch.restore()
             batch.run(sync=False)
             state["ran"] = True
-            pending.extend(shard.gather_many(concat_previous(), dst=0, copy_stream=side))
+            locals_ = concat_previous()
+            if sink["obj"] is None and args.concat_transport == "peer":
+                cap = int(sum(int(t.numel()) for t in locals_) * 1.25) * world + (1 << 20)
+                sink["obj"] = shard.PeerSink(cap, dev, dst=0)
+            if sink["obj"] is not None:
+                pending.extend(sink["obj"].gather_many(locals_))
+            else:
+                pending.extend(shard.gather_many(locals_, dst=0, copy_stream=side))
             state["ran"] = False
             return
         locals_ = concat_previous() if (world > 1 and state["ran"]) else None
@@ -275,6 +286,8 @@ def main():
             locals_ = concat_previous()
             if args.concat_mode == "async":
                 exchange_on_side_stream(locals_)
+            elif sink["obj"] is not None:
+                pending.extend(sink["obj"].gather_many(locals_))
             else:
                 pending.extend(shard.gather_many(locals_, dst=0))
             state["ran"] = False
@@ -418,7 +431,8 @@ def main():
                 "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
                 "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
                 "multi_gpu": None if world == 1 else {
-                    "partition": "static VM ranges, one process per GPU", "collective": "NCCL send/recv concat on rank 0 inside the timed step",
+                    "partition": "static VM ranges, one process per GPU", "collective": ("copy-engine peer copies (CUDA IPC) into rank 0's buffer + one size all_gather + one 4-byte all_reduce"
+                                   if args.concat_transport == "peer" and args.concat_mode == "simple" else "NCCL send/recv concat on rank 0") + " inside the timed step",
                     "concat_streams": [records.STREAM_NAMES[k] for k in concat_kinds],
                     "concat_bytes_per_step": int(sum(sbytes[k] for k in concat_kinds)) * world}}
         print(json.dumps(line))

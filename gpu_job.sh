@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python tools/fuzz_gpu.py 60 1000 > gpurun_out/fuzz_octet.log 2>&1; tail -5 gpurun_out/fuzz_octet.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:zkb_run_kernel -s 3 -c 1 -f -o gpurun_out/prof_oct_keccak python bench.py --workload keccak --vms 28416 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu4.json 2>gpurun_out/ncu4.err
