@@ -199,6 +199,7 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        size_pg = dist.new_group(backend="gloo")      # host-side exchange of the per-step stream sizes
 
     vm_ids = np.arange(args.vms, dtype=np.uint64) + np.uint64(rank * args.vms)   # static VM-range partition
     cfg = w.config(args.vms, device=local_rank)
@@ -270,7 +271,7 @@ def main():
             if sink["obj"] is not None:
                 pending.extend(sink["obj"].gather_many(locals_))
             else:
-                pending.extend(shard.gather_many(locals_, dst=0, copy_stream=side))
+                pending.extend(shard.gather_many(locals_, dst=0, copy_stream=side, size_group=size_pg))
             state["ran"] = False
             return
         locals_ = concat_previous() if (world > 1 and state["ran"]) else None

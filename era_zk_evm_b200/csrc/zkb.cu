@@ -1096,10 +1096,15 @@ int32_t zkb_read_stream(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
 static void refresh_offsets(ZkbBatch* b) {
   if (b->offsets_valid) return;
   uint32_t n = b->cfg.n_vms;
-  for (uint32_t kind = 0; kind < ZKB_N_STREAMS; kind++) {
-    uint64_t* off = b->h_offsets[kind];
-    off[0] = 0;
-    for (uint32_t v = 0; v < n; v++) off[v + 1] = off[v] + (uint64_t)b->h_counts[(size_t)v * 8 + kind] * REC_BYTES[kind];
+  // ONE pass over the per-VM summary (8 words per VM, the six counts side by side) for all six prefix sums
+  uint64_t run[ZKB_N_STREAMS];
+  for (uint32_t kind = 0; kind < ZKB_N_STREAMS; kind++) b->h_offsets[kind][0] = run[kind] = 0;
+  for (uint32_t v = 0; v < n; v++) {
+    const uint32_t* c = b->h_counts + (size_t)v * 8;
+    for (uint32_t kind = 0; kind < ZKB_N_STREAMS; kind++) {
+      run[kind] += (uint64_t)c[kind] * REC_BYTES[kind];
+      b->h_offsets[kind][v + 1] = run[kind];
+    }
   }
   b->offsets_valid = true;
 }

@@ -100,15 +100,23 @@ def gather_stream(batch, kind: int, dst: int = 0, group=None, device: torch.devi
     return out, offsets, counts
 
 
-def gather_many(locals_: list, dst: int = 0, group=None, copy_stream=None):
+def gather_many(locals_: list, dst: int = 0, group=None, copy_stream=None, size_group=None):
     """Concatenation of SEVERAL variable-length uint8 tensors per rank with ONE size exchange and one grouped batch of
-    NCCL send/recv: returns a list of PendingGather (payload transfers left in flight)."""
+    NCCL send/recv: returns a list of PendingGather (payload transfers left in flight).  size_group: a host-side (gloo)
+    group for the size exchange -- the sizes are host values already, and exchanging them on the host keeps the caller
+    from blocking on its own CUDA stream (the pack kernels) just to read six integers back."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = locals_[0].device
-    n = torch.tensor([t.numel() for t in locals_], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = torch.stack(sizes).cpu().numpy()                       # [world, k]
+    if size_group is not None:
+        n = torch.tensor([t.numel() for t in locals_], dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=size_group)
+        sizes = torch.stack(sizes).numpy()
+    else:
+        n = torch.tensor([t.numel() for t in locals_], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+        sizes = torch.stack(sizes).cpu().numpy()                   # [world, k]
     ops, outs = [], []
     for j, local in enumerate(locals_):
         offsets = np.concatenate([[0], np.cumsum(sizes[:, j])]).astype(np.int64)
