@@ -44,6 +44,13 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
   uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(&smem[oct]);
   asm volatile("" : "+r"(s_addr), "+r"(lane));
   VmSmem& S = *reinterpret_cast<VmSmem*>(__cvta_shared_to_generic(s_addr));
+#elif defined(ZKB_PINNED_LANE)
+  asm volatile("" : "+r"(lane));
+  VmSmem& S = smem[oct];
+#elif defined(ZKB_PINNED_SADDR)
+  uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(&smem[oct]);
+  asm volatile("" : "+r"(s_addr));
+  VmSmem& S = *reinterpret_cast<VmSmem*>(__cvta_shared_to_generic(s_addr));
 #else
   VmSmem& S = smem[oct];
 #endif

@@ -1,2 +1,4 @@
-mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:zkb_run_kernel -s 3 -c 1 -f -o gpurun_out/prof_oct_keccak python bench.py --workload keccak --vms 28416 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu4.json 2>gpurun_out/ncu4.err
+B="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
+for v in base pinlane pinsaddr base pinlane pinsaddr; do for w in erc20; do
+  echo "== $v $w"; ZKB_LIB_PATH=build/variants/libzkb_$v.so timeout 300 $B --workload $w 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value']/1e6, d['roofline']['kernel_ms'])"
+done; done
