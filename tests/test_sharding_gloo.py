@@ -62,6 +62,13 @@ def _worker(rank, world, port, n_total, out_dir):
         if rank == 0:
             assert np.array_equal(many[0][0].numpy(), result[records.STREAM_LOG][0])
             assert np.array_equal(many[1][0].numpy(), result[records.STREAM_REFUND][0])
+        # the same with the sizes exchanged over a separate host-side group (bench.py's default at N > 1)
+        size_pg = dist.new_group(backend="gloo")
+        many2 = [pg.wait() for pg in gather_many(locs, dst=0, size_group=size_pg)]
+        if rank == 0:
+            assert np.array_equal(many2[0][0].numpy(), result[records.STREAM_LOG][0])
+            assert np.array_equal(many2[1][0].numpy(), result[records.STREAM_REFUND][0])
+            assert many2[0][1].tolist() == many[0][1].tolist()
         # ragged edge: an empty contribution from one rank, and the all-gather flavour
         local = torch.arange(5 * rank, dtype=torch.uint8)
         cat, offs = all_gather_varlen(local)
