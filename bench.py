@@ -135,8 +135,8 @@ def main():
                     help="N > 1: simple (default, fastest measured) = launch, pack, exchange; async = pack, launch the next "
                          "pass, then exchange sizes + payload on a side stream; overlap = exchange between restore and launch")
     ap.add_argument("--concat-transport", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: nccl (default) = grouped NCCL send/recv; peer = ranks copy their packed streams into rank 0's "
-                         "IPC-mapped buffer with the copy engines (measured 37 GB/s per link on this pool: tools/peer_copy_bw.py)")
+                    help="N > 1: nccl = grouped NCCL send/recv; peer = every rank pushes its packed streams into rank 0's IPC-mapped "
+                         "buffer with a small copy kernel over NVLink peer memory (zkb_peer_push_async), underneath the next launch")
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -267,7 +267,7 @@ def main():
             locals_ = concat_previous()
             if sink["obj"] is None and args.concat_transport == "peer":
                 cap = int(sum(int(t.numel()) for t in locals_) * 1.25) * world + (1 << 20)
-                sink["obj"] = shard.PeerSink(cap, dev, dst=0)
+                sink["obj"] = shard.PeerSink(cap, dev, dst=0, size_group=size_pg)
             if sink["obj"] is not None:
                 pending.extend(sink["obj"].gather_many(locals_))
             else:
@@ -432,7 +432,7 @@ def main():
                 "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
                 "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
                 "multi_gpu": None if world == 1 else {
-                    "partition": "static VM ranges, one process per GPU", "collective": ("copy-engine peer copies (CUDA IPC) into rank 0's buffer + one size all_gather + one 4-byte all_reduce"
+                    "partition": "static VM ranges, one process per GPU", "collective": ("one-sided peer pushes (CUDA IPC, zkb_peer_push_kernel over NVLink) into rank 0's buffer + host-side size exchange + one 4-byte all_reduce"
                                    if args.concat_transport == "peer" and args.concat_mode == "simple" else "NCCL send/recv concat on rank 0") + " inside the timed step",
                     "concat_streams": [records.STREAM_NAMES[k] for k in concat_kinds],
                     "concat_bytes_per_step": int(sum(sbytes[k] for k in concat_kinds)) * world}}

@@ -414,6 +414,27 @@ __global__ void __launch_bounds__(128) zkb_restore_sparse_kernel(const DevBatch 
   }
 }
 
+// K10: one-sided push of a packed stream into a peer GPU's memory (multi-GPU concat, row e): grid-stride 16-byte copies
+// whose stores travel over NVLink.  Launched with a handful of 128-thread CTAs so that it co-resides with the persistent
+// interpreter (which leaves ~4 K registers and ~40 KB of shared memory per SM unused).
+#define ZKB_PUSH_THREADS 128  // 4 warps x 32 registers = 4 K registers: what the interpreter CTA leaves free on an SM (61 440 of 65 536)
+template <typename V>  // uint4, or uint2 when a rank's share starts on an 8-byte boundary (RefundRec is 8 bytes)
+__global__ void __launch_bounds__(ZKB_PUSH_THREADS) zkb_peer_push_kernel(const V* __restrict__ src, V* __restrict__ dst, uint64_t n16,
+                                                            const uint8_t* __restrict__ tail_src, uint8_t* __restrict__ tail_dst, uint32_t n_tail) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent vector transfers in flight per thread
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const V a = __ldg(src + i), b = __ldg(src + i + stride), c = __ldg(src + i + 2 * stride), d = __ldg(src + i + 3 * stride);
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldg(src + i);
+  if (blockIdx.x == 0 && threadIdx.x < n_tail) tail_dst[threadIdx.x] = tail_src[threadIdx.x];
+}
+
 static thread_local std::string g_err;
 static int32_t set_err(int32_t code, const std::string& msg) {
   g_err = msg;
@@ -1355,6 +1376,69 @@ int32_t zkb_ingest_bytecodes(ZkbBatch* b, const uint8_t* words_be, const uint64_
     rc = zkb_load_bytecode(b, hashes_be_out + 32 * (size_t)i, words_be + 32 * offsets_words[i], (uint32_t)(offsets_words[i + 1] - offsets_words[i]));
     if (rc != ZKB_OK) return rc;
   }
+  return ZKB_OK;
+}
+
+int32_t zkb_peer_push_async(int32_t device, int32_t peer_device, const void* src, void* dst_peer, uint64_t n_bytes, uint32_t n_ctas,
+                            void* cuda_stream) {
+  if ((!src || !dst_peer) && n_bytes) return ZKB_ERR_INVALID_ARGUMENT;
+  if (n_bytes == 0) return ZKB_OK;
+  if (((uintptr_t)src | (uintptr_t)dst_peer) & 7u) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_peer_push_async: pointers must be 8-byte aligned");
+  const bool wide = ((((uintptr_t)src | (uintptr_t)dst_peer) & 15u) == 0);
+  CUDA_OK(cudaSetDevice(device));
+  if (peer_device != device) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess) cudaGetLastError();   // already enabled (also by the lazy IPC mapping): fine
+  }
+  const uint32_t vec = wide ? 16u : 8u;
+  const uint64_t n16 = n_bytes / vec;
+  const uint32_t n_tail = (uint32_t)(n_bytes % vec);
+  const uint8_t* ts = (const uint8_t*)src + n16 * vec;
+  uint8_t* td = (uint8_t*)dst_peer + n16 * vec;
+  if (wide)
+    zkb_peer_push_kernel<uint4><<<std::max(1u, n_ctas), ZKB_PUSH_THREADS, 0, (cudaStream_t)cuda_stream>>>((const uint4*)src, (uint4*)dst_peer, n16, ts, td, n_tail);
+  else
+    zkb_peer_push_kernel<uint2><<<std::max(1u, n_ctas), ZKB_PUSH_THREADS, 0, (cudaStream_t)cuda_stream>>>((const uint2*)src, (uint2*)dst_peer, n16, ts, td, n_tail);
+  CUDA_OK(cudaGetLastError());
+  return ZKB_OK;
+}
+
+int32_t zkb_peer_sink_create(int32_t device, uint64_t n_bytes, void** dptr_out, uint8_t ipc_handle_out[64]) {
+  if (!dptr_out || !ipc_handle_out || n_bytes == 0) return ZKB_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CUDA_OK(cudaSetDevice(device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, n_bytes);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("peer sink cudaMalloc: ") + cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_err(ZKB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle_out, &h, 64);
+  *dptr_out = p;
+  return ZKB_OK;
+}
+
+int32_t zkb_peer_sink_open(int32_t device, const uint8_t ipc_handle[64], void** dptr_out) {
+  if (!dptr_out || !ipc_handle) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(device));   // opened with the READER's device current: lazy peer access maps it for this device's kernels
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  *dptr_out = p;
+  return ZKB_OK;
+}
+
+int32_t zkb_peer_sink_close(int32_t device, void* dptr, uint32_t owner) {
+  if (!dptr) return ZKB_OK;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaDeviceSynchronize());
+  if (owner) CUDA_OK(cudaFree(dptr));
+  else CUDA_OK(cudaIpcCloseMemHandle(dptr));
   return ZKB_OK;
 }
 

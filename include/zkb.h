@@ -239,6 +239,21 @@ int32_t zkb_hash_bytecodes(int32_t device, const uint8_t* words_be, const uint64
 /* hash (at-rest marker) + zkb_load_bytecode of every bytecode: populate() for callers that hold code, not hashes */
 int32_t zkb_ingest_bytecodes(ZkbBatch* b, const uint8_t* words_be, const uint64_t* offsets_words, uint32_t n, uint8_t* hashes_be_out);
 
+/* ---- multi-GPU concat over peer memory ------------------------------------------------------ */
+/* One-sided push of a packed stream into another GPU's memory over NVLink: a grid-stride 16-byte copy kernel of
+ * n_ctas small CTAs (128 threads, no shared memory) whose stores land in `dst_peer`, a device pointer of ANOTHER GPU
+ * that the caller has mapped into this process (CUDA IPC) -- peer access from `device` to the owner of dst_peer is
+ * enabled on first use.  The CTAs are small enough to co-reside with the persistent interpreter CTAs, so the push of
+ * pass k runs underneath the launch of pass k + 1 and the receiving GPU spends no SM on it.  src / dst must be 8-byte
+ * aligned (16-byte aligned pointers get 16-byte transfers); a tail shorter than one vector is copied bytewise. */
+int32_t zkb_peer_push_async(int32_t device, int32_t peer_device, const void* src, void* dst_peer, uint64_t n_bytes, uint32_t n_ctas,
+                            void* cuda_stream);
+/* The sink of such pushes: device memory on `device` with a 64-byte CUDA IPC handle that the other ranks (one process per
+ * GPU) open with THEIR device current, which is what maps it for peer access from their kernels. */
+int32_t zkb_peer_sink_create(int32_t device, uint64_t n_bytes, void** dptr_out, uint8_t ipc_handle_out[64]);
+int32_t zkb_peer_sink_open(int32_t device, const uint8_t ipc_handle[64], void** dptr_out);
+int32_t zkb_peer_sink_close(int32_t device, void* dptr, uint32_t owner);   /* owner != 0: cudaFree, else cudaIpcCloseMemHandle */
+
 /* ---- checkpoint / accounting ---------------------------------------------------------------------- */
 /* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a
  * device-side copy of every mutable per-VM array, restore puts it back (asynchronously on `cuda_stream`). */

@@ -38,6 +38,29 @@ if rank == 1:
             torch.cuda.synchronize(); torch.cuda.synchronize(0)
             dt = time.perf_counter() - t0
             print(f"{name}: {n / dt / 1e9:.1f} GB/s ({dt * 1e3:.2f} ms)", flush=True)
+# the product's own sink: cudaMalloc + IPC handle opened with the reader's device current (peer-mapped for kernels)
+lib0 = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "era_zk_evm_b200", "libzkb.so"))
+hbuf = (ctypes.c_uint8 * 64)()
+ksink = ctypes.c_void_p()
+if rank == 0:
+    assert lib0.zkb_peer_sink_create(local, ctypes.c_uint64(2 * n), ctypes.byref(ksink), hbuf) == 0
+hpay = [bytes(hbuf)]
+dist.broadcast_object_list(hpay, src=0)
+if rank != 0:
+    hb = (ctypes.c_uint8 * 64).from_buffer_copy(hpay[0])
+    rc = lib0.zkb_peer_sink_open(local, hb, ctypes.byref(ksink))
+    assert rc == 0, rc
+if rank == 1:
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "era_zk_evm_b200", "libzkb.so"))
+    lib.zkb_peer_push_async.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
+    for n_ctas in (4, 8, 16, 32, 64, 148, 296):
+        for it in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            rc = lib.zkb_peer_push_async(local, 0, src.data_ptr(), ksink.value + n, n, n_ctas, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, rc
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        print(f"zkb_peer_push_kernel {n_ctas} CTAs: {n / dt / 1e9:.1f} GB/s ({dt * 1e3:.2f} ms)", flush=True)
 dist.barrier()
 if rank == 0:
     torch.cuda.synchronize()
