@@ -1,0 +1,77 @@
+"""-m gpu, needs >= 2 GPUs (skipped on a single-GPU box): the N > 1 concat of the per-GPU query-log streams on real
+devices -- NCCL send/recv (shard.gather_many) and the one-sided NVLink push (shard.PeerSink over zkb_peer_push_async) --
+must both deliver, on rank 0, exactly the rank-ordered concatenation of what the oracle emits for the whole batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_total, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from era_zk_evm_b200 import GpuVmBatch, records, shard, workloads
+        size_pg = dist.new_group(backend="gloo")
+        w = workloads.Erc20(n_transfers=2)
+        lo, hi = shard.partition(n_total, world, rank)
+        ids = np.arange(lo, hi)
+        b = GpuVmBatch(w.config(len(ids), device=rank))
+        w.setup(b, ids)
+        b.run()
+        kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_REFUND]
+        stream = torch.cuda.current_stream().cuda_stream
+        locals_ = [shard.device_bytes_as_tensor(*b.pack_stream_device_async(k, stream), dev) for k in kinds]
+        nccl = [pg.wait() for pg in shard.gather_many(locals_, dst=0, size_group=size_pg)]
+        cap = int(sum(int(t.numel()) for t in locals_) * 1.25) * world + (1 << 20)
+        sink = shard.PeerSink(cap, dev, dst=0, size_group=size_pg)
+        for attempt in range(3):                       # both buffers of the double-buffered sink, then the first again
+            peer = [pg.wait() for pg in sink.gather_many(locals_)]
+            torch.cuda.synchronize()
+            if rank == 0:
+                for (a, ao), (p, po) in zip(nccl, peer):
+                    assert ao.tolist() == po.tolist()
+                    assert torch.equal(a, p), f"peer push differs from the NCCL concat (attempt {attempt})"
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "gathered.npz"), **{f"k{k}": t[0].cpu().numpy() for k, t in zip(kinds, nccl)})
+        dist.barrier()
+        sink.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_concat_nccl_and_peer_push_match_the_oracle(tmp_path, oracle_mod):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from era_zk_evm_b200 import records, workloads
+    n_total, world = 150, 2
+    mp.spawn(_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "gathered.npz"))
+    w = workloads.Erc20(n_transfers=2)
+    orc = oracle_mod.OracleBatch(w.config(n_total))
+    w.setup(orc, np.arange(n_total))
+    orc.run_threads(0, 0)
+    for k in (records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_REFUND):
+        want = np.concatenate([orc.read_stream(vm, k).view(np.uint8) for vm in range(n_total)])
+        assert np.array_equal(got[f"k{k}"], want), records.STREAM_NAMES[k]
