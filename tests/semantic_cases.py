@@ -1,6 +1,8 @@
 """Hand-derived per-quirk programs.  Every expectation below is derived from the reference
 SOURCE (file:line cited), not from the oracle: the CPU suite runs them on the oracle (pinning the restatement), the
 `-m gpu` suite runs the same functions on the CUDA batch."""
+import numpy as np
+
 from era_zk_evm_b200 import isa, records
 from era_zk_evm_b200.asm import (Code, DStackAbs, DStackPush, Imm, Program, R, StackAbs, StackPop, far_call_abi, ret_abi)
 from era_zk_evm_b200.isa import C
@@ -243,6 +245,80 @@ def case_refund_aware_storage_oracle(B):
         assert [int(x["rw_flag"]) for x in lg] == [1, 1, 0, 1, 1, 1]
         assert H.val(lg[5]["read_value"]) == 0                      # W5 saw the rolled-back slot
         b.close()
+
+
+def case_ret_label_bounds_and_unidirectional_forwarding(B):
+    """ret.rs quirks.
+    (a) :202 the to-label variant is honoured only when the FINISHED frame is local: pc := imm0 instead of the saved pc;
+        :254-259 a near-call return propagates the (grown) heap bound to the caller's frame; :243 unspent ergs return.
+    (b) :202 for a far frame the label is ignored: the caller resumes at its saved pc.
+    (c) :61-75 returning a FORWARDED pointer whose page lies below the callee's own base page (its calldata) is a
+        panic: the frame finishes with panicked = true, pc := the far call's exception handler, LT flag set (:262-264),
+        r1 := the empty fat pointer (still marked as a pointer, :213-218), everything else zeroed."""
+    price = lambda row: isa.OPCODE_PRICES[int(row["raw_opcode"]) & 0x7FF]
+    # ---- (a)
+    p = Program()
+    p.add(Imm(77), 0, 2)
+    p.near_call(0, "body", "handler")
+    p.label("after")
+    p.jump("bad")                              # the saved pc: a label return must not come back here
+    p.label("handler")
+    p.jump("bad")
+    p.label("lbl")
+    p.ret(isa.RET_OK, R(0))
+    p.label("bad")
+    p.ret(isa.RET_PANIC, R(0))
+    p.label("body")
+    p.st(Imm(5000), 2)                         # grows the heap bound 4096 -> 5032 inside the near frame
+    p.ret(isa.RET_OK, R(0), label="lbl")
+    b = H.launch(B, p, 1, ergs=1 << 20, heap_bound=4096, cfg_over=dict(heap_bytes=8192))   # the device build's heap slabs are bounded
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "near_call", "uma", "ret", "ret"]
+    nc, st, nret = r[1], r[2], r[3]
+    assert int(st["heap_bound"]) == 5032 and int(st["callstack_depth"]) == 2
+    assert int(nret["pc_after"]) == p.labels["lbl"] and int(nret["callstack_depth"]) == 1
+    assert int(nret["heap_bound"]) == 5032 and int(nret["flags_after"]) == 0          # bound propagated, no panic flag
+    growth = 5032 - 4096
+    assert int(nret["ergs_after"]) == int(r[0]["ergs_after"]) - price(nc) - price(st) - growth - price(nret)
+    assert b.vm_status()[0, 0] == 1
+    b.close()
+    # ---- (b) + (c)
+    ignores_label = Program()
+    ignores_label.ret(isa.RET_OK, R(0), label=7)
+    forwards_calldata = Program()
+    forwards_calldata.const("fwd", C.FWD_FORWARD_FAT_POINTER << 224)
+    forwards_calldata.add(Code("fwd"), 0, 4)
+    forwards_calldata.ptr(isa.PTR_PACK, 1, 4, 3)        # low 128 of r1 (the calldata pointer) | forwarding byte; still a pointer
+    forwards_calldata.ret(isa.RET_OK, R(3))
+    p = Program()
+    p.const("abi", far_call_abi(1 << 16, start=0, length=64))
+    p.add(Code("abi"), 0, 1)
+    p.add(Imm(0x1111), 0, 2)
+    p.far_call(R(1), 2, "h1")
+    p.add(Code("abi"), 0, 1)                   # pc 3: where a well-behaved return resumes
+    p.add(Imm(0x2222), 0, 2)
+    p.add(Imm(55), 0, 9)                       # r9 must be zeroed by the panicking return
+    p.far_call(R(1), 2, "h2")
+    p.ret(isa.RET_OK, R(0))                    # not reached: the second callee panics
+    p.label("h1")
+    p.ret(isa.RET_PANIC, R(0))
+    p.label("h2")
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 24, heap_bound=4096, contracts={0x1111: ignores_label, 0x2222: forwards_calldata})
+    r = H.rows(b)
+    fams = [H.family_of(x) for x in r]
+    assert fams == ["add", "add", "far_call", "ret", "add", "add", "add", "far_call", "add", "ptr", "ret", "ret"]
+    ret_b = r[3]
+    assert int(ret_b["pc_after"]) == 3 and int(ret_b["flags_after"]) == 0 and int(ret_b["callstack_depth"]) == 1
+    ret_c = r[10]
+    assert int(ret_c["bits"]) & records_bit("SRC0_PTR")                                # it WAS a pointer (ret.rs:61 passes)
+    assert int(ret_c["pc_after"]) == p.labels["h2"] and int(ret_c["flags_after"]) == 1 and int(ret_c["callstack_depth"]) == 1
+    assert H.val(ret_c["dst0"]) == 0 and int(ret_c["bits"]) & records_bit("DST0_PTR")   # r1 = FatPointer::empty(), is_pointer
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    assert [(int(f["kind"]), int(f["panicked"])) for f in fr] == [(1, 0), (1, 0), (2, 0), (1, 0), (2, 1), (2, 0)]
+    ls = b.read_local_state(0)
+    assert all(int(x) == 0 for x in np.asarray(ls.registers).reshape(15, 8)[8])        # r9 zeroed (ret.rs:224-231)
+    b.close()
 
 
 def callee_returning(value_word: int, sub=isa.RET_OK) -> Program:
