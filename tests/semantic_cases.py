@@ -321,6 +321,97 @@ def case_ret_label_bounds_and_unidirectional_forwarding(B):
     b.close()
 
 
+def case_far_call_delegate_and_mimic(B):
+    """far_call.rs:505-534: Normal -> (this, sender) = (callee, caller); Delegate -> the callee runs with the CALLER's
+    this / msg_sender and the caller FRAME's context value, only code_address is the callee's; Mimic (kernel only) ->
+    msg_sender comes from r15 (CALL_IMPLICIT_PARAMETER_REG_IDX).  :524-534 Normal / Mimic take the context value from
+    the context_u128 REGISTER, :558 which every far call then zeroes."""
+    d = Program()
+    d.context(isa.CTX_THIS, 1)
+    d.context(isa.CTX_CALLER, 2)
+    d.context(isa.CTX_CODE_ADDRESS, 3)
+    d.context(isa.CTX_GET_U128, 4)
+    d.ret(isa.RET_OK, R(0))
+    a = Program()
+    a.const("abi", far_call_abi(1 << 18))
+    a.add(Code("abi"), 0, 1)
+    a.add(Imm(0x2222), 0, 2)
+    a.far_call(R(1), 2, "fail", sub=isa.FC_DELEGATE)
+    a.context(isa.CTX_GET_U128, 6)
+    a.ret(isa.RET_OK, R(0))
+    a.label("fail")
+    a.ret(isa.RET_PANIC, R(0))
+    m = Program()
+    m.context(isa.CTX_THIS, 1)
+    m.context(isa.CTX_CALLER, 2)
+    m.context(isa.CTX_GET_U128, 4)
+    m.ret(isa.RET_OK, R(0))
+    p = Program()
+    p.const("abi", far_call_abi(1 << 20))
+    p.add(Imm(0xABCD), 0, 5)
+    p.context(isa.CTX_SET_U128, 0, 5)
+    p.add(Code("abi"), 0, 1)
+    p.add(Imm(0x1111), 0, 2)
+    p.far_call(R(1), 2, "fail")
+    p.add(Imm(0x55), 0, 5)
+    p.context(isa.CTX_SET_U128, 0, 5)
+    p.add(Code("abi"), 0, 1)
+    p.add(Imm(0x3333), 0, 2)
+    p.add(Imm(0x7777), 0, 15)
+    p.far_call(R(1), 2, "fail", sub=isa.FC_MIMIC)
+    p.ret(isa.RET_OK, R(0))
+    p.label("fail")
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 24, contracts={0x1111: a, 0x2222: d, 0x3333: m})
+    r = H.rows(b)
+    fams = [H.family_of(x) for x in r]
+    assert fams == ["add", "context", "add", "add", "far_call", "add", "add", "far_call"] + ["context"] * 4 + ["ret", "context", "ret"] + \
+        ["add", "context", "add", "add", "add", "far_call"] + ["context"] * 3 + ["ret", "ret"]
+    assert all(int(x["error_flags"]) == 0 for x in r)
+    assert H.val(r[1]["context_u128"]) == 0xABCD and H.val(r[4]["context_u128"]) == 0          # set, then zeroed by the call
+    # inside the delegate callee: the caller's identity, the callee's code
+    assert [H.val(r[i]["dst0"]) for i in (8, 9, 10, 11)] == [0x1111, H.BOOT_ADDRESS, 0x2222, 0xABCD]
+    assert H.val(r[13]["dst0"]) == 0xABCD                                                      # A's own frame value
+    # inside the mimic callee: msg_sender from r15, context value from the register
+    assert [H.val(r[i]["dst0"]) for i in (21, 22, 23)] == [0x3333, 0x7777, 0x55]
+    assert b.vm_status()[0, 0] == 1
+    b.close()
+
+
+def case_far_call_to_malformed_code_hash(B):
+    """far_call.rs:176-246 a stored code hash that is not a versioned ContractCodeSha256 hash (version byte != 1) is an
+    exception: no decommit (:435-439 the callee's code page is UNMAPPED_PAGE), set_shorthand_panic (helpers.rs:336-338);
+    :502-503 the page counter still moves; the new frame still starts and the NEXT cycle executes the exception-revert
+    encoding in it without a code fetch (cycle.rs:104-115): the frame finishes as panicked, pc := the call's handler,
+    LT flag (ret.rs:262-264)."""
+    target = 0xDEAD4444                                # not a kernel address: a zero hash would fall back to the default AA
+    p = Program()
+    p.const("abi", far_call_abi(1 << 16))
+    p.const("target", target)
+    p.add(Code("abi"), 0, 1)
+    p.add(Code("target"), 0, 2)
+    p.far_call(R(1), 2, "handler")
+    p.ret(isa.RET_PANIC, R(0))                         # pc 3: never reached
+    p.label("handler")
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 20, storage=[(0, C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, target, 0x1234)])
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "add", "far_call", "ret", "ret"]
+    fc, ex, last = r[2], r[3], r[4]
+    assert int(fc["callstack_depth"]) == 2 and int(fc["code_page"]) == C.UNMAPPED_PAGE and int(fc["pc_after"]) == 0
+    assert int(fc["memory_page_counter"]) == 1024 + C.NEW_MEMORY_PAGES_PER_FAR_CALL
+    assert int(fc["bits"]) & records_bit("PENDING") and int(fc["n_log"]) == 1
+    assert len(b.read_stream(0, records.STREAM_DECOMMIT)) == 0
+    assert int(ex["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(ex["masked_variant"]) == isa.PANIC_VARIANT_IDX
+    assert int(ex["n_mem"]) == 0 and int(ex["error_flags"]) == 0                       # no fetch, not an error mask
+    assert int(ex["callstack_depth"]) == 1 and int(ex["pc_after"]) == p.labels["handler"] and int(ex["flags_after"]) == 1
+    assert int(ex["bits"]) & records_bit("PENDING") == 0
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    assert [(int(f["kind"]), int(f["panicked"])) for f in fr] == [(1, 0), (1, 0), (2, 1), (2, 0)]
+    assert int(last["callstack_depth"]) == 0 and b.vm_status()[0, 0] == 1
+    b.close()
+
+
 def callee_returning(value_word: int, sub=isa.RET_OK) -> Program:
     c = Program()
     c.const("v", value_word)
