@@ -556,6 +556,56 @@ def case_uma_unaligned_and_fat_pointer_tail(B):
     b.close()
 
 
+def case_uma_exceptions_mutate_bound_and_ergs_first(B):
+    """uma.rs:152-217 the heap bound is raised and the growth charged BEFORE the exceptions are looked at; :195-217 a
+    shortfall zeroes the frame's ergs (NOT_ENOUGH_ERGS_TO_GROW_MEMORY), :127-132 an offset above MAX_OFFSET_TO_DEREF costs
+    u32::MAX (so it always ends the same way) and leaves the bound alone; :345-347 any exception = no register write,
+    no memory access, set_shorthand_panic: the NEXT cycle runs the exception-revert encoding (cycle.rs:104-115), whose
+    own price can no longer be paid (cycle.rs:147-163: error flag NOT_ENOUGH_ERGS) before it panics the near frame;
+    ret.rs:254-259 the raised bound survives the panicking near return."""
+    def run(address_value):
+        p = Program()
+        p.const("addr", address_value)
+        p.add(Imm(9), 0, 3)
+        p.add(Imm(1000), 0, 4)
+        p.add(Code("addr"), 0, 1)
+        p.near_call(4, "body", "handler")          # passes exactly 1000 ergs
+        p.label("after")
+        p.ret(isa.RET_PANIC, R(0))                 # not reached
+        p.label("handler")
+        p.ret(isa.RET_OK, R(0))
+        p.label("body")
+        p.ld(R(1), 3)
+        p.ret(isa.RET_OK, R(0))                    # not reached
+        b = H.launch(B, p, 1, ergs=1 << 20, heap_bound=4096, cfg_over=dict(heap_bytes=8192))
+        r = H.rows(b)
+        assert [H.family_of(x) for x in r] == ["add", "add", "add", "near_call", "uma", "ret", "ret"]
+        return p, b, r
+    # (i) growth the frame cannot pay for: 6000 + 32 - 4096 = 1936 > 1000 - price
+    p, b, r = run(6000)
+    nc, uma, ex = r[3], r[4], r[5]
+    assert int(nc["ergs_after"]) == 1000
+    assert int(uma["heap_bound"]) == 6032 and int(uma["ergs_after"]) == 0
+    assert int(uma["bits"]) & records_bit("PENDING") and not int(uma["bits"]) & records_bit("DST0_VALID")
+    assert int(uma["n_mem"]) == 1                                                      # the code fetch only: access skipped
+    assert int(ex["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(ex["masked_variant"]) == isa.PANIC_VARIANT_IDX
+    assert int(ex["error_flags"]) == 2 and int(ex["n_mem"]) == 0
+    assert int(ex["callstack_depth"]) == 1 and int(ex["pc_after"]) == p.labels["handler"] and int(ex["flags_after"]) == 1
+    assert int(ex["heap_bound"]) == 6032                                               # propagated by the near return
+    nc_price = isa.OPCODE_PRICES[int(nc["raw_opcode"]) & 0x7FF]
+    assert int(ex["ergs_after"]) == int(r[2]["ergs_after"]) - nc_price - 1000            # nothing came back
+    b.close()
+    # (ii) offset above MAX_OFFSET_TO_DEREF: offset + 32 wraps, the bound stays, the cost is u32::MAX
+    p, b, r = run((1 << 32) - 20)
+    uma, ex = r[4], r[5]
+    assert (1 << 32) - 20 > C.MAX_OFFSET_TO_DEREF
+    assert int(uma["heap_bound"]) == 4096 and int(uma["ergs_after"]) == 0
+    assert int(uma["bits"]) & records_bit("PENDING") and not int(uma["bits"]) & records_bit("DST0_VALID") and int(uma["n_mem"]) == 1
+    assert int(ex["masked_variant"]) == isa.PANIC_VARIANT_IDX and int(ex["pc_after"]) == p.labels["handler"]
+    assert int(ex["heap_bound"]) == 4096 and int(ex["flags_after"]) == 1
+    b.close()
+
+
 def case_context_and_cycle_bookkeeping(B):
     """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
     fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
