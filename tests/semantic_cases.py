@@ -606,6 +606,45 @@ def case_uma_exceptions_mutate_bound_and_ergs_first(B):
     b.close()
 
 
+def case_near_call_ergs_clamp_and_precompile_shortfall(B):
+    """near_call.rs:32-46 asking for more ergs than the frame has passes everything and leaves 0 (it is not an error);
+    log.rs:120-147,255-264 a precompile call whose extra cost (src1.low_u32) exceeds the frame's ergs zeroes them and
+    writes 0 to dst0 WITHOUT a log query or a precompile run; the opcode flags reset at the near call (near_call.rs:24)."""
+    p = Program()
+    p.const("big", 0xFFFFFFFF)
+    p.add(Imm(0), 0, 5)
+    p.sub(Imm(1), 5, 5, set_flags=True, swap=True)     # 0 - 1: sets LT so that the reset below is observable
+    p.add(Code("big"), 0, 4)
+    p.near_call(4, "body", "handler")                  # wants 2^32 - 1 ergs
+    p.label("after")
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.ret(isa.RET_OK, R(0))
+    p.label("body")
+    p.add(Imm(7), 0, 6)
+    p.precompile(0, 4, 6)                              # extra cost r4 = 2^32 - 1 > ergs: dst0 (r6) := 0
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 20)
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "sub", "add", "near_call", "add", "log", "ret", "ret"]
+    assert int(r[1]["flags_after"]) == 1
+    nc, pre, nret = r[3], r[5], r[6]
+    nc_price = isa.OPCODE_PRICES[int(nc["raw_opcode"]) & 0x7FF]
+    assert int(nc["flags_after"]) == 0
+    assert int(nc["ergs_after"]) == int(r[2]["ergs_after"]) - nc_price           # the callee got everything that was left
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    near = [f for f in fr if int(f["kind"]) == 1 and int(f["is_local_frame"]) == 1][0]
+    assert int(near["prev_ergs_remaining"]) == 0 and int(near["ergs_remaining"]) == int(nc["ergs_after"])
+    assert int(pre["ergs_after"]) == 0 and int(pre["n_log"]) == 0 and int(pre["n_mem"]) <= 1
+    assert int(pre["bits"]) & records_bit("DST0_VALID") and H.val(pre["dst0"]) == 0 and not int(pre["bits"]) & records_bit("PENDING")
+    assert len(b.read_stream(0, records.STREAM_LOG)) == 0
+    # the near frame's `ret.ok` can no longer pay its own price: NOT_ENOUGH_ERGS masks it into a panic (cycle.rs:147-163)
+    assert int(nret["error_flags"]) == 2 and int(nret["masked_variant"]) == isa.PANIC_VARIANT_IDX
+    assert int(nret["pc_after"]) == p.labels["handler"] and int(nret["callstack_depth"]) == 1 and int(nret["ergs_after"]) == 0
+    assert b.vm_status()[0, 0] == 1
+    b.close()
+
+
 def case_context_and_cycle_bookkeeping(B):
     """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
     fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
