@@ -645,6 +645,119 @@ def case_near_call_ergs_clamp_and_precompile_shortfall(B):
     b.close()
 
 
+def case_context_setters_reach_the_log_queries(B):
+    """context.rs:41-50 (kernel only) set_ergs_per_pubdata_byte := src0.low_u32(), increment_tx_number := wrapping +1;
+    log.rs:72-74,87 every LogQuery carries the current tx_number_in_block, log.rs:119 the pubdata cost of a storage write
+    is ergs_per_pubdata * 64 and goes to spent_pubdata_counter (:146); aux bytes: storage 0, event 1 (log.rs:88,236)."""
+    p = Program()
+    p.add(Imm(5), 0, 1)
+    p.context(isa.CTX_SET_ERGS_PER_PUBDATA, 0, 1)
+    p.context(isa.CTX_INC_TX)
+    p.context(isa.CTX_INC_TX)
+    p.add(Imm(7), 0, 2)
+    p.add(Imm(9), 0, 3)
+    p.sstore(2, 3)
+    p.event(2, 3, first=True)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 20)
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "context", "context", "context", "add", "add", "log", "log", "ret"]
+    assert all(int(x["error_flags"]) == 0 for x in r)
+    assert [int(x["ergs_per_pubdata"]) for x in r[:3]] == [0, 5, 5]
+    assert [int(x["tx_number"]) for x in r[1:5]] == [0, 1, 2, 2]
+    sst = r[6]
+    price = isa.OPCODE_PRICES[int(sst["raw_opcode"]) & 0x7FF]
+    cost = 5 * C.INITIAL_STORAGE_WRITE_PUBDATA_BYTES
+    assert int(r[5]["ergs_after"]) - int(sst["ergs_after"]) == price + cost and int(sst["spent_pubdata"]) == cost
+    assert int(r[7]["spent_pubdata"]) == cost                                        # events cost no pubdata
+    lg = b.read_stream(0, records.STREAM_LOG)
+    assert [int(x["tx_number_in_block"]) for x in lg] == [2, 2]
+    assert [int(x["aux_byte"]) for x in lg] == [C.STORAGE_AUX_BYTE, C.EVENT_AUX_BYTE]
+    assert [int(x["is_service"]) for x in lg] == [0, 1]                               # FIRST_MESSAGE_FLAG (log.rs:70)
+    assert H.val(lg[1]["key"]) == 7 and H.val(lg[1]["written_value"]) == 9 and bytes(lg[1]["address"]) == H.BOOT_ADDRESS.to_bytes(20, "big")
+    b.close()
+
+
+def case_ptr_arithmetic_and_its_panics(B):
+    """ptr.rs:33-94 add / sub move FatPointer.offset (u32, checked), keep the rest of the low 128 bits and src0's high
+    128 bits, result is a pointer; :96-139 pack = low128(src0) | high128(src1) and needs src1.low_u128() == 0;
+    :140-192 shrink takes src1 off the length.  Panics (set_shorthand_panic, no dst write): src0 not a pointer (:35),
+    src1 a pointer (:41), src1 >= MAX_OFFSET_FOR_ADD_SUB (:47), offset under/overflow (:65-74), pack with dirty low half
+    (:110), shrink below zero."""
+    page = H.BOOT_PAGE + 2
+    ptr0 = (page << 32) | (8 << 64) | (40 << 96)               # offset 0, caller's heap page, start 8, length 40
+
+    def call(callee):
+        p = Program()
+        p.const("abi", far_call_abi(1 << 16, start=8, length=40))
+        p.const("callee", USER)
+        p.add(Code("abi"), 0, 8)
+        p.add(Code("callee"), 0, 7)
+        p.far_call(R(8), 7, "handler")
+        p.ret(isa.RET_OK, R(0))
+        p.label("handler")
+        p.ret(isa.RET_OK, R(0))
+        b = H.launch(B, p, 1, contracts={USER: callee}, ergs=1 << 22, heap_bound=64)
+        return p, b, [x for x in H.rows(b) if int(x["callstack_depth"]) == 2 or H.family_of(x) == "ptr"], H.rows(b)
+
+    ok = Program()
+    ok.const("hi", 0xAB << 128)
+    ok.add(Imm(8), 0, 2)
+    ok.ptr(isa.PTR_ADD, 1, 2, 3)                               # offset 8
+    ok.add(Imm(3), 0, 2)
+    ok.ptr(isa.PTR_SUB, 3, 2, 4)                               # offset 5
+    ok.add(Imm(10), 0, 2)
+    ok.ptr(isa.PTR_SHRINK, 1, 2, 5)                            # length 30
+    ok.add(Code("hi"), 0, 6)
+    ok.ptr(isa.PTR_PACK, 1, 6, 7)
+    ok.ret(isa.RET_OK, R(0))
+    _, b, _, rows = call(ok)
+    pr = [x for x in rows if H.family_of(x) == "ptr"]
+    assert [H.val(x["dst0"]) for x in pr] == [ptr0 | 8, ptr0 | 5, (ptr0 & ~(0xFFFFFFFF << 96)) | (30 << 96), ptr0 | (0xAB << 128)]
+    assert all(int(x["bits"]) & records_bit("DST0_PTR") and not int(x["bits"]) & records_bit("PENDING") for x in pr)
+    b.close()
+
+    def failing(build):
+        c = Program()
+        c.const("big", 1 << 32)
+        c.const("dirty", (0xAB << 128) | 1)
+        build(c)
+        c.ret(isa.RET_OK, R(0))                                # not reached
+        p, b, _, rows = call(c)
+        bad = [x for x in rows if H.family_of(x) == "ptr"][-1]
+        nxt = rows[[int(x["cycle"]) for x in rows].index(int(bad["cycle"])) + 1]
+        assert int(bad["bits"]) & records_bit("PENDING") and not int(bad["bits"]) & records_bit("DST0_VALID"), build.__name__
+        assert int(nxt["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(nxt["pc_after"]) == p.labels["handler"]
+        assert int(nxt["flags_after"]) == 1 and int(nxt["callstack_depth"]) == 1
+        b.close()
+
+    def src0_not_a_pointer(c):
+        c.add(Imm(8), 0, 2)
+        c.ptr(isa.PTR_ADD, 2, 2, 3)
+
+    def src1_is_a_pointer(c):
+        c.ptr(isa.PTR_ADD, 1, 1, 3)
+
+    def offset_too_far(c):
+        c.add(Code("big"), 0, 2)
+        c.ptr(isa.PTR_ADD, 1, 2, 3)
+
+    def offset_underflow(c):
+        c.add(Imm(1), 0, 2)
+        c.ptr(isa.PTR_SUB, 1, 2, 3)
+
+    def pack_dirty_low_half(c):
+        c.add(Code("dirty"), 0, 2)
+        c.ptr(isa.PTR_PACK, 1, 2, 3)
+
+    def shrink_below_zero(c):
+        c.add(Imm(41), 0, 2)
+        c.ptr(isa.PTR_SHRINK, 1, 2, 3)
+
+    for build in (src0_not_a_pointer, src1_is_a_pointer, offset_too_far, offset_underflow, pack_dirty_low_half, shrink_below_zero):
+        failing(build)
+
+
 def case_context_and_cycle_bookkeeping(B):
     """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
     fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
