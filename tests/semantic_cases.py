@@ -758,6 +758,59 @@ def case_ptr_arithmetic_and_its_panics(B):
         failing(build)
 
 
+def case_l1_message_pubdata_and_decommit_shortfall(B):
+    """log.rs:121-124 an L1 message costs ergs_per_pubdata * L1_MESSAGE_PUBDATA_BYTES on top of its price and counts as
+    spent pubdata (:146); aux byte 2 (log.rs:228).  far_call.rs:423-433 a frame that cannot pay 4 ergs per code word of a
+    FRESH decommitment gets NOT_ENOUGH_ERGS_TO_DECOMMIT: nothing is burnt ("do not burn"), nothing is decommitted, the
+    callee frame starts on the unmapped page with 63/64 of what is left (:468-487) and panics in the next cycle."""
+    callee = Program()
+    for _ in range(400):
+        callee.add(Imm(1), 1, 1)
+    callee.ret(isa.RET_OK, R(0))
+    n_words = len(callee.bytecode()) // 32
+    p = Program()
+    p.const("abi", far_call_abi(0xFFFFFFFF))
+    p.const("callee", USER)
+    p.add(Imm(2), 0, 1)
+    p.context(isa.CTX_SET_ERGS_PER_PUBDATA, 0, 1)
+    p.add(Imm(7), 0, 2)
+    p.to_l1(2, 2)
+    p.add(Imm(300), 0, 4)
+    p.near_call(4, "body", "handler")                   # the body runs on 300 ergs
+    p.label("after")
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.ret(isa.RET_OK, R(0))
+    p.label("body")
+    p.add(Code("abi"), 0, 8)
+    p.add(Code("callee"), 0, 7)
+    p.far_call(R(8), 7, "inner")
+    p.label("inner")
+    p.ret(isa.RET_PANIC, R(0))                          # handler of the far call, inside the near frame
+    b = H.launch(B, p, 1, contracts={USER: callee}, ergs=1 << 20)
+    r = H.rows(b)
+    fams = [H.family_of(x) for x in r]
+    assert fams == ["add", "context", "add", "log", "add", "near_call", "add", "add", "far_call", "ret", "ret", "ret"]
+    l1 = r[3]
+    cost = 2 * C.L1_MESSAGE_PUBDATA_BYTES
+    assert int(r[2]["ergs_after"]) - int(l1["ergs_after"]) == isa.OPCODE_PRICES[int(l1["raw_opcode"]) & 0x7FF] + cost
+    assert int(l1["spent_pubdata"]) == cost
+    lg = b.read_stream(0, records.STREAM_LOG)
+    assert int(lg[0]["aux_byte"]) == C.L1_MESSAGE_AUX_BYTE and int(lg[0]["rw_flag"]) == 1
+    fc = r[8]
+    fc_price = isa.OPCODE_PRICES[int(fc["raw_opcode"]) & 0x7FF]
+    left = int(r[7]["ergs_after"]) - fc_price
+    assert C.ERGS_PER_CODE_WORD_DECOMMITTMENT * n_words > left                       # the premise of this case
+    assert int(fc["bits"]) & records_bit("PENDING") and int(fc["code_page"]) == C.UNMAPPED_PAGE
+    assert int(fc["ergs_after"]) == (left // 64) * 63                                 # nothing burnt before the 63/64 split
+    assert len(b.read_stream(0, records.STREAM_DECOMMIT)) == 0
+    ex = r[9]
+    assert int(ex["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(ex["pc_after"]) == p.labels["inner"]
+    assert int(ex["callstack_depth"]) == 2 and int(ex["flags_after"]) == 1
+    assert int(ex["ergs_after"]) == left - isa.OPCODE_PRICES[isa.PANIC_VARIANT_IDX]   # callee's rest came back (ret.rs:243)
+    b.close()
+
+
 def case_context_and_cycle_bookkeeping(B):
     """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
     fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
