@@ -199,7 +199,11 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        size_pg = dist.new_group(backend="gloo")      # host-side exchange of the per-step stream sizes
+        try:
+            size_pg = dist.new_group(backend="gloo")  # host-side exchange of the per-step stream sizes
+        except Exception as e:                        # no usable host interface: fall back to the device all_gather
+            print(f"bench.py: gloo size group unavailable ({e}); sizes go through NCCL", file=sys.stderr)
+            size_pg = None
 
     vm_ids = np.arange(args.vms, dtype=np.uint64) + np.uint64(rank * args.vms)   # static VM-range partition
     cfg = w.config(args.vms, device=local_rank)
