@@ -811,6 +811,66 @@ def case_l1_message_pubdata_and_decommit_shortfall(B):
     b.close()
 
 
+def case_far_call_forwarding_modes(B):
+    """far_call.rs:284-312 ForwardFatPointer narrows the forwarded pointer (start += offset, length -= offset, offset = 0)
+    and keeps its page; UseAuxHeap points the fresh slice at the caller's aux heap page (base + 3); :247-256 forwarding a
+    register that is not a pointer is INPUT_IS_NOT_POINTER_WHEN_EXPECTED: the pointer is masked to FatPointer::empty(),
+    the callee frame starts on the unmapped page and panics in its first cycle."""
+    heap = bytes(range(1, 65))
+    boot_heap_page = H.BOOT_PAGE + 2
+    callee_b = Program()
+    callee_b.ld_ptr(R(1), 2)
+    callee_b.ret(isa.RET_OK, R(0))
+    a = Program()
+    a.const("fwd_hi", ((1 << 16) << 192) | (C.FWD_FORWARD_FAT_POINTER << 224))
+    a.const("aux_abi", far_call_abi(1 << 16, start=0, length=64, fwd=C.FWD_USE_AUX_HEAP))
+    a.const("bad_abi", far_call_abi(1 << 16, fwd=C.FWD_FORWARD_FAT_POINTER))
+    a.add(Imm(8), 0, 2)
+    a.ptr(isa.PTR_ADD, 1, 2, 3)                         # offset 8 into the calldata slice [8, 48)
+    a.add(Code("fwd_hi"), 0, 4)
+    a.ptr(isa.PTR_PACK, 3, 4, 5)                        # pointer in the low half, ergs + forwarding byte in the high half
+    a.add(Imm(0x2222), 0, 6)
+    a.far_call(R(5), 6, "fail")                         # (1) forward
+    a.add(Imm(0xA5A5), 0, 9)
+    a.st_aux(Imm(0), 9)
+    a.add(Code("aux_abi"), 0, 7)
+    a.add(Imm(0x2222), 0, 6)
+    a.far_call(R(7), 6, "fail")                         # (2) fresh slice of the aux heap
+    a.add(Code("bad_abi"), 0, 8)
+    a.add(Imm(0x2222), 0, 6)
+    a.far_call(R(8), 6, "fail2")                        # (3) "forward" a plain value
+    a.ret(isa.RET_PANIC, R(0))                          # not reached
+    a.label("fail2")
+    a.ret(isa.RET_OK, R(0))
+    a.label("fail")
+    a.ret(isa.RET_PANIC, R(0))
+    p = Program()
+    p.const("abi", far_call_abi(1 << 20, start=8, length=40))
+    p.add(Code("abi"), 0, 1)
+    p.add(Imm(0x1111), 0, 2)
+    p.far_call(R(1), 2, "bfail")
+    p.ret(isa.RET_OK, R(0))
+    p.label("bfail")
+    p.ret(isa.RET_PANIC, R(0))
+    b = H.launch(B, p, 1, contracts={0x1111: a, 0x2222: callee_b}, heap=heap, heap_bound=64, ergs=1 << 24)
+    r = H.rows(b)
+    calls = [x for x in r if H.family_of(x) == "far_call"]
+    loads = [x for x in r if H.family_of(x) == "uma" and int(x["callstack_depth"]) == 3]
+    assert len(calls) == 4 and len(loads) == 2
+    a_base = 1024
+    assert H.val(calls[0]["dst0"]) == (boot_heap_page << 32) | (8 << 64) | (40 << 96)
+    assert H.val(calls[1]["dst0"]) == (boot_heap_page << 32) | (16 << 64) | (32 << 96) and int(calls[1]["bits"]) & records_bit("DST0_PTR")
+    assert H.val(loads[0]["dst0"]) == int.from_bytes(heap[16:48], "big")
+    assert H.val(calls[2]["dst0"]) == ((a_base + 3) << 32) | (0 << 64) | (64 << 96)
+    assert H.val(loads[1]["dst0"]) == 0xA5A5
+    bad = calls[3]
+    assert H.val(bad["dst0"]) == 0 and int(bad["bits"]) & records_bit("PENDING") and int(bad["code_page"]) == C.UNMAPPED_PAGE
+    nxt = r[[int(x["cycle"]) for x in r].index(int(bad["cycle"])) + 1]
+    assert int(nxt["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(nxt["pc_after"]) == a.labels["fail2"] and int(nxt["flags_after"]) == 1
+    assert b.vm_status()[0, 0] == 1 and int(r[-1]["callstack_depth"]) == 0 and int(r[-1]["flags_after"]) == 0
+    b.close()
+
+
 def case_context_and_cycle_bookkeeping(B):
     """mod.rs:232-234 timestamp += TIME_DELTA_PER_CYCLE per cycle from STARTING_TIMESTAMP; cycle.rs:59-100 one code
     fetch per code word (4 instructions); context.rs:53-64,87-88 getters; jump.rs:24-25 pc = low 16 bits of src0."""
