@@ -432,7 +432,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
-                "e2e": e2e, "gpu_launches": args.steps * (1 + (len(concat_kinds) if world > 1 else 0)), "roofline": roofline,
+                "e2e": e2e, "gpu_launches": args.steps * (2 + (len(concat_kinds) if world > 1 else 0)),   # interpreter + sparse restore (+ packs) "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
                 "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
                 "multi_gpu": None if world == 1 else {
