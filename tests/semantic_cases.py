@@ -4,7 +4,8 @@ SOURCE (file:line cited), not from the oracle: the CPU suite runs them on the or
 import numpy as np
 
 from era_zk_evm_b200 import isa, records
-from era_zk_evm_b200.asm import (Code, DStackAbs, DStackPush, Imm, Program, R, StackAbs, StackPop, far_call_abi, ret_abi)
+from era_zk_evm_b200.asm import (Code, DStackAbs, DStackPush, DStackRel, Imm, Program, R, StackAbs, StackPop, StackRel,
+                                  far_call_abi, ret_abi)
 from era_zk_evm_b200.isa import C
 
 import vm_harness as H
@@ -868,6 +869,74 @@ def case_far_call_forwarding_modes(B):
     nxt = r[[int(x["cycle"]) for x in r].index(int(bad["cycle"])) + 1]
     assert int(nxt["raw_opcode"]) == isa.EXCEPTION_REVERT_ENCODING and int(nxt["pc_after"]) == a.labels["fail2"] and int(nxt["flags_after"]) == 1
     assert b.vm_status()[0, 0] == 1 and int(r[-1]["callstack_depth"]) == 0 and int(r[-1]["flags_after"]) == 0
+    b.close()
+
+
+def case_far_revert_returns_data_and_rolls_storage_back(B):
+    """ret.rs:232 Revert finishes the frame as panicked (storage.rs:156-176 its writes are undone) and continues at the
+    call's exception handler (:248), but unlike Panic it keeps its returndata (:35-41 only Panic zeroes src0) and does
+    not set the LT flag (:262-264); helpers.rs:255-261 the tracer sees finish_execution_context(panicked = true)."""
+    callee = Program()
+    callee.const("abi", ret_abi(start=0, length=32))
+    callee.add(Imm(7), 0, 1)
+    callee.add(Imm(99), 0, 2)
+    callee.sstore(1, 2)                                 # 5 -> 99 under the callee's own address: rolled back
+    callee.st(Imm(0), 2)                                # returndata word = 99
+    callee.add(Code("abi"), 0, 3)
+    callee.ret(isa.RET_REVERT, R(3))
+    p = Program()
+    p.const("abi", far_call_abi(1 << 20))
+    p.const("callee", USER)
+    p.add(Code("abi"), 0, 8)
+    p.add(Code("callee"), 0, 7)
+    p.far_call(R(8), 7, "handler")
+    p.ret(isa.RET_PANIC, R(0))                          # a revert never resumes here
+    p.label("handler")
+    p.ld_ptr(R(1), 4)
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, contracts={USER: callee}, storage=[(0, USER, 7, 5)], ergs=1 << 24, ergs_per_pubdata=0)
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "add", "far_call", "add", "add", "log", "uma", "add", "ret", "uma", "ret"]
+    rev = r[8]
+    assert int(rev["pc_after"]) == p.labels["handler"] and int(rev["flags_after"]) == 0 and int(rev["callstack_depth"]) == 1
+    assert int(rev["bits"]) & records_bit("DST0_PTR") and (H.val(rev["dst0"]) >> 96) & 0xFFFFFFFF == 32   # returndata kept
+    assert H.val(r[9]["dst0"]) == 99                                                                    # and readable
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    assert [(int(f["kind"]), int(f["panicked"])) for f in fr] == [(1, 0), (1, 0), (2, 1), (2, 0)]
+    assert b.read_storage(0, 0, USER, 7) == 5                                                            # rolled back
+    lg = [x for x in b.read_stream(0, records.STREAM_LOG) if int(x["rw_flag"]) == 1]
+    assert len(lg) == 1 and H.val(lg[0]["read_value"]) == 5 and H.val(lg[0]["written_value"]) == 99       # the witness keeps the write
+    b.close()
+
+
+def case_stack_and_code_operand_addressing(B):
+    """mem_ops.rs:14-125: every stack address is (reg.low_u64() as u16).wrapping_add(imm) (:34-35); absolute = that
+    (:111-121), relative = sp - that (:88-98), push writes at the OLD sp and adds (:55-70), pop subtracts and reads at
+    the NEW sp (:71-86), code-page operands read constant words of the current code page (:100-110).  Reads are
+    witnessed at t + 0 and the destination write at t + 3 (mod.rs:220-231); stack page = base page + 1."""
+    p = Program()
+    p.const("k", 0x1234567890ABCDEF << 64)
+    p.add(Imm(3), 0, 1)                                  # r1 = 3 (used as the register part of addresses)
+    p.add(Code("k"), 0, DStackAbs(2, reg=1))             # stack[3 + 2] = k                    (absolute, reg + imm)
+    p.nop(R(0), DStackPush(8))                           # sp = 8
+    p.add(StackRel(0, reg=1), 0, DStackRel(1))           # reads stack[8 - 3] = k, writes stack[8 - 1]
+    p.add(StackPop(1), 0, 2)                             # sp = 7, reads stack[7] = k -> r2
+    p.add(Imm(1), 2, DStackPush(0, reg=1))               # writes stack[7] = k + 1, sp = 7 + 3 = 10
+    p.add(StackAbs(7), 0, 4)                             # r4 = k + 1
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, ergs=1 << 20)
+    r = H.rows(b)
+    k = 0x1234567890ABCDEF << 64
+    assert [int(x["sp_after"]) for x in r[:7]] == [0, 0, 8, 8, 7, 10, 10]
+    assert H.val(r[3]["src0"]) == k and H.val(r[4]["dst0"]) == k and H.val(r[6]["dst0"]) == k + 1
+    mem = [m for m in b.read_stream(0, records.STREAM_MEM) if int(m["memory_type"]) == C.MEM_STACK]
+    got = [(int(m["index"]), int(m["rw_flag"]), H.val(m["value"]), int(m["timestamp"]) - C.STARTING_TIMESTAMP) for m in mem]
+    dt = C.TIME_DELTA_PER_CYCLE
+    assert got == [(5, 1, k, 1 * dt + 3), (5, 0, k, 3 * dt), (7, 1, k, 3 * dt + 3), (7, 0, k, 4 * dt), (7, 1, k + 1, 5 * dt + 3),
+                   (7, 0, k + 1, 6 * dt)]
+    assert all(int(m["page"]) == H.BOOT_PAGE + 1 for m in mem)
+    code_reads = [m for m in b.read_stream(0, records.STREAM_MEM) if int(m["memory_type"]) == C.MEM_CODE and H.val(m["value"]) == k]
+    assert len(code_reads) == 1 and int(code_reads[0]["page"]) == H.BOOT_PAGE
     b.close()
 
 
