@@ -196,8 +196,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         try:
             size_pg = dist.new_group(backend="gloo")  # host-side exchange of the per-step stream sizes
@@ -432,7 +430,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
-                "e2e": e2e, "gpu_launches": args.steps * (2 + (len(concat_kinds) if world > 1 else 0)),   # interpreter + sparse restore (+ packs) "roofline": roofline,
+                "e2e": e2e,
+                # interpreter + sparse restore (+ packs)
+                "gpu_launches": args.steps * (2 + (len(concat_kinds) if world > 1 else 0)),
+                "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
                 "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
                 "multi_gpu": None if world == 1 else {

@@ -173,6 +173,9 @@ class Batch:
             "ingest_bytecodes": [vp, C.c_char_p, vp, u32, vp],
             "flatten_logs": [vp, vp], "flat_counts": [vp, u32, u32, u32, vp, vp],
             "read_flat": [vp, u32, u32, vp, u64, C.POINTER(u64)],
+            "read_bytecode": [vp, C.c_char_p, vp, u32, C.POINTER(u32)],
+            "set_calldata": [vp, u32, u32, vp, u32, u32],
+            "read_calldata": [vp, u32, u32, u32, vp],
         }
         for name, args in sigs.items():
             fn = self._f(name)
@@ -206,6 +209,27 @@ class Batch:
             return
         self._check(self._f("load_bytecode")(self._h, int_to_be32(code_hash), code, len(code) // 32))
         self._loaded.add(code_hash)
+
+    def read_bytecode(self, code_hash: int) -> bytes:
+        """the code words filed under `code_hash` (SimpleDecommitter.known_hashes, decommitter.rs:10-13)"""
+        n = C.c_uint32()
+        self._check(self._f("read_bytecode")(self._h, int_to_be32(code_hash), None, 0, C.byref(n)))
+        out = np.zeros(n.value * 32, dtype=np.uint8)
+        self._check(self._f("read_bytecode")(self._h, int_to_be32(code_hash), out.ctypes.data, n.value, C.byref(n)))
+        return out.tobytes()
+
+    def set_calldata(self, words: np.ndarray, vm_lo=0, vm_hi=None, per_vm=False):
+        """= SimpleMemory::polulate_bootloaders_calldata (memory.rs:293-298); words: uint8[..., 32 * n_words] big-endian"""
+        vm_hi = self.n_vms if vm_hi is None else vm_hi
+        words = np.ascontiguousarray(words, dtype=np.uint8)
+        n_words = (words.size // (vm_hi - vm_lo) if per_vm else words.size) // 32
+        self._check(self._f("set_calldata")(self._h, vm_lo, vm_hi, words.ctypes.data, n_words, int(per_vm)))
+
+    def read_calldata(self, vm: int, word_lo: int, n_words: int) -> np.ndarray:
+        """= dump_page_content(BOOTLOADER_CALLDATA_PAGE, word_lo .. word_lo + n_words) (memory.rs:300-344)"""
+        out = np.zeros((n_words, 32), dtype=np.uint8)
+        self._check(self._f("read_calldata")(self._h, vm, word_lo, n_words, out.ctypes.data))
+        return out
 
     def ingest_bytecodes(self, codes) -> list:
         """hash (GPU, row f-4) + populate: returns the versioned code hashes as ints (= zkb_ingest_bytecodes)"""

@@ -503,6 +503,9 @@ struct ZkbBatch {
   std::vector<Region> snap;
   std::vector<uint32_t> snap_counts;
   bool has_snapshot = false;
+  // pages_with_extended_lifetime[BOOTLOADER_CALLDATA_PAGE] (memory.rs:230-231,293-298): host-resident, because the
+  // reference registers no indirection for it -- no VM instruction can read it (see zkb_set_calldata in zkb.h)
+  std::vector<std::vector<uint8_t>> calldata;
 };
 
 static void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {
@@ -808,6 +811,7 @@ int32_t zkb_reset(ZkbBatch* b) {
   std::fill(b->h_root.begin(), b->h_root.end(), 0u);
   std::fill(b->h_bootrec.begin(), b->h_bootrec.end(), 0u);
   std::fill(b->boot_code.begin(), b->boot_code.end(), -1);
+  b->calldata.clear();
   b->hot_dirty = b->root_dirty = true;
   b->hot_stale = false;
   return clear_cold_state(b);
@@ -824,6 +828,39 @@ int32_t zkb_load_bytecode(ZkbBatch* b, const uint8_t hash_be[32], const uint8_t*
   for (uint32_t i = 0; i < n_words; i++) be32_to_limbs(words_be + 32 * (size_t)i, &b->h_code_words[((size_t)bc.offset_words + i) * 8]);
   b->codes.push_back(bc);
   b->codes_dirty = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_read_bytecode(ZkbBatch* b, const uint8_t hash_be[32], uint8_t* words_be_out, uint32_t max_words, uint32_t* n_words_out) {
+  if (!b || !hash_be || (!words_be_out && max_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  int id = find_code(b, hash_be);
+  if (id < 0) return set_err(ZKB_ERR_UNKNOWN_BYTECODE, "read_bytecode: bytecode hash not loaded");
+  const Bytecode& bc = b->codes[id];
+  if (n_words_out) *n_words_out = bc.len_words;
+  for (uint32_t i = 0; i < std::min(max_words, bc.len_words); i++)
+    limbs_to_be32(&b->h_code_words[((size_t)bc.offset_words + i) * 8], words_be_out + 32 * (size_t)i);
+  return ZKB_OK;
+}
+
+int32_t zkb_set_calldata(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* words_be, uint32_t n_words, uint32_t per_vm) {
+  if (!range_ok(b, vm_lo, vm_hi) || (!words_be && n_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  if (b->calldata.empty()) b->calldata.resize(b->cfg.n_vms);
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    const uint8_t* src = per_vm ? words_be + (size_t)(v - vm_lo) * n_words * 32 : words_be;
+    b->calldata[v].assign(src, src + (size_t)n_words * 32);
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_read_calldata(ZkbBatch* b, uint32_t vm, uint32_t word_lo, uint32_t n_words, uint8_t* words_be_out) {
+  if (!b || vm >= b->cfg.n_vms || (!words_be_out && n_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  memset(words_be_out, 0, (size_t)n_words * 32);
+  if (b->calldata.empty()) return ZKB_OK;
+  const std::vector<uint8_t>& page = b->calldata[vm];
+  for (uint32_t i = 0; i < n_words; i++) {
+    const size_t at = ((size_t)word_lo + i) * 32;
+    if (at + 32 <= page.size()) memcpy(words_be_out + 32 * (size_t)i, page.data() + at, 32);
+  }
   return ZKB_OK;
 }
 

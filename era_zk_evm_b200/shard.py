@@ -34,12 +34,13 @@ class PendingGather:
     """handle of an asynchronous gather: `wait()` returns (concatenated tensor on dst | None, rank byte offsets)"""
 
     def __init__(self, out, offsets, works, keep=()):
+        # `works` may be SHARED between the handles of one gather_many call (one grouped batch of transfers carries
+        # every stream): whichever handle is waited on first drains the list in place, the others then find it empty
         self.out, self.offsets, self._works, self._keep = out, offsets, works, keep
 
     def wait(self):
-        for w in self._works:
-            w.wait()
-        self._works = []
+        while self._works:
+            self._works.pop().wait()
         return self.out, self.offsets
 
 
@@ -136,7 +137,8 @@ def gather_many(locals_: list, dst: int = 0, group=None, copy_stream=None, size_
                 ops.append(dist.P2POp(dist.isend, local, dst, group))
         outs.append((out, offsets))
     works = dist.batch_isend_irecv(ops) if ops else []
-    return [PendingGather(out, offsets, works if j == 0 else [], keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]
+    # every handle carries the SAME work list (waiting twice is harmless): any one of them may be waited on first
+    return [PendingGather(out, offsets, works, keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]
 
 
 class PeerSink:
@@ -217,4 +219,4 @@ class PeerSink:
                 outs.append((out, offsets))
                 base += (total + 255) // 256 * 256
             work = dist.all_reduce(self._flag, group=self.group, async_op=True)   # behind every rank's pushes
-        return [PendingGather(out, offsets, [work] if j == 0 else [], keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]
+        return [PendingGather(out, offsets, [work], keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]

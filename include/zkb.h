@@ -155,6 +155,19 @@ int32_t zkb_reset(ZkbBatch* b);
 /* ---- population ---------------------------------------------------------------------------------- */
 /* = SimpleDecommitter::populate (decommitter.rs:23-28); words are 32-byte big-endian code words */
 int32_t zkb_load_bytecode(ZkbBatch* b, const uint8_t hash_be[32], const uint8_t* words_be, uint32_t n_words);
+/* the code words filed under `hash_be` by zkb_load_bytecode (SimpleDecommitter.known_hashes, decommitter.rs:10-13): what
+ * decommit_into_memory hands to the tracer on a FRESH decommit (decommitter.rs:81-97 -> helpers.rs:185-191).  Copies at
+ * most max_words 32-byte big-endian words; *n_words_out = the code's length.  Unknown hash: ZKB_ERR_UNKNOWN_BYTECODE. */
+int32_t zkb_read_bytecode(ZkbBatch* b, const uint8_t hash_be[32], uint8_t* words_be_out, uint32_t max_words, uint32_t* n_words_out);
+/* = SimpleMemory::polulate_bootloaders_calldata (memory.rs:293-298): replaces the content of the always-present
+ * extended-lifetime page BOOTLOADER_CALLDATA_PAGE (memory.rs:230-231) of VMs [vm_lo, vm_hi).  per_vm as in
+ * zkb_populate_storage.  As in the reference the page has NO entry in page_numbers_indirections (memory.rs:232 registers
+ * only page 0), so a fat-pointer read of it hits `expect("fat pointer only points to reachable memory")`
+ * (memory.rs:478-481) = ZKB_VM_REFERENCE_PANIC; its content is visible through zkb_read_calldata only. */
+int32_t zkb_set_calldata(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* words_be, uint32_t n_words, uint32_t per_vm);
+/* = dump_page_content(BOOTLOADER_CALLDATA_PAGE, word_lo .. word_lo + n_words) (memory.rs:300-344): words beyond the
+ * populated length read as zero */
+int32_t zkb_read_calldata(ZkbBatch* b, uint32_t vm, uint32_t word_lo, uint32_t n_words, uint8_t* words_be_out);
 /* = BlockProperties (block_properties/mod.rs:4-7) */
 int32_t zkb_set_block_properties(ZkbBatch* b, const uint8_t default_aa_code_hash_be[32], uint8_t zkporter_is_available);
 /* = InMemoryStorage::populate (storage.rs:26-32).  per_vm == 0: the n entries are applied to every VM in

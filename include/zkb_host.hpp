@@ -23,6 +23,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -58,6 +59,7 @@ int32_t ZKB_FN(sync)(ZkbBatch*);
 int32_t ZKB_FN(vm_status)(ZkbBatch*, uint32_t, uint32_t, ZkbVmStatus*);
 int32_t ZKB_FN(read_local_state)(ZkbBatch*, uint32_t, ZkbLocalState*);
 int32_t ZKB_FN(read_stream)(ZkbBatch*, uint32_t, uint32_t, void*, uint64_t, uint64_t*);
+int32_t ZKB_FN(read_bytecode)(ZkbBatch*, const uint8_t*, uint8_t*, uint32_t, uint32_t*);
 }
 
 namespace zkb_host {
@@ -76,7 +78,22 @@ struct U256 {
       l[2 * i + 1] = (uint32_t)(limbs[i] >> 32);
     }
   }
+  static U256 from_be(const uint8_t* b) {
+    U256 v;
+    for (int i = 0; i < 4; i++)
+      for (int k = 0; k < 8; k++) v.limbs[3 - i] = v.limbs[3 - i] << 8 | b[8 * i + k];
+    return v;
+  }
+  void to_be(uint8_t* b) const {
+    for (int i = 0; i < 4; i++)
+      for (int k = 0; k < 8; k++) b[8 * i + k] = (uint8_t)(limbs[3 - i] >> (56 - 8 * k));
+  }
   bool operator==(const U256& o) const { return limbs == o.limbs; }
+  bool operator<(const U256& o) const {
+    for (int i = 3; i >= 0; i--)
+      if (limbs[i] != o.limbs[i]) return limbs[i] < o.limbs[i];
+    return false;
+  }
   bool operator!=(const U256& o) const { return !(*this == o); }
   uint32_t low_u32() const { return (uint32_t)limbs[0]; }
 };
@@ -110,6 +127,23 @@ enum class RefundKind : uint32_t { None = 0, RepeatedWrite = 1 };
 struct RefundType {
   RefundKind kind;
   uint32_t value;
+};
+// PrecompileCyclesWitness (zk_evm_abstractions, third output of execute_precompile, helpers.rs:211-221): per round of the
+// precompile's state machine, the request that started it (first round only), the memory reads the round consumed and
+// the writes it produced.  The rounds are a pure regrouping of the call's memory witness, so the replay rebuilds them
+// on the host from the precompile-origin MemoryQueryRecs: keccak256 -- one round per 136-byte block, a round reads the
+// input words it is the first to touch (<= 6), the digest write belongs to the last round; sha256 -- two reads per
+// round, digest write in the last; ecrecover -- a single round of four reads and two writes.  (The external enum's
+// exact field layout is not in /root/reference; this mirrors its content, see INTEGRATION.md.)
+enum class PrecompileKind : uint8_t { Keccak256 = 0, Sha256 = 1, ECRecover = 2 };
+struct PrecompileRoundWitness {
+  bool has_new_request = false;
+  LogQuery new_request{};
+  std::vector<MemoryQuery> reads, writes;
+};
+struct PrecompileCyclesWitness {
+  PrecompileKind kind = PrecompileKind::Keccak256;
+  std::vector<PrecompileRoundWitness> rounds;
 };
 struct PrimitiveValue {
   U256 value;
@@ -154,7 +188,7 @@ struct VmWitnessTracer {
   virtual void add_log_query(uint32_t, const LogQuery&) {}
   virtual void add_decommittment(uint32_t, const DecommittmentQuery&, const std::vector<U256>& /*code words if fresh*/) {}
   virtual void add_precompile_call_result(uint32_t, const LogQuery&, const std::vector<MemoryQuery>& /*mem_witness_in*/,
-                                          const std::vector<MemoryQuery>& /*memory_witness_out*/) {}
+                                          const std::vector<MemoryQuery>& /*memory_witness_out*/, const PrecompileCyclesWitness&) {}
   virtual void add_revertable_precompile_call(uint32_t, const LogQuery&) {}  // never called by the reference either
   virtual void start_new_execution_context(uint32_t, const CallStackEntry& /*previous*/, const CallStackEntry& /*new*/) {}
   virtual void finish_execution_context(uint32_t, bool /*panicked*/) {}
@@ -193,6 +227,7 @@ class GpuVmBatch {
   GpuVmBatch& operator=(GpuVmBatch&& o) noexcept {
     std::swap(h_, o.h_);
     std::swap(owned_, o.owned_);
+    std::swap(code_cache_, o.code_cache_);
     cfg_ = o.cfg_;
     return *this;
   }
@@ -235,6 +270,21 @@ class GpuVmBatch {
     return st.code == ZKB_VM_ENDED;
   }
 
+  // SimpleDecommitter.known_hashes[hash] (decommitter.rs:10-13): the words a fresh decommit hands to the tracer
+  const std::vector<U256>& code_words(const U256& hash) {
+    auto it = code_cache_.find(hash);
+    if (it != code_cache_.end()) return it->second;
+    uint8_t hb[32];
+    hash.to_be(hb);
+    uint32_t n = 0;
+    check(ZKB_FN(read_bytecode)(h_, hb, nullptr, 0, &n), "read_bytecode");
+    std::vector<uint8_t> raw((size_t)n * 32);
+    if (n) check(ZKB_FN(read_bytecode)(h_, hb, raw.data(), n, &n), "read_bytecode");
+    std::vector<U256> words(n);
+    for (uint32_t i = 0; i < n; i++) words[i] = U256::from_be(raw.data() + 32 * (size_t)i);
+    return code_cache_.emplace(hash, std::move(words)).first->second;
+  }
+
   template <class Rec>
   std::vector<Rec> read_stream(uint32_t vm, uint32_t kind) {
     uint64_t n = 0;
@@ -259,6 +309,7 @@ class GpuVmBatch {
   ZkbBatch* h_ = nullptr;
   bool owned_ = false;
   ZkbConfig cfg_;
+  std::map<U256, std::vector<U256>> code_cache_;
 };
 
 // ---- record decoding ------------------------------------------------------------------------------------------------
@@ -322,6 +373,43 @@ inline CallStackEntry from_frame(const ZkbFrame& f) {
   e.heap_bound = f.heap_bound;
   e.aux_heap_bound = f.aux_heap_bound;
   return e;
+}
+
+// regroups one precompile call's memory witness into its rounds (see PrecompileCyclesWitness above)
+inline PrecompileCyclesWitness precompile_rounds(const LogQuery& request, const std::vector<MemoryQuery>& in, const std::vector<MemoryQuery>& out) {
+  PrecompileCyclesWitness w;
+  const uint32_t addr_low = (uint32_t)request.address[18] << 8 | request.address[19];
+  size_t k = 0;
+  if (addr_low == ZK_ECRECOVER_PRECOMPILE_ADDRESS) {
+    w.kind = PrecompileKind::ECRecover;
+    w.rounds.emplace_back();
+    w.rounds[0].reads = in;
+    k = in.size();
+  } else if (addr_low == ZK_SHA256_PRECOMPILE_ADDRESS) {
+    w.kind = PrecompileKind::Sha256;
+    for (; k + 2 <= in.size(); k += 2) {
+      w.rounds.emplace_back();
+      w.rounds.back().reads.assign(in.begin() + k, in.begin() + k + 2);
+    }
+  } else {
+    w.kind = PrecompileKind::Keccak256;
+    // PrecompileCallABI: input byte offset [0,32), byte length [32,64) of the query key (keccak256.rs:100-111)
+    const uint64_t in_off = (uint32_t)request.key.limbs[0], in_len = (uint32_t)(request.key.limbs[0] >> 32), end = in_off + in_len;
+    uint64_t next_word = in_off / 32;
+    for (uint64_t blk = 0; blk < in_len / 136 + 1; blk++) {
+      w.rounds.emplace_back();
+      const uint64_t a0 = in_off + blk * 136, nb = std::min<uint64_t>(136, end - a0);
+      if (nb == 0) continue;
+      const uint64_t last = (a0 + nb - 1) / 32;
+      for (; next_word <= last && k < in.size(); next_word++, k++) w.rounds.back().reads.push_back(in[k]);
+    }
+  }
+  if (w.rounds.empty()) w.rounds.emplace_back();
+  if (k != in.size()) throw std::runtime_error("replay: precompile read witness does not match its request");
+  w.rounds.front().has_new_request = true;
+  w.rounds.front().new_request = request;
+  w.rounds.back().writes = out;
+  return w;
 }
 
 inline VmLocalState GpuVmBatch::replay(uint32_t vm, VmWitnessTracer& wt, const VmLocalState& initial) {
@@ -394,11 +482,16 @@ inline VmLocalState GpuVmBatch::replay(uint32_t vm, VmWitnessTracer& wt, const V
     // 3. precompile memory witness (helpers.rs:208-222)
     for (; k < m_end && mems[k].origin != ZKB_MEMORIGIN_VM; k++)
       (mems[k].origin == ZKB_MEMORIGIN_PRECOMPILE_IN ? pre_in : pre_out).push_back(decode(mems[k]));
-    if (family == ZK_OP_LOG && sub == ZK_LOG_PRECOMPILE && n_log) wt.add_precompile_call_result(cyc, last_log, pre_in, pre_out);
+    if (family == ZK_OP_LOG && sub == ZK_LOG_PRECOMPILE && n_log)
+      wt.add_precompile_call_result(cyc, last_log, pre_in, pre_out, precompile_rounds(last_log, pre_in, pre_out));
     // 4. decommitment (helpers.rs:164-194)
     for (uint32_t i = 0; i < n_dec; i++) {
       const ZkbDecommitRec& d = decs[id + i];
-      wt.add_decommittment(cyc, DecommittmentQuery{U256::from_limbs32(d.hash), d.timestamp, d.memory_page, d.decommitted_length, d.is_fresh != 0}, {});
+      // B = true decommitter (decommitter.rs:43-47,81-97): the code words on a fresh decommit, an empty vector on a repeat
+      const U256 hash = U256::from_limbs32(d.hash);
+      static const std::vector<U256> no_words;
+      wt.add_decommittment(cyc, DecommittmentQuery{hash, d.timestamp, d.memory_page, d.decommitted_length, d.is_fresh != 0},
+                           d.is_fresh ? code_words(hash) : no_words);
     }
     // 5. frames (helpers.rs:225-264)
     for (uint32_t i = 0; i < n_frame; i++) {

@@ -2016,6 +2016,40 @@ int32_t orc_load_bytecode(OrcBatch* b, const uint8_t hash_be[32], const uint8_t*
   return ZKB_OK;
 }
 
+// SimpleDecommitter.known_hashes lookup (decommitter.rs:10-13): the words a fresh decommit hands to the tracer (:81-97)
+int32_t orc_read_bytecode(OrcBatch* b, const uint8_t hash_be[32], uint8_t* words_be_out, uint32_t max_words, uint32_t* n_words_out) {
+  if (!b || !hash_be) return ZKB_ERR_INVALID_ARGUMENT;
+  auto it = b->known_hashes.find(U256::from_be(hash_be));
+  if (it == b->known_hashes.end()) return ZKB_ERR_UNKNOWN_BYTECODE;
+  const std::vector<U256>& w = *it->second;
+  if (n_words_out) *n_words_out = (uint32_t)w.size();
+  for (uint32_t i = 0; i < std::min<uint32_t>(max_words, (uint32_t)w.size()); i++) w[i].to_be(words_be_out + 32 * (size_t)i);
+  return ZKB_OK;
+}
+
+// SimpleMemory::polulate_bootloaders_calldata (memory.rs:293-298)
+int32_t orc_set_calldata(OrcBatch* b, uint32_t vm_lo, uint32_t vm_hi, const uint8_t* words_be, uint32_t n_words, uint32_t per_vm) {
+  if (!b || vm_lo > vm_hi || vm_hi > b->cfg.n_vms || (!words_be && n_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  for (uint32_t v = vm_lo; v < vm_hi; v++) {
+    const uint8_t* src = per_vm ? words_be + (size_t)(v - vm_lo) * n_words * 32 : words_be;
+    std::vector<U256> values(n_words);
+    for (uint32_t i = 0; i < n_words; i++) values[i] = U256::from_be(src + 32 * (size_t)i);
+    b->vms[v]->memory.pages_with_extended_lifetime.at(ZK_BOOTLOADER_CALLDATA_PAGE) = std::move(values);
+  }
+  return ZKB_OK;
+}
+
+// dump_page_content(BOOTLOADER_CALLDATA_PAGE, range) (memory.rs:300-344)
+int32_t orc_read_calldata(OrcBatch* b, uint32_t vm, uint32_t word_lo, uint32_t n_words, uint8_t* words_be_out) {
+  if (!b || vm >= b->cfg.n_vms || (!words_be_out && n_words)) return ZKB_ERR_INVALID_ARGUMENT;
+  const std::vector<U256>& page = b->vms[vm]->memory.pages_with_extended_lifetime.at(ZK_BOOTLOADER_CALLDATA_PAGE);
+  for (uint32_t i = 0; i < n_words; i++) {
+    const size_t at = (size_t)word_lo + i;
+    (at < page.size() ? page[at] : U256()).to_be(words_be_out + 32 * (size_t)i);
+  }
+  return ZKB_OK;
+}
+
 int32_t orc_set_block_properties(OrcBatch* b, const uint8_t default_aa_code_hash_be[32], uint8_t zkporter_is_available) {
   b->block_properties.default_aa_code_hash = U256::from_be(default_aa_code_hash_be);
   b->block_properties.zkporter_is_available = zkporter_is_available != 0;

@@ -51,14 +51,35 @@ struct Recorder : VmWitnessTracer {
     check_cycle(c);
     if (q.timestamp != cur_ts + 1) note("log query not at t+1 (mod.rs:224-227)");
   }
-  void add_decommittment(uint32_t c, const DecommittmentQuery& q, const std::vector<U256>&) override {
+  uint64_t fresh_code_words = 0, precompile_rounds_seen = 0;
+  void add_decommittment(uint32_t c, const DecommittmentQuery& q, const std::vector<U256>& words) override {
     n[5]++;
     check_cycle(c);
     if (q.timestamp != cur_ts + 1) note("decommit not at t+1");
+    // decommitter.rs:43-47,81-97: the code words on a fresh decommit, nothing on a repeat
+    if (q.is_fresh && words.size() != q.decommitted_length) note("fresh decommit without its code words");
+    if (!q.is_fresh && !words.empty()) note("repeated decommit carries code words");
+    if (q.is_fresh) {
+      fresh_code_words += words.size();
+      // versioned hash: bytes 2..3 = length in words (far_call.rs:169-252)
+      if (((q.hash.limbs[3] >> 32) & 0xFFFFu) != words.size()) note("code words do not match the length in the versioned hash");
+    }
   }
-  void add_precompile_call_result(uint32_t c, const LogQuery&, const std::vector<MemoryQuery>& in, const std::vector<MemoryQuery>& out) override {
+  void add_precompile_call_result(uint32_t c, const LogQuery& req, const std::vector<MemoryQuery>& in, const std::vector<MemoryQuery>& out,
+                                  const PrecompileCyclesWitness& w) override {
     n[6]++;
     check_cycle(c);
+    size_t reads = 0, writes = 0;
+    for (auto& r : w.rounds) {
+      reads += r.reads.size();
+      writes += r.writes.size();
+      if (r.reads.size() > 6) note("precompile round with more than 6 reads");
+    }
+    if (reads != in.size() || writes != out.size()) note("precompile rounds do not partition the memory witness");
+    if (w.rounds.empty() || !w.rounds.front().has_new_request || w.rounds.front().new_request.timestamp != req.timestamp)
+      note("first precompile round without its request");
+    if (w.kind == PrecompileKind::Keccak256 && w.rounds.size() != ((uint32_t)(req.key.limbs[0] >> 32)) / 136 + 1) note("keccak round count");
+    precompile_rounds_seen += w.rounds.size();
     for (auto& q : in)
       if (q.rw_flag || q.timestamp != cur_ts + 1) note("precompile read witness malformed");
     for (auto& q : out)

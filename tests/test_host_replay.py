@@ -97,3 +97,36 @@ def test_replay_reconstructs_the_local_state(name, kwargs, n, oracle_mod):
     b.run_threads(0, 0)
     totals = replay_all(shim, b, spy, range(n))
     assert totals[0] == b.totals()[0]
+
+
+def test_read_bytecode_and_bootloader_calldata_roundtrip(oracle_mod):
+    """zkb_read_bytecode = SimpleDecommitter.known_hashes (decommitter.rs:10-13); zkb_set_calldata / zkb_read_calldata =
+    polulate_bootloaders_calldata + dump_page_content of BOOTLOADER_CALLDATA_PAGE (memory.rs:293-344) -- through the
+    oracle's mirror of the boundary here, through libzkb.so in the -m gpu suite"""
+    _check_bytecode_and_calldata(oracle_mod.OracleBatch)
+
+
+def _check_bytecode_and_calldata(batch_cls):
+    w = workloads.Erc20(n_transfers=1)
+    b = batch_cls(w.config(5))
+    w.setup(b, np.arange(5))
+    for h, code in w.codes.values():
+        assert b.read_bytecode(h) == code
+    with pytest.raises(Exception):
+        b.read_bytecode(12345)
+    rng = np.random.default_rng(7)
+    shared = rng.integers(0, 256, size=3 * 32, dtype=np.uint8)
+    b.set_calldata(shared)
+    per_vm = rng.integers(0, 256, size=(2, 2 * 32), dtype=np.uint8)
+    b.set_calldata(per_vm, vm_lo=1, vm_hi=3, per_vm=True)
+    assert b.read_calldata(0, 0, 3).tobytes() == shared.tobytes()
+    assert b.read_calldata(4, 1, 4).tobytes() == shared[32:].tobytes() + bytes(64)     # beyond the page: zero
+    assert b.read_calldata(2, 0, 2).tobytes() == per_vm[1].tobytes()
+    b.run() if hasattr(b, "run") else None
+    b.close()
+
+
+@pytest.mark.gpu
+def test_read_bytecode_and_bootloader_calldata_roundtrip_gpu():
+    from era_zk_evm_b200 import GpuVmBatch
+    _check_bytecode_and_calldata(GpuVmBatch)

@@ -33,7 +33,7 @@ def main():
         w.setup(orc, ids)
         gpu.run()
         orc.run_threads(0, 0)
-        problems = compare_batches(gpu, orc, max_report=2)
+        problems = compare_batches(gpu, orc, max_report=2, allow_capacity_stops=gpu.n_vms)
         st = orc.vm_status()
         total_cycles += int(st[:, 1].sum())
         caps = int((gpu.vm_status()[:, 0] >= 16).sum())
