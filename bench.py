@@ -10,8 +10,9 @@ every VM runs from its bootloader entry to the end of execution, all witness str
 value     device throughput: inputs resident in HBM, each step = device-side restore of the initial batch state
           (zkb_restore, D2D) + ONE launch of the persistent interpreter kernel; CUDA events, max over ranks.
 e2e       the same metric through the public host API with HOST buffers: per sub-batch reset + populate (H2D) + run +
-          packed fetch of all six witness streams into pinned host memory (D2H), copies overlapped with the next
-          sub-batch's compute, every step.
+          fetch of all six witness streams into pinned host memory (D2H) as ONE lossless blob (device-side transport
+          encoder, include/zkb_codec.h; `e2e_raw_transport` = the same with the canonical records uncompressed),
+          copies overlapped with the next sub-batch's compute, every step.
 roofline  algorithmic bytes (exact byte length of the emitted streams) / average kernel duration, against the
           measured HBM copy bandwidth in MEASURED_PEAKS.json.
 --impl reference: the CPU restatement of the reference path (oracle/, "port": the Rust crate cannot be built in
@@ -359,11 +360,11 @@ def main():
     # The batch is processed as S sub-batches: inputs of sub-batch k go H2D, its interpreter launch runs on one stream,
     # its six witness streams are packed and copied D2H into pinned host memory on another stream while sub-batch
     # k+1 is populated and executed.  Every input byte and every witness byte crosses PCIe inside the timed region.
-    e2e = None
+    e2e = e2e_raw = None
     if not args.no_e2e:
         n_sub = max(1, min(args.sub_batches, args.vms // 1024))
         bounds = [shard.partition(args.vms, n_sub, i) for i in range(n_sub)]
-        subs, sub_ids, pinned = [], [], []
+        subs, sub_ids = [], []
         for lo, hi in bounds:
             scfg = w.config(hi - lo, device=local_rank)
             subs.append(GpuVmBatch(scfg))
@@ -371,52 +372,82 @@ def main():
             w.prepared(vm_ids[lo:hi]) if hasattr(w, "prepared") and hasattr(w, "inputs") else None
         run_stream, copy_stream = torch.cuda.Stream(), torch.cuda.Stream()
         share = [(hi - lo) / args.vms for lo, hi in bounds]
-        for sh in share:   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
-            pinned.append([torch.empty(int(nb * sh * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) for nb in sbytes])
         e2e_steps = max(1, min(args.steps, 3))
-        phase = {"setup_s": 0.0, "wait_run_s": 0.0}
 
-        def e2e_step():
-            for i, sb in enumerate(subs):
+        def measure(transport):
+            """transport = "encoded": ONE lossless blob per sub-batch (device-side encoder, include/zkb_codec.h) crosses PCIe;
+            "raw": the six canonical streams, packed.  Either way every witness byte the host needs lands in pinned host
+            memory inside the timed region."""
+            if transport == "encoded":   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
+                pinned = [[torch.empty(int(sum(sbytes) * sh * 0.5) + (1 << 20), dtype=torch.uint8, pin_memory=True)] for sh in share]
+            else:
+                pinned = [[torch.empty(int(nb * sh * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) for nb in sbytes] for sh in share]
+            phase = {"setup_s": 0.0, "wait_run_s": 0.0}
+            blob_bytes = [0] * n_sub
+
+            def e2e_step():
+                for i, sb in enumerate(subs):
+                    t0 = time.perf_counter()
+                    sb.reset()
+                    w.setup(sb, sub_ids[i])
+                    sb.run(stream=run_stream.cuda_stream, sync=False)
+                    t1 = time.perf_counter()
+                    if transport == "encoded":
+                        blob_bytes[i] = sb.fetch_encoded_async(pinned[i][0].data_ptr(), pinned[i][0].numel(), stream=copy_stream.cuda_stream)
+                    else:
+                        for k in range(records.N_STREAMS):
+                            sb.fetch_stream_packed_async(k, pinned[i][k].data_ptr(), pinned[i][k].numel(), stream=copy_stream.cuda_stream)
+                    t2 = time.perf_counter()
+                    phase["setup_s"] += t1 - t0
+                    phase["wait_run_s"] += t2 - t1
+                copy_stream.synchronize()
+
+            e2e_step()   # warm-up (also sizes the pack / blob buffers)
+            for sb in subs:
+                sb.transfer_stats(reset=True)
+            phase["setup_s"] = phase["wait_run_s"] = 0.0
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / e2e_steps
+            h2d = sum(sb.transfer_stats()[0] for sb in subs)
+            d2h = sum(sb.transfer_stats()[1] for sb in subs)
+            e2e_cycles = sum(sb.totals()[0] for sb in subs)
+            assert e2e_cycles == cycles, (e2e_cycles, cycles)
+            te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s = float(te.item())
+            out = {"value": total_cycles / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": n_sub, "transport": transport,
+                   "host_ms_per_step": {k: v * 1e3 / e2e_steps for k, v in phase.items()},
+                   "pcie_floor_ms": d2h / e2e_steps / 54.5e9 * 1e3,
+                   "path": "per sub-batch: GpuVmBatch.reset + Workload.setup (populate_* / set_register / push_bootloader_context from host "
+                           "arrays, H2D) + run + " + ("zkb_fetch_encoded_async: device-side lossless encode of all six streams, ONE D2H of the blob"
+                                                       if transport == "encoded" else "fetch_stream_packed_async x6") +
+                           " into pinned host memory, copy of k overlapped with compute of k+1"}
+            if transport == "encoded":
+                # outside the timed region: the blob decodes (host, zkb_decode_all) to exactly the canonical streams the raw
+                # transport delivers, and how fast one pass of the host decoder is
+                blob = pinned[0][0][:blob_bytes[0]].numpy()
                 t0 = time.perf_counter()
-                sb.reset()
-                w.setup(sb, sub_ids[i])
-                sb.run(stream=run_stream.cuda_stream, sync=False)
-                t1 = time.perf_counter()
-                for k in range(records.N_STREAMS):
-                    sb.fetch_stream_packed_async(k, pinned[i][k].data_ptr(), pinned[i][k].numel(), stream=copy_stream.cuda_stream)
-                t2 = time.perf_counter()
-                phase["setup_s"] += t1 - t0
-                phase["wait_run_s"] += t2 - t1
-            copy_stream.synchronize()
+                dec = subs[0].decode_all(blob, records.STREAM_ROWS)
+                dt = time.perf_counter() - t0
+                raw_rows, _ = subs[0].fetch_stream_packed(records.STREAM_ROWS)
+                assert dec.tobytes() == raw_rows.tobytes(), "encoded transport did not decode to the canonical rows"
+                out["raw_bytes_per_step"] = int(sum(sbytes))
+                out["ratio"] = d2h / e2e_steps / max(1, sum(sbytes))
+                out["host_decode"] = {"rows_gb_per_s": dec.nbytes / dt / 1e9, "threads": os.cpu_count(),
+                                      "checked": "decoded rows of sub-batch 0 == fetch_stream_packed(rows), byte for byte"}
+            return out
 
-        e2e_step()   # warm-up (also sizes the pack buffers)
-        for sb in subs:
-            sb.transfer_stats(reset=True)
-        phase = {"setup_s": 0.0, "wait_run_s": 0.0}
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        h2d = sum(sb.transfer_stats()[0] for sb in subs)
-        d2h = sum(sb.transfer_stats()[1] for sb in subs)
-        e2e_cycles = sum(sb.totals()[0] for sb in subs)
-        assert e2e_cycles == cycles, (e2e_cycles, cycles)
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {"value": total_cycles / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": n_sub,
-               "host_ms_per_step": {k: v * 1e3 / e2e_steps for k, v in phase.items()},
-               "pcie_floor_ms": d2h / e2e_steps / 54.5e9 * 1e3,
-               "path": "per sub-batch: GpuVmBatch.reset + Workload.setup (populate_* / set_register / push_bootloader_context from host "
-                       "arrays, H2D) + run + fetch_stream_packed_async x6 into pinned host (D2H), copy of k overlapped with compute of k+1"}
+        e2e = measure("encoded")
+        e2e_raw = measure("raw")
         for sb in subs:
             sb.close()
-        del pinned, subs
+        del subs
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -430,7 +461,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
-                "e2e": e2e,
+                "e2e": e2e, "e2e_raw_transport": e2e_raw,
                 # interpreter + sparse restore (+ packs)
                 "gpu_launches": args.steps * (2 + (len(concat_kinds) if world > 1 else 0)),
                 "roofline": roofline,

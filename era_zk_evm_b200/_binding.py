@@ -132,6 +132,33 @@ def hash_bytecodes(lib, prefix: str, codes, marker: int = 0, device: int = 0) ->
     return [int.from_bytes(out[i].tobytes(), "big") for i in range(len(codes))]
 
 
+class EncodedWitness:
+    """host-side view of a blob produced by fetch_encoded*: canonical records back, byte for byte (zkb_decode_stream)"""
+
+    def __init__(self, lib: C.CDLL, prefix: str, blob: np.ndarray):
+        self._blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ds, self._dc = getattr(lib, prefix + "decode_stream"), getattr(lib, prefix + "decode_counts")
+        self._ds.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        self._dc.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        self._ds.restype = self._dc.restype = C.c_int32
+
+    def counts(self, vm: int) -> np.ndarray:
+        out = np.zeros(8, dtype=np.uint32)
+        if self._dc(self._blob.ctypes.data, self._blob.size, vm, out.ctypes.data) != 0:
+            raise ZkbError("decode_counts: malformed blob / VM out of range")
+        return out
+
+    def read_stream(self, vm: int, kind: int) -> np.ndarray:
+        n = C.c_uint64()
+        if self._ds(self._blob.ctypes.data, self._blob.size, vm, kind, None, 0, C.byref(n)) != 0:
+            raise ZkbError("decode_stream: malformed blob")
+        buf = np.zeros(max(n.value, 1), dtype=np.uint8)
+        if self._ds(self._blob.ctypes.data, self._blob.size, vm, kind, buf.ctypes.data, n.value, C.byref(n)) != 0:
+            raise ZkbError("decode_stream: malformed blob")
+        from .records import DTYPES
+        return buf[:n.value].view(DTYPES[kind])
+
+
 class Batch:
     """Thin object wrapper over the C ABI; method names follow the reference's own
     (`populate`, `push_bootloader_context`, `execution_has_ended`, ...)."""
@@ -176,6 +203,11 @@ class Batch:
             "read_bytecode": [vp, C.c_char_p, vp, u32, C.POINTER(u32)],
             "set_calldata": [vp, u32, u32, vp, u32, u32],
             "read_calldata": [vp, u32, u32, u32, vp],
+            "fetch_encoded": [vp, vp, u64, C.POINTER(u64)],
+            "fetch_encoded_async": [vp, vp, u64, C.POINTER(u64), vp],
+            "decode_stream": [vp, u64, u32, u32, vp, u64, C.POINTER(u64)],
+            "decode_counts": [vp, u64, u32, vp],
+            "decode_all": [vp, u64, u32, vp, u64, vp, u32],
         }
         for name, args in sigs.items():
             fn = self._f(name)
@@ -230,6 +262,31 @@ class Batch:
         out = np.zeros((n_words, 32), dtype=np.uint8)
         self._check(self._f("read_calldata")(self._h, vm, word_lo, n_words, out.ctypes.data))
         return out
+
+    # -- encoded transport (include/zkb_codec.h) ---------------------------------------------------------
+    def fetch_encoded(self) -> np.ndarray:
+        """all six streams of every VM as one lossless blob (uint8 array); decode with EncodedWitness"""
+        n = C.c_uint64()
+        self._check(self._f("fetch_encoded")(self._h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        self._check(self._f("fetch_encoded")(self._h, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf[:n.value]
+
+    def fetch_encoded_async(self, host_ptr: int, host_capacity: int, stream=None) -> int:
+        """enqueue encode + ONE D2H copy of the blob into pinned host memory on `stream`; returns the blob size"""
+        n = C.c_uint64()
+        self._check(self._f("fetch_encoded_async")(self._h, host_ptr, host_capacity, C.byref(n), stream))
+        return n.value
+
+    def decode_all(self, blob: np.ndarray, kind: int, n_threads: int = 0, with_offsets: bool = False):
+        """host-side bulk decode of stream `kind` of every VM of a blob -> canonical records, VM-major (uint8 array)"""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        n_vms = int(blob[:16].view(np.uint32)[2])
+        offsets = np.zeros(n_vms + 1, dtype=np.uint64)
+        self._check(self._f("decode_all")(blob.ctypes.data, blob.size, kind, None, 0, offsets.ctypes.data, n_threads))
+        out = np.empty(int(offsets[-1]), dtype=np.uint8)
+        self._check(self._f("decode_all")(blob.ctypes.data, blob.size, kind, out.ctypes.data, out.size, offsets.ctypes.data, n_threads))
+        return (out, offsets) if with_offsets else out
 
     def ingest_bytecodes(self, codes) -> list:
         """hash (GPU, row f-4) + populate: returns the versioned code hashes as ints (= zkb_ingest_bytecodes)"""

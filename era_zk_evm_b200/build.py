@@ -6,17 +6,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzkb.so")
-SOURCES = ["zkb.cu"]
-DEPS = ["zkb.cu", "vm.cuh", "u256.cuh", "keccak.cuh", "sha256.cuh", "secp256k1.cuh", "isa_tables.inc"]
+SOURCES = ["zkb.cu", "host_codec.cpp"]
+DEPS = ["zkb.cu", "host_codec.cpp", "codec.cuh", "vm.cuh", "u256.cuh", "keccak.cuh", "sha256.cuh", "secp256k1.cuh", "isa_tables.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.join(HERE, "..", "include", h) for h in ("zkb.h", "zkb_records.h")]
+    deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.join(HERE, "..", "include", h) for h in ("zkb.h", "zkb_records.h", "zkb_codec.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

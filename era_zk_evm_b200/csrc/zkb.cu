@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "vm.cuh"
+#include "codec.cuh"
 
 using namespace zkb;
 
@@ -506,6 +507,14 @@ struct ZkbBatch {
   // pages_with_extended_lifetime[BOOTLOADER_CALLDATA_PAGE] (memory.rs:230-231,293-298): host-resident, because the
   // reference registers no indirection for it -- no VM instruction can read it (see zkb_set_calldata in zkb.h)
   std::vector<std::vector<uint8_t>> calldata;
+  // transport encoder (zkb_codec.h): per-(VM, stream) sizes, their prefix sums, the blob, totals in mapped host memory
+  uint32_t* d_enc_sizes = nullptr;
+  uint64_t* d_enc_offsets = nullptr;
+  uint64_t* h_enc_totals = nullptr;
+  uint64_t* d_enc_totals = nullptr;
+  uint8_t* d_enc = nullptr;
+  uint64_t enc_capacity = 0;
+  cudaEvent_t ev_enc = nullptr;
 };
 
 static void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {
@@ -799,6 +808,9 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->h_counts) cudaFreeHost(b->h_counts);
   if (b->h_fail) cudaFreeHost(b->h_fail);
   if (b->h_offsets[0]) cudaFreeHost(b->h_offsets[0]);
+  if (b->d_enc) cudaFree(b->d_enc);
+  if (b->h_enc_totals) cudaFreeHost(b->h_enc_totals);
+  if (b->ev_enc) cudaEventDestroy(b->ev_enc);
   delete b;
   return ZKB_OK;
 }
@@ -1260,6 +1272,109 @@ int32_t zkb_fetch_stream_packed_async(ZkbBatch* b, uint32_t kind, void* host_dst
 
 int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint64_t host_capacity, uint64_t* offsets_out) {
   int32_t rc = zkb_fetch_stream_packed_async(b, kind, host_dst, host_capacity, offsets_out, nullptr);
+  if (rc != ZKB_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(nullptr));
+  return ZKB_OK;
+}
+
+// ---- transport encoding (include/zkb_codec.h) ------------------------------------------------------------------
+// size pass + scan on `st`, then (after the host has read the totals from mapped memory and sized the blob) the write
+// pass.  Returns the device blob; it stays valid until the next encode / destroy.
+static int32_t encode_async(ZkbBatch* b, cudaStream_t st, uint8_t** dptr, uint64_t* n_bytes) {
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  const uint32_t* c = nullptr;
+  int32_t rc = summary(b, &c);  // waits for THIS batch's run only
+  if (rc != ZKB_OK) return rc;
+  const size_t n = b->cfg.n_vms;
+  if (!b->d_enc_sizes) {
+    cudaError_t e = dalloc(b, &b->d_enc_sizes, n * ZKB_N_STREAMS, false);
+    if (e == cudaSuccess) e = dalloc(b, &b->d_enc_offsets, (n + 1) * ZKB_N_STREAMS, false);
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (e == cudaSuccess) e = cudaHostAlloc(&hp, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dp, hp, 0);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_enc, cudaEventDisableTiming);
+    if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("encoder buffers: ") + cudaGetErrorString(e));
+    b->h_enc_totals = (uint64_t*)hp;
+    b->d_enc_totals = (uint64_t*)dp;
+  }
+  EncArgs a{};
+  a.sizes = b->d_enc_sizes;
+  a.offsets = b->d_enc_offsets;
+  a.totals = b->d_enc_totals;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8));
+  zkb_encode_kernel<false><<<grid, 256, 0, st>>>(b->d, a);
+  zkb_encode_scan_kernel<<<ZKB_N_STREAMS, 1024, 0, st>>>(b->d, a);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(b->ev_enc, st));
+  CUDA_OK(cudaEventSynchronize(b->ev_enc));
+  ZkbEncodedHeader h{};
+  h.magic = ZKB_CODEC_MAGIC;
+  h.version = ZKB_CODEC_VERSION;
+  h.n_vms = (uint32_t)n;
+  h.counts_offset = sizeof(ZkbEncodedHeader);
+  h.offsets_offset = h.counts_offset + n * 32;
+  uint64_t at = h.offsets_offset + (n + 1) * ZKB_N_STREAMS * 8;
+  for (int k = 0; k < ZKB_N_STREAMS; k++) {
+    at = (at + 15) / 16 * 16;
+    h.payload_offset[k] = a.payload_offset[k] = at;
+    h.payload_bytes[k] = ((volatile uint64_t*)b->h_enc_totals)[k];
+    at += h.payload_bytes[k];
+  }
+  h.total_bytes = (at + 15) / 16 * 16;
+  for (size_t v = 0; v < n; v++)
+    for (int k = 0; k < ZKB_N_STREAMS; k++) h.raw_bytes += (uint64_t)c[v * 8 + k] * REC_BYTES[k];
+  if (h.total_bytes > b->enc_capacity) {
+    CUDA_OK(cudaDeviceSynchronize());  // an earlier async fetch may still read the old blob
+    if (b->d_enc) CUDA_OK(cudaFree(b->d_enc));
+    b->d_enc = nullptr;
+    b->enc_capacity = 0;
+    const uint64_t cap = h.total_bytes + h.total_bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&b->d_enc, cap);
+    if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("encoder blob cudaMalloc: ") + cudaGetErrorString(e));
+    b->enc_capacity = cap;
+  }
+  a.blob = b->d_enc;
+  a.counts_offset = h.counts_offset;
+  a.offsets_offset = h.offsets_offset;
+  zkb_encode_header_kernel<<<1, 32, 0, st>>>(h, b->d_enc);
+  zkb_encode_kernel<true><<<grid, 256, 0, st>>>(b->d, a);
+  CUDA_OK(cudaGetLastError());
+  *dptr = b->d_enc;
+  *n_bytes = h.total_bytes;
+  return ZKB_OK;
+}
+
+int32_t zkb_encode_streams_device(ZkbBatch* b, void** dptr, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
+  uint64_t total = 0;
+  int32_t rc = encode_async(b, (cudaStream_t)cuda_stream, &p, &total);
+  if (rc != ZKB_OK) return rc;
+  if (dptr) *dptr = p;
+  if (n_bytes) *n_bytes = total;
+  return ZKB_OK;
+}
+
+int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
+  uint64_t total = 0;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int32_t rc = encode_async(b, st, &p, &total);
+  if (rc != ZKB_OK) return rc;
+  if (n_bytes) *n_bytes = total;
+  if (!host_dst) return ZKB_OK;   // size query
+  if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_encoded: host buffer too small");
+  CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
+  b->d2h_bytes += total;
+  return ZKB_OK;
+}
+
+int32_t zkb_fetch_encoded(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes) {
+  int32_t rc = zkb_fetch_encoded_async(b, host_dst, host_capacity, n_bytes, nullptr);
   if (rc != ZKB_OK) return rc;
   CUDA_OK(cudaStreamSynchronize(nullptr));
   return ZKB_OK;

@@ -221,6 +221,26 @@ int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t
  * later on that stream, or a collective that waits on it, sees the packed buffer; used to overlap the multi-GPU
  * concatenation of step k with the interpreter launch of step k+1) */
 int32_t zkb_pack_stream_device_async(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
+/* ---- encoded transport (include/zkb_codec.h): the six streams of every VM as ONE lossless, self-describing blob ------
+ * The encoder runs on the device (XOR with a per-word prediction + presence bitmaps, ~30 % of the canonical bytes on the
+ * ERC-20 workload), so a PCIe-bound host loop moves 3x fewer bytes; zkb_decode_stream (host, no GPU needed) and
+ * zkb_codec::EncodedView give the canonical records back byte for byte.
+ * _async: waits (on the host) for THIS batch's last run and for the encoder's size pass (~2 ms), then enqueues the
+ * write pass + ONE D2H copy on `cuda_stream`; host_dst should be pinned; completion = stream sync.  host_dst == NULL:
+ * only *n_bytes (the blob size for the current streams) is returned. */
+int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream);
+int32_t zkb_fetch_encoded(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes);
+/* device-only variant: the blob in device memory (valid until the next encode / destroy), enqueued on cuda_stream */
+int32_t zkb_encode_streams_device(ZkbBatch* b, void** dptr, uint64_t* n_bytes, void* cuda_stream);
+/* host-side decoder: canonical records of VM `vm`'s stream `kind` out of a blob; dst == NULL returns the length only */
+int32_t zkb_decode_stream(const void* blob, uint64_t blob_bytes, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
+/* bulk host-side decode: stream `kind` of EVERY VM as canonical records, VM-major, back to back (the layout of
+ * zkb_fetch_stream_packed) on n_threads host threads (0 = all); offsets_out[n_vms + 1] = each VM's byte offset in dst.
+ * dst == NULL: offsets only (offsets_out[n_vms] = bytes needed). */
+int32_t zkb_decode_all(const void* blob, uint64_t blob_bytes, uint32_t kind, void* dst, uint64_t capacity, uint64_t* offsets_out,
+                       uint32_t n_threads);
+/* per-VM summary carried by a blob: 6 record counts, ZkbVmCode, cycles */
+int32_t zkb_decode_counts(const void* blob, uint64_t blob_bytes, uint32_t vm, uint32_t counts_out[8]);
 /* final storage value of one slot (== InMemoryStorage.inner lookup, storage.rs:9) */
 int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8_t address[20],
                          const uint8_t key_be[32], uint8_t value_be_out[32]);

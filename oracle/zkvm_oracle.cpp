@@ -41,6 +41,7 @@
 
 #include "../include/zkb.h"
 #include "../era_zk_evm_b200/csrc/isa_tables.inc"
+#include "../include/zkb_codec.h"
 #include "hashes.hpp"
 #include "secp256k1.hpp"
 #include "u256.hpp"
@@ -2263,6 +2264,96 @@ int32_t orc_read_stream(OrcBatch* b, uint32_t vm, uint32_t kind, void* dst, uint
   uint64_t n = std::min<uint64_t>(max_bytes, s.size());
   if (dst && n) memcpy(dst, s.data(), n);
   if (n_bytes) *n_bytes = s.size();
+  return ZKB_OK;
+}
+
+// ---- transport codec (include/zkb_codec.h): the scalar encoder over the oracle's streams = the checker of the CUDA
+// encoder's blob (bit-identical layout), plus the same decoder entry points under the orc_ prefix -----------------------
+static void build_encoded_blob(OrcBatch* b, std::vector<uint8_t>& blob) {
+  const size_t n = b->cfg.n_vms;
+  ZkbEncodedHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = ZKB_CODEC_MAGIC;
+  h.version = ZKB_CODEC_VERSION;
+  h.n_vms = (uint32_t)n;
+  h.counts_offset = sizeof(ZkbEncodedHeader);
+  h.offsets_offset = h.counts_offset + n * 32;
+  std::vector<uint64_t> offsets((n + 1) * ZKB_N_STREAMS, 0);
+  static const uint32_t rec_bytes[ZKB_N_STREAMS] = {ZKB_ROW_BYTES, ZKB_MEM_BYTES, ZKB_LOG_BYTES, ZKB_DECOMMIT_BYTES, ZKB_FRAME_BYTES, ZKB_REFUND_BYTES};
+  for (int k = 0; k < ZKB_N_STREAMS; k++) {
+    uint64_t run = 0;
+    for (size_t v = 0; v < n; v++) {
+      offsets[(size_t)k * (n + 1) + v] = run;
+      const auto& s = b->vms[v]->wt.s[k];
+      run += zkb_codec::encode_records(k, s.data(), s.size() / rec_bytes[k], nullptr);
+      h.raw_bytes += s.size();
+    }
+    offsets[(size_t)k * (n + 1) + n] = run;
+    h.payload_bytes[k] = run;
+  }
+  uint64_t at = h.offsets_offset + (n + 1) * ZKB_N_STREAMS * 8;
+  for (int k = 0; k < ZKB_N_STREAMS; k++) {
+    at = (at + 15) / 16 * 16;
+    h.payload_offset[k] = at;
+    at += h.payload_bytes[k];
+  }
+  h.total_bytes = (at + 15) / 16 * 16;
+  blob.assign(h.total_bytes, 0);
+  memcpy(blob.data(), &h, sizeof(h));
+  uint32_t* counts = (uint32_t*)(blob.data() + h.counts_offset);
+  for (size_t v = 0; v < n; v++) {
+    for (int k = 0; k < ZKB_N_STREAMS; k++) counts[v * 8 + k] = (uint32_t)b->vms[v]->wt.counts[k];
+    counts[v * 8 + 6] = b->vms[v]->status;
+    counts[v * 8 + 7] = b->vms[v]->monotonic_cycle_counter;
+  }
+  memcpy(blob.data() + h.offsets_offset, offsets.data(), offsets.size() * 8);
+  for (int k = 0; k < ZKB_N_STREAMS; k++)
+    for (size_t v = 0; v < n; v++) {
+      const auto& s = b->vms[v]->wt.s[k];
+      zkb_codec::encode_records(k, s.data(), s.size() / rec_bytes[k], blob.data() + h.payload_offset[k] + offsets[(size_t)k * (n + 1) + v]);
+    }
+}
+
+int32_t orc_fetch_encoded(OrcBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes) {
+  if (!b) return ZKB_ERR_INVALID_ARGUMENT;
+  std::vector<uint8_t> blob;
+  build_encoded_blob(b, blob);
+  if (n_bytes) *n_bytes = blob.size();
+  if (!host_dst) return ZKB_OK;
+  if (blob.size() > host_capacity) return ZKB_ERR_INVALID_ARGUMENT;
+  memcpy(host_dst, blob.data(), blob.size());
+  return ZKB_OK;
+}
+int32_t orc_fetch_encoded_async(OrcBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void*) {
+  return orc_fetch_encoded(b, host_dst, host_capacity, n_bytes);
+}
+int32_t orc_decode_stream(const void* blob, uint64_t blob_bytes, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
+  zkb_codec::EncodedView v;
+  if (!v.open(blob, blob_bytes)) return ZKB_ERR_INVALID_ARGUMENT;
+  const uint64_t n = v.decode(vm, kind, dst, max_bytes);
+  if (n == UINT64_MAX) return ZKB_ERR_INVALID_ARGUMENT;
+  if (n_bytes) *n_bytes = n;
+  return ZKB_OK;
+}
+int32_t orc_decode_counts(const void* blob, uint64_t blob_bytes, uint32_t vm, uint32_t counts_out[8]) {
+  zkb_codec::EncodedView v;
+  if (!v.open(blob, blob_bytes) || vm >= v.n_vms() || !counts_out) return ZKB_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < 8; i++) counts_out[i] = v.counts(vm)[i];
+  return ZKB_OK;
+}
+
+int32_t orc_decode_all(const void* blob, uint64_t blob_bytes, uint32_t kind, void* dst, uint64_t capacity, uint64_t* offsets_out, uint32_t) {
+  zkb_codec::EncodedView v;
+  if (!v.open(blob, blob_bytes) || kind >= ZKB_N_STREAMS || !offsets_out) return ZKB_ERR_INVALID_ARGUMENT;
+  const uint64_t rec = (uint64_t)ZKB_CODEC_REC_WORDS[kind] * 4;
+  offsets_out[0] = 0;
+  for (uint32_t vm = 0; vm < v.n_vms(); vm++) offsets_out[vm + 1] = offsets_out[vm] + (uint64_t)v.counts(vm)[kind] * rec;
+  if (!dst) return ZKB_OK;
+  if (offsets_out[v.n_vms()] > capacity) return ZKB_ERR_INVALID_ARGUMENT;
+  for (uint32_t vm = 0; vm < v.n_vms(); vm++) {
+    const uint64_t len = offsets_out[vm + 1] - offsets_out[vm];
+    if (v.decode(vm, kind, (uint8_t*)dst + offsets_out[vm], len) != len) return ZKB_ERR_INVALID_ARGUMENT;
+  }
   return ZKB_OK;
 }
 

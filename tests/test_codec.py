@@ -1,0 +1,142 @@
+"""The transport codec (include/zkb_codec.h).  CPU: decode(encode(streams)) == streams byte for byte on every workload,
+truncated / corrupted blobs are rejected, the compression ratio on the ERC-20 workload is what DESIGN.md quotes.
+-m gpu: the CUDA encoder's blob is bit-identical to the scalar encoder's over the oracle's streams, and decodes (on the
+host, through libzkb.so's own zkb_decode_stream) to the oracle's records."""
+import numpy as np
+import pytest
+
+from era_zk_evm_b200 import records, workloads
+from era_zk_evm_b200._binding import EncodedWitness
+
+CASES = [
+    ("alu_loop", dict(cycles=100), 5),
+    ("erc20", dict(n_transfers=3), 70),
+    ("keccak", dict(n_calls=2, preimage_bytes=200), 6),
+    ("storage", dict(n_iters=24), 9),
+    ("mixed", dict(n_programs=12), 12 * 32 + 3),
+]
+
+
+def _oracle_run(oracle_mod, name, kwargs, n):
+    w = workloads.WORKLOADS[name](**kwargs)
+    b = oracle_mod.OracleBatch(w.config(n))
+    w.setup(b, np.arange(n))
+    b.run_threads(0, 0)
+    return w, b
+
+
+@pytest.mark.parametrize("name,kwargs,n", CASES)
+def test_roundtrip_is_lossless(name, kwargs, n, oracle_mod):
+    _, b = _oracle_run(oracle_mod, name, kwargs, n)
+    blob = b.fetch_encoded()
+    view = EncodedWitness(oracle_mod.lib(), "orc_", blob)
+    st = b.vm_status()
+    raw = 0
+    for vm in range(n):
+        c = view.counts(vm)
+        assert tuple(c[6:8]) == tuple(st[vm])
+        for kind in range(records.N_STREAMS):
+            want = b.read_stream(vm, kind)
+            got = view.read_stream(vm, kind)
+            assert c[kind] == len(want)
+            assert got.tobytes() == want.tobytes(), (vm, records.STREAM_NAMES[kind])
+            raw += want.nbytes
+    assert blob.size < raw                       # it does compress
+
+
+def test_bulk_decode_matches_per_vm_decode(oracle_mod):
+    """zkb_decode_all (multi-threaded, the product's host decoder in libzkb.so -- no GPU needed) == per-VM streams"""
+    from era_zk_evm_b200 import load_library
+    import ctypes as C
+    _, b = _oracle_run(oracle_mod, "erc20", dict(n_transfers=2), 50)
+    blob = b.fetch_encoded()
+    lib = load_library()
+    lib.zkb_decode_all.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    for kind in range(records.N_STREAMS):
+        want = np.concatenate([b.read_stream(vm, kind).view(np.uint8) for vm in range(50)])
+        for threads in (1, 3, 0):
+            offsets = np.zeros(51, dtype=np.uint64)
+            assert lib.zkb_decode_all(blob.ctypes.data, blob.size, kind, None, 0, offsets.ctypes.data, threads) == 0
+            out = np.zeros(int(offsets[-1]), dtype=np.uint8)
+            assert lib.zkb_decode_all(blob.ctypes.data, blob.size, kind, out.ctypes.data, out.size, offsets.ctypes.data, threads) == 0
+            assert out.tobytes() == want.tobytes()
+        assert lib.zkb_decode_all(blob.ctypes.data, blob.size, kind, out.ctypes.data, max(out.size, 1) - 1, offsets.ctypes.data, 1) != 0 or out.size == 0
+
+
+def test_empty_and_unstarted_vms_encode(oracle_mod):
+    """ragged input: VMs that never ran (no bootloader frame, zero records) next to finished ones"""
+    w = workloads.AluLoop(cycles=100)
+    b = oracle_mod.OracleBatch(w.config(4))
+    blob0 = b.fetch_encoded()                    # nothing populated at all
+    v0 = EncodedWitness(oracle_mod.lib(), "orc_", blob0)
+    assert all(len(v0.read_stream(vm, k)) == 0 for vm in range(4) for k in range(6))
+    w.setup(b, np.arange(4))
+    b.run_threads(17, 1)                          # stopped in the middle of the loop
+    v1 = EncodedWitness(oracle_mod.lib(), "orc_", b.fetch_encoded())
+    for vm in range(4):
+        assert v1.read_stream(vm, 0).tobytes() == b.read_stream(vm, 0).tobytes()
+        assert len(v1.read_stream(vm, 0)) == 17
+
+
+def test_malformed_blobs_are_rejected(oracle_mod):
+    _, b = _oracle_run(oracle_mod, "erc20", dict(n_transfers=1), 3)
+    blob = b.fetch_encoded().copy()
+    lib = oracle_mod.lib()
+    from era_zk_evm_b200._binding import ZkbError
+    with pytest.raises(ZkbError):
+        EncodedWitness(lib, "orc_", blob[: blob.size // 2]).read_stream(0, 0)          # truncated
+    bad = blob.copy()
+    bad[0] ^= 0xFF                                                                      # magic
+    with pytest.raises(ZkbError):
+        EncodedWitness(lib, "orc_", bad).counts(0)
+    with pytest.raises(ZkbError):
+        EncodedWitness(lib, "orc_", blob).counts(3)                                     # VM out of range
+    # a presence bitmap that claims more residual words than the VM's slice holds
+    hdr = blob[:128].view(np.uint64)
+    payload0 = int(hdr[5])
+    bad = blob.copy()
+    bad[payload0:payload0 + 8] = 0xFF
+    with pytest.raises(ZkbError):
+        EncodedWitness(lib, "orc_", bad).read_stream(0, 0)
+
+
+def test_erc20_ratio(oracle_mod):
+    """the figure DESIGN.md / bench.py quote: the blob is ~30 % of the canonical bytes on the ERC-20 workload"""
+    _, b = _oracle_run(oracle_mod, "erc20", dict(n_transfers=8), 64)
+    blob = b.fetch_encoded()
+    raw = sum(b.totals()[1])
+    assert 0.2 < blob.size / raw < 0.36, blob.size / raw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kwargs,n", CASES + [("erc20", dict(n_transfers=8), 1000)])
+def test_cuda_encoder_matches_the_scalar_encoder(name, kwargs, n, oracle_mod):
+    from era_zk_evm_b200 import GpuVmBatch, load_library
+    w, orc = _oracle_run(oracle_mod, name, kwargs, n)
+    gpu = GpuVmBatch(w.config(n))
+    w.setup(gpu, np.arange(n))
+    gpu.run()
+    blob_gpu, blob_orc = gpu.fetch_encoded(), orc.fetch_encoded()
+    assert blob_gpu.size == blob_orc.size
+    assert blob_gpu.tobytes() == blob_orc.tobytes()
+    view = EncodedWitness(load_library(), "zkb_", blob_gpu)       # the product's own host decoder
+    for vm in list(range(min(n, 40))) + [n - 1]:
+        for kind in range(records.N_STREAMS):
+            assert view.read_stream(vm, kind).tobytes() == orc.read_stream(vm, kind).tobytes()
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_on_a_resumed_run(oracle_mod):
+    """streams are cumulative across zkb_run calls: encoding after a partial run and after the final one"""
+    from era_zk_evm_b200 import GpuVmBatch
+    w = workloads.Erc20(n_transfers=2)
+    n = 37
+    gpu, orc = GpuVmBatch(w.config(n)), oracle_mod.OracleBatch(w.config(n))
+    w.setup(gpu, np.arange(n))
+    w.setup(orc, np.arange(n))
+    gpu.run(max_cycles_per_vm=41)
+    orc.run_threads(41, 1)
+    assert gpu.fetch_encoded().tobytes() == orc.fetch_encoded().tobytes()
+    gpu.run()
+    orc.run_threads(0, 1)
+    assert gpu.fetch_encoded().tobytes() == orc.fetch_encoded().tobytes()
