@@ -29,9 +29,17 @@ __device__ __forceinline__ uint64_t oshfl64(uint64_t v, int src) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// variable rotate: swap the halves for n >= 32, then two funnel shifts by n mod 32 (a shift of 0 returns the high operand)
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, uint32_t n) {
+#ifdef ZKB_OLD_ROTL
   n &= 63u;
   return n ? (x << n) | (x >> (64u - n)) : x;
+#endif
+  const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  const bool sw = (n & 32u) != 0;
+  const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;   // (b : a) = x rotated by 0 or 32
+  const uint32_t m = n & 31u;
+  return ((uint64_t)__funnelshift_l(a, b, m) << 32) | __funnelshift_l(b, a, m);
 }
 
 struct KeccakState {
@@ -92,6 +100,110 @@ __device__ __forceinline__ void keccak_f1600(KeccakState& s, const KeccakLanes& 
     }
     osync();
   }
+}
+
+}  // namespace zkb
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Thread-per-state keccak256 sponge over a VM heap slab: the DEFERRED half of the keccak256 precompile.
+//
+// The interpreter cycle that executes the precompile only moves data (it emits the memory-read witness, reserves the
+// output word and stashes a descriptor); the permutations run after the cycle, batched over the VMs of the CTA with
+// ONE THREAD PER STATE: 25 x u64 in registers, every rotation amount a compile-time constant (2 funnel shifts), chi as
+// one LOP3 per 32-bit half -- ~190 instructions per round and state against ~720 lane-instructions (90 warp
+// instructions for four VMs on 32 lanes) of the octet-cooperative layout above, which stays in use only for the
+// ecrecover address hash.
+namespace zkb {
+
+__device__ __forceinline__ uint64_t kc_rotl(uint64_t x, const int n) { return n == 0 ? x : (x << n) | (x >> (64 - n)); }
+
+__device__ __forceinline__ void keccak_f1600_regs(uint64_t (&st)[25]) {
+#pragma unroll 1
+  for (int round = 0; round < 24; round++) {
+    uint64_t bc[5];
+#pragma unroll
+    for (int x = 0; x < 5; x++) bc[x] = st[x] ^ st[x + 5] ^ st[x + 10] ^ st[x + 15] ^ st[x + 20];
+#pragma unroll
+    for (int x = 0; x < 5; x++) {
+      const uint64_t d = bc[(x + 4) % 5] ^ kc_rotl(bc[(x + 1) % 5], 1);
+#pragma unroll
+      for (int y = 0; y < 25; y += 5) st[x + y] ^= d;
+    }
+    // rho + pi along the 24-cycle of the lane permutation
+    constexpr int piln[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    constexpr int rotc[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    uint64_t t = st[1];
+#pragma unroll
+    for (int i = 0; i < 24; i++) {
+      const uint64_t keep = st[piln[i]];
+      st[piln[i]] = kc_rotl(t, rotc[i]);
+      t = keep;
+    }
+    // chi
+#pragma unroll
+    for (int y = 0; y < 25; y += 5) {
+#pragma unroll
+      for (int x = 0; x < 5; x++) bc[x] = st[y + x];
+#pragma unroll
+      for (int x = 0; x < 5; x++) st[y + x] = bc[x] ^ (~bc[(x + 1) % 5] & bc[(x + 2) % 5]);
+    }
+    st[0] ^= c_keccak_rc[round];
+  }
+}
+
+__device__ __forceinline__ uint64_t kc_bswap64(uint64_t v) {
+  return ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
+}
+
+// 8 bytes of the big-endian byte stream of a heap slab, starting at stream unit q (8-byte aligned position 8 q), as a
+// little-endian u64 (stream byte 8 q is the least significant).  A U256 word is stored as 8 little-endian u32 limbs =
+// the 32 stream bytes reversed, so the unit is one aligned 8-byte load, byte-swapped.  Beyond the slab: zero.
+__device__ __forceinline__ uint64_t kc_stream_unit(const uint8_t* slab, uint64_t q, uint32_t heap_words) {
+  const uint64_t w = q >> 2;
+  if (slab == nullptr || w >= heap_words) return 0ull;
+  return kc_bswap64(*reinterpret_cast<const uint64_t*>(slab + w * 32 + 24 - (q & 3u) * 8));
+}
+
+// keccak256 of stream bytes [in_off, in_off + in_len) of `slab`; digest as four little-endian u64 (the first 32 bytes)
+__device__ __forceinline__ void keccak256_slab(const uint8_t* slab, uint32_t heap_words, uint32_t in_off, uint32_t in_len, uint64_t digest[4]) {
+  uint64_t st[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) st[i] = 0ull;
+  const uint64_t end = (uint64_t)in_off + in_len;
+  const uint32_t n_blocks = in_len / 136 + 1;
+  const uint32_t k8 = (in_off & 7u) * 8;
+#pragma unroll 1
+  for (uint32_t blk = 0; blk < n_blocks; blk++) {
+    const uint64_t a0 = (uint64_t)in_off + (uint64_t)blk * 136;
+    const uint32_t nb = (uint32_t)min((uint64_t)136, end - a0);  // valid bytes in this block
+    uint64_t q = a0 >> 3;
+    uint64_t cur = nb ? kc_stream_unit(slab, q, heap_words) : 0ull;
+#pragma unroll
+    for (int i = 0; i < 17; i++) {
+      const uint32_t b0 = 8u * (uint32_t)i;
+      uint64_t v = 0ull;
+      if (b0 < nb) {
+        v = cur;
+        if (k8) {  // the rate word straddles two aligned units
+          const uint64_t nxt = kc_stream_unit(slab, q + 1, heap_words);
+          v = (cur >> k8) | (nxt << (64 - k8));
+          cur = nxt;
+        } else {
+          cur = kc_stream_unit(slab, q + 1, heap_words);
+        }
+        q++;
+        if (b0 + 8 > nb) v &= (1ull << (8 * (nb - b0))) - 1ull;
+      }
+      if (nb < 136) {  // final block: pad10*1 with the keccak domain byte 0x01
+        if ((uint32_t)i == nb / 8) v ^= 1ull << (8 * (nb % 8));
+        if (i == 16) v ^= 0x80ull << 56;
+      }
+      st[i] ^= v;
+    }
+    keccak_f1600_regs(st);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) digest[i] = st[i];
 }
 
 }  // namespace zkb

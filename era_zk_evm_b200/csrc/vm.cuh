@@ -62,8 +62,14 @@ struct VmHot {
 // internal status (never leaves the kernel): the VM finished a cycle whose ecrecover is still to be computed; the
 // schedulers park the VM state in HBM, run the recovery (DeferredEcrecover) and resume
 #define ZKB_VM_YIELD_ECRECOVER 0x100u
+// ... or whose keccak256 digest is still to be computed: the schedulers run the sponge batched over the VMs of the CTA,
+// one THREAD per state (run_deferred_keccak), and the VM continues in place -- nothing of it has to be parked
+#define ZKB_VM_YIELD_KECCAK 0x101u
 // kbuf layout while an ecrecover is pending
-enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 61, KB_EC_SLAB = 62, KB_EC_OUT_WORD = 63 };  // 48..63: unused by keccak / sha256 / pop_frame
+enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 61, KB_EC_SLAB = 62, KB_EC_OUT_WORD = 63 };  // 48..63: unused by sha256 / pop_frame
+// ... and while a keccak256 is pending (the descriptor of the deferred sponge)
+// (VmSmem.kc[]: its own words, the in-cycle keccak uses most of kbuf as scratch)
+enum { KB_KC_PENDING = 0, KB_KC_IN_OFF = 1, KB_KC_IN_LEN = 2, KB_KC_SRC_SLAB = 3, KB_KC_OUT_SLAB = 4, KB_KC_OUT_WORD = 5, KB_KC_MEM_INDEX = 6, KB_KC_VM = 7 };
 // block-placement hint: keeps the per-cycle hot path contiguous in the instruction stream (the interpreter's first-order
 // cost is instruction fetch)
 #define ZK_UNLIKELY(x) __builtin_expect(!!(x), 0)
@@ -128,8 +134,16 @@ struct __align__(16) VmSmem {
   uint32_t u[4];       // U_* below
   uint64_t gp[6];      // GP_* below: per-VM base pointers into the HBM slabs
   uint32_t ul[8][8];   // UL_* below
-  uint32_t pad[12];
+  uint32_t kc[8];      // KB_KC_*: descriptor of a pending (deferred) keccak256
+  uint32_t pad[4];
+  // keccak lane scratch (25 x u64).  The four VMs of a warp sit 8 banks apart and an 8-byte access is served per
+  // half-warp (two VMs): with both at their natural offset their ten-bank windows overlap in two banks (1.9 G bank
+  // conflicts on the keccak workload, ncu r01); the odd VM of each pair starts 8 words later, which clears them.
+#ifdef ZKB_NO_KS_SKEW
   __device__ __forceinline__ uint64_t* ks() { return reinterpret_cast<uint64_t*>(kbuf); }
+#else
+  __device__ __forceinline__ uint64_t* ks() { return reinterpret_cast<uint64_t*>(kbuf + ((threadIdx.x >> 3) & 1u) * 8u); }
+#endif
 };
 enum { U_FAR_DEPTH = 0, U_CODE_LEN = 1 };
 enum { UL_JOURNAL_LEN = 0, UL_N_DECOMMIT, UL_SLAB_FREE, UL_COUNT2 /* LOG, DECOMMIT, FRAME, REFUND */ };
@@ -633,6 +647,7 @@ struct Vm {
   __device__ void op_ret(uint32_t sub, u256l src0, bool src0_ptr);
   __device__ void op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr);
   __device__ void keccak_precompile(u256l abi);
+  __device__ void keccak_precompile_inline(u256l abi);
   __device__ void sha256_precompile(u256l abi);
   __device__ void ecrecover_precompile(u256l abi);
   __device__ void memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page);
@@ -909,7 +924,10 @@ __device__ __forceinline__ void Vm::cycle_once() {
   row_ptr += ZKB_ROW_BYTES;
   // rare end-of-cycle state changes, keyed on the opcode family so that ordinary cycles pay one compare:
   if (family - ZK_OP_LOG <= 2u) {  // LOG, FAR_CALL, RET
-    if (family == ZK_OP_LOG && S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;  // the cycle is complete; its ecrecover is not
+    if (family == ZK_OP_LOG) {  // the cycle is complete; its precompile's result is not
+      if (S.kc[KB_KC_PENDING]) status = ZKB_VM_YIELD_KECCAK;
+      else if (S.kbuf[KB_EC_PENDING]) status = ZKB_VM_YIELD_ECRECOVER;
+    }
     if (family == ZK_OP_RET && S.row[L_DEPTH] == 0) status = ZKB_VM_ENDED;              // execution_has_ended (mod.rs:96-98)
   }
 }
@@ -1109,7 +1127,72 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
 
 // keccak256 precompile (external DefaultPrecompilesProcessor; memory ABI pinned by keccak256.rs:100-139):
 // byte offset/length in, one output word (word index) out; one FatPointer-type read per distinct input word.
+// The cycle itself only moves data, like ecrecover's: it emits the read witness (one record per input word, in order),
+// reserves the output word and its write record (placeholder value) and leaves a descriptor in the VM's scratch; the
+// sponge runs AFTER the cycle (run_deferred_keccak, one thread per state, batched over the CTA) and patches the digest
+// into the heap word and the record.  Nothing inside the cycle depends on the digest.
 __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
+  const uint32_t in_off = oshfl(abi, 0), in_len = oshfl(abi, 1);
+  const uint32_t out_word = oshfl(abi, 2);
+  const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
+  const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
+#ifdef ZKB_NO_DEFERRED_KECCAK
+  if (true) {
+#else
+  if (in_len < 2u * 136u) {  // at most two permutations: in place
+#endif
+    keccak_precompile_inline(abi);
+    return;
+  }
+  // resolve the source page once (fat-pointer indirection, memory.rs:475-521)
+  uint32_t src_slab = ZKB_NO_SLAB;
+  if (in_len > 0 && page_read != 0) {
+    int e = pt_find(page_read);
+    if (e < 0) {
+      fail(ZKB_VM_REFERENCE_PANIC);
+      return;
+    }
+    uint32_t info = S.pt[e * 2 + 1];
+    uint32_t kind = info & 0xFFu, x = (info >> 8) & 0xFFu;
+    src_slab = kind == PT_EXT ? x : level_slab(x, kind == PT_AUX_LIVE ? 1 : 0);
+  }
+  if (in_len > 0) {
+    const uint64_t w_first = in_off / 32, w_last = ((uint64_t)in_off + in_len - 1) / 32;
+    for (uint64_t w = w_first; w <= w_last; w++) {
+      const u256l word = slab_read(src_slab, (uint32_t)min(w, (uint64_t)0xFFFFFFFFu));
+      emit_mem(ts_read, page_read, (uint32_t)w, ZK_MEM_FAT_PTR, 0, 0, ZKB_MEMORIGIN_PRECOMPILE_IN, word);
+      if (ZK_UNLIKELY(status != ZKB_VM_RUNNING)) return;
+    }
+  }
+  // the write goes through MemoryType::Heap: the reference checks the page only by debug_assert (memory.rs:447)
+  if (page_write != L(L_BASE_PAGE) + 2) {
+    fail(ZKB_VM_REFERENCE_PANIC);
+    return;
+  }
+  uint32_t s = cur_slab(0, true, out_word);
+  if (status != ZKB_VM_RUNNING) return;
+  const uint32_t record = n_mem;
+  slab_write(s, out_word, 0u);
+  emit_mem(ts_write, page_write, out_word, ZK_MEM_HEAP, 1, 0, ZKB_MEMORIGIN_PRECOMPILE_OUT, 0u);
+  if (status != ZKB_VM_RUNNING) return;
+  osync();
+  if (lane == 0) {
+    S.kc[KB_KC_PENDING] = 1u;
+    S.kc[KB_KC_IN_OFF] = in_off;
+    S.kc[KB_KC_IN_LEN] = in_len;
+    S.kc[KB_KC_SRC_SLAB] = src_slab;
+    S.kc[KB_KC_OUT_SLAB] = s;
+    S.kc[KB_KC_OUT_WORD] = out_word;
+    S.kc[KB_KC_MEM_INDEX] = record;
+    S.kc[KB_KC_VM] = vm;
+  }
+  osync();
+}
+
+// The in-cycle variant for SHORT inputs (at most two rate blocks, e.g. the 64-byte mapping-slot preimages of a token
+// contract): the octet absorbs and permutes on the spot (keccak.cuh, octet-cooperative layout).  One or two
+// permutations are cheaper here than a CTA-wide deferred phase, whose cost is the single-thread latency of a permutation.
+__device__ __forceinline__ void Vm::keccak_precompile_inline(u256l abi) {
   const uint32_t in_off = oshfl(abi, 0), in_len = oshfl(abi, 1);
   const uint32_t out_word = oshfl(abi, 2);
   const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
@@ -1828,7 +1911,10 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   srow[lane] = zero4;
   srow[8 + lane] = (lane >= 2 && lane < 6) ? reinterpret_cast<const uint4*>(hot->live)[lane - 2] : zero4;
-  if (lane == 0) S.kbuf[KB_EC_PENDING] = 0u;
+  if (lane == 0) {
+    S.kbuf[KB_EC_PENDING] = 0u;
+    S.kc[KB_KC_PENDING] = 0u;
+  }
   S.pw[lane] = hot->prev_word[lane];
   v.tx_psp = hot->live[L_TX_PSP - 40];
   const uint32_t* x = hot->x;
@@ -1954,6 +2040,32 @@ __device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, VmSmem& S,
                          B.witness ? B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES : nullptr, lane);
 }
 
+// The deferred half of the keccak256 precompile for the VM in shared-memory slot `S` (one THREAD per VM; the caller
+// has synchronised with the octet that left the descriptor).  Reads the message from the VM's heap slab, patches the
+// digest into the reserved heap word and memory-query record.  Scalar arguments only (see run_deferred_ecrecover).
+__device__ __noinline__ void run_deferred_keccak(uint32_t* kbuf, uint32_t* heap_all, uint32_t n_slabs, uint32_t heap_words, uint8_t* mem_stream_all,
+                                                 uint32_t mem_cap) {
+  if (!kbuf[KB_KC_PENDING]) return;
+  const uint32_t vm = kbuf[KB_KC_VM], src_slab = kbuf[KB_KC_SRC_SLAB];
+  uint32_t* vm_heap = heap_all + (size_t)vm * n_slabs * heap_words * 8;
+  const uint8_t* src = src_slab == ZKB_NO_SLAB ? nullptr : reinterpret_cast<const uint8_t*>(vm_heap + (size_t)src_slab * heap_words * 8);
+  uint64_t digest[4];
+  keccak256_slab(src, heap_words, kbuf[KB_KC_IN_OFF], kbuf[KB_KC_IN_LEN], digest);
+  // digest = 32 stream bytes = one big-endian word: stored byte-reversed (little-endian limbs)
+  uint64_t out[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = kc_bswap64(digest[3 - i]);
+  uint64_t* hw = reinterpret_cast<uint64_t*>(vm_heap + ((size_t)kbuf[KB_KC_OUT_SLAB] * heap_words + kbuf[KB_KC_OUT_WORD]) * 8);
+#pragma unroll
+  for (int i = 0; i < 4; i++) hw[i] = out[i];
+  if (mem_stream_all) {
+    uint64_t* r = reinterpret_cast<uint64_t*>(mem_stream_all + ((size_t)vm * mem_cap + kbuf[KB_KC_MEM_INDEX]) * ZKB_MEM_BYTES + 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = out[i];
+  }
+  kbuf[KB_KC_PENDING] = 0u;
+}
+
 // Runs the four VMs of one warp (VM `vm_idx` on the calling octet) to the end, or for max_cycles cycles each.
 //
 // Inside the warp the four octets re-converge at one warp vote per VM cycle, so VMs that follow the same path through
@@ -1962,8 +2074,16 @@ __device__ __forceinline__ void deferred_ecrecover(const DevBatch& B, VmSmem& S,
 // handler at the same time and share its instruction-cache lines (the interpreter is ~170 KB of SASS against a 32 KB
 // L1.5 instruction cache; free-running warps spend most of their issue slots waiting for instruction fetch).
 // All threads of the warp (LOCKSTEP: of the CTA) must call, also for vm_idx >= n_vms.
+// kc_flags: three CTA-shared words, a ring indexed by the lockstep period: octets that yield a keccak raise
+// kc_flags[period % 3] before the period's CTA barrier, everybody reads it after the barrier, thread 0 clears the word
+// of period + 2 (last read before this barrier, next written after the following one): no race, no second barrier.
+// Returns 0 when every VM of the group has ended (or used up max_cycles), 1 when VMs of the group wait for their deferred
+// keccak256: the caller runs the sponges (deferred_keccak_phase) and calls again -- the VM state is parked in HBM across
+// that phase (this function loads at entry and stores at exit anyway), so no interpreter register is live across the
+// call of the ~5 000-instruction sponge.  n = cycles run so far in this launch (carried across re-entries).
 template <bool LOCKSTEP>
-__device__ __forceinline__ void run_vm_group(const DevBatch& B, VmSmem& S, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles) {
+__device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, uint32_t* kc_flags, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles,
+                                                 uint32_t& n) {
   const bool valid = vm_idx < B.n_vms && B.hot[vm_idx < B.n_vms ? vm_idx : 0].x[X_STATUS] == ZKB_VM_RUNNING;
   VmHot* hot = B.hot + (valid ? vm_idx : 0);
   Vm v(B, S, valid ? vm_idx : 0, lane);
@@ -1972,7 +2092,7 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, VmSmem& S, uint3
     vm_load(v, hot);
     if (S.row[L_DEPTH] == 0) v.status = ZKB_VM_ENDED;  // nothing to run; later ends are detected by the RET that pops the last frame
   }
-  uint32_t n = 0;
+  uint32_t period = 0, reason = 0;
   while (true) {
     // up to ZKB_LOCKSTEP_PERIOD cycles between two CTA barriers: the warps may drift by a few hundred instructions
     // (still inside the I-cache window) and the barrier waits for the slowest SUM of cycles, not the slowest cycle
@@ -1993,13 +2113,30 @@ __device__ __forceinline__ void run_vm_group(const DevBatch& B, VmSmem& S, uint3
       vm_load(v, hot);
       active = !(max_cycles && n >= max_cycles);
     }
+    const bool kc_yield = valid && v.status == ZKB_VM_YIELD_KECCAK;
     if (LOCKSTEP) {
-      if (!__syncthreads_or(active ? 1 : 0)) break;
+      if (kc_yield) kc_flags[period] = 1u;   // (several octets may write the same 1)
+      const int any = __syncthreads_or(active ? 1 : 0);
+      if (kc_flags[period]) {
+        reason = 1;
+        break;
+      }
+      if (threadIdx.x == 0) kc_flags[(period + 2u) % 3u] = 0u;
+      period = (period + 1u) % 3u;
+      if (!any) break;
     } else {
+      if (__any_sync(ZK_FULL, kc_yield)) {
+        reason = 1;
+        break;
+      }
       if (!__any_sync(ZK_FULL, active)) break;
     }
   }
-  if (valid) vm_store(v, hot);
+  if (valid) {
+    if (v.status == ZKB_VM_YIELD_KECCAK) v.status = ZKB_VM_RUNNING;  // it continues after the caller's deferred phase
+    vm_store(v, hot);
+  }
+  return reason;
 }
 
 }  // namespace zkb

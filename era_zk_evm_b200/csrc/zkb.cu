@@ -34,6 +34,9 @@ template <bool LOCKSTEP>
 __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) zkb_run_kernel(const DevBatch B, uint32_t max_cycles) {
   extern __shared__ uint4 smem_raw[];
   __shared__ uint32_t s_base;
+  __shared__ uint32_t s_kc_flags[3];
+  if (threadIdx.x < 3) s_kc_flags[threadIdx.x] = 0u;
+  __syncthreads();
   VmSmem* smem = reinterpret_cast<VmSmem*>(smem_raw);
   uint32_t lane = oct_lane();
   const uint32_t warp = threadIdx.x >> 5, oct = threadIdx.x >> 3;  // oct = VM slot within the CTA
@@ -55,13 +58,21 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
 #else
   VmSmem& S = smem[oct];
 #endif
+  uint8_t* mem_all = B.witness ? B.streams[ZKB_STREAM_MEM] : nullptr;
   if (!LOCKSTEP) {
     while (true) {
       uint32_t vm_base = 0;
       if ((threadIdx.x & 31u) == 0) vm_base = atomicAdd(B.queue, (uint32_t)ZK_VMS_PER_WARP);
       vm_base = __shfl_sync(ZK_FULL, vm_base, 0);
       if (vm_base >= B.n_vms) break;
-      run_vm_group<false>(B, S, vm_base + oct_index(), lane, max_cycles);
+      uint32_t n = 0;
+      while (run_vm_group<false>(B, S, s_kc_flags, vm_base + oct_index(), lane, max_cycles, n)) {
+        // deferred keccak256 of the warp's yielded VMs: lanes 0..3 take its four slots (one thread per state)
+        __syncwarp();
+        const uint32_t wl = threadIdx.x & 31u;
+        if (wl < ZK_VMS_PER_WARP) run_deferred_keccak(smem[warp * ZK_VMS_PER_WARP + wl].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        __syncwarp();
+      }
     }
   } else {
     while (true) {
@@ -69,7 +80,14 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
       __syncthreads();
       const uint32_t base = s_base;
       if (base >= B.n_vms) break;
-      run_vm_group<true>(B, S, base + oct, lane, max_cycles);
+      uint32_t n = 0;
+      while (run_vm_group<true>(B, S, s_kc_flags, base + oct, lane, max_cycles, n)) {
+        // deferred keccak256 of every yielded VM of the CTA: thread t < VMs per CTA takes slot t (one thread per state)
+        __syncthreads();
+        if (threadIdx.x < ZKB_VMS_PER_CTA) run_deferred_keccak(smem[threadIdx.x].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        if (threadIdx.x < 3) s_kc_flags[threadIdx.x] = 0u;
+        __syncthreads();
+      }
       __syncthreads();
     }
   }
@@ -514,7 +532,9 @@ struct ZkbBatch {
   uint64_t* d_enc_totals = nullptr;
   uint8_t* d_enc = nullptr;
   uint64_t enc_capacity = 0;
-  cudaEvent_t ev_enc = nullptr;
+  cudaEvent_t ev_enc = nullptr, ev_enc_done = nullptr, ev_blob_read = nullptr;
+  cudaStream_t enc_stream = nullptr;   // the encoder's own stream: its passes never queue behind a D2H copy in flight
+  bool blob_read_pending = false;
 };
 
 static void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {
@@ -811,6 +831,9 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->d_enc) cudaFree(b->d_enc);
   if (b->h_enc_totals) cudaFreeHost(b->h_enc_totals);
   if (b->ev_enc) cudaEventDestroy(b->ev_enc);
+  if (b->ev_enc_done) cudaEventDestroy(b->ev_enc_done);
+  if (b->ev_blob_read) cudaEventDestroy(b->ev_blob_read);
+  if (b->enc_stream) cudaStreamDestroy(b->enc_stream);
   delete b;
   return ZKB_OK;
 }
@@ -1280,7 +1303,7 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
 // ---- transport encoding (include/zkb_codec.h) ------------------------------------------------------------------
 // size pass + scan on `st`, then (after the host has read the totals from mapped memory and sized the blob) the write
 // pass.  Returns the device blob; it stays valid until the next encode / destroy.
-static int32_t encode_async(ZkbBatch* b, cudaStream_t st, uint8_t** dptr, uint64_t* n_bytes) {
+static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dptr, uint64_t* n_bytes) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
   const uint32_t* c = nullptr;
   int32_t rc = summary(b, &c);  // waits for THIS batch's run only
@@ -1294,6 +1317,9 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t st, uint8_t** dptr, uint64
     if (e == cudaSuccess) e = cudaHostAlloc(&hp, 64, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dp, hp, 0);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_enc, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_enc_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_blob_read, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->enc_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("encoder buffers: ") + cudaGetErrorString(e));
     b->h_enc_totals = (uint64_t*)hp;
     b->d_enc_totals = (uint64_t*)dp;
@@ -1305,6 +1331,9 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t st, uint8_t** dptr, uint64
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
   const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8));
+  // The run has finished (summary() waited for it), so the passes need no dependency on the caller's stream -- and they
+  // must not sit on it: in a pipelined host loop that stream still carries the previous sub-batch's D2H copy.
+  cudaStream_t st = b->enc_stream;
   zkb_encode_kernel<false><<<grid, 256, 0, st>>>(b->d, a);
   zkb_encode_scan_kernel<<<ZKB_N_STREAMS, 1024, 0, st>>>(b->d, a);
   CUDA_OK(cudaGetLastError());
@@ -1339,9 +1368,12 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t st, uint8_t** dptr, uint64
   a.blob = b->d_enc;
   a.counts_offset = h.counts_offset;
   a.offsets_offset = h.offsets_offset;
+  if (b->blob_read_pending) CUDA_OK(cudaStreamWaitEvent(st, b->ev_blob_read, 0));  // the previous blob is still being copied out
   zkb_encode_header_kernel<<<1, 32, 0, st>>>(h, b->d_enc);
   zkb_encode_kernel<true><<<grid, 256, 0, st>>>(b->d, a);
   CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(b->ev_enc_done, st));
+  CUDA_OK(cudaStreamWaitEvent(user_stream, b->ev_enc_done, 0));   // whatever the caller queues next sees the finished blob
   *dptr = b->d_enc;
   *n_bytes = h.total_bytes;
   return ZKB_OK;
@@ -1369,6 +1401,8 @@ int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capac
   if (!host_dst) return ZKB_OK;   // size query
   if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_encoded: host buffer too small");
   CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaEventRecord(b->ev_blob_read, st));
+  b->blob_read_pending = true;
   b->d2h_bytes += total;
   return ZKB_OK;
 }

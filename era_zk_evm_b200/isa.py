@@ -16,8 +16,9 @@ product; the interpreter logic is written twice, independently.
 """
 from __future__ import annotations
 
+import json
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 # ---------------------------------------------------------------------------------------------
 # opcode families (order = reference's `Opcode` enum order as dispatched in
@@ -132,6 +133,9 @@ def _price(family: int, sub: int) -> int:
     raise AssertionError
 
 
+PREDICATES = ("kernel_only", "static_forbidden", "src0_ptr_ok", "src1_ptr_ok", "swap")
+
+
 @dataclass(frozen=True)
 class Variant:
     family: int
@@ -139,6 +143,37 @@ class Variant:
     src: int
     dst: int
     flags: int  # bit0 = flag0, bit1 = flag1
+    # per-variant predicates and price; None = derived from (family, sub, flags) by the reconstruction below, a value =
+    # taken from a dump of the real crate (load_json)
+    given: tuple = field(default=None, compare=False)   # (kernel_only, static_forbidden, src0_ptr_ok, src1_ptr_ok, swap, price)
+
+    @property
+    def predicates(self) -> dict:
+        if self.given is not None:
+            return dict(zip(PREDICATES, (bool(x) for x in self.given[:5])))
+        f, s = self.family, self.sub
+        return {
+            # OpcodeVariant::requires_kernel_mode (cycle.rs:174)
+            "kernel_only": (f == CONTEXT and s in (CTX_SET_U128, CTX_SET_ERGS_PER_PUBDATA, CTX_INC_TX)) or
+                           (f == LOG and s in (LOG_TO_L1, LOG_EVENT, LOG_PRECOMPILE)) or (f == FAR_CALL and s == FC_MIMIC),
+            # !OpcodeVariant::can_be_used_in_static_context (cycle.rs:178)
+            "static_forbidden": (f == CONTEXT and s in (CTX_SET_U128, CTX_SET_ERGS_PER_PUBDATA, CTX_INC_TX)) or
+                                (f == LOG and s in (LOG_SSTORE, LOG_TO_L1, LOG_EVENT)),
+            # Opcode::src0_can_be_pointer (cycle.rs:379)
+            "src0_ptr_ok": f in (PTR, FAR_CALL, RET) or (f == UMA and s == UMA_PTR_READ),
+            # Opcode::src1_can_be_pointer (cycle.rs:387).  Recollection of zkevm_opcode_defs 1.4.x: the function returns
+            # `false` for every opcode.  (SURVEY Appendix A guessed "Ptr* only, so that ptr.rs:41 is reachable"; with
+            # `false` that check is still reachable -- in kernel mode, where cycle.rs:374-396 erases nothing -- and in user
+            # mode a pointer in src1 is demoted to an integer before ptr.rs sees it.)  Unpinned either way: a dump of the
+            # real crate (load_json) overrides it per variant.
+            "src1_ptr_ok": False,
+            # swap flag: arithmetic families carry {set_flags=flag0, swap=flag1}; ptr carries {swap=flag0}
+            "swap": (f in (SUB, DIV, SHIFT) and bool(self.flags & 2)) or (f == PTR and bool(self.flags & 1)),
+        }
+
+    @property
+    def price(self) -> int:
+        return int(self.given[5]) if self.given is not None else _price(self.family, self.sub)
 
     @property
     def entry(self) -> int:
@@ -148,15 +183,8 @@ class Variant:
             e |= E_FLAG0
         if self.flags & 2:
             e |= E_FLAG1
-        kernel_only = (f == CONTEXT and s in (CTX_SET_U128, CTX_SET_ERGS_PER_PUBDATA, CTX_INC_TX)) or \
-                      (f == LOG and s in (LOG_TO_L1, LOG_EVENT, LOG_PRECOMPILE)) or \
-                      (f == FAR_CALL and s == FC_MIMIC)
-        static_forbidden = (f == CONTEXT and s in (CTX_SET_U128, CTX_SET_ERGS_PER_PUBDATA, CTX_INC_TX)) or \
-                           (f == LOG and s in (LOG_SSTORE, LOG_TO_L1, LOG_EVENT))
-        src0_ptr_ok = f in (PTR, FAR_CALL, RET) or (f == UMA and s == UMA_PTR_READ)
-        src1_ptr_ok = False
-        # swap flag: arithmetic families carry {set_flags=flag0, swap=flag1}; ptr carries {swap=flag0}
-        swap = (f in (SUB, DIV, SHIFT) and bool(self.flags & 2)) or (f == PTR and bool(self.flags & 1))
+        pr = self.predicates
+        kernel_only, static_forbidden, src0_ptr_ok, src1_ptr_ok, swap = (pr[k] for k in PREDICATES)
         if kernel_only:
             e |= E_KERNEL_ONLY
         if static_forbidden:
@@ -208,17 +236,71 @@ def _synthesize():
     return out, n_valid
 
 
-VARIANTS, N_VALID_VARIANTS = _synthesize()
-OPCODE_TABLE = [v.entry for v in VARIANTS]
-OPCODE_PRICES = [_price(v.family, v.sub) for v in VARIANTS]
-VARIANT_INDEX = {}
-for _i, _v in enumerate(VARIANTS[:N_VALID_VARIANTS]):
-    VARIANT_INDEX.setdefault((_v.family, _v.sub, _v.src, _v.dst, _v.flags), _i)
+# ---------------------------------------------------------------------------------------------
+# pinning hook: the whole table as JSON.  `python -m era_zk_evm_b200.isa --to-json f.json` writes the reconstruction;
+# a dump of the REAL zkevm_opcode_defs tables in the same schema (INTEGRATION.md §7 has the 40-line Rust program that
+# prints it from OPCODES_TABLE / OPCODES_PRICES / system_params) is installed with `--from-json f.json` (or the
+# environment variable ZKB_ISA_JSON at import time): oracle, kernels, assembler and tests then run on the crate's own
+# variant indices, prices, predicates and constants without a code change.
+# ---------------------------------------------------------------------------------------------
+JSON_SCHEMA = "zkb-isa/1"
+ISA_SOURCE = "reconstruction (era_zk_evm_b200/isa.py)"
 
-NOP_VARIANT_IDX = VARIANT_INDEX[(NOP, 0, SRC_REG, DST_REG, 0)]
-PANIC_VARIANT_IDX = VARIANT_INDEX[(RET, RET_PANIC, SRC_REG, DST_REG, 0)]
-NOP_ENCODING = NOP_VARIANT_IDX              # E::nop_encoding()           (cycle.rs:126)
-EXCEPTION_REVERT_ENCODING = PANIC_VARIANT_IDX  # E::exception_revert_encoding() (cycle.rs:115)
+
+def to_json() -> dict:
+    consts = {k: (list(v) if isinstance(v, tuple) else v) for k, v in sorted(vars(C).items()) if not k.startswith("_")}
+    variants = []
+    for v in VARIANTS[:N_VALID_VARIANTS]:
+        d = {"family": FAMILY_NAMES[v.family], "sub": v.sub, "src": v.src, "dst": v.dst, "flags": v.flags, "price": v.price}
+        d.update({k: bool(x) for k, x in v.predicates.items()})
+        variants.append(d)
+    return {"schema": JSON_SCHEMA, "source": ISA_SOURCE, "variant_bits": VARIANT_BITS, "constants": consts, "variants": variants}
+
+
+def load_json(obj) -> None:
+    """replaces the table, prices, predicates and constants of this module by those of `obj` (a dict or a path)"""
+    global VARIANTS, N_VALID_VARIANTS, ISA_SOURCE
+    if not isinstance(obj, dict):
+        with open(obj) as f:
+            obj = json.load(f)
+    if obj.get("schema") != JSON_SCHEMA or obj.get("variant_bits") != VARIANT_BITS:
+        raise ValueError(f"not a {JSON_SCHEMA} table with {VARIANT_BITS} variant bits")
+    for k, v in obj["constants"].items():
+        if not hasattr(C, k):
+            raise ValueError(f"unknown constant {k}")
+        setattr(C, k, tuple(v) if isinstance(v, list) else int(v))
+    out = []
+    for d in obj["variants"]:
+        fam = FAMILY_NAMES.index(d["family"])
+        given = tuple(bool(d[k]) for k in PREDICATES) + (int(d["price"]),)
+        out.append(Variant(fam, int(d["sub"]), int(d["src"]), int(d["dst"]), int(d["flags"]), given))
+    if not out or out[0].family != INVALID or len(out) > (1 << VARIANT_BITS):
+        raise ValueError("variant 0 must be the invalid opcode and the table must fit the variant bits")
+    n_valid = len(out)
+    out.extend([Variant(INVALID, 0, SRC_REG, DST_REG, 0)] * ((1 << VARIANT_BITS) - len(out)))
+    VARIANTS, N_VALID_VARIANTS = out, n_valid
+    ISA_SOURCE = str(obj.get("source", "json"))
+    _index()
+
+
+def _index() -> None:
+    global OPCODE_TABLE, OPCODE_PRICES, VARIANT_INDEX, NOP_VARIANT_IDX, PANIC_VARIANT_IDX, NOP_ENCODING, EXCEPTION_REVERT_ENCODING
+    OPCODE_TABLE = [v.entry for v in VARIANTS]
+    OPCODE_PRICES = [v.price for v in VARIANTS]
+    VARIANT_INDEX = {}
+    for i, v in enumerate(VARIANTS[:N_VALID_VARIANTS]):
+        VARIANT_INDEX.setdefault((v.family, v.sub, v.src, v.dst, v.flags), i)
+    NOP_VARIANT_IDX = VARIANT_INDEX[(NOP, 0, SRC_REG, DST_REG, 0)]
+    PANIC_VARIANT_IDX = VARIANT_INDEX[(RET, RET_PANIC, SRC_REG, DST_REG, 0)]
+    NOP_ENCODING = NOP_VARIANT_IDX              # E::nop_encoding()           (cycle.rs:126)
+    EXCEPTION_REVERT_ENCODING = PANIC_VARIANT_IDX  # E::exception_revert_encoding() (cycle.rs:115)
+
+
+VARIANTS, N_VALID_VARIANTS = _synthesize()
+_index()
+_OVERRIDE = os.path.join(os.path.dirname(__file__), "isa_pinned.json")   # written by --from-json
+if os.environ.get("ZKB_ISA_JSON") or os.path.exists(_OVERRIDE):
+    load_json(os.environ.get("ZKB_ISA_JSON") or _OVERRIDE)
 
 
 def gen_header() -> str:
@@ -226,6 +308,8 @@ def gen_header() -> str:
              "// Reconstructed ISA data standing in for the external crate zkevm_opcode_defs@v1.4.1",
              "// (absent from /root/reference; parity unpinned, SURVEY.md Appendix A).",
              "#pragma once", "#include <stdint.h>", ""]
+    if not ISA_SOURCE.startswith("reconstruction"):
+        lines[1:3] = [f"// ISA data source: {ISA_SOURCE} (installed with isa.py --from-json)"]
     for k, v in sorted(vars(C).items()):
         if k.startswith("_"):
             continue
@@ -275,4 +359,16 @@ def write_header(path: str | None = None) -> str:
 
 
 if __name__ == "__main__":
-    print(write_header(), N_VALID_VARIANTS, "variants")
+    import sys
+    argv = sys.argv[1:]
+    if argv[:1] == ["--to-json"]:
+        with open(argv[1], "w") as f:
+            json.dump(to_json(), f, indent=1)
+        print(argv[1], N_VALID_VARIANTS, "variants,", ISA_SOURCE)
+    elif argv[:1] == ["--from-json"]:
+        load_json(argv[1])                       # validates
+        with open(argv[1]) as f, open(_OVERRIDE, "w") as g:
+            g.write(f.read())
+        print(write_header(), N_VALID_VARIANTS, "variants from", ISA_SOURCE, "(pinned in", _OVERRIDE + "; delete it to go back)")
+    else:
+        print(write_header(), N_VALID_VARIANTS, "variants,", ISA_SOURCE)

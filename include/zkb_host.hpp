@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "zkb.h"
+#include "zkb_codec.h"
 
 #ifndef ZK_TABLE_QUALIFIER
 #define ZK_TABLE_QUALIFIER static const
@@ -300,6 +301,18 @@ class GpuVmBatch {
   // dst0 on the stack) -> end_execution_cycle.  `initial` is the state passed to the first cycle (the state right
   // after push_bootloader_context).  Returns the final tracked VmLocalState.
   VmLocalState replay(uint32_t vm, VmWitnessTracer& wt, const VmLocalState& initial);
+  // The same replay straight from an ENCODED blob (zkb_fetch_encoded*, include/zkb_codec.h): what a PCIe-bound host loop
+  // receives.  Only this VM's slices of the blob are decoded (a few hundred KB), nothing is expanded up front.
+  VmLocalState replay_encoded(const zkb_codec::EncodedView& blob, uint32_t vm, VmWitnessTracer& wt, const VmLocalState& initial);
+  struct VmStreams {
+    std::vector<ZkbCycleRow> rows;
+    std::vector<ZkbMemoryQueryRec> mems;
+    std::vector<ZkbLogQueryRec> logs;
+    std::vector<ZkbDecommitRec> decs;
+    std::vector<ZkbFrameRec> frames;
+    std::vector<ZkbRefundRec> refunds;
+  };
+  VmLocalState replay_records(const VmStreams& s, VmWitnessTracer& wt, const VmLocalState& initial);
 
  private:
   GpuVmBatch() { std::memset(&cfg_, 0, sizeof(cfg_)); }
@@ -413,12 +426,41 @@ inline PrecompileCyclesWitness precompile_rounds(const LogQuery& request, const 
 }
 
 inline VmLocalState GpuVmBatch::replay(uint32_t vm, VmWitnessTracer& wt, const VmLocalState& initial) {
-  auto rows = read_stream<ZkbCycleRow>(vm, ZKB_STREAM_ROWS);
-  auto mems = read_stream<ZkbMemoryQueryRec>(vm, ZKB_STREAM_MEM);
-  auto logs = read_stream<ZkbLogQueryRec>(vm, ZKB_STREAM_LOG);
-  auto decs = read_stream<ZkbDecommitRec>(vm, ZKB_STREAM_DECOMMIT);
-  auto frames = read_stream<ZkbFrameRec>(vm, ZKB_STREAM_FRAME);
-  auto refunds = read_stream<ZkbRefundRec>(vm, ZKB_STREAM_REFUND);
+  VmStreams s;
+  s.rows = read_stream<ZkbCycleRow>(vm, ZKB_STREAM_ROWS);
+  s.mems = read_stream<ZkbMemoryQueryRec>(vm, ZKB_STREAM_MEM);
+  s.logs = read_stream<ZkbLogQueryRec>(vm, ZKB_STREAM_LOG);
+  s.decs = read_stream<ZkbDecommitRec>(vm, ZKB_STREAM_DECOMMIT);
+  s.frames = read_stream<ZkbFrameRec>(vm, ZKB_STREAM_FRAME);
+  s.refunds = read_stream<ZkbRefundRec>(vm, ZKB_STREAM_REFUND);
+  return replay_records(s, wt, initial);
+}
+
+inline VmLocalState GpuVmBatch::replay_encoded(const zkb_codec::EncodedView& blob, uint32_t vm, VmWitnessTracer& wt, const VmLocalState& initial) {
+  VmStreams s;
+  auto take = [&](uint32_t kind, auto& vec) {
+    using Rec = typename std::remove_reference<decltype(vec)>::type::value_type;
+    const uint64_t n = blob.decode(vm, kind, nullptr, 0);
+    if (n == UINT64_MAX) throw std::runtime_error("replay_encoded: malformed blob");
+    vec.resize(n / sizeof(Rec));
+    if (n && blob.decode(vm, kind, vec.data(), n) != n) throw std::runtime_error("replay_encoded: malformed blob");
+  };
+  take(ZKB_STREAM_ROWS, s.rows);
+  take(ZKB_STREAM_MEM, s.mems);
+  take(ZKB_STREAM_LOG, s.logs);
+  take(ZKB_STREAM_DECOMMIT, s.decs);
+  take(ZKB_STREAM_FRAME, s.frames);
+  take(ZKB_STREAM_REFUND, s.refunds);
+  return replay_records(s, wt, initial);
+}
+
+inline VmLocalState GpuVmBatch::replay_records(const VmStreams& streams, VmWitnessTracer& wt, const VmLocalState& initial) {
+  const auto &rows = streams.rows;
+  const auto &mems = streams.mems;
+  const auto &logs = streams.logs;
+  const auto &decs = streams.decs;
+  const auto &frames = streams.frames;
+  const auto &refunds = streams.refunds;
   size_t im = 0, il = 0, id = 0, ifr = 0, ir = 0;
   VmLocalState st = initial;
   // the bootloader push (helpers.rs:289-316) is the VM's first frame record and belongs to no cycle; `initial`

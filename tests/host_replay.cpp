@@ -98,7 +98,7 @@ struct Recorder : VmWitnessTracer {
 
 extern "C" int host_replay_check(void* handle, uint32_t n_vms, uint32_t vm, const ZkbFrame* boot, const uint8_t* init_regs_be,
                                  uint32_t init_ptr_mask, uint32_t init_page_counter, uint32_t init_epp, uint64_t counts[10], char* err,
-                                 int errlen) {
+                                 int errlen, const void* encoded_blob, uint64_t encoded_bytes) {
   try {
     GpuVmBatch b = GpuVmBatch::wrap((ZkbBatch*)handle, n_vms);
     VmLocalState init;
@@ -120,6 +120,18 @@ extern "C" int host_replay_check(void* handle, uint32_t n_vms, uint32_t vm, cons
     init.current = from_frame(*boot);
     Recorder rec;
     VmLocalState fin = b.replay(vm, rec, init);
+    if (encoded_blob) {   // the same replay straight from the transport blob must make the same calls and end in the same state
+      zkb_codec::EncodedView view;
+      if (!view.open(encoded_blob, encoded_bytes)) throw std::runtime_error("encoded blob rejected");
+      Recorder rec2;
+      VmLocalState fin2 = b.replay_encoded(view, vm, rec2, init);
+      if (std::memcmp(rec.n, rec2.n, sizeof(rec.n)) || !rec2.problem.empty()) throw std::runtime_error("replay_encoded: callback counts differ from replay");
+      if (fin2.monotonic_cycle_counter != fin.monotonic_cycle_counter || fin2.timestamp != fin.timestamp || fin2.current.pc != fin.current.pc ||
+          fin2.current.ergs_remaining != fin.current.ergs_remaining)
+        throw std::runtime_error("replay_encoded: final state differs from replay");
+      for (int r = 0; r < 15; r++)
+        if (fin2.registers[r].value != fin.registers[r].value) throw std::runtime_error("replay_encoded: registers differ from replay");
+    }
     std::memcpy(counts, rec.n, sizeof(rec.n));
     if (!rec.problem.empty()) throw std::runtime_error(rec.problem);
     // the tracked state must equal the batch's own final VmLocalState

@@ -21,14 +21,14 @@ def build_shim(prefix: str, lib_path: str) -> C.CDLL:
     out = os.path.join(out_dir, f"libhostreplay_{prefix}.so")
     src = os.path.join(ROOT, "tests", "host_replay.cpp")
     deps = [src, os.path.join(ROOT, "include", "zkb_host.hpp"), os.path.join(ROOT, "include", "zkb.h"),
-            os.path.join(ROOT, "include", "zkb_records.h")]
+            os.path.join(ROOT, "include", "zkb_records.h"), os.path.join(ROOT, "include", "zkb_codec.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", f"-DZKB_HOST_PREFIX={prefix}", "-o", out, src,
                                lib_path, f"-Wl,-rpath,{os.path.dirname(lib_path)}"])
     lib = C.CDLL(out)
     lib.host_replay_check.restype = C.c_int
     lib.host_replay_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ZkbFrame), C.c_char_p, C.c_uint32, C.c_uint32,
-                                      C.c_uint32, C.POINTER(C.c_uint64 * 10), C.c_char_p, C.c_int]
+                                      C.c_uint32, C.POINTER(C.c_uint64 * 10), C.c_char_p, C.c_int, C.c_void_p, C.c_uint64]
     return lib
 
 
@@ -65,11 +65,12 @@ class InitialStateSpy:
 
 def replay_all(shim, batch, spy, vms):
     totals = np.zeros(10, dtype=np.uint64)
+    blob = batch.fetch_encoded()          # replay_encoded (straight from the transport blob) is checked against replay
     for vm in vms:
         counts = (C.c_uint64 * 10)()
         err = C.create_string_buffer(512)
         rc = shim.host_replay_check(batch._h, batch.n_vms, vm, C.byref(spy.frame), spy.regs[vm].tobytes(), spy.ptr_mask,
-                                    spy.fields.get(0, 8), spy.fields.get(1, 0), C.byref(counts), err, 512)
+                                    spy.fields.get(0, 8), spy.fields.get(1, 0), C.byref(counts), err, 512, blob.ctypes.data, blob.size)
         assert rc == 0, f"vm {vm}: {err.value.decode()}"
         c = np.array(list(counts), dtype=np.uint64)
         n = [len(batch.read_stream(vm, k)) for k in range(records.N_STREAMS)]
