@@ -45,8 +45,13 @@ enum {
 };
 enum {
   X_TIMESTAMP = 0, X_CYCLE = 1, X_FLAGS = 2, X_PENDING = 3, X_STATUS = 4, X_PTRMASK = 5, X_PREV_CODE_PAGE = 6,
-  X_FAR_DEPTH = 7, X_JOURNAL_LEN = 8, X_N_DECOMMIT = 9, X_SLAB_FREE = 10, X_COUNT0 = 11 /* ..16 */, X_ABS_STEP = 17
+  X_FAR_DEPTH = 7, X_JOURNAL_LEN = 8, X_N_DECOMMIT = 9, X_SLAB_FREE = 10, X_COUNT0 = 11 /* ..16 */, X_ABS_STEP = 17,
+  X_DEFER = 18 /* 0, or the DEFER_* kind of a precompile result the FAST kernel left for the FULL one */
 };
+// DevBatch.defer[vm][ZKB_DEFER_WORDS]: what a parked VM's pending precompile needs (written by the FAST kernel, read by FULL)
+enum { DEFER_NONE = 0, DEFER_ECRECOVER = 1, DEFER_KECCAK = 2, DEFER_CONTINUE = 3 /* FULL kernel: between a deferred keccak phase and its re-entry */ };
+enum { DF_EC_INPUT = 0 /* 32 words */, DF_EC_DESC = 32 /* kbuf[60..63] */, DF_KC = 36 /* kc[8] */, DF_CYCLES_RUN = 44 };
+#define ZKB_DEFER_WORDS 48u
 
 struct VmHot {
   uint32_t regs[16][8];  // regs[0] is the constant-zero r0
@@ -65,6 +70,8 @@ struct VmHot {
 // ... or whose keccak256 digest is still to be computed: the schedulers run the sponge batched over the VMs of the CTA,
 // one THREAD per state (run_deferred_keccak), and the VM continues in place -- nothing of it has to be parked
 #define ZKB_VM_YIELD_KECCAK 0x101u
+// FAST kernel only: the VM waits (between two cycles) for the FULL kernel to finish its pending precompile
+#define ZKB_VM_PARKED 0x102u
 // kbuf layout while an ecrecover is pending
 enum { KB_EC_INPUT = 0 /* 4 x 8 limbs */, KB_EC_PENDING = 60, KB_EC_MEM_INDEX = 61, KB_EC_SLAB = 62, KB_EC_OUT_WORD = 63 };  // 48..63: unused by sha256 / pop_frame
 // ... and while a keccak256 is pending (the descriptor of the deferred sponge)
@@ -106,7 +113,8 @@ struct DevBatch {
   uint32_t* j_slot;     // [vm][journal]
   uint32_t* j_val;      // [vm][journal][8]
   uint8_t* streams[ZKB_N_STREAMS];
-  unsigned int* queue;
+  unsigned int* queue;    // [2] VM work queues of the FAST and the FULL interpreter launch of one zkb_run
+  uint32_t* defer;        // [vm][ZKB_DEFER_WORDS]
   uint32_t* host_counts;  // [vm][8] in mapped pinned HOST memory: 6 stream counts, status, cycles (written once per run)
 };
 
@@ -151,6 +159,14 @@ enum { GP_STACK = 0 /* stack page of the current far level */, GP_STACK_PTR, GP_
 static_assert(sizeof(VmSmem) == 1952 && (sizeof(VmSmem) / 4) % 32 == 8 && sizeof(VmSmem) % 16 == 0, "VmSmem bank skew");
 typedef VmSmem WarpSmem;
 
+// KD ("full"): this instantiation contains the out-of-line precompile routines -- the deferred keccak256 sponge for long
+// inputs and the ecrecover recovery.  Two instantiations, because the mere PRESENCE of such a callee in the kernel costs
+// the interpreter loop 6 % (ecrecover) to 15 % (keccak) through ptxas' register allocation around the call ABI
+// (measured): every zkb_run launches the FAST kernel (KD = false: no call anywhere; a VM whose cycle left such a result
+// pending is parked, between two cycles, with its descriptor in DevBatch.defer) and then the FULL kernel, which picks up
+// exactly the parked VMs, finishes the pending result and runs them on.  Batches without such precompiles (the ERC-20
+// workload hashes 64-byte preimages in the cycle) never leave the fast kernel.
+template <bool KD>
 struct Vm {
   const DevBatch& B;
   WarpSmem& S;
@@ -169,6 +185,7 @@ struct Vm {
   // decoded opcode (octet-uniform): table entry + the operand fields of the (masked) instruction
   uint32_t entry, ops_lo, ops_hi;
   uint32_t dst_loc;  // stack destination of dst0: index | 1 << 16 when valid
+  uint32_t defer_kind;  // DEFER_* of a parked VM (FAST kernel), written to x[X_DEFER] by vm_store
 
   __device__ Vm(const DevBatch& b, VmSmem& s, uint32_t vm_, uint32_t lane_) : B(b), S(s), vm(vm_), lane(lane_) {}
   // cold state accessors
@@ -658,7 +675,8 @@ struct Vm {
 // ===================================================================================================
 // one VM cycle (cycle.rs:19-429)
 // ===================================================================================================
-__device__ __forceinline__ void Vm::cycle_once() {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::cycle_once() {
   const uint32_t row_cycle = cycle, row_ts = timestamp, pc_before = pc;
   S.row[24 + lane] = 0u;  // dst0 / dst1 fields default to zero (lane l owns limb l of both, here and in dst*_update)
   S.row[32 + lane] = 0u;
@@ -933,7 +951,8 @@ __device__ __forceinline__ void Vm::cycle_once() {
 }
 
 // context.rs:36-99
-__device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_context(uint32_t sub, u256l src0) {
   if (sub == ZK_CTX_SET_U128) {
     if (lane < 4) S.row[L_CTX + lane] = src0;
     osync();
@@ -968,7 +987,8 @@ __device__ __forceinline__ void Vm::op_context(uint32_t sub, u256l src0) {
 }
 
 // shift.rs:44-67
-__device__ __forceinline__ void Vm::op_shift(uint32_t sub, u256l src0, u256l src1) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_shift(uint32_t sub, u256l src0, u256l src1) {
   uint32_t n = oshfl(src1, 0) & 0xFFu;
   bool cyclic = sub == ZK_ROL || sub == ZK_ROR, right = sub == ZK_SHR || sub == ZK_ROR;
   u256l r;
@@ -984,7 +1004,8 @@ __device__ __forceinline__ void Vm::op_shift(uint32_t sub, u256l src0, u256l src
 }
 
 // ptr.rs:32-193
-__device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1, bool src0_ptr, bool src1_ptr) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_ptr(uint32_t sub, u256l src0, u256l src1, bool src0_ptr, bool src1_ptr) {
   if (!src0_ptr || src1_ptr) {
     pending = 1;
     return;
@@ -1021,7 +1042,8 @@ __device__ __forceinline__ void Vm::op_ptr(uint32_t sub, u256l src0, u256l src1,
 }
 
 // near_call.rs:6-68
-__device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_near_call(u256l src0, uint32_t new_pc) {
   flags = 0;
   uint32_t abi_ergs = oshfl(src0, 0);
   uint32_t passed, remaining;
@@ -1046,7 +1068,8 @@ __device__ __forceinline__ void Vm::op_near_call(u256l src0, uint32_t new_pc) {
 }
 
 // log.rs:11-330
-__device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_log(uint32_t sub, u256l src0, u256l src1) {
   const bool is_first = entry & ZK_E_FLAG0;
   const uint32_t shard = (S.F[F_EH_SHARDS] >> 16) & 0xFFu;
   const uint32_t ergs_available = ergs;
@@ -1131,16 +1154,13 @@ __device__ __forceinline__ void Vm::op_log(uint32_t sub, u256l src0, u256l src1)
 // reserves the output word and its write record (placeholder value) and leaves a descriptor in the VM's scratch; the
 // sponge runs AFTER the cycle (run_deferred_keccak, one thread per state, batched over the CTA) and patches the digest
 // into the heap word and the record.  Nothing inside the cycle depends on the digest.
-__device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::keccak_precompile(u256l abi) {
   const uint32_t in_off = oshfl(abi, 0), in_len = oshfl(abi, 1);
   const uint32_t out_word = oshfl(abi, 2);
   const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
   const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
-#ifdef ZKB_NO_DEFERRED_KECCAK
-  if (true) {
-#else
   if (in_len < 2u * 136u) {  // at most two permutations: in place
-#endif
     keccak_precompile_inline(abi);
     return;
   }
@@ -1192,7 +1212,8 @@ __device__ __forceinline__ void Vm::keccak_precompile(u256l abi) {
 // The in-cycle variant for SHORT inputs (at most two rate blocks, e.g. the 64-byte mapping-slot preimages of a token
 // contract): the octet absorbs and permutes on the spot (keccak.cuh, octet-cooperative layout).  One or two
 // permutations are cheaper here than a CTA-wide deferred phase, whose cost is the single-thread latency of a permutation.
-__device__ __forceinline__ void Vm::keccak_precompile_inline(u256l abi) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::keccak_precompile_inline(u256l abi) {
   const uint32_t in_off = oshfl(abi, 0), in_len = oshfl(abi, 1);
   const uint32_t out_word = oshfl(abi, 2);
   const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
@@ -1275,7 +1296,8 @@ __device__ __forceinline__ void Vm::keccak_precompile_inline(u256l abi) {
 // sha256 precompile (external DefaultPrecompilesProcessor; memory ABI reconstructed): the caller
 // passes pre-padded 64-byte blocks: input offset in WORDS, number of rounds in precompile_interpreted_data, two
 // Heap-type word reads per round at timestamp+1, one digest word written at timestamp+2 after the last round.
-__device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::sha256_precompile(u256l abi) {
   const uint32_t in_word = oshfl(abi, 0), out_word = oshfl(abi, 2);
   const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
   const uint64_t rounds = (uint64_t)oshfl(abi, 6) | (uint64_t)oshfl(abi, 7) << 32;
@@ -1315,7 +1337,8 @@ __device__ __forceinline__ void Vm::sha256_precompile(u256l abi) {
 // the output words and stashes the inputs; the ~6 000 modular multiplications of the recovery run AFTER the cycle, with
 // the VM state parked in HBM (run_deferred_ecrecover), and patch the two values in place.  Nothing inside the cycle
 // depends on them, and the interpreter's hot loop carries no live state across the call.
-__device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::ecrecover_precompile(u256l abi) {
   const uint32_t in_word = oshfl(abi, 0), out_word = oshfl(abi, 2);
   const uint32_t page_read = oshfl(abi, 4), page_write = oshfl(abi, 5);
   const uint32_t ts_read = timestamp + 1, ts_write = timestamp + 2;
@@ -1357,7 +1380,8 @@ __device__ __forceinline__ void Vm::ecrecover_precompile(u256l abi) {
 }
 
 // SimpleMemory::start_global_frame (memory.rs:573-657) for the level far_depth() (already incremented)
-__device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::memory_start_global_frame(uint32_t caller_level, uint32_t caller_base, uint32_t calldata_page) {
   uint32_t level = far_depth();
   // the caller's level entry goes back to HBM, the callee starts with no heaps and an untouched stack page
   if (lane < 4) {
@@ -1384,7 +1408,8 @@ __device__ __forceinline__ void Vm::memory_start_global_frame(uint32_t caller_le
 }
 
 // SimpleMemory::finish_global_frame (memory.rs:660-758)
-__device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::memory_finish_global_frame(uint32_t level, uint32_t base_page, uint32_t returndata_page) {
   // stack page goes back to the pool: clear what was touched (stack_on_return, memory.rs:185-188)
   uint32_t hwm = S.lv[2];  // S.lv still holds the finished level's entry (the parent's is reloaded at the end)
   const size_t fpage = (size_t)vm * (B.max_far_depth + 1) + level;  // g_stack() already points at the caller's page
@@ -1435,7 +1460,8 @@ __device__ __forceinline__ void Vm::memory_finish_global_frame(uint32_t level, u
 }
 
 // far_call.rs:35-613
-__device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l src1, bool abi_is_ptr, uint32_t new_pc, bool kernel_mode) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_far_call(uint32_t sub, u256l src0, u256l src1, bool abi_is_ptr, uint32_t new_pc, bool kernel_mode) {
   enum { EX_NOT_PTR = 1, EX_HASH_FORMAT = 2, EX_ERGS_DECOMMIT = 4, EX_ERGS_GROW = 8, EX_MALFORMED_PTR = 16, EX_CONSTRUCTED_SYSTEM = 32 };
   flags = 0;
   const bool is_call_shard = entry & ZK_E_FLAG0, is_static_call = entry & ZK_E_FLAG1;
@@ -1684,7 +1710,8 @@ __device__ __forceinline__ void Vm::op_far_call(uint32_t sub, u256l src0, u256l 
 }
 
 // ret.rs:9-265
-__device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_ptr) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_ret(uint32_t sub, u256l src0, bool src0_ptr) {
   uint32_t variant = sub;
   flags = 0;
   if (variant == ZK_RET_PANIC) {
@@ -1779,7 +1806,8 @@ __device__ __forceinline__ void Vm::op_ret(uint32_t sub, u256l src0, bool src0_p
 }
 
 // uma.rs:26-425
-__device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr) {
+template <bool KD>
+__device__ __forceinline__ void Vm<KD>::op_uma(uint32_t sub, u256l src0, u256l src1, bool src0_ptr) {
   const bool inc = entry & ZK_E_FLAG0;
   uint32_t p_off = oshfl(src0, 0), p_page = oshfl(src0, 1);
   const uint32_t p_start = oshfl(src0, 2), p_len = oshfl(src0, 3);
@@ -1898,7 +1926,8 @@ __device__ __forceinline__ void Vm::op_uma(uint32_t sub, u256l src0, u256l src1,
 // load / run / store one VM
 // ===================================================================================================
 // load VM `v.vm`'s hot state from HBM into shared memory / octet-uniform registers
-__device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
+template <bool KD>
+__device__ __forceinline__ void vm_load(Vm<KD>& v, const VmHot* hot) {
   VmSmem& S = v.S;
   const uint32_t lane = v.lane;
   uint4* sregs = reinterpret_cast<uint4*>(&S.regs[0][0]);
@@ -1937,6 +1966,7 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
   v.rowbits = 0;
   v.ccount = 0;
   v.entry = v.ops_lo = v.ops_hi = v.dst_loc = 0;
+  v.defer_kind = DEFER_NONE;
   v.set_vm_pointers();
   osync();
   v.load_frame_from_F();
@@ -1954,7 +1984,8 @@ __device__ __forceinline__ void vm_load(Vm& v, const VmHot* hot) {
 }
 
 // write the hot state back to HBM (the batch is resumable: zkb_run may be called again)
-__device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
+template <bool KD>
+__device__ __forceinline__ void vm_store(Vm<KD>& v, VmHot* hot) {
   VmSmem& S = v.S;
   const uint32_t lane = v.lane;
   osync();
@@ -1977,7 +2008,8 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
       out = i == X_CYCLE ? v.cycle : out;
       out = i == X_FLAGS ? v.flags : out;
       out = i == X_PENDING ? v.pending : out;
-      out = i == X_STATUS ? v.status : out;
+      out = i == X_STATUS ? (v.status == ZKB_VM_PARKED ? (uint32_t)ZKB_VM_RUNNING : v.status) : out;
+      out = i == X_DEFER ? v.defer_kind : out;
       out = i == X_PTRMASK ? v.ptr_mask : out;
       out = i == X_PREV_CODE_PAGE ? v.prev_code_page : out;
       out = i == X_FAR_DEPTH ? v.far_depth() : out;
@@ -1992,7 +2024,8 @@ __device__ __forceinline__ void vm_store(Vm& v, VmHot* hot) {
   }
   // the per-VM summary goes straight to mapped host memory (one 32-byte posted write per VM and run): the host can
   // size and enqueue the witness download without a D2H copy of its own queueing behind the copies already in flight
-  const uint32_t st_out = (v.status == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : v.status;
+  const uint32_t st_now = v.status == ZKB_VM_PARKED ? (uint32_t)ZKB_VM_RUNNING : v.status;
+  const uint32_t st_out = (st_now == ZKB_VM_RUNNING && S.row[L_DEPTH] == 0 && v.cycle > 0) ? (uint32_t)ZKB_VM_ENDED : st_now;
   uint32_t summary = lane == 6 ? st_out : v.cycle;
 #pragma unroll
   for (int k = 0; k < ZKB_N_STREAMS; k++) summary = lane == (uint32_t)k ? v.stream_count(k) : summary;
@@ -2081,16 +2114,34 @@ __device__ __noinline__ void run_deferred_keccak(uint32_t* kbuf, uint32_t* heap_
 // keccak256: the caller runs the sponges (deferred_keccak_phase) and calls again -- the VM state is parked in HBM across
 // that phase (this function loads at entry and stores at exit anyway), so no interpreter register is live across the
 // call of the ~5 000-instruction sponge.  n = cycles run so far in this launch (carried across re-entries).
-template <bool LOCKSTEP>
+template <bool LOCKSTEP, bool KD>
 __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, uint32_t* kc_flags, uint32_t vm_idx, uint32_t lane, uint32_t max_cycles,
                                                  uint32_t& n) {
-  const bool valid = vm_idx < B.n_vms && B.hot[vm_idx < B.n_vms ? vm_idx : 0].x[X_STATUS] == ZKB_VM_RUNNING;
+  // the FAST kernel runs the VMs that are not parked, the FULL kernel exactly the parked ones (a VM that merely ran out
+  // of max_cycles in the fast kernel is not touched again by this zkb_run)
+  const uint32_t* x0 = B.hot[vm_idx < B.n_vms ? vm_idx : 0].x;
+  const bool valid = vm_idx < B.n_vms && x0[X_STATUS] == ZKB_VM_RUNNING && ((x0[X_DEFER] != DEFER_NONE) == KD);
   VmHot* hot = B.hot + (valid ? vm_idx : 0);
-  Vm v(B, S, valid ? vm_idx : 0, lane);
+  Vm<KD> v(B, S, valid ? vm_idx : 0, lane);
   v.status = ZKB_VM_ENDED;
   if (valid) {
+    const uint32_t kind = KD ? x0[X_DEFER] : (uint32_t)DEFER_NONE;
     vm_load(v, hot);
     if (S.row[L_DEPTH] == 0) v.status = ZKB_VM_ENDED;  // nothing to run; later ends are detected by the RET that pops the last frame
+    if (KD) {  // pick the parked VM up where the fast kernel left it: descriptor back into the scratch, result still pending
+      const uint32_t* df = B.defer + (size_t)vm_idx * ZKB_DEFER_WORDS;
+      n = df[DF_CYCLES_RUN];
+      if (kind == DEFER_ECRECOVER) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) S.kbuf[KB_EC_INPUT + 8 * i + lane] = df[DF_EC_INPUT + 8 * i + lane];
+        if (lane < 4) S.kbuf[KB_EC_PENDING + lane] = df[DF_EC_DESC + lane];
+        v.status = ZKB_VM_YIELD_ECRECOVER;
+      } else if (kind == DEFER_KECCAK) {
+        S.kc[lane] = df[DF_KC + lane];
+        v.status = ZKB_VM_YIELD_KECCAK;
+      }
+      osync();
+    }
   }
   uint32_t period = 0, reason = 0;
   while (true) {
@@ -2106,14 +2157,31 @@ __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, u
         active = v.status == ZKB_VM_RUNNING && !(max_cycles && n >= max_cycles);
       }
     }
-    if (valid && v.status == ZKB_VM_YIELD_ECRECOVER) {  // park the VM, finish the pending recovery, resume
+    if (!KD) {
+      // FAST kernel: a pending precompile result parks the VM for the FULL kernel (descriptor -> DevBatch.defer)
+      if (valid && (v.status == ZKB_VM_YIELD_ECRECOVER || v.status == ZKB_VM_YIELD_KECCAK)) {
+        uint32_t* df = B.defer + (size_t)v.vm * ZKB_DEFER_WORDS;
+        osync();
+        if (v.status == ZKB_VM_YIELD_ECRECOVER) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) df[DF_EC_INPUT + 8 * i + lane] = S.kbuf[KB_EC_INPUT + 8 * i + lane];
+          if (lane < 4) df[DF_EC_DESC + lane] = S.kbuf[KB_EC_PENDING + lane];
+          v.defer_kind = DEFER_ECRECOVER;
+        } else {
+          df[DF_KC + lane] = S.kc[lane];
+          v.defer_kind = DEFER_KECCAK;
+        }
+        if (lane == 0) df[DF_CYCLES_RUN] = n;
+        v.status = ZKB_VM_PARKED;
+      }
+    } else if (valid && v.status == ZKB_VM_YIELD_ECRECOVER) {  // park the VM, finish the pending recovery, resume
       v.status = ZKB_VM_RUNNING;
       vm_store(v, hot);
       deferred_ecrecover(B, S, v.vm, lane);
       vm_load(v, hot);
       active = !(max_cycles && n >= max_cycles);
     }
-    const bool kc_yield = valid && v.status == ZKB_VM_YIELD_KECCAK;
+    const bool kc_yield = KD && valid && v.status == ZKB_VM_YIELD_KECCAK;
     if (LOCKSTEP) {
       if (kc_yield) kc_flags[period] = 1u;   // (several octets may write the same 1)
       const int any = __syncthreads_or(active ? 1 : 0);
@@ -2134,6 +2202,10 @@ __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, u
   }
   if (valid) {
     if (v.status == ZKB_VM_YIELD_KECCAK) v.status = ZKB_VM_RUNNING;  // it continues after the caller's deferred phase
+    if (KD && reason) {  // the FULL kernel comes back for this VM right after the deferred phase
+      v.defer_kind = DEFER_CONTINUE;
+      if (lane == 0) B.defer[(size_t)v.vm * ZKB_DEFER_WORDS + DF_CYCLES_RUN] = n;
+    }
     vm_store(v, hot);
   }
   return reason;

@@ -30,14 +30,15 @@ using namespace zkb;
 // LOCKSTEP = true : each CTA pulls ZKB_VMS_PER_CTA consecutive VMs and steps them together (run_vm_group).
 #define ZKB_VMS_PER_CTA (ZKB_WARPS_PER_CTA * ZK_VMS_PER_WARP)
 #define ZKB_RUN_SMEM_BYTES (ZKB_VMS_PER_CTA * sizeof(VmSmem))
-template <bool LOCKSTEP>
+template <bool LOCKSTEP, bool KD>
 __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) zkb_run_kernel(const DevBatch B, uint32_t max_cycles) {
   extern __shared__ uint4 smem_raw[];
   __shared__ uint32_t s_base;
   __shared__ uint32_t s_kc_flags[3];
-  if (threadIdx.x < 3) s_kc_flags[threadIdx.x] = 0u;
-  __syncthreads();
   VmSmem* smem = reinterpret_cast<VmSmem*>(smem_raw);
+  if (threadIdx.x < 3) s_kc_flags[threadIdx.x] = 0u;
+  if ((threadIdx.x & 7u) == 0) smem[threadIdx.x >> 3].kc[KB_KC_PENDING] = 0u;   // slots that never load a VM must not look pending
+  __syncthreads();
   uint32_t lane = oct_lane();
   const uint32_t warp = threadIdx.x >> 5, oct = threadIdx.x >> 3;  // oct = VM slot within the CTA
 #ifdef ZKB_PINNED_BASE
@@ -62,29 +63,33 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
   if (!LOCKSTEP) {
     while (true) {
       uint32_t vm_base = 0;
-      if ((threadIdx.x & 31u) == 0) vm_base = atomicAdd(B.queue, (uint32_t)ZK_VMS_PER_WARP);
+      if ((threadIdx.x & 31u) == 0) vm_base = atomicAdd(B.queue + (KD ? 1 : 0), (uint32_t)ZK_VMS_PER_WARP);
       vm_base = __shfl_sync(ZK_FULL, vm_base, 0);
       if (vm_base >= B.n_vms) break;
       uint32_t n = 0;
-      while (run_vm_group<false>(B, S, s_kc_flags, vm_base + oct_index(), lane, max_cycles, n)) {
+      while (run_vm_group<false, KD>(B, S, s_kc_flags, vm_base + oct_index(), lane, max_cycles, n)) {
         // deferred keccak256 of the warp's yielded VMs: lanes 0..3 take its four slots (one thread per state)
         __syncwarp();
         const uint32_t wl = threadIdx.x & 31u;
-        if (wl < ZK_VMS_PER_WARP) run_deferred_keccak(smem[warp * ZK_VMS_PER_WARP + wl].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        if constexpr (KD) {
+          if (wl < ZK_VMS_PER_WARP) run_deferred_keccak(smem[warp * ZK_VMS_PER_WARP + wl].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        }
         __syncwarp();
       }
     }
   } else {
     while (true) {
-      if (threadIdx.x == 0) s_base = atomicAdd(B.queue, (uint32_t)ZKB_VMS_PER_CTA);
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue + (KD ? 1 : 0), (uint32_t)ZKB_VMS_PER_CTA);
       __syncthreads();
       const uint32_t base = s_base;
       if (base >= B.n_vms) break;
       uint32_t n = 0;
-      while (run_vm_group<true>(B, S, s_kc_flags, base + oct, lane, max_cycles, n)) {
+      while (run_vm_group<true, KD>(B, S, s_kc_flags, base + oct, lane, max_cycles, n)) {
         // deferred keccak256 of every yielded VM of the CTA: thread t < VMs per CTA takes slot t (one thread per state)
         __syncthreads();
-        if (threadIdx.x < ZKB_VMS_PER_CTA) run_deferred_keccak(smem[threadIdx.x].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        if constexpr (KD) {
+          if (threadIdx.x < ZKB_VMS_PER_CTA) run_deferred_keccak(smem[threadIdx.x].kc, B.heap_mem, B.n_slabs, B.heap_words, mem_all, B.cap[ZKB_STREAM_MEM]);
+        }
         if (threadIdx.x < 3) s_kc_flags[threadIdx.x] = 0u;
         __syncthreads();
       }
@@ -127,7 +132,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
   const uint32_t lane = oct_lane(), oct = threadIdx.x >> 3;
   uint32_t vm = vm_lo + blockIdx.x * 16 + oct;
   if (vm >= vm_hi) return;  // octet-uniform: whole octets leave together
-  Vm v(B, smem[oct], vm, lane);
+  Vm<false> v(B, smem[oct], vm, lane);
   v.status = ZKB_VM_RUNNING;
   v.journal_len() = 0;
   const DevStorageInit* e = per_vm ? entries + (size_t)(vm - vm_lo) * n : entries;
@@ -135,7 +140,7 @@ __global__ void zkb_populate_storage_kernel(const DevBatch B, uint32_t vm_lo, ui
     uint32_t aw = lane < 5 ? e[i].addr[lane] : 0u;
     u256l key = e[i].key[lane];
     u256l val = e[i].value[lane];
-    v.storage_access(e[i].shard, aw, key, Vm::ST_POPULATE, val);
+    v.storage_access(e[i].shard, aw, key, Vm<false>::ST_POPULATE, val);
   }
   if (v.status != ZKB_VM_RUNNING && lane == 0) *fail_flag = v.status;
 }
@@ -747,6 +752,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   if (c.witness_mode)
     for (int k = 0; k < ZKB_N_STREAMS; k++) ALLOC(d.streams[k], n * (size_t)c.cap_records[k] * REC_BYTES[k], false);
   ALLOC(d.queue, 4, true);
+  ALLOC(d.defer, n * ZKB_DEFER_WORDS, true);
   ALLOC(b->d_offsets, (n + 1) * ZKB_N_STREAMS, false);
 #undef ALLOC
   if (e != cudaSuccess) {
@@ -798,9 +804,11 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   CUDA_OK(cudaEventCreate(&b->ev1));
   CUDA_OK(cudaEventCreateWithFlags(&b->ev_setup, cudaEventDisableTiming));
   int per_sm = 0, n_sm = 0;
-  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
-  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false>, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(zkb_run_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZKB_RUN_SMEM_BYTES));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zkb_run_kernel<false, false>, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES));
   CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   b->grid = std::max(1, per_sm * n_sm);  // persistent grid: a multiple of the SM count (148 on B200)
   if (cfg->reserved[0] > 0 && (int)cfg->reserved[0] < n_sm) b->grid = per_sm * (n_sm - (int)cfg->reserved[0]);
@@ -1057,16 +1065,21 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
     CUDA_OK(cudaEventRecord(b->ev_setup, 0));
     CUDA_OK(cudaStreamWaitEvent(st, b->ev_setup, 0));
   }
-  CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 4, st));
+  CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 8, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
   int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_VMS_PER_CTA - 1) / ZKB_VMS_PER_CTA));
-  if (b->lockstep)
-    zkb_run_kernel<true><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
-  else
-    zkb_run_kernel<false><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
+  // FAST kernel (no out-of-line precompile routine anywhere in it), then the FULL kernel for the VMs the fast one parked
+  // with a pending ecrecover / long keccak256 (none on most batches: its CTAs then find nothing to do and exit)
+  if (b->lockstep) {
+    zkb_run_kernel<true, false><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
+    zkb_run_kernel<true, true><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
+  } else {
+    zkb_run_kernel<false, false><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
+    zkb_run_kernel<false, true><<<grid, ZKB_WARPS_PER_CTA * 32, ZKB_RUN_SMEM_BYTES, st>>>(b->d, max_cycles_per_vm);
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(b->ev1, st));
-  b->n_launches = 1;
+  b->n_launches = 2;
   b->hot_stale = true;
   b->launched = true;
   b->offsets_valid = false;
@@ -1656,6 +1669,7 @@ int32_t zkb_snapshot(ZkbBatch* b) {
     add(d.slab_hwm, n * c.n_heap_slabs * 4);
     add(d.pt, n * ZKB_PT_ENTRIES * 8);
     add(d.dec, n * ZKB_DEC_ENTRIES * 8);
+    add(d.defer, n * ZKB_DEFER_WORDS * 4);
     add(d.st_tags, n * c.storage_slots * 4);
     add(d.st_keys, n * c.storage_slots * 32);
     add(d.st_addr, n * c.storage_slots * 32);

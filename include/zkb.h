@@ -76,7 +76,8 @@ typedef struct ZkbConfig {
                                 (storage.rs:80-86); 1..64 = a storage write to a slot whose cold/warm marker
                                 (storage.rs:10,105-110,126-131) is already set is answered with
                                 RefundType::RepeatedWrite{pubdata_bytes = this value} on the rollup shard, which
-                                log.rs:99-119 subtracts from INITIAL_STORAGE_WRITE_PUBDATA_BYTES. */
+                                log.rs:99-119 subtracts from INITIAL_STORAGE_WRITE_PUBDATA_BYTES.
+                                reserved[2] = unused. */
 } ZkbConfig;
 
 /* mirror of CallStackEntry (execution_stack.rs:6-24) */

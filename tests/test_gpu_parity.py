@@ -96,6 +96,40 @@ def test_snapshot_restore_reruns_identically(name, kwargs, n, cycles_before_snap
             assert (st[:, 1] <= cycles_before_snapshot).all()       # back at the snapshot's cycle counts
 
 
+@pytest.mark.parametrize("defer", [0, 1])
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("kwargs,n", [(dict(n_calls=3), 40), (dict(n_calls=2, preimage_bytes=200), 16), (dict(n_calls=2, preimage_bytes=273), 101)])
+def test_keccak_paths_give_identical_results(defer, schedule, kwargs, n, oracle_mod):
+    """ZkbConfig.reserved[2] bit 0 selects the kernel with the deferred thread-per-state sponge for long keccak256 inputs;
+    both kernels, under both schedules, must emit the oracle's bytes (digest patched into the heap word and the record)"""
+    from era_zk_evm_b200 import GpuVmBatch
+    w = workloads.KeccakHeavy(**kwargs)
+    ids = list(range(n))
+    cfg = w.config(n)
+    cfg.reserved[2] = defer
+    cfg.schedule = schedule
+    gpu, orc = GpuVmBatch(cfg), oracle_mod.OracleBatch(cfg)
+    w.setup(gpu, ids)
+    w.setup(orc, ids)
+    gpu.run()
+    orc.run_threads(0, 0)
+    problems = compare_batches(gpu, orc)
+    assert not problems, "\n".join(problems)
+
+
+def test_deferred_keccak_survives_resumed_runs(oracle_mod):
+    """max_cycles slices that end right on / around the yielding cycle"""
+    w = workloads.KeccakHeavy(n_calls=2)
+    gpu, orc = _pair(w, list(range(9)), oracle_mod)
+    for _ in range(400):
+        gpu.run(max_cycles_per_vm=3)
+        if gpu.execution_has_ended():
+            break
+    orc.run_threads(0, 0)
+    problems = compare_batches(gpu, orc)
+    assert not problems, "\n".join(problems)
+
+
 def test_resumable_run_matches_single_run(oracle_mod):
     w = workloads.Erc20(n_transfers=2)
     gpu, orc = _pair(w, list(range(33)), oracle_mod)
