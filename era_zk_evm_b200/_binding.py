@@ -208,6 +208,7 @@ class Batch:
             "decode_stream": [vp, u64, u32, u32, vp, u64, C.POINTER(u64)],
             "decode_counts": [vp, u64, u32, vp],
             "decode_all": [vp, u64, u32, vp, u64, vp, u32],
+            "net_storage_history": [vp, vp, u64, vp, vp, C.POINTER(u64), vp],
         }
         for name, args in sigs.items():
             fn = self._f(name)
@@ -287,6 +288,21 @@ class Batch:
         out = np.empty(int(offsets[-1]), dtype=np.uint8)
         self._check(self._f("decode_all")(blob.ctypes.data, blob.size, kind, out.ctypes.data, out.size, offsets.ctypes.data, n_threads))
         return (out, offsets) if with_offsets else out
+
+    def net_storage_history(self):
+        """flatten_and_net_history().1 of every VM (storage.rs:50-73): (records sorted by VM and slot, boundary flags --
+        1 = first query of its slot --, per-VM record offsets, number of slots)"""
+        from .records import LOG_DTYPE
+        offsets = np.zeros(self.n_vms + 1, dtype=np.uint64)
+        n_slots = C.c_uint64()
+        self._check(self._f("net_storage_history")(self._h, None, 0, None, offsets.ctypes.data, C.byref(n_slots), None))
+        total = int(offsets[-1])
+        out = np.zeros(max(total, 1), dtype=LOG_DTYPE)
+        flags = np.zeros(max(total, 1), dtype=np.uint8)
+        if total:
+            self._check(self._f("net_storage_history")(self._h, out.ctypes.data, out.nbytes, flags.ctypes.data, offsets.ctypes.data,
+                                                        C.byref(n_slots), None))
+        return out[:total], flags[:total], offsets, n_slots.value
 
     def ingest_bytecodes(self, codes) -> list:
         """hash (GPU, row f-4) + populate: returns the versioned code hashes as ints (= zkb_ingest_bytecodes)"""

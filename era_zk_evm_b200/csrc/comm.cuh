@@ -1,0 +1,373 @@
+// Multi-GPU stream exchange behind the C ABI (SURVEY §8e, §8b `zkb_gather`): NCCL driven from C++ so that a host in any
+// language reaches it (round 1 had it only in Python over torch.distributed).  One process per GPU; the host hands a
+// 128-byte NCCL unique id from rank 0 to every rank through its own channel and calls zkb_comm_create.
+//
+// NCCL is resolved at run time (dlopen "libnccl.so.2"): libzkb.so has no link-time dependency on it, a single-GPU user
+// never loads it, and inside a process that already carries a libnccl (PyTorch's) the same copy is picked up.
+//
+//   zkb_gather_streams   concatenation of whole streams on ONE rank, in rank order (variable length): the sink can rotate
+//                        from step to step (dst_rank = step % world), so no GPU takes every step's ingress
+//   zkb_exchange_logs    the balanced form for the query log: every LOG record goes to rank  slot_hash(shard, address,
+//                        key) % world  -- the partition a global per-slot sort / dedup wants anyway (zkb_sort_log_queries
+//                        runs on each rank's share afterwards).  Per-GPU ingress is then ~1/world of every rank's log =
+//                        its own log's size, whatever world is.  The pack is fused into the partition: one kernel reads
+//                        the records straight from the per-VM slabs and drops them into the per-destination send regions
+//                        (deterministic positions from a count + scan pass; no atomics), NCCL moves the regions all-to-all.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace zkb {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+static NcclApi* nccl_api(std::string* why) {
+  static NcclApi api;
+  static bool tried = false, ok = false;
+  static std::string err;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) {
+      err = std::string("dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+    } else {
+      bool all = true;
+      auto sym = [&](const char* name) {
+        void* p = dlsym(api.handle, name);
+        if (!p) {
+          all = false;
+          err = std::string("libnccl: missing symbol ") + name;
+        }
+        return p;
+      };
+      api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+      api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+      api.Send = (decltype(api.Send))sym("ncclSend");
+      api.Recv = (decltype(api.Recv))sym("ncclRecv");
+      api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+      ok = all;
+    }
+  }
+  if (!ok && why) *why = err;
+  return ok ? &api : nullptr;
+}
+
+// ---- kernels of the hash-partitioned exchange ----------------------------------------------------------------------
+// pass 1: per VM and destination, how many of the VM's LOG records go there.  One warp per VM; lane l takes records
+// l, l + 32, ...
+__global__ void __launch_bounds__(256) zkb_bucket_count_kernel(const DevBatch B, uint32_t world, uint32_t* __restrict__ counts /* [world][n_vms] */) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t vm = blockIdx.x * 8 + warp; vm < B.n_vms; vm += gridDim.x * 8) {
+    const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
+    const uint32_t* recs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
+    uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t r = lane; r < n; r += 32) {
+      const uint32_t* p = recs + (size_t)r * 32;
+      const uint32_t dst = (uint32_t)((slot_hash64(p[1] >> 24, p + 2, p + 8) >> 20) % world);
+#pragma unroll
+      for (uint32_t d = 0; d < 8; d++) mine[d] += dst == d ? 1u : 0u;
+    }
+#pragma unroll
+    for (uint32_t d = 0; d < 8; d++) {
+      uint32_t v = mine[d];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && d < world) counts[(size_t)d * B.n_vms + vm] = v;
+    }
+  }
+}
+
+// exclusive scan of counts[d][0..n) per destination d (one block each); totals[d] = records this rank sends to d
+__global__ void __launch_bounds__(1024) zkb_bucket_scan_kernel(uint32_t* __restrict__ counts, uint32_t n, uint64_t* __restrict__ totals) {
+  __shared__ uint32_t s_sum[1024];
+  uint32_t* c = counts + (size_t)blockIdx.x * n;
+  const uint32_t t = threadIdx.x, per = (n + 1023) / 1024;
+  const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+  uint32_t local = 0;
+  for (uint32_t i = lo; i < hi; i++) local += c[i];
+  s_sum[t] = local;
+  __syncthreads();
+  for (uint32_t o = 1; o < 1024; o <<= 1) {
+    uint32_t v = t >= o ? s_sum[t - o] : 0;
+    __syncthreads();
+    s_sum[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_sum[t] - local;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t v = c[i];
+    c[i] = run;
+    run += v;
+  }
+  if (t == 1023) totals[blockIdx.x] = s_sum[1023];
+}
+
+// pass 2 (the fused pack): records straight from the per-VM slabs into the per-destination regions of the send buffer,
+// at  region_base[d] + offs[d][vm] + (rank of the record among the VM's records for d).  One warp per VM; a record is
+// moved by the whole warp (32 lanes x 4 bytes), in record order, so positions are deterministic.
+__global__ void __launch_bounds__(256) zkb_bucket_pack_kernel(const DevBatch B, uint32_t world, const uint32_t* __restrict__ offs /* [world][n_vms] */,
+                                                              const uint64_t* __restrict__ totals, uint32_t* __restrict__ send) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint64_t base[8];
+  uint64_t run = 0;
+#pragma unroll
+  for (uint32_t d = 0; d < 8; d++) {
+    base[d] = run;
+    run += d < world ? totals[d] : 0ull;
+  }
+  for (uint32_t vm = blockIdx.x * 8 + warp; vm < B.n_vms; vm += gridDim.x * 8) {
+    const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
+    const uint32_t* recs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
+    uint32_t next[8];
+#pragma unroll
+    for (uint32_t d = 0; d < 8; d++) next[d] = d < world ? offs[(size_t)d * B.n_vms + vm] : 0u;
+    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+      // lane l classifies record r0 + l; then the warp moves the 32 records one after the other
+      uint32_t my_dst = 0xFFu;
+      if (r0 + lane < n) {
+        const uint32_t* p = recs + (size_t)(r0 + lane) * 32;
+        my_dst = (uint32_t)((slot_hash64(p[1] >> 24, p + 2, p + 8) >> 20) % world);
+      }
+      const uint32_t m = min(32u, n - r0);
+      for (uint32_t k = 0; k < m; k++) {
+        const uint32_t d = __shfl_sync(0xffffffffu, my_dst, k);
+        uint32_t pos = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 8; q++)
+          if (q == d) pos = next[q]++;
+        send[(base[d] + pos) * 32 + lane] = recs[(size_t)(r0 + k) * 32 + lane];
+      }
+    }
+  }
+}
+
+}  // namespace zkb
+
+struct ZkbComm {
+  int device = 0, rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  zkb::NcclApi* api = nullptr;
+  uint8_t* recv = nullptr;      // grow-only receive / concat buffer
+  uint64_t recv_capacity = 0;
+  uint8_t* send = nullptr;      // grow-only send buffer of the exchange
+  uint64_t send_capacity = 0;
+  uint64_t* d_sizes = nullptr;  // [world][8] sizes matrix on the device
+  uint64_t* h_sizes = nullptr;  // pinned mirror
+  uint32_t* d_counts = nullptr; // [world][n_vms] of the exchange
+  uint64_t counts_capacity = 0;
+  cudaEvent_t ev = nullptr;
+};
+
+#define NCCL_OK(c, expr)                                                                                          \
+  do {                                                                                                            \
+    ncclResult_t _r = (expr);                                                                                     \
+    if (_r != ncclSuccess) return set_err(ZKB_ERR_CUDA, std::string(#expr) + ": " + (c)->api->GetErrorString(_r)); \
+  } while (0)
+
+static int32_t comm_ensure(uint8_t** buf, uint64_t* cap, uint64_t need) {
+  if (need <= *cap) return ZKB_OK;
+  CUDA_OK(cudaDeviceSynchronize());
+  if (*buf) CUDA_OK(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  const uint64_t c = need + need / 8 + 4096;
+  cudaError_t e = cudaMalloc(buf, c);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("comm buffer cudaMalloc: ") + cudaGetErrorString(e));
+  *cap = c;
+  return ZKB_OK;
+}
+
+extern "C" {
+
+int32_t zkb_comm_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return ZKB_ERR_INVALID_ARGUMENT;
+  std::string why;
+  zkb::NcclApi* api = zkb::nccl_api(&why);
+  if (!api) return set_err(ZKB_ERR_CUDA, why);
+  static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+  ncclUniqueId id;
+  ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) return set_err(ZKB_ERR_CUDA, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+  memcpy(id_out, &id, 128);
+  return ZKB_OK;
+}
+
+int32_t zkb_comm_create(int32_t device, int32_t rank, int32_t world, const uint8_t id[128], ZkbComm** out) {
+  if (!id || !out || world < 1 || world > 8 || rank < 0 || rank >= world) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_comm_create: rank / world (1..8)");
+  std::string why;
+  zkb::NcclApi* api = zkb::nccl_api(&why);
+  if (!api) return set_err(ZKB_ERR_CUDA, why);
+  CUDA_OK(cudaSetDevice(device));
+  ZkbComm* c = new ZkbComm();
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  c->api = api;
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t r = api->CommInitRank(&c->comm, world, uid, rank);
+  if (r != ncclSuccess) {
+    std::string msg = std::string("ncclCommInitRank: ") + api->GetErrorString(r);
+    delete c;
+    return set_err(ZKB_ERR_CUDA, msg);
+  }
+  cudaError_t e = cudaMalloc(&c->d_sizes, (size_t)world * 8 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sizes, (size_t)world * 8 * sizeof(uint64_t), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_comm_create: ") + cudaGetErrorString(e));
+  *out = c;
+  return ZKB_OK;
+}
+
+int32_t zkb_comm_destroy(ZkbComm* c) {
+  if (!c) return ZKB_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->comm) c->api->CommDestroy(c->comm);
+  if (c->recv) cudaFree(c->recv);
+  if (c->send) cudaFree(c->send);
+  if (c->d_sizes) cudaFree(c->d_sizes);
+  if (c->h_sizes) cudaFreeHost(c->h_sizes);
+  if (c->d_counts) cudaFree(c->d_counts);
+  if (c->ev) cudaEventDestroy(c->ev);
+  delete c;
+  return ZKB_OK;
+}
+
+// every rank's 8-word size vector to every rank (device all-gather + one small D2H): h_sizes[r][k]
+static int32_t comm_exchange_sizes(ZkbComm* c, const uint64_t mine[8], cudaStream_t st) {
+  memcpy(c->h_sizes + (size_t)c->rank * 8, mine, 64);
+  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 8, c->h_sizes + (size_t)c->rank * 8, 64, cudaMemcpyHostToDevice, st));
+  NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 8, c->d_sizes, 8, ncclUint64, c->comm, st));
+  CUDA_OK(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)c->world * 64, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+int32_t zkb_gather_streams(ZkbBatch* b, ZkbComm* c, uint32_t kinds_mask, int32_t dst_rank, void** dptr_out, uint64_t* offsets_out, void* cuda_stream) {
+  if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world || !(kinds_mask & 63u)) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  uint8_t* packed[ZKB_N_STREAMS] = {};
+  uint64_t mine[8] = {};
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+    if (!((kinds_mask >> k) & 1u)) continue;
+    int32_t rc = pack_async(b, k, st, &packed[k], &mine[k]);
+    if (rc != ZKB_OK) return rc;
+  }
+  int32_t rc = comm_exchange_sizes(c, mine, st);
+  if (rc != ZKB_OK) return rc;
+  // layout on dst: for each kind in the mask (ascending), the ranks' shares in rank order; kinds start 256-byte aligned
+  uint64_t kind_base[ZKB_N_STREAMS] = {}, at = 0;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+    if (!((kinds_mask >> k) & 1u)) continue;
+    kind_base[k] = at;
+    uint64_t run = 0;
+    for (int r = 0; r < c->world; r++) {
+      if (offsets_out) offsets_out[(size_t)k * (c->world + 1) + r] = at + run;
+      run += c->h_sizes[(size_t)r * 8 + k];
+    }
+    if (offsets_out) offsets_out[(size_t)k * (c->world + 1) + c->world] = at + run;
+    at = (at + run + 255) / 256 * 256;
+  }
+  if (c->rank == dst_rank) {
+    rc = comm_ensure(&c->recv, &c->recv_capacity, at);
+    if (rc != ZKB_OK) return rc;
+  }
+  NCCL_OK(c, c->api->GroupStart());
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+    if (!((kinds_mask >> k) & 1u)) continue;
+    if (c->rank == dst_rank) {
+      uint64_t run = kind_base[k];
+      for (int r = 0; r < c->world; r++) {
+        const uint64_t sz = c->h_sizes[(size_t)r * 8 + k];
+        if (r == c->rank) {
+          if (sz) CUDA_OK(cudaMemcpyAsync(c->recv + run, packed[k], sz, cudaMemcpyDeviceToDevice, st));
+        } else if (sz) {
+          NCCL_OK(c, c->api->Recv(c->recv + run, sz, ncclUint8, r, c->comm, st));
+        }
+        run += sz;
+      }
+    } else if (mine[k]) {
+      NCCL_OK(c, c->api->Send(packed[k], mine[k], ncclUint8, dst_rank, c->comm, st));
+    }
+  }
+  NCCL_OK(c, c->api->GroupEnd());
+  if (dptr_out) *dptr_out = c->rank == dst_rank ? c->recv : nullptr;
+  return ZKB_OK;
+}
+
+int32_t zkb_exchange_logs(ZkbBatch* b, ZkbComm* c, void** dptr_out, uint64_t* n_records_out, uint64_t* src_offsets_out, void* cuda_stream) {
+  if (!b || !c || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const uint32_t* cnt = nullptr;
+  int32_t rc = summary(b, &cnt);   // waits for THIS batch's run
+  if (rc != ZKB_OK) return rc;
+  const uint32_t n = b->cfg.n_vms, world = (uint32_t)c->world;
+  if ((uint64_t)world * n > c->counts_capacity) {
+    if (c->d_counts) CUDA_OK(cudaFree(c->d_counts));
+    c->d_counts = nullptr;
+    CUDA_OK(cudaMalloc(&c->d_counts, (size_t)world * n * 4));
+    c->counts_capacity = (uint64_t)world * n;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + 7) / 8, (uint32_t)n_sm * 8));
+  uint64_t* d_tot = c->d_sizes + (size_t)c->rank * 8;   // this rank's row of the sizes matrix: records for each destination
+  CUDA_OK(cudaMemsetAsync(d_tot, 0, 64, st));
+  zkb::zkb_bucket_count_kernel<<<grid, 256, 0, st>>>(b->d, world, c->d_counts);
+  zkb::zkb_bucket_scan_kernel<<<world, 1024, 0, st>>>(c->d_counts, n, d_tot);
+  CUDA_OK(cudaGetLastError());
+  NCCL_OK(c, c->api->AllGather(d_tot, c->d_sizes, 8, ncclUint64, c->comm, st));
+  CUDA_OK(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)world * 64, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  uint64_t send_total = 0, recv_total = 0;
+  for (uint32_t d = 0; d < world; d++) send_total += c->h_sizes[(size_t)c->rank * 8 + d];
+  for (uint32_t s = 0; s < world; s++) recv_total += c->h_sizes[(size_t)s * 8 + c->rank];
+  rc = comm_ensure(&c->send, &c->send_capacity, send_total * ZKB_LOG_BYTES);
+  if (rc == ZKB_OK) rc = comm_ensure(&c->recv, &c->recv_capacity, recv_total * ZKB_LOG_BYTES);
+  if (rc != ZKB_OK) return rc;
+  if (send_total) zkb::zkb_bucket_pack_kernel<<<grid, 256, 0, st>>>(b->d, world, c->d_counts, d_tot, (uint32_t*)c->send);
+  CUDA_OK(cudaGetLastError());
+  NCCL_OK(c, c->api->GroupStart());
+  uint64_t s_at = 0, r_at = 0;
+  for (uint32_t p = 0; p < world; p++) {
+    const uint64_t s_n = c->h_sizes[(size_t)c->rank * 8 + p] * ZKB_LOG_BYTES, r_n = c->h_sizes[(size_t)p * 8 + c->rank] * ZKB_LOG_BYTES;
+    if (src_offsets_out) src_offsets_out[p] = r_at / ZKB_LOG_BYTES;
+    if ((int)p == c->rank) {
+      if (s_n) CUDA_OK(cudaMemcpyAsync(c->recv + r_at, c->send + s_at, s_n, cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (s_n) NCCL_OK(c, c->api->Send(c->send + s_at, s_n, ncclUint8, (int)p, c->comm, st));
+      if (r_n) NCCL_OK(c, c->api->Recv(c->recv + r_at, r_n, ncclUint8, (int)p, c->comm, st));
+    }
+    s_at += s_n;
+    r_at += r_n;
+  }
+  NCCL_OK(c, c->api->GroupEnd());
+  if (src_offsets_out) src_offsets_out[world] = recv_total;
+  if (dptr_out) *dptr_out = c->recv;
+  if (n_records_out) *n_records_out = recv_total;
+  return ZKB_OK;
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@
 
 #include "vm.cuh"
 #include "codec.cuh"
+#include "logsort.cuh"
 
 using namespace zkb;
 
@@ -1465,6 +1466,122 @@ int32_t zkb_flatten_logs(ZkbBatch* b, void* cuda_stream) {
   return ZKB_OK;
 }
 
+// K11 driver: stable radix sort of n LogQueryRec by (group, slot hash) + gather + boundary flags (logsort.cuh)
+static int32_t logsort_device(int32_t device, const uint32_t* d_recs, uint64_t n, const uint32_t* d_group_of, uint32_t* d_out, uint8_t* d_boundary,
+                              uint64_t* n_groups_out, uint32_t key_bits, cudaStream_t st) {
+  CUDA_OK(cudaSetDevice(device));
+  if (n_groups_out) *n_groups_out = 0;
+  if (n == 0) return ZKB_OK;
+  if (n >= (1ull << 32)) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_sort_log_queries: more than 2^32 records");
+  const uint32_t n_tiles = (uint32_t)((n + ZKB_SORT_TILE - 1) / ZKB_SORT_TILE);
+  uint64_t *keys[2] = {nullptr, nullptr};
+  uint32_t *idx[2] = {nullptr, nullptr}, *hist = nullptr;
+  unsigned long long* d_ng = nullptr;
+  cudaError_t e = cudaMalloc(&keys[0], n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&keys[1], n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&idx[0], n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&idx[1], n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&hist, (size_t)256 * n_tiles * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_ng, 8);
+  auto release = [&]() {
+    cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(idx[0]); cudaFree(idx[1]); cudaFree(hist); cudaFree(d_ng);
+  };
+  if (e != cudaSuccess) {
+    release();
+    return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_sort_log_queries cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  zkb_logsort_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_recs, n, d_group_of, keys[0], idx[0]);
+  int cur = 0;
+  for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+    zkb_logsort_hist_kernel<<<n_tiles, ZKB_SORT_THREADS, 0, st>>>(keys[cur], n, shift, hist, n_tiles);
+    zkb_logsort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * n_tiles, n, nullptr);
+    zkb_logsort_scatter_kernel<<<n_tiles, ZKB_SORT_THREADS, 0, st>>>(keys[cur], idx[cur], n, shift, hist, n_tiles, keys[cur ^ 1], idx[cur ^ 1]);
+    cur ^= 1;
+  }
+  cudaMemsetAsync(d_ng, 0, 8, st);
+  zkb_logsort_gather_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_recs, keys[cur], idx[cur], n, d_out, d_boundary, d_ng);
+  unsigned long long ng = 0;
+  e = cudaMemcpyAsync(&ng, d_ng, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  release();
+  if (e != cudaSuccess) return set_err(ZKB_ERR_CUDA, std::string("zkb_sort_log_queries: ") + cudaGetErrorString(e));
+  if (n_groups_out) *n_groups_out = ng;
+  return ZKB_OK;
+}
+
+int32_t zkb_sort_log_queries(int32_t device, const void* d_recs, uint64_t n_records, const uint32_t* d_group_of, void* d_sorted_out,
+                             uint8_t* d_boundary_out, uint64_t* n_groups_out, void* cuda_stream) {
+  if (n_records && (!d_recs || !d_sorted_out || !d_boundary_out)) return ZKB_ERR_INVALID_ARGUMENT;
+  return logsort_device(device, (const uint32_t*)d_recs, n_records, d_group_of, (uint32_t*)d_sorted_out, d_boundary_out, n_groups_out,
+                        d_group_of ? 64u : 48u, (cudaStream_t)cuda_stream);
+}
+
+// per-VM expansion of "record i belongs to VM v" for the flattened storage histories (VM-major packed)
+__global__ void zkb_fill_groups_kernel(const uint64_t* __restrict__ offsets, uint32_t n_vms, uint32_t* __restrict__ group_of) {
+  const uint32_t vm = blockIdx.x;
+  if (vm >= n_vms) return;
+  for (uint64_t i = offsets[vm] + threadIdx.x; i < offsets[vm + 1]; i += blockDim.x) group_of[i] = vm;
+}
+__global__ void zkb_pack_hist_kernel(const uint32_t* __restrict__ hist, uint32_t cap_hist, const uint64_t* __restrict__ offsets, uint32_t n_vms,
+                                     uint32_t* __restrict__ out) {
+  const uint32_t vm = blockIdx.x;
+  if (vm >= n_vms) return;
+  const uint64_t lo = offsets[vm], n = offsets[vm + 1] - lo;
+  const uint4* src = reinterpret_cast<const uint4*>(hist + (size_t)vm * cap_hist * 32);
+  uint4* dst = reinterpret_cast<uint4*>(out + lo * 32);
+  for (uint64_t i = threadIdx.x; i < n * 8; i += blockDim.x) dst[i] = src[i];
+}
+
+int32_t zkb_net_storage_history(ZkbBatch* b, void* host_sorted_out, uint64_t host_capacity, uint8_t* host_boundary_out, uint64_t* offsets_out,
+                                uint64_t* n_slots_out, void* cuda_stream) {
+  if (!b || !offsets_out) return ZKB_ERR_INVALID_ARGUMENT;
+  if (!b->flat_valid) {
+    int32_t rc = zkb_flatten_logs(b, cuda_stream);
+    if (rc != ZKB_OK) return rc;
+  }
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t n = b->cfg.n_vms;
+  offsets_out[0] = 0;
+  for (size_t v = 0; v < n; v++) offsets_out[v + 1] = offsets_out[v] + b->h_flat_counts[v * 4 + 0];   // records, not bytes
+  const uint64_t total = offsets_out[n];
+  if (n_slots_out) *n_slots_out = 0;
+  if (!host_sorted_out || total == 0) return ZKB_OK;   // size query
+  if (total * ZKB_LOG_BYTES > host_capacity || !host_boundary_out) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_net_storage_history: host buffers too small");
+  if (n >= (1u << 20)) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_net_storage_history: more than 2^20 VMs per batch");
+  uint64_t* d_off = nullptr;
+  uint32_t *d_packed = nullptr, *d_sorted = nullptr, *d_group = nullptr;
+  uint8_t* d_bound = nullptr;
+  cudaError_t e = cudaMalloc(&d_off, (n + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_packed, total * ZKB_LOG_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&d_sorted, total * ZKB_LOG_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&d_group, total * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_bound, total);
+  auto release = [&]() {
+    cudaFree(d_off); cudaFree(d_packed); cudaFree(d_sorted); cudaFree(d_group); cudaFree(d_bound);
+  };
+  if (e != cudaSuccess) {
+    release();
+    return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_net_storage_history cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  e = cudaMemcpyAsync(d_off, offsets_out, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+  zkb_pack_hist_kernel<<<(unsigned)n, 128, 0, st>>>(b->flat.hist[0], b->flat.cap_hist, d_off, (uint32_t)n, d_packed);
+  zkb_fill_groups_kernel<<<(unsigned)n, 64, 0, st>>>(d_off, (uint32_t)n, d_group);
+  uint64_t n_slots = 0;
+  int32_t rc = logsort_device(b->cfg.device, d_packed, total, d_group, d_sorted, d_bound, &n_slots, 64u, st);
+  if (rc == ZKB_OK) {
+    e = cudaMemcpyAsync(host_sorted_out, d_sorted, total * ZKB_LOG_BYTES, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_boundary_out, d_bound, total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = set_err(ZKB_ERR_CUDA, cudaGetErrorString(e));
+    b->d2h_bytes += total * (ZKB_LOG_BYTES + 1);
+  }
+  release();
+  if (n_slots_out) *n_slots_out = n_slots;
+  return rc;
+}
+
 int32_t zkb_flat_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out) {
   if (!range_ok(b, vm_lo, vm_hi) || kind >= 4 || !b->flat_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_flat_counts: call zkb_flatten_logs first");
   for (uint32_t v = vm_lo; v < vm_hi; v++) {
@@ -1722,3 +1839,5 @@ int32_t zkb_restore(ZkbBatch* b, void* cuda_stream) {
 }
 
 }  // extern "C"
+
+#include "comm.cuh"   // multi-GPU exchange entry points (NCCL resolved at run time)

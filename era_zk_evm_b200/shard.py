@@ -220,3 +220,90 @@ class PeerSink:
                 base += (total + 255) // 256 * 256
             work = dist.all_reduce(self._flag, group=self.group, async_op=True)   # behind every rank's pushes
         return [PendingGather(out, offsets, [work], keep=tuple(locals_)) for j, (out, offsets) in enumerate(outs)]
+
+
+# ---------------------------------------------------------------------------------------------
+# the C-ABI collectives (zkb_comm_* / zkb_gather_streams / zkb_exchange_logs): NCCL driven from libzkb.so itself, so a
+# host in any language reaches them; torch.distributed is used here only to hand rank 0's NCCL unique id to the others
+# ---------------------------------------------------------------------------------------------
+def slot_hash64(recs: np.ndarray) -> np.ndarray:
+    """numpy restatement of slot_hash64 (csrc/logsort.cuh) over LOG_DTYPE records: the identity hash of a storage slot
+    (shard_id, address, key) that decides which rank a query goes to and how zkb_sort_log_queries orders slots"""
+    m = np.uint64(0xFF51AFD7ED558CCD)
+    h = np.uint64(0x9E3779B97F4A7C15) ^ recs["shard_id"].astype(np.uint64)
+    addr_words = np.ascontiguousarray(recs["address"]).view("<u4").reshape(len(recs), 5).astype(np.uint64)
+    keys = recs["key"].astype(np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(5):
+            h = (h ^ addr_words[:, i]) * m
+            h ^= h >> np.uint64(32)
+        for i in range(8):
+            h = (h ^ keys[:, i]) * m
+            h ^= h >> np.uint64(32)
+    return h
+
+
+def log_destination(recs: np.ndarray, world: int) -> np.ndarray:
+    return ((slot_hash64(recs) >> np.uint64(20)) % np.uint64(world)).astype(np.int64)
+
+
+class Comm:
+    """ZkbComm: one per process / GPU.  Collective constructor (needs an initialised torch.distributed group only to
+    broadcast the 128-byte NCCL unique id)."""
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes as C
+        from .batch import load_library
+        self._C, lib = C, load_library()
+        self._lib = lib
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+        lib.zkb_comm_unique_id.argtypes = [vp]
+        lib.zkb_comm_create.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
+        lib.zkb_comm_destroy.argtypes = [vp]
+        lib.zkb_gather_streams.argtypes = [vp, vp, u32, i32, C.POINTER(vp), vp, vp]
+        lib.zkb_exchange_logs.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(u64), vp, vp]
+        lib.zkb_last_error.restype = C.c_char_p
+        self.rank, self.world, self.device = dist.get_rank(group), dist.get_world_size(group), device
+        uid = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            self._check(lib.zkb_comm_unique_id(uid))
+        payload = [bytes(uid)]
+        dist.broadcast_object_list(payload, src=0, group=group)
+        uid = (C.c_uint8 * 128).from_buffer_copy(payload[0])
+        self._h = C.c_void_p()
+        self._check(lib.zkb_comm_create(device.index, self.rank, self.world, uid, C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.zkb_last_error()
+            raise RuntimeError(f"zkb comm call failed with status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self._lib.zkb_comm_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def gather_streams(self, batch, kinds, dst: int, stream=None):
+        """collective; on `dst`: {kind: (uint8 tensor view of the concat, byte offsets[world + 1] relative to it)}, else {}"""
+        C = self._C
+        mask = 0
+        for k in kinds:
+            mask |= 1 << k
+        offsets = np.zeros((6, self.world + 1), dtype=np.uint64)
+        p = C.c_void_p()
+        self._check(self._lib.zkb_gather_streams(batch._h, self._h, mask, dst, C.byref(p), offsets.ctypes.data, stream))
+        out = {}
+        if self.rank == dst:
+            for k in kinds:
+                lo, hi = int(offsets[k, 0]), int(offsets[k, self.world])
+                out[k] = (device_bytes_as_tensor(p.value + lo, hi - lo, self.device), (offsets[k] - offsets[k, 0]).astype(np.int64))
+        return out
+
+    def exchange_logs(self, batch, stream=None):
+        """collective; returns (uint8 tensor view of this rank's share of every rank's LOG records, first record of every
+        source rank [world + 1])"""
+        C = self._C
+        p, n = C.c_void_p(), C.c_uint64()
+        src = np.zeros(self.world + 1, dtype=np.uint64)
+        self._check(self._lib.zkb_exchange_logs(batch._h, self._h, C.byref(p), C.byref(n), src.ctypes.data, stream))
+        return device_bytes_as_tensor(p.value, n.value * 128, self.device), src.astype(np.int64)

@@ -261,6 +261,24 @@ int32_t zkb_flatten_logs(ZkbBatch* b, void* cuda_stream);
 int32_t zkb_flat_counts(ZkbBatch* b, uint32_t kind, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out, uint32_t* status_out);
 int32_t zkb_read_flat(ZkbBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
 
+/* Per-slot grouping of log queries = the second half of flatten_and_net_history, `.1`: every query filed under its slot
+ * (shard_id, address, key), history order kept inside a slot (src/testing/storage.rs:50-73).  One stable radix sort on the
+ * device (K11, csrc/logsort.cuh) by key = group << 44 | hash44(slot), then a gather of the 128-byte records:
+ *   d_recs          n_records ZkbLogQueryRec in device memory (any origin: a batch's LOG stream, an exchange's output)
+ *   d_group_of      optional u32 per record (20 bits used): records are grouped by it FIRST (e.g. the VM index, so that
+ *                   every VM keeps its own slot map as the reference's per-VM InMemoryStorage does); NULL = one global map
+ *   d_sorted_out    the records, ordered by (group, slot hash, input position)
+ *   d_boundary_out  one byte per output record: 1 = first query of its slot (slots of equal hash are told apart by their
+ *                   full identity); *n_groups_out = number of slots.
+ * Slots come out in hash order (the reference's HashMap has no order at all); tests compare slot by slot. */
+int32_t zkb_sort_log_queries(int32_t device, const void* d_recs, uint64_t n_records, const uint32_t* d_group_of, void* d_sorted_out,
+                             uint8_t* d_boundary_out, uint64_t* n_groups_out, void* cuda_stream);
+/* flatten_and_net_history().1 of EVERY VM of the batch: the storage histories (ZKB_FLAT_STORAGE_HISTORY, incl. rollback
+ * queries) grouped per VM and slot.  offsets_out[n_vms + 1] = first RECORD of each VM in the output; host_sorted_out ==
+ * NULL only fills offsets_out (offsets_out[n_vms] records are needed).  Runs zkb_flatten_logs first if it has not run. */
+int32_t zkb_net_storage_history(ZkbBatch* b, void* host_sorted_out, uint64_t host_capacity, uint8_t* host_boundary_out, uint64_t* offsets_out,
+                                uint64_t* n_slots_out, void* cuda_stream);
+
 /* ---- bytecode ingestion: the step right BEFORE the path ----------------------------- */
 /* Versioned code hashes of n bytecodes, computed on the GPU: byte 0 = version (1), byte 1 = marker (0 at rest,
  * 1 being constructed), bytes 2..3 = length in 32-byte words (big-endian u16), bytes 4..31 = sha256(code)[4..32] --
@@ -287,6 +305,26 @@ int32_t zkb_peer_push_async(int32_t device, int32_t peer_device, const void* src
 int32_t zkb_peer_sink_create(int32_t device, uint64_t n_bytes, void** dptr_out, uint8_t ipc_handle_out[64]);
 int32_t zkb_peer_sink_open(int32_t device, const uint8_t ipc_handle[64], void** dptr_out);
 int32_t zkb_peer_sink_close(int32_t device, void* dptr, uint32_t owner);   /* owner != 0: cudaFree, else cudaIpcCloseMemHandle */
+
+/* ---- multi-GPU stream exchange over NCCL, from C (SURVEY §8b `zkb_gather`, §8e) ---------------------------------------
+ * One process per GPU.  Rank 0 calls zkb_comm_unique_id, the host passes the 128 bytes to every rank over its own channel
+ * (MPI, a socket, torch.distributed ...), every rank calls zkb_comm_create (collective).  NCCL is dlopen'ed on first use
+ * (libnccl.so.2): no link-time dependency.  world <= 8 (one NVSwitch node). */
+typedef struct ZkbComm ZkbComm;
+int32_t zkb_comm_unique_id(uint8_t id_out[128]);
+int32_t zkb_comm_create(int32_t device, int32_t rank, int32_t world, const uint8_t id[128], ZkbComm** out);
+int32_t zkb_comm_destroy(ZkbComm* c);
+/* Collective: concatenates, on rank dst_rank, every stream kind in kinds_mask (bit k = ZkbStreamKind k) of every rank's
+ * batch, in rank order (VM-major inside a rank).  Sizes by one all-gather, payload by one grouped batch of
+ * ncclSend / ncclRecv on cuda_stream.  *dptr_out (dst_rank only, else NULL): the concat buffer, valid until the next
+ * collective on this comm; offsets_out[kind * (world + 1) + r] = byte offset of rank r's share of `kind` in it (entries of
+ * kinds outside the mask are left alone).  The sink may change from call to call (dst_rank = step % world). */
+int32_t zkb_gather_streams(ZkbBatch* b, ZkbComm* c, uint32_t kinds_mask, int32_t dst_rank, void** dptr_out, uint64_t* offsets_out, void* cuda_stream);
+/* Collective: balanced all-to-all of the LOG streams.  Every LogQueryRec goes to rank (slot_hash64(shard, address, key)
+ * >> 20) % world (csrc/logsort.cuh), so all queries of a storage slot meet on one GPU and every GPU receives ~1/world of
+ * every rank's log.  *dptr_out: this rank's share (device memory, valid until the next collective on this comm), ordered
+ * by (source rank, VM, position in the VM's log); src_offsets_out[world + 1]: first RECORD of every source rank. */
+int32_t zkb_exchange_logs(ZkbBatch* b, ZkbComm* c, void** dptr_out, uint64_t* n_records_out, uint64_t* src_offsets_out, void* cuda_stream);
 
 /* ---- checkpoint / accounting ---------------------------------------------------------------------- */
 /* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a

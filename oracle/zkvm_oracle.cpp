@@ -2433,6 +2433,59 @@ int32_t orc_read_flat(OrcBatch* b, uint32_t vm, uint32_t kind, void* dst, uint64
   return ZKB_OK;
 }
 
+// flatten_and_net_history().1 (storage.rs:50-73) of every VM: the storage history filed per slot, history order kept
+// inside a slot.  The reference returns a HashMap (no slot order); the wire order here is the one zkb_net_storage_history
+// documents -- slots by the 44-bit slot hash, colliding slots by first appearance -- so that the GPU output can be
+// compared byte for byte.  The hash is restated (era_zk_evm_b200/csrc/logsort.cuh slot_hash64).
+static uint64_t orc_slot_hash64(const ZkbLogQueryRec& r) {
+  uint32_t aw[5];
+  memcpy(aw, r.address, 20);
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ r.shard_id;
+  for (int i = 0; i < 5; i++) {
+    h = (h ^ aw[i]) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  for (int i = 0; i < 8; i++) {
+    h = (h ^ r.key[i]) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  return h;
+}
+static bool same_slot(const ZkbLogQueryRec& a, const ZkbLogQueryRec& b) {
+  return a.shard_id == b.shard_id && memcmp(a.address, b.address, 20) == 0 && memcmp(a.key, b.key, 32) == 0;
+}
+int32_t orc_net_storage_history(OrcBatch* b, void* host_sorted_out, uint64_t host_capacity, uint8_t* host_boundary_out, uint64_t* offsets_out,
+                                uint64_t* n_slots_out, void*) {
+  if (!b || !offsets_out) return ZKB_ERR_INVALID_ARGUMENT;
+  const size_t n = b->cfg.n_vms;
+  std::vector<std::vector<ZkbLogQueryRec>> per_vm(n);
+  offsets_out[0] = 0;
+  for (size_t v = 0; v < n; v++) {
+    if (b->vms[v]->status == ZKB_VM_ENDED) flat_of(*b->vms[v], 0, &per_vm[v]);
+    offsets_out[v + 1] = offsets_out[v] + per_vm[v].size();
+  }
+  if (n_slots_out) *n_slots_out = 0;
+  if (!host_sorted_out || offsets_out[n] == 0) return ZKB_OK;
+  if (offsets_out[n] * sizeof(ZkbLogQueryRec) > host_capacity || !host_boundary_out) return ZKB_ERR_INVALID_ARGUMENT;
+  ZkbLogQueryRec* out = (ZkbLogQueryRec*)host_sorted_out;
+  uint64_t slots = 0;
+  for (size_t v = 0; v < n; v++) {
+    const auto& h = per_vm[v];
+    std::vector<size_t> order(h.size());
+    for (size_t i = 0; i < h.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return (orc_slot_hash64(h[x]) >> 20) < (orc_slot_hash64(h[y]) >> 20); });
+    for (size_t i = 0; i < h.size(); i++) {
+      const uint64_t at = offsets_out[v] + i;
+      out[at] = h[order[i]];
+      const bool first = i == 0 || (orc_slot_hash64(h[order[i]]) >> 20) != (orc_slot_hash64(h[order[i - 1]]) >> 20) || !same_slot(h[order[i]], h[order[i - 1]]);
+      host_boundary_out[at] = first ? 1 : 0;
+      slots += first ? 1 : 0;
+    }
+  }
+  if (n_slots_out) *n_slots_out = slots;
+  return ZKB_OK;
+}
+
 int32_t orc_read_storage(OrcBatch* b, uint32_t vm, uint8_t shard_id, const uint8_t address[20], const uint8_t key_be[32], uint8_t value_be_out[32]) {
   if (vm >= b->cfg.n_vms) return ZKB_ERR_INVALID_ARGUMENT;
   SlotKey k{shard_id, addr_from(address), U256::from_be(key_be)};
