@@ -122,6 +122,14 @@ def sized_cpu_sample(workload, vms_cap, target_seconds=12.0):
 
 
 def main():
+    # libraries under us (NCCL's version banner) write to fd 1: keep the real stdout for the ONE JSON line, send the rest to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -131,14 +139,8 @@ def main():
     ap.add_argument("--transfers", type=int, default=8)
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
-    ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left free for the NCCL kernels of the concat")
-    ap.add_argument("--concat-mode", default="simple", choices=["async", "overlap", "simple"],
-                    help="N > 1: simple (default, fastest measured) = launch, pack, exchange; async = pack, launch the next "
-                         "pass, then exchange sizes + payload on a side stream; overlap = exchange between restore and launch")
-    ap.add_argument("--concat-transport", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: nccl = grouped NCCL send/recv; peer = every rank pushes its packed streams into rank 0's IPC-mapped "
-                         "buffer with a small copy kernel over NVLink peer memory (zkb_peer_push_async), underneath the next launch")
-    ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on rank 0")
+    ap.add_argument("--reserve-sms", type=int, default=2, help="N > 1: SMs the persistent interpreter grid leaves free for the NCCL kernels of the exchange (they do not fit next to an interpreter CTA)")
+    ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on the (rotating) sink rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -186,7 +188,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample,
                                  "note": "C++ restatement of the reference path (oracle/), not the Rust crate: no rustc/cargo in this image"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm --------------------------
@@ -198,24 +200,48 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        try:
-            size_pg = dist.new_group(backend="gloo")  # host-side exchange of the per-step stream sizes
-        except Exception as e:                        # no usable host interface: fall back to the device all_gather
-            print(f"bench.py: gloo size group unavailable ({e}); sizes go through NCCL", file=sys.stderr)
-            size_pg = None
 
     vm_ids = np.arange(args.vms, dtype=np.uint64) + np.uint64(rank * args.vms)   # static VM-range partition
     cfg = w.config(args.vms, device=local_rank)
     if world > 1:
         cfg.reserved[0] = args.reserve_sms
-    batch = GpuVmBatch(cfg)
-    w.setup(batch, vm_ids)
-    batch.snapshot()
-    # the query logs a downstream consumer sorts / dedups globally; cycle rows, memory queries and frame records are
-    # per-VM witness and stay sharded unless --gather-rows asks for them
-    concat_kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_REFUND] + \
-        ([records.STREAM_ROWS, records.STREAM_MEM, records.STREAM_FRAME] if args.gather_rows else [])
-    cur_stream = torch.cuda.current_stream().cuda_stream
+    # N > 1: TWO batch objects per GPU take turns, so that the exchange of pass k - 1 (its own pack kernels + the NCCL
+    # transfers) runs while pass k is being interpreted -- what a host loop that streams blocks through the GPUs does anyway.
+    # Every timed step is still one full pass (restore + launch) plus one full exchange.
+    from era_zk_evm_b200 import ZkbError
+    batches = []
+    for _ in range(2 if world > 1 else 1):
+        bt = None
+        try:
+            bt = GpuVmBatch(cfg)
+            w.setup(bt, vm_ids)
+            bt.snapshot()
+            batches.append(bt)
+        except ZkbError as e:     # a configuration that does not fit twice in HBM runs unpipelined on one batch
+            if bt is not None:
+                bt.close()
+            if not batches or "memory" not in str(e):
+                raise
+            print(f"bench.py: second pipeline batch does not fit in HBM ({e}); running unpipelined", file=sys.stderr)
+    if world > 1:             # every rank must take the same turns
+        nb = torch.tensor([len(batches)], device="cuda")
+        dist.all_reduce(nb, op=dist.ReduceOp.MIN)
+        while len(batches) > int(nb.item()):
+            batches.pop().close()
+    batch = batches[0]
+    dev = torch.device("cuda", local_rank)
+    main_stream = torch.cuda.current_stream()
+    cur_stream = main_stream.cuda_stream
+    # N > 1 -- the only exchange on this path, through the C-ABI collectives (NCCL driven from libzkb.so):
+    #   LOG        balanced all-to-all by storage-slot hash (zkb_exchange_logs): every GPU receives ~1/N of every GPU's
+    #              query log, i.e. a constant ingress whatever N is, and holds all queries of "its" slots
+    #   the rest   concatenation on ONE rank (zkb_gather_streams), the sink rotating with the step number
+    # Cycle rows and memory queries are per-VM witness and stay sharded unless --gather-rows asks for them.
+    gather_kinds = [records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND] + \
+        ([records.STREAM_ROWS, records.STREAM_MEM] if args.gather_rows else [])
+    comm = shard.Comm(dev) if world > 1 else None
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    state = {"step": 0, "last": None, "pending": None}
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,98 +249,46 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    pending = []
-    state = {"ran": False}
-    dev = torch.device("cuda", local_rank)
-
-    def concat_previous():
-        """the only exchange on this path: the per-GPU query-log streams of the step that just finished are packed
-        (VM-major, straight into the NCCL send buffers) and concatenated on rank 0.  Only the pack kernels are ordered
-        before the next launch; the NCCL transfers stay in flight underneath it."""
-        for pg in pending:         # stream-level wait: the pack buffers are about to be reused
-            pg.wait()
-        pending.clear()
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)   # rank 0's own share is copied out of the pack buffer there
-        packed = [batch.pack_stream_device_async(kind, cur_stream) for kind in concat_kinds]   # waits for the run, enqueues the packs
-        return [shard.device_bytes_as_tensor(p, nb, dev) for p, nb in packed]
-
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
-    sink = {"obj": None}
-    packed_ev = torch.cuda.Event() if world > 1 else None
-
-    def exchange_on_side_stream(locals_):
-        """size exchange + NCCL send/recv of the packed buffers on a side stream: the host-side wait for the sizes and the
-        transfers themselves run underneath the interpreter launch that is already queued on the main stream"""
-        packed_ev.record()                      # main stream: the pack kernels of the finished pass
-        with torch.cuda.stream(side):
-            side.wait_event(packed_ev)
-            pending.extend(shard.gather_many(locals_, dst=0))
+    def exchange(bt):
+        dst = state["step"] % world
+        state["step"] += 1
+        share, got = comm.exchange_step(bt, gather_kinds, dst, stream=side.cuda_stream)   # one size exchange, one host sync
+        state["last"] = (dst, share, got, bt)
 
     def step():
-        """one pass of the hot path over the batch (+ at N > 1 the concat of the previous pass, overlapped)"""
-        if world > 1 and args.concat_mode == "async":
-            # pass k-1 is still running: wait for it (the pack needs its record counts), pack its query-log streams,
-            # queue restore + launch of pass k right behind the packs, THEN do the exchange of pass k-1 on the side stream
-            locals_ = concat_previous() if state["ran"] else None
+        """one pass of the hot path over one batch.  At N > 1 the PREVIOUS pass's streams are exchanged first, on a side
+        stream (the host waits for that pass's launch: the collectives need its record counts), then this pass is queued:
+        the exchange's pack kernels and NCCL transfers run underneath this pass's interpreter launch."""
+        if world == 1:
             batch.restore()
             batch.run(sync=False)
-            state["ran"] = True
-            if locals_ is not None:
-                exchange_on_side_stream(locals_)
             return
-        if world > 1 and args.concat_mode == "simple":
-            batch.restore()
-            batch.run(sync=False)
-            state["ran"] = True
-            locals_ = concat_previous()
-            if sink["obj"] is None and args.concat_transport == "peer":
-                cap = int(sum(int(t.numel()) for t in locals_) * 1.25) * world + (1 << 20)
-                sink["obj"] = shard.PeerSink(cap, dev, dst=0, size_group=size_pg)
-            if sink["obj"] is not None:
-                pending.extend(sink["obj"].gather_many(locals_))
-            else:
-                pending.extend(shard.gather_many(locals_, dst=0, copy_stream=side, size_group=size_pg))
-            state["ran"] = False
-            return
-        locals_ = concat_previous() if (world > 1 and state["ran"]) else None
-        batch.restore()
-        if locals_ is not None:
-            pending.extend(shard.gather_many(locals_, dst=0))
-        batch.run(sync=False)
-        state["ran"] = True
+        prev = state["pending"]
+        cur = batches[0] if prev is None else batches[(batches.index(prev) + 1) % len(batches)]
+        if len(batches) == 1 and prev is not None:      # unpipelined: the exchange must have read the batch before it is reset
+            exchange(prev)
+            prev = None
+        if state["step"] > 0:
+            comm.wait_packed(cur_stream)   # the last exchange that read `cur`'s streams (two steps back when pipelined: long finished)
+        cur.restore()
+        cur.run(sync=False)                # queued behind the previous pass: the GPU never waits for the host below
+        if prev is not None:
+            exchange(prev)                 # host waits for the PREVIOUS pass; its packs + transfers run underneath `cur`'s launch
+        state["pending"] = cur
 
     def drain():
-        batch.sync()
-        if world > 1 and state["ran"]:
-            locals_ = concat_previous()
-            if args.concat_mode == "async":
-                exchange_on_side_stream(locals_)
-            elif sink["obj"] is not None:
-                pending.extend(sink["obj"].gather_many(locals_))
-            else:
-                pending.extend(shard.gather_many(locals_, dst=0))
-            state["ran"] = False
-        for pg in pending:
-            pg.wait()
-        pending.clear()
+        for bt in batches:
+            bt.sync()
+        if world > 1 and state["pending"] is not None:
+            exchange(state["pending"])
+            state["pending"] = None
+        if side is not None:
+            side.synchronize()
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 0)):
         step()
         drain()
-    if world > 1 and os.environ.get("ZKB_BENCH_PHASES"):      # diagnostic: the concat's phases, serialised
-        def timed(fn):
-            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, (time.perf_counter() - t0) * 1e3
-        batch.restore(); batch.run(sync=True)
-        locals_, t_pack = timed(concat_previous)
-        pend, t_x = timed(lambda: shard.gather_many(locals_, dst=0))
-        _, t_wait = timed(lambda: [pg.wait() for pg in pend])
-        _, t_restore = timed(batch.restore)
-        print(f"[rank {rank}] phases ms: pack {t_pack:.2f} exchange(enqueue+sizes) {t_x:.2f} wait {t_wait:.2f} restore {t_restore:.2f} "
-              f"bytes {sum(int(t.numel()) for t in locals_)}", file=sys.stderr)
-        batch.run(sync=True)
-        state["ran"] = False
     cycles, sbytes = batch.totals()
     st = batch.vm_status()
     if not (st[:, 0] == 1).all():
@@ -330,8 +304,10 @@ def main():
             step()
             if world == 1:
                 batch.sync()
-            kernel_ms.append(batch.last_run_ms()[0])
+                kernel_ms.append(batch.last_run_ms()[0])
         drain()
+        if world > 1:   # (asking for a launch's duration waits for it: only after the pipelined loop)
+            kernel_ms = [bt.last_run_ms()[0] for bt in batches]
         ev1.record()
         barrier()
         total_ms = ev0.elapsed_time(ev1)
@@ -449,6 +425,53 @@ def main():
             sb.close()
         del subs
 
+    # ---- N > 1: the exchange verifies itself on the hardware (outside the timed region) ----
+    multi_gpu = None
+    if world > 1:
+        step()
+        drain()
+        dst, (share, src_off), got, vb = state["last"]
+        logs, _ = vb.fetch_stream_packed(records.STREAM_LOG)
+        logs = logs.view(records.LOG_DTYPE)
+        dest = shard.log_destination(logs, world)
+
+        def digest(a):   # (bytes, wrapping sum of the 8-byte words, their xor)
+            a8 = np.ascontiguousarray(a).view(np.uint8)
+            v = a8[: a8.size // 8 * 8].view(np.uint64)
+            return [int(a8.size), int(np.add.reduce(v, dtype=np.uint64)) if v.size else 0, int(np.bitwise_xor.reduce(v)) if v.size else 0]
+
+        mine = {"sent": [digest(logs[dest == d]) for d in range(world)],
+                "packed": {k: digest(vb.fetch_stream_packed(k)[0]) for k in gather_kinds}}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        share_np = share.cpu().numpy()
+        problems = []
+        for s_rank in range(world):   # what rank s_rank says it sent here == what arrived from it
+            seg = share_np[int(src_off[s_rank]) * 128: int(src_off[s_rank + 1]) * 128]
+            if digest(seg) != everyone[s_rank]["sent"][rank]:
+                problems.append(f"exchange: share of rank {s_rank} on rank {rank} differs")
+        if rank == dst:
+            for k, (t, offs) in got.items():
+                t_np = t.cpu().numpy()
+                for s_rank in range(world):
+                    if digest(t_np[int(offs[s_rank]): int(offs[s_rank + 1])]) != everyone[s_rank]["packed"][k]:
+                        problems.append(f"gather: {records.STREAM_NAMES[k]} of rank {s_rank} on sink {dst} differs")
+        allp = [None] * world
+        dist.all_gather_object(allp, problems)
+        flat = [p for ps in allp for p in ps]
+        if flat:
+            raise SystemExit("bench.py: multi-GPU exchange verification FAILED: " + "; ".join(flat[:4]))
+        rx = [None] * world
+        dist.all_gather_object(rx, int(share_np.size))
+        multi_gpu = {"partition": "static VM ranges, one process per GPU",
+                     "collective": "C ABI (libzkb.so drives NCCL): zkb_exchange_logs = balanced all-to-all of LOG by storage-slot hash; "
+                                   "zkb_gather_streams = concat of " + "/".join(records.STREAM_NAMES[k] for k in gather_kinds) +
+                                   " on a sink that rotates with the step; inside the timed step, transfers overlapped with the next launch",
+                     "exchange_ingress_bytes_per_step_per_gpu": rx,
+                     "gather_bytes_per_step": int(sum(sbytes[k] for k in gather_kinds)) * world,
+                     "verified": "every rank's received LOG share and the sink's gathered streams checked against the senders' digests "
+                                 "(size, 64-bit sum, xor) after the timed region"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n, repeats = sized_cpu_sample(w, args.vms)
@@ -462,20 +485,18 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
                 "e2e": e2e, "e2e_raw_transport": e2e_raw,
-                # interpreter + sparse restore (+ packs)
-                "gpu_launches": args.steps * (2 + (len(concat_kinds) if world > 1 else 0)),
+                # per step: sparse restore + FAST + FULL interpreter launches (+ at N > 1: bucket count / scan / pack, one pack per gathered stream)
+                "gpu_launches": args.steps * (3 + ((3 + len(gather_kinds)) if world > 1 else 0)),
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "cycles_per_step": total_cycles,
                 "stream_bytes_per_step_per_gpu": dict(zip(records.STREAM_NAMES, sbytes)),
-                "multi_gpu": None if world == 1 else {
-                    "partition": "static VM ranges, one process per GPU", "collective": ("one-sided peer pushes (CUDA IPC, zkb_peer_push_kernel over NVLink) into rank 0's buffer + host-side size exchange + one 4-byte all_reduce"
-                                   if args.concat_transport == "peer" and args.concat_mode == "simple" else "NCCL send/recv concat on rank 0") + " inside the timed step",
-                    "concat_streams": [records.STREAM_NAMES[k] for k in concat_kinds],
-                    "concat_bytes_per_step": int(sum(sbytes[k] for k in concat_kinds)) * world}}
-        print(json.dumps(line))
+                "multi_gpu": multi_gpu}
+        emit(line)
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
-    batch.close()
+    for bt in batches:
+        bt.close()
     return 0
 
 

@@ -74,9 +74,10 @@ static NcclApi* nccl_api(std::string* why) {
 // ---- kernels of the hash-partitioned exchange ----------------------------------------------------------------------
 // pass 1: per VM and destination, how many of the VM's LOG records go there.  One warp per VM; lane l takes records
 // l, l + 32, ...
-__global__ void __launch_bounds__(256) zkb_bucket_count_kernel(const DevBatch B, uint32_t world, uint32_t* __restrict__ counts /* [world][n_vms] */) {
+// (128 threads x <= 32 registers: fits next to the persistent interpreter CTA on an SM, which leaves 4 K registers free)
+__global__ void __launch_bounds__(128, 16) zkb_bucket_count_kernel(const DevBatch B, uint32_t world, uint32_t* __restrict__ counts /* [world][n_vms] */) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t vm = blockIdx.x * 8 + warp; vm < B.n_vms; vm += gridDim.x * 8) {
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
     const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
     const uint32_t* recs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
     uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -96,35 +97,38 @@ __global__ void __launch_bounds__(256) zkb_bucket_count_kernel(const DevBatch B,
   }
 }
 
-// exclusive scan of counts[d][0..n) per destination d (one block each); totals[d] = records this rank sends to d
-__global__ void __launch_bounds__(1024) zkb_bucket_scan_kernel(uint32_t* __restrict__ counts, uint32_t n, uint64_t* __restrict__ totals) {
-  __shared__ uint32_t s_sum[1024];
+// exclusive scan of counts[d][0..n) per destination d (one 128-thread block each -- small enough to sit next to the
+// persistent interpreter CTA); totals[d] = records this rank sends to d
+__global__ void __launch_bounds__(128, 16) zkb_bucket_scan_kernel(uint32_t* __restrict__ counts, uint32_t n, uint64_t* __restrict__ totals) {
+  __shared__ uint32_t s_warp[4];
   uint32_t* c = counts + (size_t)blockIdx.x * n;
-  const uint32_t t = threadIdx.x, per = (n + 1023) / 1024;
-  const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
-  uint32_t local = 0;
-  for (uint32_t i = lo; i < hi; i++) local += c[i];
-  s_sum[t] = local;
-  __syncthreads();
-  for (uint32_t o = 1; o < 1024; o <<= 1) {
-    uint32_t v = t >= o ? s_sum[t - o] : 0;
+  const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+  uint64_t carry = 0;
+  for (uint32_t base = 0; base < n; base += 128) {
+    const uint32_t i = base + t;
+    const uint32_t v = i < n ? c[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    s_sum[t] += v;
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; w++) before += s_warp[w];
+    const uint32_t tile_total = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+    if (i < n) c[i] = (uint32_t)carry + before + incl - v;
+    carry += tile_total;
     __syncthreads();
   }
-  uint32_t run = s_sum[t] - local;
-  for (uint32_t i = lo; i < hi; i++) {
-    const uint32_t v = c[i];
-    c[i] = run;
-    run += v;
-  }
-  if (t == 1023) totals[blockIdx.x] = s_sum[1023];
+  if (t == 0) totals[blockIdx.x] = carry;
 }
 
 // pass 2 (the fused pack): records straight from the per-VM slabs into the per-destination regions of the send buffer,
 // at  region_base[d] + offs[d][vm] + (rank of the record among the VM's records for d).  One warp per VM; a record is
 // moved by the whole warp (32 lanes x 4 bytes), in record order, so positions are deterministic.
-__global__ void __launch_bounds__(256) zkb_bucket_pack_kernel(const DevBatch B, uint32_t world, const uint32_t* __restrict__ offs /* [world][n_vms] */,
+__global__ void __launch_bounds__(128, 16) zkb_bucket_pack_kernel(const DevBatch B, uint32_t world, const uint32_t* __restrict__ offs /* [world][n_vms] */,
                                                               const uint64_t* __restrict__ totals, uint32_t* __restrict__ send) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint64_t base[8];
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(256) zkb_bucket_pack_kernel(const DevBatch B, 
     base[d] = run;
     run += d < world ? totals[d] : 0ull;
   }
-  for (uint32_t vm = blockIdx.x * 8 + warp; vm < B.n_vms; vm += gridDim.x * 8) {
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
     const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
     const uint32_t* recs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
     uint32_t next[8];
@@ -166,15 +170,18 @@ struct ZkbComm {
   int device = 0, rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   zkb::NcclApi* api = nullptr;
-  uint8_t* recv = nullptr;      // grow-only receive / concat buffer
+  uint8_t* recv = nullptr;      // grow-only receive buffer of the exchange
   uint64_t recv_capacity = 0;
+  uint8_t* concat = nullptr;    // grow-only concat buffer of the gather (its own: a gather must not clobber the last exchange's share)
+  uint64_t concat_capacity = 0;
   uint8_t* send = nullptr;      // grow-only send buffer of the exchange
   uint64_t send_capacity = 0;
-  uint64_t* d_sizes = nullptr;  // [world][8] sizes matrix on the device
+  uint64_t* d_sizes = nullptr;  // [world][16] sizes matrix on the device: [0..8) records per exchange destination, [8..14) packed stream bytes
   uint64_t* h_sizes = nullptr;  // pinned mirror
   uint32_t* d_counts = nullptr; // [world][n_vms] of the exchange
   uint64_t counts_capacity = 0;
   cudaEvent_t ev = nullptr;
+  cudaEvent_t ev_packed = nullptr;   // recorded once the last collective has read everything it needs from the batch
 };
 
 #define NCCL_OK(c, expr)                                                                                          \
@@ -230,9 +237,10 @@ int32_t zkb_comm_create(int32_t device, int32_t rank, int32_t world, const uint8
     delete c;
     return set_err(ZKB_ERR_CUDA, msg);
   }
-  cudaError_t e = cudaMalloc(&c->d_sizes, (size_t)world * 8 * sizeof(uint64_t));
-  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sizes, (size_t)world * 8 * sizeof(uint64_t), cudaHostAllocDefault);
+  cudaError_t e = cudaMalloc(&c->d_sizes, (size_t)world * 16 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sizes, (size_t)world * 16 * sizeof(uint64_t), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming);
   if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_comm_create: ") + cudaGetErrorString(e));
   *out = c;
   return ZKB_OK;
@@ -244,130 +252,153 @@ int32_t zkb_comm_destroy(ZkbComm* c) {
   cudaDeviceSynchronize();
   if (c->comm) c->api->CommDestroy(c->comm);
   if (c->recv) cudaFree(c->recv);
+  if (c->concat) cudaFree(c->concat);
   if (c->send) cudaFree(c->send);
   if (c->d_sizes) cudaFree(c->d_sizes);
   if (c->h_sizes) cudaFreeHost(c->h_sizes);
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->ev) cudaEventDestroy(c->ev);
+  if (c->ev_packed) cudaEventDestroy(c->ev_packed);
   delete c;
   return ZKB_OK;
 }
 
-// every rank's 8-word size vector to every rank (device all-gather + one small D2H): h_sizes[r][k]
-static int32_t comm_exchange_sizes(ZkbComm* c, const uint64_t mine[8], cudaStream_t st) {
-  memcpy(c->h_sizes + (size_t)c->rank * 8, mine, 64);
-  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 8, c->h_sizes + (size_t)c->rank * 8, 64, cudaMemcpyHostToDevice, st));
-  NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 8, c->d_sizes, 8, ncclUint64, c->comm, st));
-  CUDA_OK(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)c->world * 64, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  return ZKB_OK;
-}
-
-int32_t zkb_gather_streams(ZkbBatch* b, ZkbComm* c, uint32_t kinds_mask, int32_t dst_rank, void** dptr_out, uint64_t* offsets_out, void* cuda_stream) {
-  if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world || !(kinds_mask & 63u)) return ZKB_ERR_INVALID_ARGUMENT;
+// One step of the multi-GPU path: (optionally) the balanced LOG exchange and (optionally) the concat of whole streams on
+// dst_rank, with ONE size all-gather and ONE host synchronisation in front of all the transfers, which are then left in
+// flight on `st`:
+//   local prep   exchange: bucket count + scan;  gather: the pack kernels          (reads of the batch end here: ev_packed)
+//   sizes        all-gather of 16 words per rank, D2H, stream sync
+//   transfers    one grouped batch of ncclSend / ncclRecv for both
+static int32_t comm_step(ZkbBatch* b, ZkbComm* c, bool do_exchange, uint32_t kinds_mask, int32_t dst_rank, void** share_out, uint64_t* n_share_out,
+                         uint64_t* src_offsets_out, void** concat_out, uint64_t* concat_offsets_out, cudaStream_t st) {
   CUDA_OK(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const uint32_t* cnt = nullptr;
+  int32_t rc = summary(b, &cnt);   // waits for THIS batch's run
+  if (rc != ZKB_OK) return rc;
+  const uint32_t n = b->cfg.n_vms, world = (uint32_t)c->world;
+  uint64_t* h_mine = c->h_sizes + (size_t)c->rank * 16;
+  uint64_t* d_mine = c->d_sizes + (size_t)c->rank * 16;
+  memset(h_mine, 0, 128);
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + 3) / 4, (uint32_t)n_sm * 4));
+  // ---- local prep ----
   uint8_t* packed[ZKB_N_STREAMS] = {};
-  uint64_t mine[8] = {};
   for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
     if (!((kinds_mask >> k) & 1u)) continue;
-    int32_t rc = pack_async(b, k, st, &packed[k], &mine[k]);
+    rc = pack_async(b, k, st, &packed[k], &h_mine[8 + k]);
     if (rc != ZKB_OK) return rc;
   }
-  int32_t rc = comm_exchange_sizes(c, mine, st);
-  if (rc != ZKB_OK) return rc;
-  // layout on dst: for each kind in the mask (ascending), the ranks' shares in rank order; kinds start 256-byte aligned
+  CUDA_OK(cudaMemcpyAsync(d_mine + 8, h_mine + 8, 64, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(d_mine, 0, 64, st));
+  if (do_exchange) {
+    if ((uint64_t)world * n > c->counts_capacity) {
+      if (c->d_counts) CUDA_OK(cudaFree(c->d_counts));
+      c->d_counts = nullptr;
+      CUDA_OK(cudaMalloc(&c->d_counts, (size_t)world * n * 4));
+      c->counts_capacity = (uint64_t)world * n;
+    }
+    zkb::zkb_bucket_count_kernel<<<grid, 128, 0, st>>>(b->d, world, c->d_counts);
+    zkb::zkb_bucket_scan_kernel<<<world, 128, 0, st>>>(c->d_counts, n, d_mine);
+    CUDA_OK(cudaGetLastError());
+  }
+  // ---- sizes ----
+  NCCL_OK(c, c->api->AllGather(d_mine, c->d_sizes, 16, ncclUint64, c->comm, st));
+  CUDA_OK(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)world * 128, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  auto H = [&](uint32_t r, uint32_t i) { return c->h_sizes[(size_t)r * 16 + i]; };
+  uint64_t send_total = 0, recv_total = 0;
+  if (do_exchange) {
+    for (uint32_t d = 0; d < world; d++) send_total += H(c->rank, d);
+    for (uint32_t s = 0; s < world; s++) recv_total += H(s, c->rank);
+    rc = comm_ensure(&c->send, &c->send_capacity, send_total * ZKB_LOG_BYTES);
+    if (rc == ZKB_OK) rc = comm_ensure(&c->recv, &c->recv_capacity, recv_total * ZKB_LOG_BYTES);
+    if (rc != ZKB_OK) return rc;
+    if (send_total) zkb::zkb_bucket_pack_kernel<<<grid, 128, 0, st>>>(b->d, world, c->d_counts, d_mine, (uint32_t*)c->send);
+    CUDA_OK(cudaGetLastError());
+  }
+  CUDA_OK(cudaEventRecord(c->ev_packed, st));   // nothing below reads the batch's stream slabs
+  // concat layout on dst: for each kind in the mask (ascending), the ranks' shares in rank order; kinds start 256-byte aligned
   uint64_t kind_base[ZKB_N_STREAMS] = {}, at = 0;
   for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
     if (!((kinds_mask >> k) & 1u)) continue;
     kind_base[k] = at;
     uint64_t run = 0;
-    for (int r = 0; r < c->world; r++) {
-      if (offsets_out) offsets_out[(size_t)k * (c->world + 1) + r] = at + run;
-      run += c->h_sizes[(size_t)r * 8 + k];
+    for (uint32_t r = 0; r < world; r++) {
+      if (concat_offsets_out) concat_offsets_out[(size_t)k * (world + 1) + r] = at + run;
+      run += H(r, 8 + k);
     }
-    if (offsets_out) offsets_out[(size_t)k * (c->world + 1) + c->world] = at + run;
+    if (concat_offsets_out) concat_offsets_out[(size_t)k * (world + 1) + world] = at + run;
     at = (at + run + 255) / 256 * 256;
   }
-  if (c->rank == dst_rank) {
-    rc = comm_ensure(&c->recv, &c->recv_capacity, at);
+  if (kinds_mask && c->rank == dst_rank) {
+    rc = comm_ensure(&c->concat, &c->concat_capacity, at);
     if (rc != ZKB_OK) return rc;
   }
+  // ---- transfers ----
   NCCL_OK(c, c->api->GroupStart());
+  if (do_exchange) {
+    uint64_t s_at = 0, r_at = 0;
+    for (uint32_t p = 0; p < world; p++) {
+      const uint64_t s_n = H(c->rank, p) * ZKB_LOG_BYTES, r_n = H(p, c->rank) * ZKB_LOG_BYTES;
+      if (src_offsets_out) src_offsets_out[p] = r_at / ZKB_LOG_BYTES;
+      if ((int)p == c->rank) {
+        if (s_n) CUDA_OK(cudaMemcpyAsync(c->recv + r_at, c->send + s_at, s_n, cudaMemcpyDeviceToDevice, st));
+      } else {
+        if (s_n) NCCL_OK(c, c->api->Send(c->send + s_at, s_n, ncclUint8, (int)p, c->comm, st));
+        if (r_n) NCCL_OK(c, c->api->Recv(c->recv + r_at, r_n, ncclUint8, (int)p, c->comm, st));
+      }
+      s_at += s_n;
+      r_at += r_n;
+    }
+    if (src_offsets_out) src_offsets_out[world] = recv_total;
+  }
   for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
     if (!((kinds_mask >> k) & 1u)) continue;
     if (c->rank == dst_rank) {
       uint64_t run = kind_base[k];
-      for (int r = 0; r < c->world; r++) {
-        const uint64_t sz = c->h_sizes[(size_t)r * 8 + k];
-        if (r == c->rank) {
-          if (sz) CUDA_OK(cudaMemcpyAsync(c->recv + run, packed[k], sz, cudaMemcpyDeviceToDevice, st));
+      for (uint32_t r = 0; r < world; r++) {
+        const uint64_t sz = H(r, 8 + k);
+        if ((int)r == c->rank) {
+          if (sz) CUDA_OK(cudaMemcpyAsync(c->concat + run, packed[k], sz, cudaMemcpyDeviceToDevice, st));
         } else if (sz) {
-          NCCL_OK(c, c->api->Recv(c->recv + run, sz, ncclUint8, r, c->comm, st));
+          NCCL_OK(c, c->api->Recv(c->concat + run, sz, ncclUint8, (int)r, c->comm, st));
         }
         run += sz;
       }
-    } else if (mine[k]) {
-      NCCL_OK(c, c->api->Send(packed[k], mine[k], ncclUint8, dst_rank, c->comm, st));
+    } else if (H(c->rank, 8 + k)) {
+      NCCL_OK(c, c->api->Send(packed[k], H(c->rank, 8 + k), ncclUint8, dst_rank, c->comm, st));
     }
   }
   NCCL_OK(c, c->api->GroupEnd());
-  if (dptr_out) *dptr_out = c->rank == dst_rank ? c->recv : nullptr;
+  if (share_out) *share_out = do_exchange ? c->recv : nullptr;
+  if (n_share_out) *n_share_out = recv_total;
+  if (concat_out) *concat_out = (kinds_mask && c->rank == dst_rank) ? c->concat : nullptr;
+  return ZKB_OK;
+}
+
+int32_t zkb_gather_streams(ZkbBatch* b, ZkbComm* c, uint32_t kinds_mask, int32_t dst_rank, void** dptr_out, uint64_t* offsets_out, void* cuda_stream) {
+  if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world || !(kinds_mask & 63u)) return ZKB_ERR_INVALID_ARGUMENT;
+  return comm_step(b, c, false, kinds_mask & 63u, dst_rank, nullptr, nullptr, nullptr, dptr_out, offsets_out, (cudaStream_t)cuda_stream);
+}
+
+int32_t zkb_comm_wait_packed(ZkbComm* c, void* cuda_stream) {
+  if (!c) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, c->ev_packed, 0));
   return ZKB_OK;
 }
 
 int32_t zkb_exchange_logs(ZkbBatch* b, ZkbComm* c, void** dptr_out, uint64_t* n_records_out, uint64_t* src_offsets_out, void* cuda_stream) {
   if (!b || !c || !b->cfg.witness_mode) return ZKB_ERR_INVALID_ARGUMENT;
-  CUDA_OK(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const uint32_t* cnt = nullptr;
-  int32_t rc = summary(b, &cnt);   // waits for THIS batch's run
-  if (rc != ZKB_OK) return rc;
-  const uint32_t n = b->cfg.n_vms, world = (uint32_t)c->world;
-  if ((uint64_t)world * n > c->counts_capacity) {
-    if (c->d_counts) CUDA_OK(cudaFree(c->d_counts));
-    c->d_counts = nullptr;
-    CUDA_OK(cudaMalloc(&c->d_counts, (size_t)world * n * 4));
-    c->counts_capacity = (uint64_t)world * n;
-  }
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
-  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + 7) / 8, (uint32_t)n_sm * 8));
-  uint64_t* d_tot = c->d_sizes + (size_t)c->rank * 8;   // this rank's row of the sizes matrix: records for each destination
-  CUDA_OK(cudaMemsetAsync(d_tot, 0, 64, st));
-  zkb::zkb_bucket_count_kernel<<<grid, 256, 0, st>>>(b->d, world, c->d_counts);
-  zkb::zkb_bucket_scan_kernel<<<world, 1024, 0, st>>>(c->d_counts, n, d_tot);
-  CUDA_OK(cudaGetLastError());
-  NCCL_OK(c, c->api->AllGather(d_tot, c->d_sizes, 8, ncclUint64, c->comm, st));
-  CUDA_OK(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)world * 64, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  uint64_t send_total = 0, recv_total = 0;
-  for (uint32_t d = 0; d < world; d++) send_total += c->h_sizes[(size_t)c->rank * 8 + d];
-  for (uint32_t s = 0; s < world; s++) recv_total += c->h_sizes[(size_t)s * 8 + c->rank];
-  rc = comm_ensure(&c->send, &c->send_capacity, send_total * ZKB_LOG_BYTES);
-  if (rc == ZKB_OK) rc = comm_ensure(&c->recv, &c->recv_capacity, recv_total * ZKB_LOG_BYTES);
-  if (rc != ZKB_OK) return rc;
-  if (send_total) zkb::zkb_bucket_pack_kernel<<<grid, 256, 0, st>>>(b->d, world, c->d_counts, d_tot, (uint32_t*)c->send);
-  CUDA_OK(cudaGetLastError());
-  NCCL_OK(c, c->api->GroupStart());
-  uint64_t s_at = 0, r_at = 0;
-  for (uint32_t p = 0; p < world; p++) {
-    const uint64_t s_n = c->h_sizes[(size_t)c->rank * 8 + p] * ZKB_LOG_BYTES, r_n = c->h_sizes[(size_t)p * 8 + c->rank] * ZKB_LOG_BYTES;
-    if (src_offsets_out) src_offsets_out[p] = r_at / ZKB_LOG_BYTES;
-    if ((int)p == c->rank) {
-      if (s_n) CUDA_OK(cudaMemcpyAsync(c->recv + r_at, c->send + s_at, s_n, cudaMemcpyDeviceToDevice, st));
-    } else {
-      if (s_n) NCCL_OK(c, c->api->Send(c->send + s_at, s_n, ncclUint8, (int)p, c->comm, st));
-      if (r_n) NCCL_OK(c, c->api->Recv(c->recv + r_at, r_n, ncclUint8, (int)p, c->comm, st));
-    }
-    s_at += s_n;
-    r_at += r_n;
-  }
-  NCCL_OK(c, c->api->GroupEnd());
-  if (src_offsets_out) src_offsets_out[world] = recv_total;
-  if (dptr_out) *dptr_out = c->recv;
-  if (n_records_out) *n_records_out = recv_total;
-  return ZKB_OK;
+  return comm_step(b, c, true, 0u, 0, dptr_out, n_records_out, src_offsets_out, nullptr, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int32_t zkb_exchange_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32_t dst_rank, void** share_out, uint64_t* n_share_out,
+                          uint64_t* src_offsets_out, void** concat_out, uint64_t* concat_offsets_out, void* cuda_stream) {
+  if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world) return ZKB_ERR_INVALID_ARGUMENT;
+  return comm_step(b, c, true, gather_kinds_mask & 63u, dst_rank, share_out, n_share_out, src_offsets_out, concat_out, concat_offsets_out,
+                   (cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

@@ -262,6 +262,8 @@ class Comm:
         lib.zkb_comm_destroy.argtypes = [vp]
         lib.zkb_gather_streams.argtypes = [vp, vp, u32, i32, C.POINTER(vp), vp, vp]
         lib.zkb_exchange_logs.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(u64), vp, vp]
+        lib.zkb_comm_wait_packed.argtypes = [vp, vp]
+        lib.zkb_exchange_step.argtypes = [vp, vp, u32, i32, C.POINTER(vp), C.POINTER(u64), vp, C.POINTER(vp), vp, vp]
         lib.zkb_last_error.restype = C.c_char_p
         self.rank, self.world, self.device = dist.get_rank(group), dist.get_world_size(group), device
         uid = (C.c_uint8 * 128)()
@@ -283,6 +285,10 @@ class Comm:
             self._lib.zkb_comm_destroy(self._h)
             self._h = self._C.c_void_p()
 
+    def wait_packed(self, stream=None):
+        """`stream` waits until the last collective has finished reading the batch (its pack kernels), not its transfers"""
+        self._check(self._lib.zkb_comm_wait_packed(self._h, stream))
+
     def gather_streams(self, batch, kinds, dst: int, stream=None):
         """collective; on `dst`: {kind: (uint8 tensor view of the concat, byte offsets[world + 1] relative to it)}, else {}"""
         C = self._C
@@ -298,6 +304,25 @@ class Comm:
                 lo, hi = int(offsets[k, 0]), int(offsets[k, self.world])
                 out[k] = (device_bytes_as_tensor(p.value + lo, hi - lo, self.device), (offsets[k] - offsets[k, 0]).astype(np.int64))
         return out
+
+    def exchange_step(self, batch, gather_kinds, dst: int, stream=None):
+        """collective: exchange_logs + gather_streams with one size exchange; returns ((share, src offsets), {kind: (concat, offsets)})"""
+        C = self._C
+        mask = 0
+        for k in gather_kinds:
+            mask |= 1 << k
+        p, n, q = C.c_void_p(), C.c_uint64(), C.c_void_p()
+        src = np.zeros(self.world + 1, dtype=np.uint64)
+        offsets = np.zeros((6, self.world + 1), dtype=np.uint64)
+        self._check(self._lib.zkb_exchange_step(batch._h, self._h, mask, dst, C.byref(p), C.byref(n), src.ctypes.data, C.byref(q),
+                                                offsets.ctypes.data, stream))
+        share = (device_bytes_as_tensor(p.value, n.value * 128, self.device), src.astype(np.int64))
+        got = {}
+        if self.rank == dst:
+            for k in gather_kinds:
+                lo, hi = int(offsets[k, 0]), int(offsets[k, self.world])
+                got[k] = (device_bytes_as_tensor(q.value + lo, hi - lo, self.device), (offsets[k] - offsets[k, 0]).astype(np.int64))
+        return share, got
 
     def exchange_logs(self, batch, stream=None):
         """collective; returns (uint8 tensor view of this rank's share of every rank's LOG records, first record of every

@@ -325,6 +325,14 @@ int32_t zkb_gather_streams(ZkbBatch* b, ZkbComm* c, uint32_t kinds_mask, int32_t
  * every rank's log.  *dptr_out: this rank's share (device memory, valid until the next collective on this comm), ordered
  * by (source rank, VM, position in the VM's log); src_offsets_out[world + 1]: first RECORD of every source rank. */
 int32_t zkb_exchange_logs(ZkbBatch* b, ZkbComm* c, void** dptr_out, uint64_t* n_records_out, uint64_t* src_offsets_out, void* cuda_stream);
+/* Both of the above in ONE collective step: one size all-gather and one host synchronisation in front of all transfers, which
+ * are then left in flight on cuda_stream.  What a multi-GPU host loop calls once per pass. */
+int32_t zkb_exchange_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32_t dst_rank, void** share_out, uint64_t* n_share_out,
+                          uint64_t* src_offsets_out, void** concat_out, uint64_t* concat_offsets_out, void* cuda_stream);
+/* Makes cuda_stream wait until the LAST collective on `c` has read everything it needs from its batch (its pack kernels):
+ * a host loop runs the collectives of pass k on a side stream, orders only this before the restore / launch of pass k + 1
+ * on the main stream, and leaves the NCCL transfers in flight underneath that launch. */
+int32_t zkb_comm_wait_packed(ZkbComm* c, void* cuda_stream);
 
 /* ---- checkpoint / accounting ---------------------------------------------------------------------- */
 /* VmLocalState (+ backends) is a plain cloneable value in the reference (vm_state/mod.rs:53): snapshot keeps a
