@@ -139,8 +139,11 @@ def main():
     ap.add_argument("--transfers", type=int, default=8)
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
-    ap.add_argument("--reserve-sms", type=int, default=2, help="N > 1: SMs the persistent interpreter grid leaves free for the NCCL kernels of the exchange (they do not fit next to an interpreter CTA)")
-    ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the cycle rows + memory queries on the (rotating) sink rank")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs the persistent interpreter grid leaves free for the NCCL kernels of the exchange (they do not fit next to an interpreter CTA); -1 = 0 with --transport push, 4 with nccl")
+    ap.add_argument("--transport", default="push", choices=["push", "nccl"],
+                    help="N > 1: push = one-sided writes over NVLink peer memory (zkb_push_step: co-resident kernels, no host sync); "
+                         "nccl = grouped ncclSend / ncclRecv (zkb_exchange_step).  --gather-rows always uses nccl")
+    ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the per-VM witness (cycle rows, memory queries, frame records) on the (rotating) sink rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -204,12 +207,12 @@ def main():
     vm_ids = np.arange(args.vms, dtype=np.uint64) + np.uint64(rank * args.vms)   # static VM-range partition
     cfg = w.config(args.vms, device=local_rank)
     if world > 1:
-        cfg.reserved[0] = args.reserve_sms
+        cfg.reserved[0] = args.reserve_sms if args.reserve_sms >= 0 else (0 if (args.transport == "push" and not args.gather_rows) else 4)
     # N > 1: TWO batch objects per GPU take turns, so that the exchange of pass k - 1 (its own pack kernels + the NCCL
     # transfers) runs while pass k is being interpreted -- what a host loop that streams blocks through the GPUs does anyway.
     # Every timed step is still one full pass (restore + launch) plus one full exchange.
     from era_zk_evm_b200 import ZkbError
-    batches = []
+    batches, split = [], False
     for _ in range(2 if world > 1 else 1):
         bt = None
         try:
@@ -217,17 +220,28 @@ def main():
             w.setup(bt, vm_ids)
             bt.snapshot()
             batches.append(bt)
-        except ZkbError as e:     # a configuration that does not fit twice in HBM runs unpipelined on one batch
+        except ZkbError as e:     # a configuration that does not fit twice in HBM is pipelined as two HALF batches instead
             if bt is not None:
                 bt.close()
             if not batches or "memory" not in str(e):
                 raise
-            print(f"bench.py: second pipeline batch does not fit in HBM ({e}); running unpipelined", file=sys.stderr)
+            print(f"bench.py: a second full batch does not fit in HBM ({e}); pipelining two half batches", file=sys.stderr)
+            split = True
     if world > 1:             # every rank must take the same turns
-        nb = torch.tensor([len(batches)], device="cuda")
-        dist.all_reduce(nb, op=dist.ReduceOp.MIN)
-        while len(batches) > int(nb.item()):
-            batches.pop().close()
+        nb = torch.tensor([1 if split else 0], device="cuda")
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        if int(nb.item()):
+            split = True
+            for bt in batches:
+                bt.close()
+            torch.cuda.empty_cache()
+            batches = []
+            half = args.vms // 2
+            for ids in (vm_ids[:half], vm_ids[half:]):
+                bt = GpuVmBatch(w.config(len(ids), device=local_rank))
+                w.setup(bt, ids)
+                bt.snapshot()
+                batches.append(bt)
     batch = batches[0]
     dev = torch.device("cuda", local_rank)
     main_stream = torch.cuda.current_stream()
@@ -236,9 +250,10 @@ def main():
     #   LOG        balanced all-to-all by storage-slot hash (zkb_exchange_logs): every GPU receives ~1/N of every GPU's
     #              query log, i.e. a constant ingress whatever N is, and holds all queries of "its" slots
     #   the rest   concatenation on ONE rank (zkb_gather_streams), the sink rotating with the step number
-    # Cycle rows and memory queries are per-VM witness and stay sharded unless --gather-rows asks for them.
-    gather_kinds = [records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND] + \
-        ([records.STREAM_ROWS, records.STREAM_MEM] if args.gather_rows else [])
+    # Cycle rows, memory queries and frame records are per-VM witness (no cross-VM consumer) and stay sharded unless
+    # --gather-rows asks for them (measured separately: profiles/bench_r02_n8_mixed_rows*.json).
+    gather_kinds = [records.STREAM_DECOMMIT, records.STREAM_REFUND] + \
+        ([records.STREAM_ROWS, records.STREAM_MEM, records.STREAM_FRAME] if args.gather_rows else [])
     comm = shard.Comm(dev) if world > 1 else None
     side = torch.cuda.Stream(device=dev) if world > 1 else None
     state = {"step": 0, "last": None, "pending": None}
@@ -249,13 +264,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_push = world > 1 and args.transport == "push" and not args.gather_rows
+    run_done = {id(bt): torch.cuda.Event() for bt in batches}     # pass finished (main stream)
+    read_done = {id(bt): torch.cuda.Event() for bt in batches}    # the exchange has read the batch's streams (side stream)
+
     def exchange(bt):
         dst = state["step"] % world
         state["step"] += 1
-        share, got = comm.exchange_step(bt, gather_kinds, dst, stream=side.cuda_stream)   # one size exchange, one host sync
-        state["last"] = (dst, share, got, bt)
+        if use_push:
+            # one-sided: nothing here waits on the host -- the side stream waits for the pass, the kernels read the record
+            # counts on the device and write straight into the destination GPUs' memory
+            side.wait_event(run_done[id(bt)])
+            tag = comm.push_step(bt, gather_kinds, dst, stream=side.cuda_stream)
+            read_done[id(bt)].record(side)
+            state["last"] = (dst, tag, None, bt)
+        else:
+            share, got = comm.exchange_step(bt, gather_kinds, dst, stream=side.cuda_stream)   # one size exchange, one host sync
+            state["last"] = (dst, share, got, bt)
 
     def step():
+        """one pass of the hot path over the GPU's batch (two half-batch passes when the batch is pipelined as halves)"""
+        for _ in range(2 if split else 1):
+            one_pass()
+
+    def one_pass():
         """one pass of the hot path over one batch.  At N > 1 the PREVIOUS pass's streams are exchanged first, on a side
         stream (the host waits for that pass's launch: the collectives need its record counts), then this pass is queued:
         the exchange's pack kernels and NCCL transfers run underneath this pass's interpreter launch."""
@@ -268,10 +300,14 @@ def main():
         if len(batches) == 1 and prev is not None:      # unpipelined: the exchange must have read the batch before it is reset
             exchange(prev)
             prev = None
-        if state["step"] > 0:
+        if use_push:
+            if state["step"] >= len(batches):
+                read_done[id(cur)].synchronize()        # bounds the host's lead to the pipeline depth; long finished
+        elif state["step"] > 0:
             comm.wait_packed(cur_stream)   # the last exchange that read `cur`'s streams (two steps back when pipelined: long finished)
         cur.restore()
         cur.run(sync=False)                # queued behind the previous pass: the GPU never waits for the host below
+        run_done[id(cur)].record(main_stream)
         if prev is not None:
             exchange(prev)                 # host waits for the PREVIOUS pass; its packs + transfers run underneath `cur`'s launch
         state["pending"] = cur
@@ -285,12 +321,18 @@ def main():
         if side is not None:
             side.synchronize()
         torch.cuda.synchronize()
+        if use_push:
+            dist.barrier()   # every rank's pushes have landed (each rank synchronised its own side stream above)
 
     for _ in range(max(args.warmup, 0)):
         step()
         drain()
     cycles, sbytes = batch.totals()
     st = batch.vm_status()
+    if split:   # the GPU's batch = both halves
+        c2, s2 = batches[1].totals()
+        cycles, sbytes = cycles + c2, [a + b for a, b in zip(sbytes, s2)]
+        st = np.concatenate([st, batches[1].vm_status()])
     if not (st[:, 0] == 1).all():
         raise SystemExit(f"bench.py: {int((st[:, 0] != 1).sum())} VMs did not end: {st[st[:, 0] != 1][:4]}")
     alg_bytes = int(sum(sbytes))
@@ -307,7 +349,7 @@ def main():
                 kernel_ms.append(batch.last_run_ms()[0])
         drain()
         if world > 1:   # (asking for a launch's duration waits for it: only after the pipelined loop)
-            kernel_ms = [bt.last_run_ms()[0] for bt in batches]
+            kernel_ms = [sum(bt.last_run_ms()[0] for bt in batches)] if split else [bt.last_run_ms()[0] for bt in batches]
         ev1.record()
         barrier()
         total_ms = ev0.elapsed_time(ev1)
@@ -428,9 +470,20 @@ def main():
     # ---- N > 1: the exchange verifies itself on the hardware (outside the timed region) ----
     multi_gpu = None
     if world > 1:
-        step()
+        one_pass()
         drain()
-        dst, (share, src_off), got, vb = state["last"]
+        if use_push:
+            dst, tag, _, vb = state["last"]
+            dist.barrier()
+            shares, concat = comm.push_result(vb, tag)
+            src_off = np.concatenate([[0], np.cumsum([t.numel() // 128 for t in shares])])
+            share = torch.cat(shares) if shares else torch.empty(0, dtype=torch.uint8, device=dev)
+            got = {}
+            for k, parts in concat.items():
+                offs = np.concatenate([[0], np.cumsum([t.numel() for t in parts])])
+                got[k] = (torch.cat(parts), offs)
+        else:
+            dst, (share, src_off), got, vb = state["last"]
         logs, _ = vb.fetch_stream_packed(records.STREAM_LOG)
         logs = logs.view(records.LOG_DTYPE)
         dest = shard.log_destination(logs, world)
@@ -464,9 +517,10 @@ def main():
         rx = [None] * world
         dist.all_gather_object(rx, int(share_np.size))
         multi_gpu = {"partition": "static VM ranges, one process per GPU",
-                     "collective": "C ABI (libzkb.so drives NCCL): zkb_exchange_logs = balanced all-to-all of LOG by storage-slot hash; "
-                                   "zkb_gather_streams = concat of " + "/".join(records.STREAM_NAMES[k] for k in gather_kinds) +
-                                   " on a sink that rotates with the step; inside the timed step, transfers overlapped with the next launch",
+                     "collective": ("C ABI zkb_push_step: ONE-SIDED writes over NVLink peer memory (CUDA IPC) by co-resident 128-thread kernels, "
+                                    "no NCCL on the data path, no host sync" if use_push else "C ABI zkb_exchange_step: grouped ncclSend / ncclRecv") +
+                                   "; LOG partitioned over the ranks by storage-slot hash, " + "/".join(records.STREAM_NAMES[k] for k in gather_kinds) +
+                                   " concatenated on a sink that rotates with the step; inside the timed step, underneath the next pass's launch",
                      "exchange_ingress_bytes_per_step_per_gpu": rx,
                      "gather_bytes_per_step": int(sum(sbytes[k] for k in gather_kinds)) * world,
                      "verified": "every rank's received LOG share and the sink's gathered streams checked against the senders' digests "

@@ -16,6 +16,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
+#include <time.h>
 
 namespace zkb {
 
@@ -164,6 +165,113 @@ __global__ void __launch_bounds__(128, 16) zkb_bucket_pack_kernel(const DevBatch
   }
 }
 
+
+// ---- one-sided variants: the same partition, written STRAIGHT into the destination GPU's memory over NVLink ----------
+// (peer memory mapped through CUDA IPC).  No NCCL on the data path, so no SM has to be kept free for it: every kernel
+// here is 128 threads x <= 32 registers and co-resides with the persistent interpreter CTA, i.e. the exchange of pass k
+// runs underneath the interpreter launch of pass k + 1 without any host synchronisation (counts are read on the device).
+// Receive layout on every rank: `world` fixed-capacity regions, region s = what source rank s sent; a mailbox row per
+// source carries its record / byte counts and the step tag that marks the row complete.
+struct PushPeers {
+  uint8_t* rbuf[8];      // receive buffers of all ranks (own = local pointer)
+  uint64_t* mbox[8];     // mailboxes of all ranks: [world][16] u64
+};
+
+__global__ void __launch_bounds__(128, 16) zkb_bucket_push_kernel(const DevBatch B, uint32_t world, uint32_t my_rank, const uint32_t* __restrict__ offs,
+                                                                 PushPeers P, uint64_t region_bytes) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t sub = lane >> 3, l8 = lane & 7u;   // a record is moved by 8 lanes x 16 bytes: four records per warp step
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
+    const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
+    const uint32_t* recs = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
+    uint32_t next[8];
+#pragma unroll
+    for (uint32_t d = 0; d < 8; d++) next[d] = d < world ? offs[(size_t)d * B.n_vms + vm] : 0u;
+    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+      // lane l classifies record r0 + l ...
+      uint32_t my_dst = 0u;
+      if (r0 + lane < n) {
+        const uint32_t* p = recs + (size_t)(r0 + lane) * 32;
+        my_dst = (uint32_t)((slot_hash64(p[1] >> 24, p + 2, p + 8) >> 20) % world);
+      }
+      const uint32_t m = min(32u, n - r0);
+      // ... then the warp moves them four at a time (positions are handed out in record order: deterministic layout)
+      for (uint32_t k = 0; k < m; k += 4) {
+        uint32_t d_mine = 0, pos_mine = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+          const uint32_t d = __shfl_sync(0xffffffffu, my_dst, (k + j) & 31u);
+          uint32_t pos = 0;
+#pragma unroll
+          for (uint32_t q = 0; q < 8; q++)
+            if (q == d && k + j < m) pos = next[q]++;
+          if (sub == j) {
+            d_mine = d;
+            pos_mine = pos;
+          }
+        }
+        if (k + sub < m) {
+          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(recs + (size_t)(r0 + k + sub) * 32) + l8);
+          uint8_t* base = P.rbuf[0];
+#pragma unroll
+          for (uint32_t q = 1; q < 8; q++)
+            if (q == d_mine) base = P.rbuf[q];
+          reinterpret_cast<uint4*>(base + (size_t)my_rank * region_bytes + (size_t)pos_mine * ZKB_LOG_BYTES)[l8] = v;
+        }
+      }
+    }
+  }
+}
+
+// per-VM byte counts of one stream kind (input of the scan that places a VM's records in the sink's region)
+__global__ void __launch_bounds__(128, 16) zkb_kind_count_kernel(const DevBatch B, uint32_t kind, uint32_t rec_bytes_k, uint32_t* __restrict__ counts) {
+  for (uint32_t vm = blockIdx.x * blockDim.x + threadIdx.x; vm < B.n_vms; vm += gridDim.x * blockDim.x) counts[vm] = B.hot[vm].x[X_COUNT0 + kind] * rec_bytes_k;
+}
+
+// concat of one stream kind into the sink's region of this rank: one warp per VM, 8-byte copies (RefundRec is 8 bytes)
+__global__ void __launch_bounds__(128, 16) zkb_kind_push_kernel(const DevBatch B, uint32_t kind, uint32_t rec_bytes_k, const uint32_t* __restrict__ offs,
+                                                               uint8_t* __restrict__ dst_region) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
+    const uint32_t bytes = B.hot[vm].x[X_COUNT0 + kind] * rec_bytes_k;
+    const uint8_t* src = B.streams[kind] + (size_t)vm * B.cap[kind] * rec_bytes_k;
+    uint8_t* dst = dst_region + offs[vm];
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      const uint32_t n16 = bytes / 16;
+      uint32_t i = lane;
+      for (; i + 96 < n16; i += 128) {   // four independent transfers in flight per lane
+        const uint4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + 32), c = __ldcs(s4 + i + 64), d = __ldcs(s4 + i + 96);
+        d4[i] = a;
+        d4[i + 32] = b;
+        d4[i + 64] = c;
+        d4[i + 96] = d;
+      }
+      for (; i < n16; i += 32) d4[i] = __ldcs(s4 + i);
+    } else {
+      const uint2* s2 = reinterpret_cast<const uint2*>(src);
+      uint2* d2 = reinterpret_cast<uint2*>(dst);
+      for (uint32_t i = lane; i < bytes / 8; i += 32) d2[i] = s2[i];
+    }
+  }
+}
+
+// the mailbox rows: what this rank sent to every destination (records of the exchange), what it pushed to the sink
+// (bytes per gathered kind), and the step tag LAST (fenced) -- a row whose tag equals the step is complete
+__global__ void zkb_mailbox_kernel(PushPeers P, uint32_t world, uint32_t my_rank, const uint64_t* __restrict__ sent /* [8] records per destination */,
+                                   uint32_t sink, uint32_t gather_mask, const uint64_t* __restrict__ kind_bytes /* [6] */, uint64_t step) {
+  const uint32_t d = threadIdx.x;
+  if (d >= world) return;
+  volatile uint64_t* row = P.mbox[d] + (size_t)my_rank * 16;
+  row[0] = sent[d];
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) row[8 + k] = d == sink ? kind_bytes[k] : 0ull;
+  row[1] = gather_mask;
+  row[14] = sink;
+  __threadfence_system();
+  row[15] = step;
+}
+
 }  // namespace zkb
 
 struct ZkbComm {
@@ -182,6 +290,19 @@ struct ZkbComm {
   uint64_t counts_capacity = 0;
   cudaEvent_t ev = nullptr;
   cudaEvent_t ev_packed = nullptr;   // recorded once the last collective has read everything it needs from the batch
+  // one-sided path (zkb_push_*): IPC-mapped receive buffers + mailboxes of every rank
+  bool push_ready = false;
+  uint8_t* rbuf = nullptr;           // [world] exchange regions, then [world] gather regions
+  uint64_t* mbox = nullptr;          // [world][16]
+  uint64_t x_region = 0, g_region = 0;
+  zkb::PushPeers peers{};
+  void* peer_opened[16] = {};
+  uint32_t* d_kind_offs = nullptr;   // [6][n_vms] per-VM byte offsets of the gathered kinds
+  uint64_t* d_kind_bytes = nullptr;  // [8]
+  uint64_t* d_sent = nullptr;        // [8]
+  uint64_t kind_offs_capacity = 0;
+  uint64_t push_step = 0;
+  uint64_t* h_mbox = nullptr;        // pinned mirror of the mailbox
 };
 
 #define NCCL_OK(c, expr)                                                                                          \
@@ -259,6 +380,14 @@ int32_t zkb_comm_destroy(ZkbComm* c) {
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->ev) cudaEventDestroy(c->ev);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+  for (void* p : c->peer_opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  if (c->rbuf) cudaFree(c->rbuf);
+  if (c->mbox) cudaFree(c->mbox);
+  if (c->d_kind_offs) cudaFree(c->d_kind_offs);
+  if (c->d_kind_bytes) cudaFree(c->d_kind_bytes);
+  if (c->d_sent) cudaFree(c->d_sent);
+  if (c->h_mbox) cudaFreeHost(c->h_mbox);
   delete c;
   return ZKB_OK;
 }
@@ -399,6 +528,158 @@ int32_t zkb_exchange_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, i
   if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world) return ZKB_ERR_INVALID_ARGUMENT;
   return comm_step(b, c, true, gather_kinds_mask & 63u, dst_rank, share_out, n_share_out, src_offsets_out, concat_out, concat_offsets_out,
                    (cudaStream_t)cuda_stream);
+}
+
+// ---- one-sided exchange over peer memory ---------------------------------------------------------------------------
+// collective, once: receive regions sized for `b`'s capacities, IPC handles all-gathered through NCCL, peers mapped
+static int32_t push_setup(ZkbBatch* b, ZkbComm* c, cudaStream_t st) {
+  const uint32_t world = (uint32_t)c->world;
+  const uint64_t n = b->cfg.n_vms;
+  c->x_region = (n * b->cfg.cap_records[ZKB_STREAM_LOG] * ZKB_LOG_BYTES + 255) / 256 * 256;
+  uint64_t g = 0;
+  const uint32_t small_kinds[3] = {ZKB_STREAM_DECOMMIT, ZKB_STREAM_FRAME, ZKB_STREAM_REFUND};
+  for (uint32_t k : small_kinds) g += (n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
+  c->g_region = g;
+  // every rank must use the same region sizes: take the maximum
+  uint64_t* h = c->h_sizes;
+  h[(size_t)c->rank * 16 + 0] = c->x_region;
+  h[(size_t)c->rank * 16 + 1] = c->g_region;
+  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 16, h + (size_t)c->rank * 16, 128, cudaMemcpyHostToDevice, st));
+  NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 16, c->d_sizes, 16, ncclUint64, c->comm, st));
+  CUDA_OK(cudaMemcpyAsync(h, c->d_sizes, (size_t)world * 128, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (uint32_t r = 0; r < world; r++) {
+    c->x_region = std::max(c->x_region, h[(size_t)r * 16 + 0]);
+    c->g_region = std::max(c->g_region, h[(size_t)r * 16 + 1]);
+  }
+  cudaError_t e = cudaMalloc(&c->rbuf, (size_t)world * (c->x_region + c->g_region));
+  if (e == cudaSuccess) e = cudaMalloc(&c->mbox, (size_t)world * 16 * 8);
+  if (e == cudaSuccess) e = cudaMemset(c->mbox, 0, (size_t)world * 16 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_kind_bytes, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_sent, 64);
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_mbox, (size_t)world * 16 * 8, cudaHostAllocDefault);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb push buffers: ") + cudaGetErrorString(e));
+  // IPC handles of (rbuf, mbox) to everybody: 2 x 64 bytes per rank through the same all-gather
+  struct Handles {
+    cudaIpcMemHandle_t rbuf, mbox;
+  };
+  static_assert(sizeof(Handles) == 128, "two CUDA IPC handles");
+  Handles mine;
+  CUDA_OK(cudaIpcGetMemHandle(&mine.rbuf, c->rbuf));
+  CUDA_OK(cudaIpcGetMemHandle(&mine.mbox, c->mbox));
+  memcpy(h + (size_t)c->rank * 16, &mine, 128);
+  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 16, h + (size_t)c->rank * 16, 128, cudaMemcpyHostToDevice, st));
+  NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 16, c->d_sizes, 16, ncclUint64, c->comm, st));
+  CUDA_OK(cudaMemcpyAsync(h, c->d_sizes, (size_t)world * 128, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (uint32_t r = 0; r < world; r++) {
+    if ((int)r == c->rank) {
+      c->peers.rbuf[r] = c->rbuf;
+      c->peers.mbox[r] = c->mbox;
+      continue;
+    }
+    Handles hr;
+    memcpy(&hr, h + (size_t)r * 16, 128);
+    void *p0 = nullptr, *p1 = nullptr;
+    cudaError_t e0 = cudaIpcOpenMemHandle(&p0, hr.rbuf, cudaIpcMemLazyEnablePeerAccess);
+    cudaError_t e1 = e0 == cudaSuccess ? cudaIpcOpenMemHandle(&p1, hr.mbox, cudaIpcMemLazyEnablePeerAccess) : e0;
+    if (e1 != cudaSuccess) return set_err(ZKB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer ") + std::to_string(r) + "): " + cudaGetErrorString(e1));
+    c->peer_opened[2 * r] = p0;
+    c->peer_opened[2 * r + 1] = p1;
+    c->peers.rbuf[r] = (uint8_t*)p0;
+    c->peers.mbox[r] = (uint64_t*)p1;
+  }
+  c->push_ready = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_push_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32_t dst_rank, uint64_t* step_out, void* cuda_stream) {
+  if (!b || !c || !b->cfg.witness_mode || dst_rank < 0 || dst_rank >= c->world) return ZKB_ERR_INVALID_ARGUMENT;
+  const uint32_t allowed = 1u << ZKB_STREAM_DECOMMIT | 1u << ZKB_STREAM_FRAME | 1u << ZKB_STREAM_REFUND;
+  if (gather_kinds_mask & ~allowed) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_step gathers DECOMMIT / FRAME / REFUND (whole-witness concat: zkb_gather_streams)");
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const uint32_t n = b->cfg.n_vms, world = (uint32_t)c->world;
+  if (!c->push_ready) {
+    int32_t rc = push_setup(b, c, st);
+    if (rc != ZKB_OK) return rc;
+  }
+  if ((uint64_t)n * b->cfg.cap_records[ZKB_STREAM_LOG] * ZKB_LOG_BYTES > c->x_region)
+    return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_step: batch larger than the one the receive regions were sized for");
+  if ((uint64_t)world * n > c->counts_capacity) {
+    if (c->d_counts) CUDA_OK(cudaFree(c->d_counts));
+    c->d_counts = nullptr;
+    CUDA_OK(cudaMalloc(&c->d_counts, (size_t)world * n * 4));
+    c->counts_capacity = (uint64_t)world * n;
+  }
+  if ((uint64_t)ZKB_N_STREAMS * n > c->kind_offs_capacity) {
+    if (c->d_kind_offs) CUDA_OK(cudaFree(c->d_kind_offs));
+    c->d_kind_offs = nullptr;
+    CUDA_OK(cudaMalloc(&c->d_kind_offs, (size_t)ZKB_N_STREAMS * n * 4));
+    c->kind_offs_capacity = (uint64_t)ZKB_N_STREAMS * n;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + 3) / 4, (uint32_t)n_sm * 2));
+  // NOTHING below waits on the host: record counts are read on the device, so the caller only has to order `st` behind
+  // the batch's launch (an event) and may queue the next pass at once
+  const uint64_t step = ++c->push_step;
+  CUDA_OK(cudaMemsetAsync(c->d_sent, 0, 64, st));
+  CUDA_OK(cudaMemsetAsync(c->d_kind_bytes, 0, 64, st));
+  zkb::zkb_bucket_count_kernel<<<grid, 128, 0, st>>>(b->d, world, c->d_counts);
+  zkb::zkb_bucket_scan_kernel<<<world, 128, 0, st>>>(c->d_counts, n, c->d_sent);
+  zkb::zkb_bucket_push_kernel<<<grid, 128, 0, st>>>(b->d, world, (uint32_t)c->rank, c->d_counts, c->peers, c->x_region);
+  uint64_t at = 0;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+    if (!((gather_kinds_mask >> k) & 1u)) continue;
+    uint32_t* offs = c->d_kind_offs + (size_t)k * n;
+    zkb::zkb_kind_count_kernel<<<std::max(1u, std::min<uint32_t>((n + 127) / 128, (uint32_t)n_sm)), 128, 0, st>>>(b->d, k, REC_BYTES[k], offs);
+    zkb::zkb_bucket_scan_kernel<<<1, 128, 0, st>>>(offs, n, c->d_kind_bytes + k);
+    uint8_t* region = c->peers.rbuf[dst_rank] + (size_t)world * c->x_region + (size_t)c->rank * c->g_region + at;
+    zkb::zkb_kind_push_kernel<<<grid, 128, 0, st>>>(b->d, k, REC_BYTES[k], offs, region);
+    at += ((uint64_t)n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
+  }
+  zkb::zkb_mailbox_kernel<<<1, 32, 0, st>>>(c->peers, world, (uint32_t)c->rank, c->d_sent, (uint32_t)dst_rank, gather_kinds_mask, c->d_kind_bytes, step);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(c->ev_packed, st));
+  if (step_out) *step_out = step;
+  return ZKB_OK;
+}
+
+// Waits (host) until every source rank's mailbox row carries `step`, i.e. all of that step's pushes into THIS rank's
+// regions have landed.  share_ptrs_out[s] / share_records_out[s]: source s's LOG records for this rank; on that step's sink
+// also concat_ptrs_out[s * 6 + k] / concat_bytes_out[s * 6 + k] for the gathered kinds.  timeout_ms = 0: a single check
+// (ZKB_ERR_CUDA "not complete" when rows are missing).
+int32_t zkb_push_result(ZkbBatch* b, ZkbComm* c, uint64_t step, uint32_t timeout_ms, void** share_ptrs_out, uint64_t* share_records_out,
+                        void** concat_ptrs_out, uint64_t* concat_bytes_out) {
+  if (!b || !c || !c->push_ready) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(c->device));
+  const uint32_t world = (uint32_t)c->world;
+  const uint64_t n = b->cfg.n_vms;
+  for (uint32_t waited = 0;; waited++) {
+    CUDA_OK(cudaMemcpy(c->h_mbox, c->mbox, (size_t)world * 16 * 8, cudaMemcpyDeviceToHost));
+    bool all = true;
+    for (uint32_t s = 0; s < world; s++) all = all && c->h_mbox[(size_t)s * 16 + 15] >= step;
+    if (all) break;
+    if (waited >= timeout_ms * 10u) return set_err(ZKB_ERR_CUDA, "zkb_push_result: not complete");
+    struct timespec ts = {0, 100000};
+    nanosleep(&ts, nullptr);
+  }
+  for (uint32_t s = 0; s < world; s++) {
+    const uint64_t* row = c->h_mbox + (size_t)s * 16;
+    if (row[15] != step) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_result: a later step has already overwritten this one");
+    if (share_ptrs_out) share_ptrs_out[s] = c->rbuf + (size_t)s * c->x_region;
+    if (share_records_out) share_records_out[s] = row[0];
+    uint64_t at = 0;
+    const bool to_me = row[14] == (uint64_t)c->rank;
+    for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+      const bool in_mask = ((row[1] >> k) & 1u) != 0;
+      if (concat_ptrs_out) concat_ptrs_out[(size_t)s * 6 + k] = (to_me && in_mask) ? c->rbuf + (size_t)world * c->x_region + (size_t)s * c->g_region + at : nullptr;
+      if (concat_bytes_out) concat_bytes_out[(size_t)s * 6 + k] = (to_me && in_mask) ? row[8 + k] : 0;
+      if (in_mask) at += (n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
+    }
+  }
+  return ZKB_OK;
 }
 
 }  // extern "C"

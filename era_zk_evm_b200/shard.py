@@ -263,6 +263,8 @@ class Comm:
         lib.zkb_gather_streams.argtypes = [vp, vp, u32, i32, C.POINTER(vp), vp, vp]
         lib.zkb_exchange_logs.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(u64), vp, vp]
         lib.zkb_comm_wait_packed.argtypes = [vp, vp]
+        lib.zkb_push_step.argtypes = [vp, vp, u32, i32, C.POINTER(u64), vp]
+        lib.zkb_push_result.argtypes = [vp, vp, u64, u32, vp, vp, vp, vp]
         lib.zkb_exchange_step.argtypes = [vp, vp, u32, i32, C.POINTER(vp), C.POINTER(u64), vp, C.POINTER(vp), vp, vp]
         lib.zkb_last_error.restype = C.c_char_p
         self.rank, self.world, self.device = dist.get_rank(group), dist.get_world_size(group), device
@@ -323,6 +325,29 @@ class Comm:
                 lo, hi = int(offsets[k, 0]), int(offsets[k, self.world])
                 got[k] = (device_bytes_as_tensor(q.value + lo, hi - lo, self.device), (offsets[k] - offsets[k, 0]).astype(np.int64))
         return share, got
+
+    def push_step(self, batch, gather_kinds, dst: int, stream=None) -> int:
+        """one-sided exchange step over NVLink peer memory (zkb_push_step): fully asynchronous on `stream`; returns the step tag"""
+        mask = 0
+        for k in gather_kinds:
+            mask |= 1 << k
+        step = self._C.c_uint64()
+        self._check(self._lib.zkb_push_step(batch._h, self._h, mask, dst, self._C.byref(step), stream))
+        return step.value
+
+    def push_result(self, batch, step: int, timeout_ms: int = 20000):
+        """waits for every source's pushes of `step`; returns ([uint8 tensor per source rank: its LOG records for this rank],
+        {kind: [uint8 tensor per source rank]} -- non-empty on that step's sink only)"""
+        C, w = self._C, self.world
+        sp, sn = (C.c_void_p * w)(), (C.c_uint64 * w)()
+        cp, cn = (C.c_void_p * (w * 6))(), (C.c_uint64 * (w * 6))()
+        self._check(self._lib.zkb_push_result(batch._h, self._h, step, timeout_ms, sp, sn, cp, cn))
+        shares = [device_bytes_as_tensor(sp[s] or 0, int(sn[s]) * 128, self.device) for s in range(w)]
+        concat = {}
+        for k in range(6):
+            if any(cp[s * 6 + k] for s in range(w)):
+                concat[k] = [device_bytes_as_tensor(cp[s * 6 + k] or 0, int(cn[s * 6 + k]) if cp[s * 6 + k] else 0, self.device) for s in range(w)]
+        return shares, concat
 
     def exchange_logs(self, batch, stream=None):
         """collective; returns (uint8 tensor view of this rank's share of every rank's LOG records, first record of every

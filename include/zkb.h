@@ -329,6 +329,19 @@ int32_t zkb_exchange_logs(ZkbBatch* b, ZkbComm* c, void** dptr_out, uint64_t* n_
  * are then left in flight on cuda_stream.  What a multi-GPU host loop calls once per pass. */
 int32_t zkb_exchange_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32_t dst_rank, void** share_out, uint64_t* n_share_out,
                           uint64_t* src_offsets_out, void** concat_out, uint64_t* concat_offsets_out, void* cuda_stream);
+/* The same step ONE-SIDED over NVLink peer memory (receive buffers of all ranks mapped through CUDA IPC at the first call,
+ * which is collective): the LOG partition and the concat of the small streams (gather_kinds_mask within DECOMMIT | FRAME |
+ * REFUND) are written straight into the destination GPUs' memory by 128-thread kernels that fit next to the persistent
+ * interpreter CTA -- no NCCL on the data path, no SM kept free for it, and NO host synchronisation: record counts are read
+ * on the device, so the caller orders cuda_stream behind the batch's launch with an event and queues the next pass at once.
+ * *step_out: the tag under which zkb_push_result finds this step's data. */
+int32_t zkb_push_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32_t dst_rank, uint64_t* step_out, void* cuda_stream);
+/* Host: waits until every source rank's pushes of `step` into THIS rank have landed (mailbox tags), then reports, per source
+ * rank s, its LOG records for this rank (share_ptrs_out[s], share_records_out[s]) and -- on that step's sink -- the gathered
+ * streams (concat_ptrs_out[s * 6 + kind], concat_bytes_out[s * 6 + kind]).  Device pointers, valid until the next step that
+ * targets them; timeout_ms = 0 checks once. */
+int32_t zkb_push_result(ZkbBatch* b, ZkbComm* c, uint64_t step, uint32_t timeout_ms, void** share_ptrs_out, uint64_t* share_records_out,
+                        void** concat_ptrs_out, uint64_t* concat_bytes_out);
 /* Makes cuda_stream wait until the LAST collective on `c` has read everything it needs from its batch (its pack kernels):
  * a host loop runs the collectives of pass k on a side stream, orders only this before the restore / launch of pass k + 1
  * on the main stream, and leaves the NCCL transfers in flight underneath that launch. */

@@ -109,6 +109,18 @@ def _cabi_worker(rank, world, port, n_total, out_dir):
             torch.cuda.synchronize()
             saved[f"x{attempt}"] = share.cpu().numpy()
             saved[f"xs{attempt}"] = src
+        # the one-sided variant over NVLink peer memory: same shares (per source), same concat on the rotating sink
+        small = [records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND]
+        for i in range(world + 1):
+            dst = i % world
+            tag = comm.push_step(b, small, dst)
+            torch.cuda.synchronize()
+            shares, concat = comm.push_result(b, tag)
+            saved[f"p{i}"] = np.concatenate([t.cpu().numpy() for t in shares]) if shares else np.zeros(0, np.uint8)
+            if rank == dst:
+                for k in small:
+                    saved[f"pc{i}_k{k}"] = np.concatenate([t.cpu().numpy() for t in concat[k]])
+            dist.barrier()      # nobody starts the next step's pushes into buffers that are still being read
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **saved)
         dist.barrier()
         comm.close()
@@ -147,3 +159,9 @@ def test_cabi_gather_and_hash_partitioned_exchange_match_the_oracle(tmp_path, or
         want = logs[dest == r]
         for attempt in range(2):
             assert got[r][f"x{attempt}"].tobytes() == want.tobytes(), f"rank {r} share (attempt {attempt})"
+        for i in range(world + 1):
+            assert got[r][f"p{i}"].tobytes() == want.tobytes(), f"rank {r} one-sided share (step {i})"
+            if i % world == r:
+                for k in (records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND):
+                    whole = np.concatenate([orc.read_stream(vm, k).view(np.uint8) for vm in range(n_total)])
+                    assert np.array_equal(got[r][f"pc{i}_k{k}"], whole), (r, i, records.STREAM_NAMES[k])
