@@ -180,6 +180,7 @@ struct PushPeers {
 __global__ void __launch_bounds__(128, 16) zkb_bucket_push_kernel(const DevBatch B, uint32_t world, uint32_t my_rank, const uint32_t* __restrict__ offs,
                                                                  PushPeers P, uint64_t region_bytes) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t cap_records = (uint32_t)(region_bytes / ZKB_LOG_BYTES);   // beyond it nothing is written; the mailbox row reports the overflow
   const uint32_t sub = lane >> 3, l8 = lane & 7u;   // a record is moved by 8 lanes x 16 bytes: four records per warp step
   for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
     const uint32_t n = B.hot[vm].x[X_COUNT0 + ZKB_STREAM_LOG];
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128, 16) zkb_bucket_push_kernel(const DevBatch
             pos_mine = pos;
           }
         }
-        if (k + sub < m) {
+        if (k + sub < m && pos_mine < cap_records) {
           const uint4 v = __ldcs(reinterpret_cast<const uint4*>(recs + (size_t)(r0 + k + sub) * 32) + l8);
           uint8_t* base = P.rbuf[0];
 #pragma unroll
@@ -230,11 +231,12 @@ __global__ void __launch_bounds__(128, 16) zkb_kind_count_kernel(const DevBatch 
 
 // concat of one stream kind into the sink's region of this rank: one warp per VM, 8-byte copies (RefundRec is 8 bytes)
 __global__ void __launch_bounds__(128, 16) zkb_kind_push_kernel(const DevBatch B, uint32_t kind, uint32_t rec_bytes_k, const uint32_t* __restrict__ offs,
-                                                               uint8_t* __restrict__ dst_region) {
+                                                               uint8_t* __restrict__ dst_region, uint64_t region_bytes) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t vm = blockIdx.x * 4 + warp; vm < B.n_vms; vm += gridDim.x * 4) {
     const uint32_t bytes = B.hot[vm].x[X_COUNT0 + kind] * rec_bytes_k;
     const uint8_t* src = B.streams[kind] + (size_t)vm * B.cap[kind] * rec_bytes_k;
+    if ((uint64_t)offs[vm] + bytes > region_bytes) continue;   // overflow: reported through the mailbox row
     uint8_t* dst = dst_region + offs[vm];
     if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
       const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -260,11 +262,16 @@ __global__ void __launch_bounds__(128, 16) zkb_kind_push_kernel(const DevBatch B
 // the mailbox rows: what this rank sent to every destination (records of the exchange), what it pushed to the sink
 // (bytes per gathered kind), and the step tag LAST (fenced) -- a row whose tag equals the step is complete
 __global__ void zkb_mailbox_kernel(PushPeers P, uint32_t world, uint32_t my_rank, const uint64_t* __restrict__ sent /* [8] records per destination */,
-                                   uint32_t sink, uint32_t gather_mask, const uint64_t* __restrict__ kind_bytes /* [6] */, uint64_t step) {
+                                   uint32_t sink, uint32_t gather_mask, const uint64_t* __restrict__ kind_bytes /* [6] */, uint64_t step,
+                                   uint64_t x_region, const uint64_t* __restrict__ g_kind) {
   const uint32_t d = threadIdx.x;
   if (d >= world) return;
   volatile uint64_t* row = P.mbox[d] + (size_t)my_rank * 16;
   row[0] = sent[d];
+  uint64_t overflow = sent[d] * ZKB_LOG_BYTES > x_region ? 1ull : 0ull;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++)
+    if (d == sink && ((gather_mask >> k) & 1u) && kind_bytes[k] > g_kind[k]) overflow = 1ull;
+  row[2] = overflow;
   for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) row[8 + k] = d == sink ? kind_bytes[k] : 0ull;
   row[1] = gather_mask;
   row[14] = sink;
@@ -294,7 +301,9 @@ struct ZkbComm {
   bool push_ready = false;
   uint8_t* rbuf = nullptr;           // [world] exchange regions, then [world] gather regions
   uint64_t* mbox = nullptr;          // [world][16]
-  uint64_t x_region = 0, g_region = 0;
+  uint64_t x_region = 0, g_region = 0;   // bytes per source rank: exchange region, gather region (sum of g_kind)
+  uint64_t g_kind[ZKB_N_STREAMS] = {};     // bytes per source rank and gathered kind
+  uint32_t g_mask = 0;
   zkb::PushPeers peers{};
   void* peer_opened[16] = {};
   uint32_t* d_kind_offs = nullptr;   // [6][n_vms] per-VM byte offsets of the gathered kinds
@@ -532,30 +541,45 @@ int32_t zkb_exchange_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, i
 
 // ---- one-sided exchange over peer memory ---------------------------------------------------------------------------
 // collective, once: receive regions sized for `b`'s capacities, IPC handles all-gathered through NCCL, peers mapped
-static int32_t push_setup(ZkbBatch* b, ZkbComm* c, cudaStream_t st) {
+static int32_t push_setup(ZkbBatch* b, ZkbComm* c, uint32_t gather_mask, cudaStream_t st) {
   const uint32_t world = (uint32_t)c->world;
   const uint64_t n = b->cfg.n_vms;
-  c->x_region = (n * b->cfg.cap_records[ZKB_STREAM_LOG] * ZKB_LOG_BYTES + 255) / 256 * 256;
-  uint64_t g = 0;
-  const uint32_t small_kinds[3] = {ZKB_STREAM_DECOMMIT, ZKB_STREAM_FRAME, ZKB_STREAM_REFUND};
-  for (uint32_t k : small_kinds) g += (n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
-  c->g_region = g;
-  // every rank must use the same region sizes: take the maximum
+  // regions are sized from what this batch ACTUALLY emitted (x 1.5: a destination cannot receive more than a source's whole
+  // log; per-VM slab capacities are several times that), the maximum over the ranks; a later, larger batch is caught by
+  // the overflow flag of the mailbox row
+  const uint32_t* cnt = nullptr;
+  int32_t rc0 = summary(b, &cnt);
+  if (rc0 != ZKB_OK) return rc0;
+  uint64_t actual[ZKB_N_STREAMS] = {};
+  for (uint64_t v = 0; v < n; v++)
+    for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) actual[k] += (uint64_t)cnt[v * 8 + k] * REC_BYTES[k];
   uint64_t* h = c->h_sizes;
-  h[(size_t)c->rank * 16 + 0] = c->x_region;
-  h[(size_t)c->rank * 16 + 1] = c->g_region;
-  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 16, h + (size_t)c->rank * 16, 128, cudaMemcpyHostToDevice, st));
+  uint64_t* mine = h + (size_t)c->rank * 16;
+  memset(mine, 0, 128);
+  mine[0] = std::min<uint64_t>(n * b->cfg.cap_records[ZKB_STREAM_LOG] * ZKB_LOG_BYTES, actual[ZKB_STREAM_LOG] + actual[ZKB_STREAM_LOG] / 2 + (1u << 20));
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++)
+    if ((gather_mask >> k) & 1u) mine[8 + k] = std::min<uint64_t>(n * b->cfg.cap_records[k] * REC_BYTES[k], actual[k] + actual[k] / 4 + (1u << 20));
+  CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 16, mine, 128, cudaMemcpyHostToDevice, st));
   NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 16, c->d_sizes, 16, ncclUint64, c->comm, st));
   CUDA_OK(cudaMemcpyAsync(h, c->d_sizes, (size_t)world * 128, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  c->x_region = 0;
+  c->g_region = 0;
+  c->g_mask = gather_mask;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) c->g_kind[k] = 0;
   for (uint32_t r = 0; r < world; r++) {
     c->x_region = std::max(c->x_region, h[(size_t)r * 16 + 0]);
-    c->g_region = std::max(c->g_region, h[(size_t)r * 16 + 1]);
+    for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) c->g_kind[k] = std::max(c->g_kind[k], h[(size_t)r * 16 + 8 + k]);
+  }
+  c->x_region = (c->x_region + 255) / 256 * 256;
+  for (uint32_t k = 0; k < ZKB_N_STREAMS; k++) {
+    c->g_kind[k] = (c->g_kind[k] + 255) / 256 * 256;
+    c->g_region += c->g_kind[k];
   }
   cudaError_t e = cudaMalloc(&c->rbuf, (size_t)world * (c->x_region + c->g_region));
   if (e == cudaSuccess) e = cudaMalloc(&c->mbox, (size_t)world * 16 * 8);
   if (e == cudaSuccess) e = cudaMemset(c->mbox, 0, (size_t)world * 16 * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_kind_bytes, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_kind_bytes, 128);   // [0..8) bytes pushed per kind, [8..14) the per-kind region sizes
   if (e == cudaSuccess) e = cudaMalloc(&c->d_sent, 64);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_mbox, (size_t)world * 16 * 8, cudaHostAllocDefault);
   if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb push buffers: ") + cudaGetErrorString(e));
@@ -564,10 +588,10 @@ static int32_t push_setup(ZkbBatch* b, ZkbComm* c, cudaStream_t st) {
     cudaIpcMemHandle_t rbuf, mbox;
   };
   static_assert(sizeof(Handles) == 128, "two CUDA IPC handles");
-  Handles mine;
-  CUDA_OK(cudaIpcGetMemHandle(&mine.rbuf, c->rbuf));
-  CUDA_OK(cudaIpcGetMemHandle(&mine.mbox, c->mbox));
-  memcpy(h + (size_t)c->rank * 16, &mine, 128);
+  Handles my_handles;
+  CUDA_OK(cudaIpcGetMemHandle(&my_handles.rbuf, c->rbuf));
+  CUDA_OK(cudaIpcGetMemHandle(&my_handles.mbox, c->mbox));
+  memcpy(h + (size_t)c->rank * 16, &my_handles, 128);
   CUDA_OK(cudaMemcpyAsync(c->d_sizes + (size_t)c->rank * 16, h + (size_t)c->rank * 16, 128, cudaMemcpyHostToDevice, st));
   NCCL_OK(c, c->api->AllGather(c->d_sizes + (size_t)c->rank * 16, c->d_sizes, 16, ncclUint64, c->comm, st));
   CUDA_OK(cudaMemcpyAsync(h, c->d_sizes, (size_t)world * 128, cudaMemcpyDeviceToHost, st));
@@ -589,6 +613,7 @@ static int32_t push_setup(ZkbBatch* b, ZkbComm* c, cudaStream_t st) {
     c->peers.rbuf[r] = (uint8_t*)p0;
     c->peers.mbox[r] = (uint64_t*)p1;
   }
+  CUDA_OK(cudaMemcpy(c->d_kind_bytes + 8, c->g_kind, sizeof(c->g_kind), cudaMemcpyHostToDevice));
   c->push_ready = true;
   return ZKB_OK;
 }
@@ -601,11 +626,10 @@ int32_t zkb_push_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const uint32_t n = b->cfg.n_vms, world = (uint32_t)c->world;
   if (!c->push_ready) {
-    int32_t rc = push_setup(b, c, st);
+    int32_t rc = push_setup(b, c, gather_kinds_mask, st);
     if (rc != ZKB_OK) return rc;
   }
-  if ((uint64_t)n * b->cfg.cap_records[ZKB_STREAM_LOG] * ZKB_LOG_BYTES > c->x_region)
-    return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_step: batch larger than the one the receive regions were sized for");
+  if (gather_kinds_mask & ~c->g_mask) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_step: stream kinds outside the mask of the first call (the receive regions are sized then)");
   if ((uint64_t)world * n > c->counts_capacity) {
     if (c->d_counts) CUDA_OK(cudaFree(c->d_counts));
     c->d_counts = nullptr;
@@ -636,10 +660,10 @@ int32_t zkb_push_step(ZkbBatch* b, ZkbComm* c, uint32_t gather_kinds_mask, int32
     zkb::zkb_kind_count_kernel<<<std::max(1u, std::min<uint32_t>((n + 127) / 128, (uint32_t)n_sm)), 128, 0, st>>>(b->d, k, REC_BYTES[k], offs);
     zkb::zkb_bucket_scan_kernel<<<1, 128, 0, st>>>(offs, n, c->d_kind_bytes + k);
     uint8_t* region = c->peers.rbuf[dst_rank] + (size_t)world * c->x_region + (size_t)c->rank * c->g_region + at;
-    zkb::zkb_kind_push_kernel<<<grid, 128, 0, st>>>(b->d, k, REC_BYTES[k], offs, region);
-    at += ((uint64_t)n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
+    zkb::zkb_kind_push_kernel<<<grid, 128, 0, st>>>(b->d, k, REC_BYTES[k], offs, region, c->g_kind[k]);
+    at += c->g_kind[k];
   }
-  zkb::zkb_mailbox_kernel<<<1, 32, 0, st>>>(c->peers, world, (uint32_t)c->rank, c->d_sent, (uint32_t)dst_rank, gather_kinds_mask, c->d_kind_bytes, step);
+  zkb::zkb_mailbox_kernel<<<1, 32, 0, st>>>(c->peers, world, (uint32_t)c->rank, c->d_sent, (uint32_t)dst_rank, gather_kinds_mask, c->d_kind_bytes, step, c->x_region, c->d_kind_bytes + 8);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(c->ev_packed, st));
   if (step_out) *step_out = step;
@@ -668,6 +692,7 @@ int32_t zkb_push_result(ZkbBatch* b, ZkbComm* c, uint64_t step, uint32_t timeout
   for (uint32_t s = 0; s < world; s++) {
     const uint64_t* row = c->h_mbox + (size_t)s * 16;
     if (row[15] != step) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_push_result: a later step has already overwritten this one");
+    if (row[2]) return set_err(ZKB_ERR_OUT_OF_MEMORY, "zkb_push_result: a receive region overflowed (the batch emitted more than the one the regions were sized from)");
     if (share_ptrs_out) share_ptrs_out[s] = c->rbuf + (size_t)s * c->x_region;
     if (share_records_out) share_records_out[s] = row[0];
     uint64_t at = 0;
@@ -676,7 +701,7 @@ int32_t zkb_push_result(ZkbBatch* b, ZkbComm* c, uint64_t step, uint32_t timeout
       const bool in_mask = ((row[1] >> k) & 1u) != 0;
       if (concat_ptrs_out) concat_ptrs_out[(size_t)s * 6 + k] = (to_me && in_mask) ? c->rbuf + (size_t)world * c->x_region + (size_t)s * c->g_region + at : nullptr;
       if (concat_bytes_out) concat_bytes_out[(size_t)s * 6 + k] = (to_me && in_mask) ? row[8 + k] : 0;
-      if (in_mask) at += (n * b->cfg.cap_records[k] * REC_BYTES[k] + 255) / 256 * 256;
+      if (in_mask) at += c->g_kind[k];
     }
   }
   return ZKB_OK;
