@@ -89,6 +89,41 @@ class GpuVmBatch(_binding.Batch):
         self._check(self._lib.zkb_fetch_stream_packed_async(self._h, kind, host_ptr, host_capacity, offsets.ctypes.data, stream))
         return offsets
 
+    # -- the device-side consumer ----------------------------------------------------
+    def consume(self, cycles_per_snapshot: int, stream=None):
+        """per-circuit-batch VmLocalState snapshots every `cycles_per_snapshot` cycles + queue commitments, on the device"""
+        lib, vp, u32, u64 = self._lib, C.c_void_p, C.c_uint32, C.c_uint64
+        lib.zkb_consume.argtypes = [vp, u32, vp]
+        lib.zkb_snapshot_counts.argtypes = [vp, u32, u32, vp]
+        lib.zkb_read_snapshots.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+        lib.zkb_read_queue_digests.argtypes = [vp, u32, u32, vp]
+        lib.zkb_fetch_consumed_async.argtypes = [vp, vp, u64, C.POINTER(u64), vp]
+        self._check(lib.zkb_consume(self._h, cycles_per_snapshot, stream))
+
+    def snapshot_counts(self) -> np.ndarray:
+        out = np.zeros(self.n_vms, dtype=np.uint32)
+        self._check(self._lib.zkb_snapshot_counts(self._h, 0, self.n_vms, out.ctypes.data))
+        return out
+
+    def read_snapshots(self, vm: int) -> np.ndarray:
+        """uint32[n_snapshots, 198]: ZkbSnapshot records of VM `vm` (ZkbLocalState first)"""
+        n = C.c_uint64()
+        self._check(self._lib.zkb_read_snapshots(self._h, vm, None, 0, C.byref(n)))
+        buf = np.zeros(max(n.value // 4, 1), dtype=np.uint32)
+        self._check(self._lib.zkb_read_snapshots(self._h, vm, buf.ctypes.data, n.value, C.byref(n)))
+        return buf[: n.value // 4].reshape(-1, 198)
+
+    def read_queue_digests(self) -> np.ndarray:
+        """uint8[n_vms, 3, 32]: sha256 of the memory / log / decommitment queue of every VM"""
+        out = np.zeros((self.n_vms, 3, 32), dtype=np.uint8)
+        self._check(self._lib.zkb_read_queue_digests(self._h, 0, self.n_vms, out.ctypes.data))
+        return out
+
+    def fetch_consumed_async(self, host_ptr: int, host_capacity: int, stream=None) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.zkb_fetch_consumed_async(self._h, host_ptr, host_capacity, C.byref(n), stream))
+        return n.value
+
     def snapshot(self):
         self._check(self._lib.zkb_snapshot(self._h))
 

@@ -12,6 +12,7 @@
 #include "vm.cuh"
 #include "codec.cuh"
 #include "logsort.cuh"
+#include "consume.cuh"
 
 using namespace zkb;
 
@@ -539,6 +540,13 @@ struct ZkbBatch {
   uint8_t* d_enc = nullptr;
   uint64_t enc_capacity = 0;
   cudaEvent_t ev_enc = nullptr, ev_enc_done = nullptr, ev_blob_read = nullptr;
+  // device-side consumer (consume.cuh): the VMs' pre-run state, snapshots, queue digests
+  VmHot* d_hot_init = nullptr;
+  ConsumeOut consume{};
+  bool consume_valid = false;
+  std::vector<uint32_t> h_n_snaps;
+  uint8_t* d_snap_pack = nullptr;
+  uint64_t snap_pack_capacity = 0;
   cudaStream_t enc_stream = nullptr;   // the encoder's own stream: its passes never queue behind a D2H copy in flight
   bool blob_read_pending = false;
 };
@@ -647,6 +655,8 @@ static int32_t upload(ZkbBatch* b) {
   if (b->hot_dirty) {
     CUDA_OK(cudaMemcpy(b->d.hot, b->h_hot.data(), b->h_hot.size() * sizeof(VmHot), cudaMemcpyHostToDevice));
     b->h2d_bytes += b->h_hot.size() * sizeof(VmHot);
+    // the consumer (zkb_consume) rebuilds every VmLocalState from the state in front of the first recorded cycle
+    CUDA_OK(cudaMemcpyAsync(b->d_hot_init, b->d.hot, b->h_hot.size() * sizeof(VmHot), cudaMemcpyDeviceToDevice, 0));
     b->hot_dirty = false;
     for (size_t v = 0; v < b->h_hot.size(); v++) {
       const VmHot& h = b->h_hot[v];
@@ -754,6 +764,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
     for (int k = 0; k < ZKB_N_STREAMS; k++) ALLOC(d.streams[k], n * (size_t)c.cap_records[k] * REC_BYTES[k], false);
   ALLOC(d.queue, 4, true);
   ALLOC(d.defer, n * ZKB_DEFER_WORDS, true);
+  ALLOC(b->d_hot_init, n, false);
   ALLOC(b->d_offsets, (n + 1) * ZKB_N_STREAMS, false);
 #undef ALLOC
   if (e != cudaSuccess) {
@@ -838,6 +849,7 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->h_fail) cudaFreeHost(b->h_fail);
   if (b->h_offsets[0]) cudaFreeHost(b->h_offsets[0]);
   if (b->d_enc) cudaFree(b->d_enc);
+  if (b->d_snap_pack) cudaFree(b->d_snap_pack);
   if (b->h_enc_totals) cudaFreeHost(b->h_enc_totals);
   if (b->ev_enc) cudaEventDestroy(b->ev_enc);
   if (b->ev_enc_done) cudaEventDestroy(b->ev_enc_done);
@@ -1085,6 +1097,7 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   b->launched = true;
   b->offsets_valid = false;
   b->flat_valid = false;
+  b->consume_valid = false;
   return ZKB_OK;
 }
 
@@ -1425,6 +1438,114 @@ int32_t zkb_fetch_encoded(ZkbBatch* b, void* host_dst, uint64_t host_capacity, u
   int32_t rc = zkb_fetch_encoded_async(b, host_dst, host_capacity, n_bytes, nullptr);
   if (rc != ZKB_OK) return rc;
   CUDA_OK(cudaStreamSynchronize(nullptr));
+  return ZKB_OK;
+}
+
+// ---- device-side consumer (consume.cuh) --------------------------------------------------------
+int32_t zkb_consume(ZkbBatch* b, uint32_t cycles_per_snapshot, void* cuda_stream) {
+  if (!b || !b->cfg.witness_mode || cycles_per_snapshot == 0) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  int32_t rc = upload(b);
+  if (rc != ZKB_OK) return rc;
+  if (wait_last_run(b) != ZKB_OK) return ZKB_ERR_CUDA;
+  const size_t n = b->cfg.n_vms;
+  const uint32_t max_snaps = b->cfg.cap_records[ZKB_STREAM_ROWS] / cycles_per_snapshot + 2;
+  ConsumeOut& o = b->consume;
+  if (!o.snaps || o.max_snaps < max_snaps) {
+    cudaError_t e = dalloc(b, &o.snaps, n * max_snaps * ZKB_SNAP_WORDS, false);
+    if (e == cudaSuccess && !o.n_snaps) e = dalloc(b, &o.n_snaps, n, true);
+    if (e == cudaSuccess && !o.finals) e = dalloc(b, &o.finals, n * 24, true);
+    if (e == cudaSuccess && !o.fstack) e = dalloc(b, &o.fstack, n * (b->cfg.max_depth + 1), true);
+    if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_consume cudaMalloc: ") + cudaGetErrorString(e));
+    o.max_snaps = max_snaps;
+  }
+  o.period = cycles_per_snapshot;
+  o.hot_init = b->d_hot_init;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
+  zkb_consume_state_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8)), 256, 0, st>>>(b->d, o);
+  zkb_consume_hash_kernel<<<(unsigned)((n * 3 + 127) / 128), 128, 0, st>>>(b->d, o);
+  CUDA_OK(cudaGetLastError());
+  b->h_n_snaps.resize(n);
+  CUDA_OK(cudaMemcpyAsync(b->h_n_snaps.data(), o.n_snaps, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  b->consume_valid = true;
+  return ZKB_OK;
+}
+
+int32_t zkb_snapshot_counts(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out) {
+  if (!range_ok(b, vm_lo, vm_hi) || !counts_out || !b->consume_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_snapshot_counts: call zkb_consume first");
+  for (uint32_t v = vm_lo; v < vm_hi; v++) counts_out[v - vm_lo] = b->h_n_snaps[v];
+  return ZKB_OK;
+}
+
+int32_t zkb_read_snapshots(ZkbBatch* b, uint32_t vm, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
+  if (!b || vm >= b->cfg.n_vms || !b->consume_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_read_snapshots: call zkb_consume first");
+  const uint64_t n = (uint64_t)b->h_n_snaps[vm] * sizeof(ZkbSnapshot);
+  if (n_bytes) *n_bytes = n;
+  const uint64_t take = std::min(n, max_bytes);
+  if (dst && take) {
+    CUDA_OK(cudaSetDevice(b->cfg.device));
+    CUDA_OK(cudaMemcpy(dst, b->consume.snaps + (size_t)vm * b->consume.max_snaps * ZKB_SNAP_WORDS, take, cudaMemcpyDeviceToHost));
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_read_queue_digests(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint8_t* digests_out) {
+  if (!range_ok(b, vm_lo, vm_hi) || !digests_out || !b->consume_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_read_queue_digests: call zkb_consume first");
+  if (vm_lo == vm_hi) return ZKB_OK;
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  std::vector<uint32_t> w((size_t)(vm_hi - vm_lo) * 24);
+  CUDA_OK(cudaMemcpy(w.data(), b->consume.finals + (size_t)vm_lo * 24, w.size() * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < w.size(); i++) {   // sha256 digests are big-endian words
+    digests_out[4 * i + 0] = (uint8_t)(w[i] >> 24);
+    digests_out[4 * i + 1] = (uint8_t)(w[i] >> 16);
+    digests_out[4 * i + 2] = (uint8_t)(w[i] >> 8);
+    digests_out[4 * i + 3] = (uint8_t)w[i];
+  }
+  return ZKB_OK;
+}
+
+// all VMs' snapshots packed VM-major (+ the queue digests) into pinned host memory, asynchronously on cuda_stream:
+// [n_vms + 1] u64 snapshot offsets (in snapshots), the snapshots, then n_vms x 3 x 32 bytes of final queue digests (as words)
+__global__ void zkb_pack_snapshots_kernel(const uint32_t* __restrict__ snaps, uint32_t max_snaps, const uint64_t* __restrict__ offsets, uint32_t n_vms,
+                                          uint32_t* __restrict__ out) {
+  const uint32_t vm = blockIdx.x;
+  if (vm >= n_vms) return;
+  const uint64_t lo = offsets[vm], n = (offsets[vm + 1] - lo) * ZKB_SNAP_WORDS;
+  const uint32_t* src = snaps + (size_t)vm * max_snaps * ZKB_SNAP_WORDS;
+  uint32_t* dst = out + lo * ZKB_SNAP_WORDS;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+int32_t zkb_fetch_consumed_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || !b->consume_valid) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_fetch_consumed_async: call zkb_consume first");
+  CUDA_OK(cudaSetDevice(b->cfg.device));
+  const size_t n = b->cfg.n_vms;
+  std::vector<uint64_t> off(n + 1, 0);
+  for (size_t v = 0; v < n; v++) off[v + 1] = off[v] + b->h_n_snaps[v];
+  const uint64_t table = (n + 1) * 8, body = off[n] * sizeof(ZkbSnapshot), tail = n * 96;
+  const uint64_t total = table + body + tail;
+  if (n_bytes) *n_bytes = total;
+  if (!host_dst) return ZKB_OK;
+  if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "zkb_fetch_consumed_async: host buffer too small");
+  if (total > b->snap_pack_capacity) {
+    CUDA_OK(cudaDeviceSynchronize());
+    if (b->d_snap_pack) CUDA_OK(cudaFree(b->d_snap_pack));
+    b->d_snap_pack = nullptr;
+    CUDA_OK(cudaMalloc(&b->d_snap_pack, total + total / 8));
+    b->snap_pack_capacity = total + total / 8;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  memcpy(host_dst, off.data(), table);   // the table is host knowledge already
+  CUDA_OK(cudaMemcpyAsync(b->d_snap_pack, host_dst, table, cudaMemcpyHostToDevice, st));
+  zkb_pack_snapshots_kernel<<<(unsigned)n, 128, 0, st>>>(b->consume.snaps, b->consume.max_snaps, (const uint64_t*)b->d_snap_pack, (uint32_t)n,
+                                                        (uint32_t*)(b->d_snap_pack + table));
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(b->d_snap_pack + table + body, b->consume.finals, tail, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync((uint8_t*)host_dst + table, b->d_snap_pack + table, body + tail, cudaMemcpyDeviceToHost, st));
+  b->d2h_bytes += body + tail;
   return ZKB_OK;
 }
 

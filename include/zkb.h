@@ -124,6 +124,17 @@ typedef struct ZkbLocalState {
   ZkbFrame current_frame;
 } ZkbLocalState;
 
+/* One per-circuit-batch snapshot of the device-side consumer (zkb_consume): the VmLocalState handed to
+ * start_new_execution_cycle of cycle `cycle` (src/witness_trace/mod.rs:11-72), how many records of the memory / log /
+ * decommitment queues precede that cycle, and the queues' running commitments at that point (chaining values of the sha256
+ * chain over the records, each zero-padded to 64-byte blocks; csrc/consume.cuh says why sha256). */
+typedef struct ZkbSnapshot {
+  ZkbLocalState state;
+  uint32_t cycle;
+  uint32_t n_mem, n_log, n_decommit;
+  uint32_t queue_state[3][8];     /* memory, log, decommitment */
+} ZkbSnapshot;
+
 typedef struct ZkbVmStatus {
   uint32_t code;     /* ZkbVmCode */
   uint32_t cycles;   /* cycles executed so far (== monotonic_cycle_counter) */
@@ -247,6 +258,21 @@ int32_t zkb_read_storage(ZkbBatch* b, uint32_t vm, uint8_t shard_id, const uint8
                          const uint8_t key_be[32], uint8_t value_be_out[32]);
 /* read back memory of the current frame's heap (debug / tests; = dump_page_content, memory.rs:300-313) */
 int32_t zkb_read_heap(ZkbBatch* b, uint32_t vm, uint32_t byte_offset, uint32_t n_bytes, uint8_t* out);
+
+/* ---- the device-side consumer: what a downstream-shaped VmWitnessTracer adapter builds, built on the GPU
+ * zkb_consume walks every VM's streams once: a ZkbSnapshot every cycles_per_snapshot cycles (cycle K, 2K, ...; cycle 0 is the
+ * state the host populated) and one after the last cycle, plus the final sha256 of each queue
+ * (== hashlib.sha256 over the queue's records, each zero-padded to a multiple of 64 bytes).  The batch must have been
+ * populated before its first run (the consumer starts from the pre-run state).  With it a host loop moves snapshots +
+ * digests + the query logs across PCIe instead of every row. */
+int32_t zkb_consume(ZkbBatch* b, uint32_t cycles_per_snapshot, void* cuda_stream);
+int32_t zkb_snapshot_counts(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t* counts_out);
+int32_t zkb_read_snapshots(ZkbBatch* b, uint32_t vm, void* dst, uint64_t max_bytes, uint64_t* n_bytes);
+/* digests_out: (vm_hi - vm_lo) x 3 x 32 bytes: sha256 of the memory, log and decommitment queue of every VM */
+int32_t zkb_read_queue_digests(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint8_t* digests_out);
+/* everything zkb_consume produced, packed, into (pinned) host memory on cuda_stream: u64 offsets[n_vms + 1] (first
+ * snapshot of every VM), the snapshots VM-major, then n_vms x 3 x 8 u32 final digest words.  host_dst == NULL: size only. */
+int32_t zkb_fetch_consumed_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream);
 
 /* ---- post-processing (the step right after the path) ---------------------------------- */
 /* Rebuilds on the device, per VM, what the reference's backends hold after the run:

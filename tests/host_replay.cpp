@@ -173,3 +173,103 @@ extern "C" int host_replay_check(void* handle, uint32_t n_vms, uint32_t vm, cons
     return 1;
   }
 }
+
+
+// ---- expected output of the device-side consumer (zkb_consume): the VmLocalState the reference hands to
+// start_new_execution_cycle every `period` cycles and after the last cycle, serialised as ZkbLocalState ----------------
+static void serialise(const VmLocalState& s, ZkbLocalState* o) {
+  std::memset(o, 0, sizeof(*o));
+  s.previous_code_word.to_limbs32(o->previous_code_word);
+  o->previous_code_memory_page = s.previous_code_memory_page;
+  for (int r = 0; r < 15; r++) {
+    s.registers[r].value.to_limbs32(o->registers[r]);
+    if (s.registers[r].is_pointer) o->register_is_pointer |= (uint16_t)(1u << r);
+  }
+  o->flags = (s.flags.overflow_or_less_than_flag ? 1 : 0) | (s.flags.equality_flag ? 2 : 0) | (s.flags.greater_than_flag ? 4 : 0);
+  o->pending_exception = s.pending_exception ? 1 : 0;
+  o->timestamp = s.timestamp;
+  o->monotonic_cycle_counter = s.monotonic_cycle_counter;
+  o->spent_pubdata_counter = s.spent_pubdata_counter;
+  o->memory_page_counter = s.memory_page_counter;
+  o->absolute_execution_step = 0;
+  o->current_ergs_per_pubdata_byte = s.current_ergs_per_pubdata_byte;
+  o->tx_number_in_block = s.tx_number_in_block;
+  o->previous_super_pc = s.previous_super_pc;
+  std::memcpy(o->context_u128_register, s.context_u128_register.data(), 16);
+  o->callstack_depth = (uint32_t)s.inner.size();
+  const CallStackEntry& c = s.current;
+  ZkbFrame& f = o->current_frame;
+  std::memcpy(f.this_address, c.this_address.data(), 20);
+  std::memcpy(f.msg_sender, c.msg_sender.data(), 20);
+  std::memcpy(f.code_address, c.code_address.data(), 20);
+  f.base_memory_page = c.base_memory_page;
+  f.code_page = c.code_page;
+  f.sp = c.sp;
+  f.pc = c.pc;
+  f.exception_handler_location = c.exception_handler_location;
+  f.ergs_remaining = c.ergs_remaining;
+  f.this_shard_id = c.this_shard_id;
+  f.caller_shard_id = c.caller_shard_id;
+  f.code_shard_id = c.code_shard_id;
+  f.is_static = c.is_static;
+  f.is_local_frame = c.is_local_frame;
+  std::memcpy(f.context_u128_value, c.context_u128_value.data(), 16);
+  f.heap_bound = c.heap_bound;
+  f.aux_heap_bound = c.aux_heap_bound;
+}
+
+struct Snapshotter : VmWitnessTracer {
+  uint32_t period;
+  std::vector<ZkbLocalState> out;
+  VmLocalState last;
+  bool any = false;
+  void start_new_execution_cycle(const VmLocalState& s) override {
+    if (s.monotonic_cycle_counter != 0 && s.monotonic_cycle_counter % period == 0) {
+      out.emplace_back();
+      serialise(s, &out.back());
+    }
+  }
+  void end_execution_cycle(const VmLocalState& s) override {
+    last = s;
+    any = true;
+  }
+};
+
+extern "C" int host_expected_snapshots(void* handle, uint32_t n_vms, uint32_t vm, const ZkbFrame* boot, const uint8_t* init_regs_be, uint32_t init_ptr_mask,
+                                       uint32_t init_page_counter, uint32_t init_epp, uint32_t period, ZkbLocalState* out, uint32_t cap,
+                                       uint32_t* n_out, char* err, int errlen) {
+  try {
+    GpuVmBatch b = GpuVmBatch::wrap((ZkbBatch*)handle, n_vms);
+    VmLocalState init;
+    init.timestamp = ZK_STARTING_TIMESTAMP;
+    init.memory_page_counter = init_page_counter;
+    init.current_ergs_per_pubdata_byte = init_epp;
+    for (int r = 0; r < 15; r++) {
+      uint32_t limbs[8];
+      for (int l = 0; l < 8; l++) {
+        const uint8_t* p = init_regs_be + 32 * r + 28 - 4 * l;
+        limbs[l] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+      }
+      init.registers[r] = PrimitiveValue{U256::from_limbs32(limbs), ((init_ptr_mask >> r) & 1u) != 0};
+    }
+    CallStackEntry root;
+    root.sp = ZK_INITIAL_SP_ON_FAR_CALL;
+    root.ergs_remaining = ZK_VM_INITIAL_FRAME_ERGS - boot->ergs_remaining;
+    init.inner.push_back(root);
+    init.current = from_frame(*boot);
+    Snapshotter sn;
+    sn.period = period;
+    b.replay(vm, sn, init);
+    if (sn.any) {   // the state after the last cycle (a boundary that coincides with it is reported once, here)
+      sn.out.emplace_back();
+      serialise(sn.last, &sn.out.back());
+    }
+    *n_out = (uint32_t)sn.out.size();
+    if (sn.out.size() > cap) throw std::runtime_error("snapshot buffer too small");
+    std::memcpy(out, sn.out.data(), sn.out.size() * sizeof(ZkbLocalState));
+    return 0;
+  } catch (const std::exception& e) {
+    std::snprintf(err, errlen, "%s", e.what());
+    return 1;
+  }
+}
