@@ -138,12 +138,13 @@ def main():
     ap.add_argument("--vms", type=int, default=65536, help="VMs per GPU")
     ap.add_argument("--transfers", type=int, default=8)
     ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
-    ap.add_argument("--sub-batches", type=int, default=8, help="e2e: sub-batches pipelined against the D2H copies")
+    ap.add_argument("--sub-batches", type=int, default=0, help="e2e: sub-batches pipelined against the D2H copies (0 = one interpreter wave, 14 208 VMs, each)")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs the persistent interpreter grid leaves free for the NCCL kernels of the exchange (they do not fit next to an interpreter CTA); -1 = 0 with --transport push, 4 with nccl")
     ap.add_argument("--transport", default="push", choices=["push", "nccl"],
                     help="N > 1: push = one-sided writes over NVLink peer memory (zkb_push_step: co-resident kernels, no host sync); "
                          "nccl = grouped ncclSend / ncclRecv (zkb_exchange_step).  --gather-rows always uses nccl")
     ap.add_argument("--gather-rows", action="store_true", help="N > 1: also concatenate the per-VM witness (cycle rows, memory queries, frame records) on the (rotating) sink rank")
+    ap.add_argument("--snapshot-period", type=int, default=256, help="e2e_device_consumer: cycles per circuit batch (zkb_consume)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -378,10 +379,16 @@ def main():
     # The batch is processed as S sub-batches: inputs of sub-batch k go H2D, its interpreter launch runs on one stream,
     # its six witness streams are packed and copied D2H into pinned host memory on another stream while sub-batch
     # k+1 is populated and executed.  Every input byte and every witness byte crosses PCIe inside the timed region.
-    e2e = e2e_raw = None
+    e2e = e2e_raw = e2e_consumer = None
     if not args.no_e2e:
-        n_sub = max(1, min(args.sub_batches, args.vms // 1024))
-        bounds = [shard.partition(args.vms, n_sub, i) for i in range(n_sub)]
+        if args.sub_batches > 0:
+            n_sub = max(1, min(args.sub_batches, args.vms // 1024))
+            bounds = [shard.partition(args.vms, n_sub, i) for i in range(n_sub)]
+        else:   # auto: whole waves of the persistent interpreter grid (148 SMs x 96 VMs) per sub-batch, so no launch runs a partial wave but the last
+            wave = 148 * 96
+            cuts = list(range(0, args.vms, wave)) + [args.vms]
+            bounds = list(zip(cuts[:-1], cuts[1:]))
+            n_sub = len(bounds)
         subs, sub_ids = [], []
         for lo, hi in bounds:
             scfg = w.config(hi - lo, device=local_rank)
@@ -396,7 +403,12 @@ def main():
             """transport = "encoded": ONE lossless blob per sub-batch (device-side encoder, include/zkb_codec.h) crosses PCIe;
             "raw": the six canonical streams, packed.  Either way every witness byte the host needs lands in pinned host
             memory inside the timed region."""
-            if transport == "encoded":   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
+            if transport == "consumer":  # snapshots + digests, and the encoded query logs
+                n_sub_vms = [hi - lo for lo, hi in bounds]
+                pinned = [[torch.empty(int(sum(sbytes[k] for k in log_kinds) * sh * 0.7) + (1 << 20), dtype=torch.uint8, pin_memory=True),
+                           torch.empty(nv * ((w.max_cycles_hint // args.snapshot_period + 2) * 792 + 104) + 4096, dtype=torch.uint8, pin_memory=True)]
+                          for sh, nv in zip(share, n_sub_vms)]
+            elif transport == "encoded":   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
                 pinned = [[torch.empty(int(sum(sbytes) * sh * 0.5) + (1 << 20), dtype=torch.uint8, pin_memory=True)] for sh in share]
             else:
                 pinned = [[torch.empty(int(nb * sh * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) for nb in sbytes] for sh in share]
@@ -410,7 +422,11 @@ def main():
                     w.setup(sb, sub_ids[i])
                     sb.run(stream=run_stream.cuda_stream, sync=False)
                     t1 = time.perf_counter()
-                    if transport == "encoded":
+                    if transport == "consumer":
+                        sb.consume(args.snapshot_period, stream=run_stream.cuda_stream)
+                        sb.fetch_encoded_kinds_async(log_kinds, pinned[i][0].data_ptr(), pinned[i][0].numel(), stream=copy_stream.cuda_stream)
+                        sb.fetch_consumed_async(pinned[i][1].data_ptr(), pinned[i][1].numel(), stream=copy_stream.cuda_stream)
+                    elif transport == "encoded":
                         blob_bytes[i] = sb.fetch_encoded_async(pinned[i][0].data_ptr(), pinned[i][0].numel(), stream=copy_stream.cuda_stream)
                     else:
                         for k in range(records.N_STREAMS):
@@ -444,7 +460,10 @@ def main():
                    "pcie_floor_ms": d2h / e2e_steps / 54.5e9 * 1e3,
                    "path": "per sub-batch: GpuVmBatch.reset + Workload.setup (populate_* / set_register / push_bootloader_context from host "
                            "arrays, H2D) + run + " + ("zkb_fetch_encoded_async: device-side lossless encode of all six streams, ONE D2H of the blob"
-                                                       if transport == "encoded" else "fetch_stream_packed_async x6") +
+                                                       if transport == "encoded" else "fetch_stream_packed_async x6" if transport == "raw" else
+                                                       f"zkb_consume (device-side VmLocalState snapshots every {args.snapshot_period} cycles + sha256 queue commitments) + "
+                                                       "D2H of the snapshots, the digests and the encoded query logs (log / decommit / frame / refund): rows and memory "
+                                                       "queries stay on the device") +
                            " into pinned host memory, copy of k overlapped with compute of k+1"}
             if transport == "encoded":
                 # outside the timed region: the blob decodes (host, zkb_decode_all) to exactly the canonical streams the raw
@@ -461,8 +480,10 @@ def main():
                                       "checked": "decoded rows of sub-batch 0 == fetch_stream_packed(rows), byte for byte"}
             return out
 
+        log_kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND]
         e2e = measure("encoded")
         e2e_raw = measure("raw")
+        e2e_consumer = measure("consumer")
         for sb in subs:
             sb.close()
         del subs
@@ -538,7 +559,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8 x u32 limbs)", "data": "synthetic", "config": config, "clocks": clocks.summary(),
-                "e2e": e2e, "e2e_raw_transport": e2e_raw,
+                "e2e": e2e, "e2e_raw_transport": e2e_raw, "e2e_device_consumer": e2e_consumer,
                 # per step: sparse restore + FAST + FULL interpreter launches (+ at N > 1: bucket count / scan / pack, one pack per gathered stream)
                 "gpu_launches": args.steps * (3 + ((3 + len(gather_kinds)) if world > 1 else 0)),
                 "roofline": roofline,

@@ -100,6 +100,16 @@ class GpuVmBatch(_binding.Batch):
         lib.zkb_fetch_consumed_async.argtypes = [vp, vp, u64, C.POINTER(u64), vp]
         self._check(lib.zkb_consume(self._h, cycles_per_snapshot, stream))
 
+    def fetch_encoded_kinds_async(self, kinds, host_ptr: int, host_capacity: int, stream=None) -> int:
+        """encoded blob of a subset of the streams (e.g. the query logs only) -> pinned host memory; returns the blob size"""
+        mask = 0
+        for k in kinds:
+            mask |= 1 << k
+        self._lib.zkb_fetch_encoded_kinds_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+        n = C.c_uint64()
+        self._check(self._lib.zkb_fetch_encoded_kinds_async(self._h, mask, host_ptr, host_capacity, C.byref(n), stream))
+        return n.value
+
     def snapshot_counts(self) -> np.ndarray:
         out = np.zeros(self.n_vms, dtype=np.uint32)
         self._check(self._lib.zkb_snapshot_counts(self._h, 0, self.n_vms, out.ctypes.data))

@@ -21,6 +21,7 @@ struct EncArgs {
   uint8_t* blob;            // pass 2: the device blob
   uint64_t counts_offset, offsets_offset;
   uint64_t payload_offset[ZKB_N_STREAMS];
+  uint32_t kinds_mask;      // streams outside the mask are left out of the blob (their counts are still reported)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const
     const uint32_t* x = B.hot[vm].x;
     uint32_t cnt[ZKB_N_STREAMS];
 #pragma unroll
-    for (int k = 0; k < ZKB_N_STREAMS; k++) cnt[k] = x[X_COUNT0 + k];
+    for (int k = 0; k < ZKB_N_STREAMS; k++) cnt[k] = ((A.kinds_mask >> k) & 1u) ? x[X_COUNT0 + k] : 0u;
     uint32_t* outp[ZKB_N_STREAMS];
 #pragma unroll
     for (int k = 0; k < ZKB_N_STREAMS; k++) outp[k] = nullptr;

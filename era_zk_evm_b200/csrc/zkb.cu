@@ -1330,7 +1330,7 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
 // ---- transport encoding (include/zkb_codec.h) ------------------------------------------------------------------
 // size pass + scan on `st`, then (after the host has read the totals from mapped memory and sized the blob) the write
 // pass.  Returns the device blob; it stays valid until the next encode / destroy.
-static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dptr, uint64_t* n_bytes) {
+static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dptr, uint64_t* n_bytes, uint32_t kinds_mask = 63u) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
   const uint32_t* c = nullptr;
   int32_t rc = summary(b, &c);  // waits for THIS batch's run only
@@ -1355,6 +1355,7 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dpt
   a.sizes = b->d_enc_sizes;
   a.offsets = b->d_enc_offsets;
   a.totals = b->d_enc_totals;
+  a.kinds_mask = kinds_mask & 63u;
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
   const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8));
@@ -1370,6 +1371,7 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dpt
   h.magic = ZKB_CODEC_MAGIC;
   h.version = ZKB_CODEC_VERSION;
   h.n_vms = (uint32_t)n;
+  h.reserved0 = (kinds_mask & 63u) == 63u ? 0u : (kinds_mask & 63u);   // 0 = every stream is in the blob
   h.counts_offset = sizeof(ZkbEncodedHeader);
   h.offsets_offset = h.counts_offset + n * 32;
   uint64_t at = h.offsets_offset + (n + 1) * ZKB_N_STREAMS * 8;
@@ -1381,7 +1383,8 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dpt
   }
   h.total_bytes = (at + 15) / 16 * 16;
   for (size_t v = 0; v < n; v++)
-    for (int k = 0; k < ZKB_N_STREAMS; k++) h.raw_bytes += (uint64_t)c[v * 8 + k] * REC_BYTES[k];
+    for (int k = 0; k < ZKB_N_STREAMS; k++)
+      if ((kinds_mask >> k) & 1u) h.raw_bytes += (uint64_t)c[v * 8 + k] * REC_BYTES[k];
   if (h.total_bytes > b->enc_capacity) {
     CUDA_OK(cudaDeviceSynchronize());  // an earlier async fetch may still read the old blob
     if (b->d_enc) CUDA_OK(cudaFree(b->d_enc));
@@ -1426,6 +1429,23 @@ int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capac
   if (rc != ZKB_OK) return rc;
   if (n_bytes) *n_bytes = total;
   if (!host_dst) return ZKB_OK;   // size query
+  if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_encoded: host buffer too small");
+  CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaEventRecord(b->ev_blob_read, st));
+  b->blob_read_pending = true;
+  b->d2h_bytes += total;
+  return ZKB_OK;
+}
+
+int32_t zkb_fetch_encoded_kinds_async(ZkbBatch* b, uint32_t kinds_mask, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream) {
+  if (!b || !b->cfg.witness_mode || !(kinds_mask & 63u)) return ZKB_ERR_INVALID_ARGUMENT;
+  uint8_t* p = nullptr;
+  uint64_t total = 0;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int32_t rc = encode_async(b, st, &p, &total, kinds_mask);
+  if (rc != ZKB_OK) return rc;
+  if (n_bytes) *n_bytes = total;
+  if (!host_dst) return ZKB_OK;
   if (total > host_capacity) return set_err(ZKB_ERR_INVALID_ARGUMENT, "fetch_encoded: host buffer too small");
   CUDA_OK(cudaMemcpyAsync(host_dst, p, total, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaEventRecord(b->ev_blob_read, st));

@@ -242,6 +242,9 @@ int32_t zkb_pack_stream_device_async(ZkbBatch* b, uint32_t kind, void** dptr, ui
  * only *n_bytes (the blob size for the current streams) is returned. */
 int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream);
 int32_t zkb_fetch_encoded(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes);
+/* the same for a subset of the streams (bit k of kinds_mask = ZkbStreamKind k): what a host that runs zkb_consume on the
+ * device still needs -- the query logs, not the rows.  Streams outside the mask decode as empty; counts are still reported. */
+int32_t zkb_fetch_encoded_kinds_async(ZkbBatch* b, uint32_t kinds_mask, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream);
 /* device-only variant: the blob in device memory (valid until the next encode / destroy), enqueued on cuda_stream */
 int32_t zkb_encode_streams_device(ZkbBatch* b, void** dptr, uint64_t* n_bytes, void* cuda_stream);
 /* host-side decoder: canonical records of VM `vm`'s stream `kind` out of a blob; dst == NULL returns the length only */

@@ -43,7 +43,8 @@ extern "C" {
 #define ZKB_CODEC_VERSION 1u
 
 typedef struct ZkbEncodedHeader {
-  uint32_t magic, version, n_vms, reserved0;
+  uint32_t magic, version, n_vms;
+  uint32_t reserved0;                       /* 0 = all six streams are in the blob; else a bit mask of the ZkbStreamKinds that are */
   uint64_t total_bytes;                     /* whole blob */
   uint64_t raw_bytes;                       /* canonical bytes it decodes to (sum over streams) */
   uint64_t counts_offset, offsets_offset;   /* from the start of the blob */
@@ -183,7 +184,8 @@ struct EncodedView {
    * UINT64_MAX on a malformed blob.  dst == NULL: length only. */
   uint64_t decode(uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes) const {
     if (vm >= h->n_vms || kind >= ZKB_N_STREAMS) return UINT64_MAX;
-    const uint64_t n = counts(vm)[kind], need = n * ZKB_CODEC_REC_WORDS[kind] * 4;
+    const bool present = h->reserved0 == 0 || ((h->reserved0 >> kind) & 1u);   /* a blob may carry a subset of the streams */
+    const uint64_t n = present ? counts(vm)[kind] : 0, need = n * ZKB_CODEC_REC_WORDS[kind] * 4;
     if (!dst) return need;
     if (need > max_bytes) return UINT64_MAX;
     const uint64_t lo = offsets(kind)[vm], hi = offsets(kind)[vm + 1];

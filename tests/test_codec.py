@@ -140,3 +140,29 @@ def test_cuda_encoder_on_a_resumed_run(oracle_mod):
     gpu.run()
     orc.run_threads(0, 1)
     assert gpu.fetch_encoded().tobytes() == orc.fetch_encoded().tobytes()
+
+
+@pytest.mark.gpu
+def test_subset_blob_carries_only_the_requested_streams(oracle_mod):
+    """zkb_fetch_encoded_kinds_async: what a host that consumes on the device still downloads (the query logs)"""
+    import torch
+    from era_zk_evm_b200 import GpuVmBatch, load_library
+    w, orc = _oracle_run(oracle_mod, "erc20", dict(n_transfers=2), 60)
+    gpu = GpuVmBatch(w.config(60))
+    w.setup(gpu, np.arange(60))
+    gpu.run()
+    kinds = [records.STREAM_LOG, records.STREAM_DECOMMIT, records.STREAM_FRAME, records.STREAM_REFUND]
+    full = gpu.fetch_encoded()
+    pinned = torch.empty(full.size, dtype=torch.uint8, pin_memory=True)
+    n = gpu.fetch_encoded_kinds_async(kinds, pinned.data_ptr(), pinned.numel())
+    torch.cuda.synchronize()
+    assert n < full.size // 3
+    view = EncodedWitness(load_library(), "zkb_", pinned[:n].numpy())
+    for vm in (0, 17, 59):
+        for kind in range(records.N_STREAMS):
+            got = view.read_stream(vm, kind)
+            if kind in kinds:
+                assert got.tobytes() == orc.read_stream(vm, kind).tobytes()
+            else:
+                assert len(got) == 0
+        assert view.counts(vm)[0] == len(orc.read_stream(vm, 0))       # the true counts are still reported
