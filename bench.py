@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--vms", type=int, default=65536, help="VMs per GPU")
     ap.add_argument("--transfers", type=int, default=8)
-    ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "keccak", "storage", "mixed"])
+    ap.add_argument("--workload", default="erc20", choices=["erc20", "alu_loop", "div_loop", "keccak", "storage", "mixed", "mixed_shuffled"])
     ap.add_argument("--sub-batches", type=int, default=0, help="e2e: sub-batches pipelined against the D2H copies (0 = one interpreter wave, 14 208 VMs, each)")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs the persistent interpreter grid leaves free for the NCCL kernels of the exchange (they do not fit next to an interpreter CTA); -1 = 0 with --transport push, 4 with nccl")
     ap.add_argument("--transport", default="push", choices=["push", "nccl"],

@@ -137,31 +137,62 @@ __device__ __forceinline__ uint32_t u_bits(u256l v) {
   return (uint32_t)top * 32u + (32u - (uint32_t)__clz(tv));
 }
 
-// div_mod for b != 0: restoring shift-subtract over the significant bit range only (bits(a) - bits(b) + 1 steps).
+// div_mod for b != 0: Knuth's algorithm D on 32-bit limbs, octet-distributed (round 1 used a bit-serial shift-subtract:
+// up to 256 steps of two votes + a subtraction; this is at most 8 steps).  Normalise so that the divisor's top limb has
+// its high bit set; per quotient limb j (from the top): estimate qhat from the two leading limbs of the running
+// remainder, subtract qhat * (divisor << 32 j) with one carry-resolved add (assembling the product) and one
+// borrow-resolved subtract, add the divisor back at most twice (the estimate from one divisor limb overshoots by <= 2).
+// The running remainder has 9 limbs: 8 in the lanes plus `top` (octet-uniform).
 __device__ __forceinline__ void u_divmod(u256l a, u256l b, uint32_t lane, u256l& q, u256l& r) {
-  uint32_t na = u_bits(a), nb = u_bits(b);
+  const uint32_t nza = oballot(a != 0), nzb = oballot(b != 0);
   q = 0;
-  if (na < nb) {
+  const int n = 32 - __clz(nzb);                  // significant limbs of b (>= 1: b != 0)
+  const int la = nza ? 32 - __clz(nza) : 0;       // significant limbs of a
+  if (la < n) {  // fewer limbs: a < b
     r = a;
     return;
   }
-  uint32_t sh = na - nb;
-  u256l d = u_shl(b, sh, lane);  // aligned divisor (fits: bits(d) == na <= 256)
-  u256l rem = a;
-  for (int i = (int)sh; i >= 0; i--) {
-    uint32_t gt = oballot(rem > d);
-    uint32_t lt = oballot(rem < d);
-    if (gt >= lt) {  // rem >= d (octet-uniform branch)
-      bool bo;
-      rem = u_sub(rem, d, lane, bo);
-      if (lane == (uint32_t)(i >> 5)) q |= 1u << (i & 31);
+  const uint32_t s = __clz(oshfl(b, n - 1));      // normalisation shift (0..31)
+  // v = b << s (fits: the top limb's leading zeros are shifted out), u = a << s (9 limbs: lanes + top)
+  const uint32_t b_dn = oshfl(b, ((int)lane + 7) & 7), a_dn = oshfl(a, ((int)lane + 7) & 7);
+  const uint32_t v = __funnelshift_l(lane ? b_dn : 0u, b, s);
+  uint32_t u = __funnelshift_l(lane ? a_dn : 0u, a, s);
+  uint32_t top = s ? (oshfl(a, 7) >> (32 - s)) : 0u;
+  const uint32_t vtop = oshfl(v, n - 1);
+  for (int j = la - n; j >= 0; j--) {
+    // leading two limbs of the remainder window: u[j + n] (= top when j + n == 8), u[j + n - 1]
+    const uint32_t uh = (j + n == 8) ? top : oshfl(u, (j + n) & 7), ul = oshfl(u, (j + n - 1) & 7);
+    const uint64_t num = (uint64_t)uh << 32 | ul;
+    uint32_t qhat = uh >= vtop ? 0xFFFFFFFFu : (uint32_t)(num / vtop);
+    // P = qhat * (v << 32 j): lane l multiplies limb v[l - j]; product limb i = lo_i + hi_(i-1)
+    const uint32_t vs = oshfl(v, ((int)lane - j) & 7);
+    const uint32_t vj = (int)lane >= j ? vs : 0u;
+    const uint64_t p = (uint64_t)qhat * vj;
+    const uint32_t p_lo = (uint32_t)p, p_hi = (uint32_t)(p >> 32);
+    const uint32_t hi_dn = oshfl(p_hi, ((int)lane + 7) & 7);
+    bool c;
+    const uint32_t P = u_addc(p_lo, lane ? hi_dn : 0u, lane, 0u, c);
+    const uint32_t P8 = oshfl(p_hi, 7) + (c ? 1u : 0u);     // limb 8 of the product (cannot overflow: qhat * v < 2^288)
+    bool bo;
+    uint32_t d = u_sub(u, P, lane, bo);
+    const uint64_t t = (uint64_t)top - P8 - (bo ? 1u : 0u);
+    uint32_t dtop = (uint32_t)t;
+    bool neg = (t >> 63) != 0;
+    while (neg) {  // qhat was too large (at most twice): add the shifted divisor back
+      qhat--;
+      bool cy;
+      d = u_addc(d, vj, lane, 0u, cy);
+      const uint64_t t2 = (uint64_t)dtop + (cy ? 1u : 0u);
+      dtop = (uint32_t)t2;
+      neg = (t2 >> 32) == 0;   // still negative until the add carries out of limb 8
     }
-    // d >>= 1
-    uint32_t up = oshfl(d, (lane + 1) & 7);
-    up = lane < 7 ? up : 0u;
-    d = __funnelshift_r(d, up, 1);
+    u = d;
+    top = dtop;
+    if ((int)lane == j) q = qhat;
   }
-  r = rem;
+  // remainder = u >> s (top is zero by now)
+  const uint32_t u_up = oshfl(u, (lane + 1) & 7);
+  r = __funnelshift_r(u, lane < 7 ? u_up : 0u, s);
 }
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }

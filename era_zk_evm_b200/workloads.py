@@ -215,6 +215,41 @@ class AluLoop(Workload):
         batch.set_register(1, u64_to_be_bytes(rnd[:, 4:8]), per_vm=True)
 
 
+class DivLoop(AluLoop):
+    """DIV-heavy variant of the register loop (U256 division): every iteration divides a 256-bit by a
+    ~128-bit value (quotient and remainder ~128 bits: four limb steps of the Knuth-D divider) and feeds both back."""
+    name = "div_loop"
+
+    def __init__(self, cycles: int = 1000, seed: int = DEFAULT_SEED):
+        Workload.__init__(self, seed)
+        self.cycles = cycles
+        self.max_cycles_hint = cycles + 16
+        k = max(1, (cycles - 4) // 7)
+        p = Program()
+        p.add(Imm(0), 0, 7)
+        p.add(R(1), 0, 8)
+        p.add(R(2), 0, 9)
+        p.label("loop")
+        p.div(R(1), 2, 3, 4)                                # r3 = r1 / r2, r4 = r1 % r2
+        p.mul(R(3), 2, 5, 6)                                # r5:r6 = q * b
+        p.add(R(5), 4, 1)                                   # r1 = q * b + rem (= the old r1)  ...
+        p.binop(isa.XOR, R(4), 1, 1)                        # ... stirred with the remainder
+        p.sub(Imm(k), 7, 0, set_flags=True, swap=True)
+        p.add(Imm(1), 7, 7)
+        p.jump("loop", cond="lt")
+        p.ret(isa.RET_OK, R(0))
+        self._add_code("boot", p)
+
+    def setup(self, batch, vm_ids):
+        vm_ids = np.asarray(vm_ids, dtype=np.uint64)
+        self._common(batch, "boot")
+        rnd = vm_random_u64(self.seed, vm_ids, 8)
+        rnd[:, 4:6] = 0                                     # divisor: 128 bits (the two most significant words cleared)
+        rnd[:, 6] |= np.uint64(1) << np.uint64(63)
+        batch.set_register(0, u64_to_be_bytes(rnd[:, 0:4]), per_vm=True)
+        batch.set_register(1, u64_to_be_bytes(rnd[:, 4:8]), per_vm=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # config 2: ERC-20-shaped transfers (mimic far call -> token -> keccak system contract x2 -> SLOAD/SSTORE
 #           -> event writer), T transfers per VM, 1/64 of the VMs start with balance 0 (revert + rollback)
@@ -547,7 +582,7 @@ class StorageHeavy(Workload):
         batch.populate_storage(ent.reshape(-1), per_vm=True)
 
 
-WORKLOADS = {"alu_loop": AluLoop, "erc20": Erc20, "keccak": KeccakHeavy, "storage": StorageHeavy}
+WORKLOADS = {"alu_loop": AluLoop, "div_loop": DivLoop, "erc20": Erc20, "keccak": KeccakHeavy, "storage": StorageHeavy}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -914,3 +949,16 @@ class Mixed(Workload):
 
 
 WORKLOADS["mixed"] = Mixed
+
+
+class MixedShuffled(Mixed):
+    """the same corpus with every VM of a warp on a DIFFERENT program (a block of unrelated
+    transactions): consecutive VMs cycle through the program pool, so the four octets of a warp never converge"""
+    name = "mixed_shuffled"
+
+    def __init__(self, **kw):
+        kw.setdefault("vms_per_program", 1)
+        super().__init__(**kw)
+
+
+WORKLOADS["mixed_shuffled"] = MixedShuffled

@@ -22,6 +22,8 @@ def _pair(w, vm_ids, oracle_mod):
 @pytest.mark.parametrize("name,kwargs,n", [
     ("alu_loop", dict(cycles=1000), 8),
     ("alu_loop", dict(cycles=100), 300),
+    ("div_loop", dict(cycles=300), 200),
+    ("mixed_shuffled", dict(n_programs=24), 24 * 8 + 3),
     ("storage", dict(), 70),
     ("keccak", dict(n_calls=3), 40),
     ("keccak", dict(n_calls=2, preimage_bytes=200), 16),
