@@ -89,6 +89,7 @@ enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
 
 struct DevBatch {
   uint32_t n_vms, witness;
+  uint32_t chunk;              // lockstep schedule: VMs a CTA pulls per turn (<= VMs per CTA; balanced over the waves by zkb_run)
   uint32_t warm_refund_bytes;  // ZkbConfig.reserved[1]: 0 = RefundType::None always (storage.rs:80-86), else the f-3 oracle
   uint32_t cap[ZKB_N_STREAMS];
   uint32_t stack_words, heap_words, n_slabs, max_far_depth, max_depth, storage_slots, journal_entries;
@@ -2195,7 +2196,7 @@ __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, u
     if (LOCKSTEP) {
       if (kc_yield) kc_flags[period] = 1u;   // (several octets may write the same 1)
       const int any = __syncthreads_or(active ? 1 : 0);
-      if (kc_flags[period]) {
+      if (KD && kc_flags[period]) {   // (only the FULL kernel ever raises it: the FAST one provably returns 0)
         reason = 1;
         break;
       }
@@ -2203,7 +2204,7 @@ __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, u
       period = (period + 1u) % 3u;
       if (!any) break;
     } else {
-      if (__any_sync(ZK_FULL, kc_yield)) {
+      if (KD && __any_sync(ZK_FULL, kc_yield)) {
         reason = 1;
         break;
       }

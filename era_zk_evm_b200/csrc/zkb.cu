@@ -81,12 +81,14 @@ __global__ void __launch_bounds__(ZKB_WARPS_PER_CTA * 32, ZKB_MIN_CTAS_PER_SM) z
     }
   } else {
     while (true) {
-      if (threadIdx.x == 0) s_base = atomicAdd(B.queue + (KD ? 1 : 0), (uint32_t)ZKB_VMS_PER_CTA);
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue + (KD ? 1 : 0), B.chunk);
       __syncthreads();
       const uint32_t base = s_base;
       if (base >= B.n_vms) break;
       uint32_t n = 0;
-      while (run_vm_group<true, KD>(B, S, s_kc_flags, base + oct, lane, max_cycles, n)) {
+      // slots beyond the chunk stay empty this turn (B.chunk < VMs per CTA evens out the last wave, see zkb_run)
+      const uint32_t vm_idx = oct < B.chunk ? base + oct : 0xFFFFFFFFu;
+      while (run_vm_group<true, KD>(B, S, s_kc_flags, vm_idx, lane, max_cycles, n)) {
         // deferred keccak256 of every yielded VM of the CTA: thread t < VMs per CTA takes slot t (one thread per state)
         __syncthreads();
         if constexpr (KD) {
@@ -502,6 +504,7 @@ struct ZkbBatch {
   uint32_t n_launches = 0;
   int grid = 0;
   bool lockstep = false;
+  bool balance_waves = false;   // lockstep: even out the last wave of VMs over all SMs (ZKB_BALANCE=1; see zkb_run)
   uint8_t* d_pack = nullptr;
   uint64_t pack_capacity = 0;
   uint64_t* d_offsets = nullptr;                  // [ZKB_N_STREAMS][n_vms + 1]
@@ -827,6 +830,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   uint32_t sched = cfg->schedule;
   if (const char* env = getenv("ZKB_SCHEDULE")) sched = (uint32_t)atoi(env);  // experiment override
   b->lockstep = sched != ZKB_SCHED_FREE;
+  if (const char* env = getenv("ZKB_BALANCE")) b->balance_waves = atoi(env) != 0;
   *out = b;
   return ZKB_OK;
 }
@@ -1080,7 +1084,21 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   }
   CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 8, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
-  int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + ZKB_VMS_PER_CTA - 1) / ZKB_VMS_PER_CTA));
+  // Lockstep schedule: a CTA pulls `chunk` VMs per turn.  With chunk = VMs per CTA a batch of 65 536 VMs is 4.61 waves of
+  // 148 x 96 VMs and the fifth wave leaves 57 SMs idle; chunk = ceil(n_vms / (waves x CTAs)) spreads the same number of
+  // waves evenly (89 VMs per turn: 4.98 waves).  ZKB_CHUNK: experiment override (0 / unset = balanced).
+  {
+    uint32_t chunk = ZKB_VMS_PER_CTA;
+    const uint64_t per_wave = (uint64_t)b->grid * ZKB_VMS_PER_CTA;
+    const uint64_t waves = std::max<uint64_t>(1, (b->cfg.n_vms + per_wave - 1) / per_wave);
+    if (b->balance_waves) chunk = (uint32_t)((b->cfg.n_vms + waves * b->grid - 1) / (waves * b->grid));
+    if (const char* env = getenv("ZKB_CHUNK")) {
+      const int v = atoi(env);
+      if (v > 0) chunk = (uint32_t)v;
+    }
+    b->d.chunk = std::min<uint32_t>(std::max<uint32_t>(chunk, 1u), ZKB_VMS_PER_CTA);
+  }
+  int grid = std::min<int>(b->grid, (int)((b->cfg.n_vms + b->d.chunk - 1) / b->d.chunk));
   // FAST kernel (no out-of-line precompile routine anywhere in it), then the FULL kernel for the VMs the fast one parked
   // with a pending ecrecover / long keccak256 (none on most batches: its CTAs then find nothing to do and exit)
   if (b->lockstep) {
