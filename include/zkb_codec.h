@@ -132,8 +132,11 @@ static inline uint64_t encode_records(uint32_t kind, const void* src, uint64_t n
 }
 
 /* decodes n records of one VM and stream from `src` (n_src bytes) into canonical bytes at `dst`; returns the number of
- * encoded bytes consumed, or UINT64_MAX when the input is truncated */
-static inline uint64_t decode_records(uint32_t kind, const uint8_t* src, uint64_t n_src, uint64_t n, void* dst) {
+ * encoded bytes consumed, or UINT64_MAX when the input is truncated.  decode_records_ref is the word-by-word inverse of
+ * encode_records (one predict() call per word); decode_records below is what the library runs: the same function with
+ * the predictions written as whole-record block operations and the residuals applied by walking the set bits of the
+ * presence mask -- ~10x faster, checked against the reference decoder in tests/test_codec.py. */
+static inline uint64_t decode_records_ref(uint32_t kind, const uint8_t* src, uint64_t n_src, uint64_t n, void* dst) {
   const uint32_t nw = ZKB_CODEC_REC_WORDS[kind], mw = ZKB_CODEC_MASK_WORDS[kind];
   uint32_t* out = (uint32_t*)dst;
   uint32_t zero[64];
@@ -166,6 +169,81 @@ static inline uint64_t decode_records(uint32_t kind, const uint8_t* src, uint64_
   return at;
 }
 
+/* XORs the residual words named by `mask` (ascending bit order) into out[]; returns the advanced read position */
+static inline const uint8_t* apply_residuals(uint64_t mask, const uint8_t* p, uint32_t* out) {
+  while (mask) {
+    uint32_t x;
+    memcpy(&x, p, 4);
+    p += 4;
+    out[__builtin_ctzll(mask)] ^= x;
+    mask &= mask - 1;
+  }
+  return p;
+}
+
+static inline uint64_t decode_records(uint32_t kind, const uint8_t* src, uint64_t n_src, uint64_t n, void* dst) {
+  const uint32_t nw = ZKB_CODEC_REC_WORDS[kind], mw = ZKB_CODEC_MASK_WORDS[kind];
+  uint32_t* out = (uint32_t*)dst;
+  if (mw == 0) {  /* REFUND: raw */
+    const uint64_t need = n * nw * 4;
+    if (need > n_src) return UINT64_MAX;
+    memcpy(out, src, (size_t)need);
+    return need;
+  }
+  uint32_t zero[64];
+  memset(zero, 0, sizeof(zero));
+  const uint32_t* prev = zero;
+  const uint8_t* p = src;
+  const uint8_t* const end = src + n_src;
+  for (uint64_t r = 0; r < n; r++, out += nw) {
+    if ((uint64_t)(end - p) < (uint64_t)mw * 4) return UINT64_MAX;
+    uint32_t m32[2] = {0, 0};
+    memcpy(m32, p, (size_t)mw * 4);
+    p += (size_t)mw * 4;
+    const uint64_t mask = (uint64_t)m32[0] | (uint64_t)m32[1] << 32;
+    if ((uint64_t)(end - p) < (uint64_t)__builtin_popcountll(mask) * 4) return UINT64_MAX;
+    switch (kind) {
+      case ZKB_STREAM_ROWS: {
+        /* every prediction that does not look at the record itself, as block operations */
+        out[0] = prev[0] + 1u;
+        out[1] = prev[1] + ZK_TIME_DELTA_PER_CYCLE;
+        out[2] = out[3] = 0u;
+        const uint32_t pc = prev[5] >> 16;
+        out[5] = pc | ((pc + 1u) & 0xFFFFu) << 16;
+        out[6] = prev[6];
+        memset(out + 8, 0, 32 * 4);
+        memcpy(out + 40, prev + 40, 24 * 4);
+        out[43] = 0u;
+        /* words 4 and 7 are predicted from the decoded raw opcode (word 2): residuals of words 0..3 first */
+        p = apply_residuals(mask & 0xFull, p, out);
+        const uint32_t v = out[2] & ((1u << ZK_VARIANT_BITS) - 1u);
+        out[4] = v | 1u << 16;
+        out[7] = prev[7] - ZK_OPCODE_PRICES[v];
+        p = apply_residuals(mask & ~0xFull, p, out);
+        break;
+      }
+      case ZKB_STREAM_MEM:
+      case ZKB_STREAM_DECOMMIT:
+        memcpy(out, prev, 16);
+        if (kind == ZKB_STREAM_MEM) out[2] = prev[2] + 1u;
+        memset(out + 4, 0, 32);
+        p = apply_residuals(mask, p, out);
+        break;
+      case ZKB_STREAM_LOG:
+        memcpy(out, prev, 32);
+        memset(out + 8, 0, 96);
+        p = apply_residuals(mask, p, out);
+        break;
+      default: /* FRAME */
+        memcpy(out, prev, 128);
+        p = apply_residuals(mask, p, out);
+        break;
+    }
+    prev = out;
+  }
+  return (uint64_t)(p - src);
+}
+
 /* a received blob: validates the header, gives per-VM access */
 struct EncodedView {
   const uint8_t* base = nullptr;
@@ -182,7 +260,7 @@ struct EncodedView {
   const uint64_t* offsets(uint32_t kind) const { return (const uint64_t*)(base + h->offsets_offset) + (size_t)kind * (h->n_vms + 1); }
   /* canonical bytes of VM `vm`'s stream `kind` -> dst (capacity max_bytes); returns the canonical length, or
    * UINT64_MAX on a malformed blob.  dst == NULL: length only. */
-  uint64_t decode(uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes) const {
+  uint64_t decode(uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, bool reference_decoder = false) const {
     if (vm >= h->n_vms || kind >= ZKB_N_STREAMS) return UINT64_MAX;
     const bool present = h->reserved0 == 0 || ((h->reserved0 >> kind) & 1u);   /* a blob may carry a subset of the streams */
     const uint64_t n = present ? counts(vm)[kind] : 0, need = n * ZKB_CODEC_REC_WORDS[kind] * 4;
@@ -190,7 +268,8 @@ struct EncodedView {
     if (need > max_bytes) return UINT64_MAX;
     const uint64_t lo = offsets(kind)[vm], hi = offsets(kind)[vm + 1];
     if (hi < lo || hi > h->payload_bytes[kind]) return UINT64_MAX;
-    const uint64_t used = decode_records(kind, base + h->payload_offset[kind] + lo, hi - lo, n, dst);
+    const uint8_t* src = base + h->payload_offset[kind] + lo;
+    const uint64_t used = reference_decoder ? decode_records_ref(kind, src, hi - lo, n, dst) : decode_records(kind, src, hi - lo, n, dst);
     return used == hi - lo ? need : UINT64_MAX;
   }
 };

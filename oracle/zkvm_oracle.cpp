@@ -2330,7 +2330,7 @@ int32_t orc_fetch_encoded_async(OrcBatch* b, void* host_dst, uint64_t host_capac
 int32_t orc_decode_stream(const void* blob, uint64_t blob_bytes, uint32_t vm, uint32_t kind, void* dst, uint64_t max_bytes, uint64_t* n_bytes) {
   zkb_codec::EncodedView v;
   if (!v.open(blob, blob_bytes)) return ZKB_ERR_INVALID_ARGUMENT;
-  const uint64_t n = v.decode(vm, kind, dst, max_bytes);
+  const uint64_t n = v.decode(vm, kind, dst, max_bytes, /*reference_decoder=*/true);   // the word-by-word inverse: checks the library's fast decoder
   if (n == UINT64_MAX) return ZKB_ERR_INVALID_ARGUMENT;
   if (n_bytes) *n_bytes = n;
   return ZKB_OK;
@@ -2352,7 +2352,7 @@ int32_t orc_decode_all(const void* blob, uint64_t blob_bytes, uint32_t kind, voi
   if (offsets_out[v.n_vms()] > capacity) return ZKB_ERR_INVALID_ARGUMENT;
   for (uint32_t vm = 0; vm < v.n_vms(); vm++) {
     const uint64_t len = offsets_out[vm + 1] - offsets_out[vm];
-    if (v.decode(vm, kind, (uint8_t*)dst + offsets_out[vm], len) != len) return ZKB_ERR_INVALID_ARGUMENT;
+    if (v.decode(vm, kind, (uint8_t*)dst + offsets_out[vm], len, true) != len) return ZKB_ERR_INVALID_ARGUMENT;
   }
   return ZKB_OK;
 }

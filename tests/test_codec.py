@@ -44,6 +44,24 @@ def test_roundtrip_is_lossless(name, kwargs, n, oracle_mod):
     assert blob.size < raw                       # it does compress
 
 
+@pytest.mark.parametrize("name,kwargs,n", CASES)
+def test_fast_decoder_matches_the_reference_decoder(name, kwargs, n, oracle_mod):
+    """libzkb.so decodes with block predictions + a walk over the mask bits (zkb_codec::decode_records); the oracle
+    library keeps the word-by-word inverse of the encoder (decode_records_ref).  Same bytes on every stream of every VM."""
+    from era_zk_evm_b200 import load_library
+    _, b = _oracle_run(oracle_mod, name, kwargs, n)
+    blob = b.fetch_encoded()
+    fast, ref = EncodedWitness(load_library(), "zkb_", blob), EncodedWitness(oracle_mod.lib(), "orc_", blob)
+    for vm in range(n):
+        for kind in range(records.N_STREAMS):
+            a = fast.read_stream(vm, kind)
+            assert a.tobytes() == ref.read_stream(vm, kind).tobytes() == b.read_stream(vm, kind).tobytes(), (vm, kind)
+    # truncated slices are rejected by the fast decoder too
+    from era_zk_evm_b200._binding import ZkbError
+    with pytest.raises(ZkbError):
+        EncodedWitness(load_library(), "zkb_", blob[: blob.size - 64]).read_stream(n - 1, records.STREAM_REFUND if name == "storage" else 0)
+
+
 def test_bulk_decode_matches_per_vm_decode(oracle_mod):
     """zkb_decode_all (multi-threaded, the product's host decoder in libzkb.so -- no GPU needed) == per-VM streams"""
     from era_zk_evm_b200 import load_library
