@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzkb.so")
 SOURCES = ["zkb.cu", "host_codec.cpp"]
-DEPS = ["zkb.cu", "host_codec.cpp", "codec.cuh", "logsort.cuh", "comm.cuh", "consume.cuh", "vm.cuh", "u256.cuh", "keccak.cuh", "sha256.cuh", "secp256k1.cuh", "isa_tables.inc"]
+DEPS = ["zkb.cu", "host_codec.cpp", "codec.cuh", "logsort.cuh", "comm.cuh", "consume.cuh", "alubench.cuh", "vm.cuh", "u256.cuh", "keccak.cuh", "sha256.cuh", "secp256k1.cuh", "isa_tables.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "-ldl"]
 

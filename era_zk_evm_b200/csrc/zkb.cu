@@ -13,6 +13,7 @@
 #include "codec.cuh"
 #include "logsort.cuh"
 #include "consume.cuh"
+#include "alubench.cuh"
 
 using namespace zkb;
 
@@ -1840,6 +1841,55 @@ int32_t zkb_hash_bytecodes(int32_t device, const uint8_t* words_be, const uint64
   cudaFree(d_off);
   cudaFree(d_hashes);
   if (e != cudaSuccess) return set_err(ZKB_ERR_CUDA, cudaGetErrorString(e));
+  return ZKB_OK;
+}
+
+// K14 (alubench.cuh): ops per second of one integer micro-benchmark at full occupancy.  For the pipe peaks an "op" is one
+// thread-level instruction (mad.lo.u32 / add.u32 / lop3.b32); for the U256 entries one 256-bit operation of one octet.
+int32_t zkb_alu_microbench(int32_t device, uint32_t op, uint32_t iters, double* ops_per_second, float* kernel_ms) {
+  if (op >= ALUB_N || iters == 0 || !ops_per_second) return ZKB_ERR_INVALID_ARGUMENT;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return set_err(ZKB_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= n_dev) return ZKB_ERR_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(device));
+  int n_sm = 148;
+  CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  const int grid = n_sm * 8;   // 8 CTAs x 256 threads = 64 warps per SM
+  uint32_t* sink = nullptr;
+  const uint32_t seed = 0x5eed0001u;
+  CUDA_OK(cudaMalloc(&sink, 1024 * 4));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  cudaError_t e = cudaSuccess;
+  float best = 0.f;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {   // first pass = warm-up, then best of three
+    cudaEventRecord(e0, 0);
+    switch (op) {
+      case ALUB_IMAD: zkb_alubench_kernel<ALUB_IMAD><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_IADD3: zkb_alubench_kernel<ALUB_IADD3><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_LOP3: zkb_alubench_kernel<ALUB_LOP3><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_U256_ADD: zkb_alubench_kernel<ALUB_U256_ADD><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_U256_SUB: zkb_alubench_kernel<ALUB_U256_SUB><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_U256_MUL: zkb_alubench_kernel<ALUB_U256_MUL><<<grid, 256>>>(iters, seed, sink); break;
+      case ALUB_U256_DIV: zkb_alubench_kernel<ALUB_U256_DIV><<<grid, 256>>>(iters, seed, sink); break;
+      default: zkb_alubench_kernel<ALUB_U256_SHL><<<grid, 256>>>(iters, seed, sink); break;
+    }
+    e = cudaGetLastError();
+    cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return set_err(ZKB_ERR_CUDA, cudaGetErrorString(e));
+  const double threads = (double)grid * 256.0;
+  const double ops = op <= ALUB_LOP3 ? threads * (double)iters * ALUB_CHAINS * ALUB_UNROLL : threads / 8.0 * (double)iters;
+  *ops_per_second = ops / ((double)best * 1e-3);
+  if (kernel_ms) *kernel_ms = best;
   return ZKB_OK;
 }
 

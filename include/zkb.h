@@ -308,6 +308,15 @@ int32_t zkb_sort_log_queries(int32_t device, const void* d_recs, uint64_t n_reco
 int32_t zkb_net_storage_history(ZkbBatch* b, void* host_sorted_out, uint64_t host_capacity, uint8_t* host_boundary_out, uint64_t* offsets_out,
                                 uint64_t* n_slots_out, void* cuda_stream);
 
+/* ---- measurement helpers -------------------------------------------------------------------------------- */
+/* K14 -- integer-pipe micro-benchmarks (row j3; BASELINE north_star: "integer-pipe utilisation for the U256 ALU against
+ * sm_100a peak").  op: 0 IMAD (mad.lo.u32), 1 IADD3 (add.u32), 2 LOP3 -- the MEASURED peaks, thread-level instructions
+ * per second at 64 warps per SM, 8 independent chains per thread; 3 u256 add, 4 sub, 5 full 256x256->512 mul, 6 div_mod
+ * (256-bit by 128-bit), 7 shl -- the octet-distributed primitives of csrc/u256.cuh that replace ethereum_types::U256 in
+ * /root/reference/src/opcodes/execution/{add,sub,mul,div,shift}.rs, 256-bit operations per second.  Best of three timed
+ * launches (CUDA events).  tools/alu_microbench.py prints the table and the utilisation figures. */
+int32_t zkb_alu_microbench(int32_t device, uint32_t op, uint32_t iters, double* ops_per_second, float* kernel_ms);
+
 /* ---- bytecode ingestion: the step right BEFORE the path ----------------------------- */
 /* Versioned code hashes of n bytecodes, computed on the GPU: byte 0 = version (1), byte 1 = marker (0 at rest,
  * 1 being constructed), bytes 2..3 = length in 32-byte words (big-endian u16), bytes 4..31 = sha256(code)[4..32] --

@@ -45,7 +45,7 @@ def test_oracle_exports_the_same_surface(oracle_mod):
     lib = oracle_mod.lib()
     shared = [n for n in declared_functions() if n not in (
         "zkb_stream_device_view", "zkb_fetch_stream_packed", "zkb_fetch_stream_packed_async", "zkb_pack_stream_device", "zkb_pack_stream_device_async", "zkb_snapshot", "zkb_restore",
-        "zkb_transfer_stats", "zkb_encode_streams_device", "zkb_fetch_encoded_kinds_async", "zkb_gather_streams", "zkb_exchange_logs", "zkb_comm_unique_id", "zkb_comm_create", "zkb_comm_destroy", "zkb_comm_wait_packed", "zkb_exchange_step", "zkb_push_step", "zkb_push_result", "zkb_consume", "zkb_snapshot_counts", "zkb_read_snapshots", "zkb_read_queue_digests", "zkb_fetch_consumed_async", "zkb_sort_log_queries", "zkb_peer_push_async", "zkb_peer_sink_create", "zkb_peer_sink_open", "zkb_peer_sink_close")]
+        "zkb_transfer_stats", "zkb_encode_streams_device", "zkb_fetch_encoded_kinds_async", "zkb_gather_streams", "zkb_exchange_logs", "zkb_comm_unique_id", "zkb_comm_create", "zkb_comm_destroy", "zkb_comm_wait_packed", "zkb_exchange_step", "zkb_push_step", "zkb_push_result", "zkb_consume", "zkb_snapshot_counts", "zkb_read_snapshots", "zkb_read_queue_digests", "zkb_fetch_consumed_async", "zkb_sort_log_queries", "zkb_alu_microbench", "zkb_peer_push_async", "zkb_peer_sink_create", "zkb_peer_sink_open", "zkb_peer_sink_close")]
     missing = [n for n in shared if not hasattr(lib, n.replace("zkb_", "orc_", 1))]
     assert not missing, missing
 
