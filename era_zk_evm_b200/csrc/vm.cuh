@@ -90,6 +90,7 @@ enum { PT_HEAP_LIVE = 1, PT_AUX_LIVE = 2, PT_EXT = 3 };
 struct DevBatch {
   uint32_t n_vms, witness;
   uint32_t chunk;              // lockstep schedule: VMs a CTA pulls per turn (<= VMs per CTA; balanced over the waves by zkb_run)
+  const uint32_t* order;       // schedule slot -> VM index (VMs regrouped by bootloader code, zkb_run); nullptr = identity
   uint32_t warm_refund_bytes;  // ZkbConfig.reserved[1]: 0 = RefundType::None always (storage.rs:80-86), else the f-3 oracle
   uint32_t cap[ZKB_N_STREAMS];
   uint32_t stack_words, heap_words, n_slabs, max_far_depth, max_depth, storage_slots, journal_entries;
@@ -2130,6 +2131,10 @@ __device__ __forceinline__ uint32_t run_vm_group(const DevBatch& B, VmSmem& S, u
                                                  uint32_t& n) {
   // the FAST kernel runs the VMs that are not parked, the FULL kernel exactly the parked ones (a VM that merely ran out
   // of max_cycles in the fast kernel is not touched again by this zkb_run)
+  // vm_idx arrives as a SCHEDULE SLOT: the host may have regrouped the VMs so that the octets of a warp (and the warps of
+  // a lockstep CTA) run the same bootloader code; every per-VM array and stream stays indexed by the real VM number, so
+  // the emitted bytes do not depend on the grouping
+  if (B.order != nullptr && vm_idx < B.n_vms) vm_idx = __ldg(B.order + vm_idx);
   const uint32_t* x0 = B.hot[vm_idx < B.n_vms ? vm_idx : 0].x;
   const bool valid = vm_idx < B.n_vms && x0[X_STATUS] == ZKB_VM_RUNNING && ((x0[X_DEFER] != DEFER_NONE) == KD);
   VmHot* hot = B.hot + (valid ? vm_idx : 0);

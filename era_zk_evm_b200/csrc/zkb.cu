@@ -497,6 +497,9 @@ struct ZkbBatch {
   uint32_t* d_code_words = nullptr;
   uint32_t* d_code_meta = nullptr;
   std::vector<int32_t> boot_code;  // per VM: code id bound by populate_code (page in boot_page)
+  uint32_t* d_order = nullptr;     // schedule slot -> VM, VMs grouped by boot_code (nullptr while the identity is already grouped)
+  bool order_dirty = true;
+  bool regroup = true;             // ZKB_REGROUP=0 turns the grouping off (experiment)
   std::vector<uint32_t> boot_page;
   uint32_t* d_fail = nullptr;   // device pointer of h_fail (mapped pinned: reading it never queues behind D2H copies)
   uint32_t* h_fail = nullptr;
@@ -832,6 +835,7 @@ int32_t zkb_create(const ZkbConfig* cfg, ZkbBatch** out) {
   if (const char* env = getenv("ZKB_SCHEDULE")) sched = (uint32_t)atoi(env);  // experiment override
   b->lockstep = sched != ZKB_SCHED_FREE;
   if (const char* env = getenv("ZKB_BALANCE")) b->balance_waves = atoi(env) != 0;
+  if (const char* env = getenv("ZKB_REGROUP")) b->regroup = atoi(env) != 0;
   *out = b;
   return ZKB_OK;
 }
@@ -872,6 +876,7 @@ int32_t zkb_reset(ZkbBatch* b) {
   std::fill(b->h_root.begin(), b->h_root.end(), 0u);
   std::fill(b->h_bootrec.begin(), b->h_bootrec.end(), 0u);
   std::fill(b->boot_code.begin(), b->boot_code.end(), -1);
+  b->order_dirty = true;
   b->calldata.clear();
   b->hot_dirty = b->root_dirty = true;
   b->hot_stale = false;
@@ -964,6 +969,7 @@ int32_t zkb_populate_code(ZkbBatch* b, uint32_t vm_lo, uint32_t vm_hi, uint32_t 
   if (id < 0) return set_err(ZKB_ERR_UNKNOWN_BYTECODE, "populate_code: bytecode hash not loaded");
   for (uint32_t v = vm_lo; v < vm_hi; v++) {
     b->boot_code[v] = id;
+    b->order_dirty = true;
     b->boot_page[v] = page;
   }
   return ZKB_OK;
@@ -1082,6 +1088,39 @@ int32_t zkb_run(ZkbBatch* b, uint32_t max_cycles_per_vm, void* cuda_stream) {
   if (st != nullptr) {  // populate_* / reset work runs on the default stream: order it before the launch on `st`
     CUDA_OK(cudaEventRecord(b->ev_setup, 0));
     CUDA_OK(cudaStreamWaitEvent(st, b->ev_setup, 0));
+  }
+  // Regroup the schedule by bootloader code: a warp runs four VMs and a lockstep CTA 96 side by side, at full speed only
+  // while they execute the same program.  A batch whose neighbours run different programs (a block of unrelated
+  // transactions) is therefore scheduled in code order: slot i runs VM order[i] (stable, so equal programs keep their
+  // relative order).  State and streams stay indexed by VM: results are unchanged, only the assignment of VMs to octets.
+  if (b->order_dirty) {
+    b->order_dirty = false;
+    const uint32_t n = b->cfg.n_vms;
+    uint32_t runs = 0;   // maximal runs of equal code in VM order; grouped already <=> one run per distinct code
+    std::vector<uint8_t> seen(b->codes.size() + 1, 0);
+    bool grouped = true;
+    for (uint32_t v = 0; v < n; v++)
+      if (v == 0 || b->boot_code[v] != b->boot_code[v - 1]) {
+        runs++;
+        uint8_t& s = seen[(size_t)(b->boot_code[v] + 1)];
+        if (s) grouped = false;
+        s = 1;
+      }
+    if (b->regroup && !grouped) {
+      std::vector<uint32_t> order(n);
+      for (uint32_t v = 0; v < n; v++) order[v] = v;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b->boot_code[x] < b->boot_code[y]; });
+      if (!b->d_order) {
+        cudaError_t e = dalloc(b, &b->d_order, n, false);
+        if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("schedule order: ") + cudaGetErrorString(e));
+      }
+      CUDA_OK(cudaMemcpyAsync(b->d_order, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));   // `order` is a pageable temporary
+      b->d.order = b->d_order;
+    } else {
+      b->d.order = nullptr;
+    }
+    (void)runs;
   }
   CUDA_OK(cudaMemsetAsync(b->d.queue, 0, 8, st));
   CUDA_OK(cudaEventRecord(b->ev0, st));
