@@ -1,4 +1,5 @@
-// Transport encoder of the witness streams (include/zkb_codec.h): XOR-with-prediction + presence bitmap, one warp per VM.
+// Transport encoder of the witness streams (include/zkb_codec.h, format v2): XOR-with-prediction + presence bitmap, one warp
+// per VM; cycle rows and memory queries are coded jointly (encode_joint), the other streams record by record.
 //
 // The canonical streams stay in HBM (they are what the device-side consumers read); this kernel is the last step before
 // the PCIe link: it reads every record once per pass (HBM-read bound: two coalesced 128-byte loads per cycle row) and
@@ -30,53 +31,190 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
   return m;
 }
 
-// cycle rows: lane l owns words l and l + 32 of the row (two coalesced 128-byte loads per row)
+__device__ __constant__ uint32_t c_mem_flag_codes[16] = {0x00000004u, 0x00000001u, 0x00000101u, 0x00000003u, 0x00000000u, 0x00000100u, 0x01000003u, 0x02000101u,
+                                                         0x00010000u, 0x00010100u, 0x00000002u, 0x00000102u, 0x01000001u, 0x02000102u, 0x00010003u, 0xFFFFFFFFu};  // == ZKB_MEM_FLAG_CODES_INIT
+
+// ---- format v2: cycle rows and memory queries of one VM, coded jointly by one warp (zkb_codec.h JointCoder is the scalar
+// statement of the same walk; the blobs are bit-identical) -------------------------------------------------------------
+// Lane l owns words l and l + 32 of the current row (two coalesced 128-byte loads per row) and word l of the current
+// memory query (lanes 0..11); lanes 0..7 keep the current code word, lane s the FIFO pointer of cache set s; the
+// 32-set x 4-way code-word cache of the VM sits in shared memory (4 KB per warp).
+struct JointWarp {
+  uint32_t prev_lo, prev_hi, pm, cw, rr, prevprev50;
+  uint32_t* cache;            // [32 sets][4 ways][8] of this warp
+  const uint32_t* mems;       // the VM's memory queries
+  uint32_t n_mem, mi;
+  uint32_t m_next;            // prefetched word `lane` of query mi
+  uint32_t* out_rows;
+  uint32_t* out_mem;
+  uint64_t rwords, mwords;
+};
+
+__device__ __forceinline__ uint32_t first_min8(const uint32_t* c) {
+  uint32_t best = c[0], sel = 0;
+#pragma unroll
+  for (uint32_t v = 1; v < 8; v++)
+    if (c[v] < best) {
+      best = c[v];
+      sel = v;
+    }
+  return sel;
+}
+
+// one memory query (JointCoder::mem_record).  w_lo / w_hi: the cycle's row; post: w3 (the raw opcode's immediates) may be used
 template <bool WRITE>
-__device__ __forceinline__ uint64_t encode_rows(const uint32_t* __restrict__ rows, uint32_t n, uint32_t* __restrict__ out, uint32_t lane) {
-  uint32_t prev_lo = 0, prev_hi = 0;
-  uint64_t words = 0;
+__device__ __forceinline__ void joint_mem(JointWarp& J, uint32_t lane, uint32_t lt, uint32_t w_lo, uint32_t w_hi, bool post, bool fe, uint32_t j) {
+  const uint32_t w = J.m_next;
+  J.mi++;
+  if (J.mi < J.n_mem) J.m_next = lane < 12 ? __ldcs(J.mems + (size_t)J.mi * 12 + lane) : 0u;   // next query in flight
+  const uint32_t flags = __shfl_sync(0xffffffffu, w, 3), index = __shfl_sync(0xffffffffu, w, 2);
+  const uint32_t type = flags & 0xFFu, rw = (flags >> 8) & 1u;
+  const uint32_t fm = __ballot_sync(0xffffffffu, lane < 15 && c_mem_flag_codes[lane & 15u] == flags);
+  const uint32_t fcode = fm ? (uint32_t)__ffs(fm) - 1u : 15u;
+  const uint32_t pm3 = __shfl_sync(0xffffffffu, J.pm, 3), pm2 = __shfl_sync(0xffffffffu, J.pm, 2);
+  const uint32_t row_ts = __shfl_sync(0xffffffffu, w_lo, 1), row_w3 = __shfl_sync(0xffffffffu, w_lo, 3), pc_before = __shfl_sync(0xffffffffu, w_lo, 5) & 0xFFFFu;
+  const uint32_t row_w8 = __shfl_sync(0xffffffffu, w_lo, 8), row_w9 = __shfl_sync(0xffffffffu, w_lo, 9), row_w10 = __shfl_sync(0xffffffffu, w_lo, 10);
+  const uint32_t prev50 = __shfl_sync(0xffffffffu, J.prev_hi, 18), prev51 = __shfl_sync(0xffffffffu, J.prev_hi, 19);
+  const uint32_t p0 = row_ts + (rw ? 3u : 0u);
+  const uint32_t p1 = type == 4u ? prev50 : type <= 2u ? prev51 + 1u + type : row_w9;
+  uint32_t p2;
+  if (j > 0 && pm3 == flags) p2 = pm2 + 1u;
+  else if (type == 4u) p2 = ((j == 0 && fe) || !post) ? pc_before >> 2 : row_w3 & 0xFFFFu;
+  else if (type == 0u) p2 = post ? (rw ? row_w3 >> 16 : row_w3 & 0xFFFFu) : 0u;
+  else if (type <= 2u) p2 = row_w8 >> 5;
+  else p2 = (row_w8 + row_w10) >> 5;
+  // value candidates, on lanes 4..11 (limb k = lane - 4)
+  const bool vl = lane >= 4 && lane < 12;
+  const uint32_t k = (lane - 4u) & 7u, set = index % ZKB_CW_SETS;
+  uint32_t cand[8];
+  cand[0] = 0u;
+  cand[1] = __shfl_sync(0xffffffffu, w_lo, (lane + 4u) & 31u);
+  cand[2] = __shfl_sync(0xffffffffu, w_lo, (lane + 12u) & 31u);
+  cand[3] = __shfl_sync(0xffffffffu, w_lo, (lane + 20u) & 31u);
+  const uint32_t d1 = __shfl_sync(0xffffffffu, w_hi, (lane - 4u) & 31u);
+  const uint32_t* cset = J.cache + set * (ZKB_CW_WAYS * 8u);
+#pragma unroll
+  for (uint32_t v = 0; v < 4; v++) cand[4 + v] = type == 4u ? cset[v * 8u + k] : (v == 0 ? d1 : 0u);
+  uint32_t cnt[8];
+#pragma unroll
+  for (uint32_t v = 0; v < 8; v++) cnt[v] = __popc(__ballot_sync(0xffffffffu, vl && w != cand[v]));
+  const uint32_t vsel = first_min8(cnt);
+  uint32_t pv = cand[0];
+#pragma unroll
+  for (uint32_t v = 1; v < 8; v++) pv = vsel == v ? cand[v] : pv;
+  const uint32_t pred = lane == 0 ? p0 : lane == 1 ? p1 : lane == 2 ? p2 : lane == 3 ? J.pm : pv;
+  uint32_t x = lane < 12 ? (w ^ pred) : 0u;
+  if (lane == 3 && fcode < 15u) x = 0u;
+  const uint32_t pres = __ballot_sync(0xffffffffu, x != 0);
+  if (WRITE) {
+    uint32_t* o = J.out_mem + J.mwords;
+    if (lane == 0) o[0] = pres | vsel << 12 | fcode << 16;
+    if (x) o[1 + __popc(pres & lt)] = x;
+  }
+  J.mwords += 1u + __popc(pres);
+  // state: code-word cache (FIFO per set), the current code word, the previous query
+  if (type == 4u) {
+    const bool hit = cnt[4] == 0 || cnt[5] == 0 || cnt[6] == 0 || cnt[7] == 0;
+    if (!hit) {
+      const uint32_t way = __shfl_sync(0xffffffffu, J.rr, set);
+      __syncwarp();
+      if (vl) J.cache[set * (ZKB_CW_WAYS * 8u) + way * 8u + k] = w;
+      if (lane == set) J.rr = (J.rr + 1u) % ZKB_CW_WAYS;
+      __syncwarp();
+    }
+    const uint32_t v = __shfl_sync(0xffffffffu, w, (lane + 4u) & 31u);
+    if (j == 0 && rw == 0 && index == pc_before >> 2 && lane < 8) J.cw = v;
+  }
+  J.pm = w;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __restrict__ rows, uint32_t n_rows, uint32_t lane) {
   const uint32_t lt = lanemask_lt();
+  J.prev_lo = J.prev_hi = J.pm = J.cw = J.rr = J.prevprev50 = 0u;
+  J.mi = 0;
+  J.rwords = J.mwords = 0;
+  __syncwarp();
+  for (uint32_t i = lane; i < ZKB_CW_SETS * ZKB_CW_WAYS * 8u; i += 32) J.cache[i] = 0u;
+  __syncwarp();
+  J.m_next = (J.n_mem && lane < 12) ? __ldcs(J.mems + lane) : 0u;
   uint32_t nx_lo = 0, nx_hi = 0;
-  if (n) {
+  if (n_rows) {
     nx_lo = __ldcs(rows + lane);
     nx_hi = __ldcs(rows + 32 + lane);
   }
-  for (uint32_t r = 0; r < n; r++) {
+  for (uint32_t r = 0; r < n_rows; r++) {
     const uint32_t w_lo = nx_lo, w_hi = nx_hi;
-    if (r + 1 < n) {  // next row's loads in flight while this one is encoded
+    if (r + 1 < n_rows) {  // next row's loads in flight while this one is encoded
       nx_lo = __ldcs(rows + (size_t)(r + 1) * 64 + lane);
       nx_hi = __ldcs(rows + (size_t)(r + 1) * 64 + 32 + lane);
     }
-    const uint32_t w2 = __shfl_sync(0xffffffffu, w_lo, 2);
-    const uint32_t vidx = w2 & ((1u << ZK_VARIANT_BITS) - 1u);
+    const uint32_t pc_before = __shfl_sync(0xffffffffu, w_lo, 5) & 0xFFFFu;
+    const uint32_t prev48 = __shfl_sync(0xffffffffu, J.prev_hi, 16), prev50 = __shfl_sync(0xffffffffu, J.prev_hi, 18);
+    const uint32_t w43 = __shfl_sync(0xffffffffu, w_hi, 11);
+    // dst0 predictor (lanes 24..31 hold dst0; src0 sits 16 lanes, src1 8 lanes below)
+    const uint32_t s0 = __shfl_sync(0xffffffffu, w_lo, (lane - 16u) & 31u), s1 = __shfl_sync(0xffffffffu, w_lo, (lane - 8u) & 31u);
+    const bool dl = lane >= 24;
+    const uint32_t sum = s0 + s1, dif = s0 - s1;
+    const uint32_t Ga = __ballot_sync(0xffffffffu, sum < s0) >> 24, Pa = __ballot_sync(0xffffffffu, sum == 0xFFFFFFFFu) >> 24;
+    const uint32_t Gs = __ballot_sync(0xffffffffu, s0 < s1) >> 24, Ps = __ballot_sync(0xffffffffu, s0 == s1) >> 24;
+    const uint32_t Ka = carry_chain(Ga, Pa), Ks = carry_chain(Gs, Ps);
+    const uint32_t addv = sum + ((Ka >> (lane & 7u)) & 1u), subv = dif - ((Ks >> (lane & 7u)) & 1u);
+    const uint32_t c0 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != 0u)), c1 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != s0));
+    const uint32_t c2 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != addv)), c3 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != subv));
+    uint32_t dsel = 0, best = c0;
+    if (c1 < best) { best = c1; dsel = 1; }
+    if (c2 < best) { best = c2; dsel = 2; }
+    if (c3 < best) { best = c3; dsel = 3; }
+    const uint32_t dpred = dsel == 0 ? 0u : dsel == 1 ? s0 : dsel == 2 ? addv : subv;
+    const uint32_t ncode = w43 < 7u ? w43 : 7u;
+    // the cycle's memory queries: the first one ahead of the opcode when an instruction fetch is expected
+    const bool fe = r == 0 || (pc_before >> 2) != (prev48 >> 16) || prev50 != J.prevprev50;
+    const uint32_t nm = min(w43 & 0xFFFFu, J.n_mem - J.mi);
+    uint32_t j = 0;
+    if (fe && nm >= 1) {
+      joint_mem<WRITE>(J, lane, lt, w_lo, w_hi, false, fe, 0);
+      j = 1;
+    }
+    const uint32_t sub = pc_before & 3u;
+    const uint32_t cw_a = __shfl_sync(0xffffffffu, J.cw, 6u - 2u * sub), cw_b = __shfl_sync(0xffffffffu, J.cw, 7u - 2u * sub);
+    const uint32_t vidx = __shfl_sync(0xffffffffu, w_lo, 2) & ((1u << ZK_VARIANT_BITS) - 1u);
     uint32_t pred_lo = 0;
-    if (lane == 0) pred_lo = prev_lo + 1u;
-    else if (lane == 1) pred_lo = prev_lo + ZK_TIME_DELTA_PER_CYCLE;
+    if (lane == 0) pred_lo = J.prev_lo + 1u;
+    else if (lane == 1) pred_lo = J.prev_lo + ZK_TIME_DELTA_PER_CYCLE;
+    else if (lane == 2) pred_lo = cw_a;
+    else if (lane == 3) pred_lo = cw_b;
     else if (lane == 4) pred_lo = vidx | 1u << 16;
     else if (lane == 5) {
-      const uint32_t p = prev_lo >> 16;
+      const uint32_t p = J.prev_lo >> 16;
       pred_lo = p | ((p + 1u) & 0xFFFFu) << 16;
-    } else if (lane == 6) pred_lo = prev_lo;
-    else if (lane == 7) pred_lo = prev_lo - ZK_OPCODE_PRICES[vidx];
-    const uint32_t pred_hi = (lane < 8 || lane == 11) ? 0u : prev_hi;  // words 32..39 operands, 43 per-cycle counts
-    const uint32_t x_lo = w_lo ^ pred_lo, x_hi = w_hi ^ pred_hi;
-    const uint32_t m_lo = __ballot_sync(0xffffffffu, x_lo != 0), m_hi = __ballot_sync(0xffffffffu, x_hi != 0);
-    const uint32_t n_lo = __popc(m_lo), n_hi = __popc(m_hi);
+    } else if (lane == 6) pred_lo = J.prev_lo;
+    else if (lane == 7) pred_lo = J.prev_lo - ZK_OPCODE_PRICES[vidx];
+    else if (dl) pred_lo = dpred;
+    uint32_t pred_hi = (lane < 8 || lane == 11) ? 0u : J.prev_hi;  // words 32..39 dst1, 43 per-cycle counts
+    if (lane == 16) pred_hi = (J.prev_hi & 0xFFFFu) | (pc_before >> 2) << 16;
+    const uint32_t x_lo = w_lo ^ pred_lo;
+    uint32_t x_hi = lane < (ZKB_ROW_TX_WORDS - 32) ? (w_hi ^ pred_hi) : 0u;   // words 55..63 are not transmitted
+    if (lane == 11 && ncode < 7u) x_hi = 0u;
+    const uint32_t m_lo = __ballot_sync(0xffffffffu, x_lo != 0), p_hi = __ballot_sync(0xffffffffu, x_hi != 0);
+    const uint32_t n_lo = __popc(m_lo), n_hi = __popc(p_hi);
     if (WRITE) {
-      uint32_t* o = out + words;
+      uint32_t* o = J.out_rows + J.rwords;
       if (lane == 0) o[0] = m_lo;
-      if (lane == 1) o[1] = m_hi;
+      if (lane == 1) o[1] = p_hi | dsel << 23 | ncode << 25;
       if (x_lo) o[2 + __popc(m_lo & lt)] = x_lo;
-      if (x_hi) o[2 + n_lo + __popc(m_hi & lt)] = x_hi;
+      if (x_hi) o[2 + n_lo + __popc(p_hi & lt)] = x_hi;
     }
-    words += 2u + n_lo + n_hi;
-    prev_lo = w_lo;
-    prev_hi = w_hi;
+    J.rwords += 2u + n_lo + n_hi;
+    for (; j < nm; j++) joint_mem<WRITE>(J, lane, lt, w_lo, w_hi, true, fe, j);
+    J.prevprev50 = prev50;
+    J.prev_lo = w_lo;
+    J.prev_hi = w_hi;
   }
-  return words * 4;
+  // memory queries no row announces (a cycle that stopped the VM emits its queries but no row): zero row context
+  for (uint32_t j = 0; J.mi < J.n_mem; j++) joint_mem<WRITE>(J, lane, lt, 0u, 0u, true, false, j);
 }
 
-// 12-word records (MEM, DECOMMIT): two records per step, one per half-warp
 template <bool WRITE, int KIND>
 __device__ __forceinline__ uint64_t encode_rec12(const uint32_t* __restrict__ recs, uint32_t n, uint32_t* __restrict__ out, uint32_t lane) {
   const uint32_t g = lane >> 4, li = lane & 15u;
@@ -89,8 +227,7 @@ __device__ __forceinline__ uint64_t encode_rec12(const uint32_t* __restrict__ re
     const uint32_t a = __shfl_sync(0xffffffffu, w, li), b = __shfl_sync(0xffffffffu, w_last, 16 + li);
     const uint32_t p = g ? a : b;  // the same word of the previous record
     uint32_t pred;
-    if (KIND == ZKB_STREAM_MEM) pred = li == 2 ? p + 1u : li < 4 ? p : 0u;
-    else pred = li < 4 ? p : 0u;
+    pred = li < 4 ? p : 0u;
     const uint32_t x = valid ? (w ^ pred) : 0u;
     const uint32_t m = __ballot_sync(0xffffffffu, x != 0);
     const uint32_t m0 = m & 0xFFFFu, m1 = m >> 16;
@@ -115,7 +252,8 @@ __device__ __forceinline__ uint64_t encode_rec32(const uint32_t* __restrict__ re
   const uint32_t lt = lanemask_lt();
   for (uint32_t r = 0; r < n; r++) {
     const uint32_t w = __ldcs(recs + (size_t)r * 32 + lane);
-    const uint32_t pred = (KIND == ZKB_STREAM_FRAME || lane < 8) ? prev : 0u;
+    const uint32_t rd = __shfl_sync(0xffffffffu, w, (lane - 8u) & 31u);   // LOG: written_value is predicted by the read value
+    const uint32_t pred = (KIND == ZKB_STREAM_FRAME || lane < 8) ? prev : (KIND == ZKB_STREAM_LOG && lane >= 24) ? rd : 0u;
     const uint32_t x = w ^ pred;
     const uint32_t m = __ballot_sync(0xffffffffu, x != 0);
     if (WRITE) {
@@ -131,6 +269,7 @@ __device__ __forceinline__ uint64_t encode_rec32(const uint32_t* __restrict__ re
 
 template <bool WRITE>
 __global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
+  __shared__ uint32_t s_cache[8][ZKB_CW_SETS * ZKB_CW_WAYS * 8];   // the code-word cache of each warp's VM
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n_vms = B.n_vms;
   for (uint32_t vm = blockIdx.x * 8 + warp; vm < n_vms; vm += gridDim.x * 8) {
@@ -158,9 +297,16 @@ __global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const
     }
     uint64_t sz[ZKB_N_STREAMS];
     const uint32_t* s0 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
-    sz[0] = encode_rows<WRITE>(s0, cnt[0], outp[0], lane);
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES);
-    sz[1] = encode_rec12<WRITE, ZKB_STREAM_MEM>(s1, cnt[1], outp[1], lane);
+    JointWarp J;
+    J.cache = s_cache[warp];
+    J.mems = s1;
+    J.n_mem = cnt[1];
+    J.out_rows = outp[0];
+    J.out_mem = outp[1];
+    encode_joint<WRITE>(J, s0, cnt[0], lane);   // (a subset blob carries ROWS and MEM together or not at all)
+    sz[0] = J.rwords * 4;
+    sz[1] = J.mwords * 4;
     const uint32_t* s2 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
     sz[2] = encode_rec32<WRITE, ZKB_STREAM_LOG>(s2, cnt[2], outp[2], lane);
     const uint32_t* s3 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_DECOMMIT] + (size_t)vm * B.cap[ZKB_STREAM_DECOMMIT] * ZKB_DECOMMIT_BYTES);

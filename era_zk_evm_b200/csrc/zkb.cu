@@ -1390,6 +1390,7 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
 // pass.  Returns the device blob; it stays valid until the next encode / destroy.
 static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dptr, uint64_t* n_bytes, uint32_t kinds_mask = 63u) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
+  if (kinds_mask & 3u) kinds_mask |= 3u;   // cycle rows and memory queries are coded jointly (format v2): both or neither
   const uint32_t* c = nullptr;
   int32_t rc = summary(b, &c);  // waits for THIS batch's run only
   if (rc != ZKB_OK) return rc;

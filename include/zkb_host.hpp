@@ -445,8 +445,11 @@ inline VmLocalState GpuVmBatch::replay_encoded(const zkb_codec::EncodedView& blo
     vec.resize(n / sizeof(Rec));
     if (n && blob.decode(vm, kind, vec.data(), n) != n) throw std::runtime_error("replay_encoded: malformed blob");
   };
-  take(ZKB_STREAM_ROWS, s.rows);
-  take(ZKB_STREAM_MEM, s.mems);
+  // cycle rows and memory queries are coded jointly (format v2): one walk decodes both
+  s.rows.resize(blob.counts(vm)[ZKB_STREAM_ROWS]);
+  s.mems.resize(blob.counts(vm)[ZKB_STREAM_MEM]);
+  if (!blob.decode_rows_mem(vm, s.rows.data(), s.rows.size() * sizeof(ZkbCycleRow), s.mems.data(), s.mems.size() * sizeof(ZkbMemoryQueryRec)))
+    throw std::runtime_error("replay_encoded: malformed blob");
   take(ZKB_STREAM_LOG, s.logs);
   take(ZKB_STREAM_DECOMMIT, s.decs);
   take(ZKB_STREAM_FRAME, s.frames);

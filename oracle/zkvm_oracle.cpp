@@ -2280,13 +2280,20 @@ static void build_encoded_blob(OrcBatch* b, std::vector<uint8_t>& blob) {
   h.offsets_offset = h.counts_offset + n * 32;
   std::vector<uint64_t> offsets((n + 1) * ZKB_N_STREAMS, 0);
   static const uint32_t rec_bytes[ZKB_N_STREAMS] = {ZKB_ROW_BYTES, ZKB_MEM_BYTES, ZKB_LOG_BYTES, ZKB_DECOMMIT_BYTES, ZKB_FRAME_BYTES, ZKB_REFUND_BYTES};
+  // sizes: rows + memory queries of a VM are coded jointly (format v2), the other streams one by one
+  std::vector<uint64_t> sz((size_t)n * ZKB_N_STREAMS, 0);
+  for (size_t v = 0; v < n; v++) {
+    const auto& w = b->vms[v]->wt;
+    zkb_codec::encode_joint(w.s[0].data(), w.s[0].size() / ZKB_ROW_BYTES, w.s[1].data(), w.s[1].size() / ZKB_MEM_BYTES, nullptr, nullptr,
+                            &sz[v * ZKB_N_STREAMS + 0], &sz[v * ZKB_N_STREAMS + 1]);
+    for (int k = 2; k < ZKB_N_STREAMS; k++) sz[v * ZKB_N_STREAMS + k] = zkb_codec::encode_records(k, w.s[k].data(), w.s[k].size() / rec_bytes[k], nullptr);
+    for (int k = 0; k < ZKB_N_STREAMS; k++) h.raw_bytes += w.s[k].size();
+  }
   for (int k = 0; k < ZKB_N_STREAMS; k++) {
     uint64_t run = 0;
     for (size_t v = 0; v < n; v++) {
       offsets[(size_t)k * (n + 1) + v] = run;
-      const auto& s = b->vms[v]->wt.s[k];
-      run += zkb_codec::encode_records(k, s.data(), s.size() / rec_bytes[k], nullptr);
-      h.raw_bytes += s.size();
+      run += sz[v * ZKB_N_STREAMS + k];
     }
     offsets[(size_t)k * (n + 1) + n] = run;
     h.payload_bytes[k] = run;
@@ -2307,11 +2314,14 @@ static void build_encoded_blob(OrcBatch* b, std::vector<uint8_t>& blob) {
     counts[v * 8 + 7] = b->vms[v]->monotonic_cycle_counter;
   }
   memcpy(blob.data() + h.offsets_offset, offsets.data(), offsets.size() * 8);
-  for (int k = 0; k < ZKB_N_STREAMS; k++)
-    for (size_t v = 0; v < n; v++) {
-      const auto& s = b->vms[v]->wt.s[k];
-      zkb_codec::encode_records(k, s.data(), s.size() / rec_bytes[k], blob.data() + h.payload_offset[k] + offsets[(size_t)k * (n + 1) + v]);
-    }
+  for (size_t v = 0; v < n; v++) {
+    const auto& w = b->vms[v]->wt;
+    uint64_t rb = 0, mb = 0;
+    zkb_codec::encode_joint(w.s[0].data(), w.s[0].size() / ZKB_ROW_BYTES, w.s[1].data(), w.s[1].size() / ZKB_MEM_BYTES,
+                            blob.data() + h.payload_offset[0] + offsets[v], blob.data() + h.payload_offset[1] + offsets[(n + 1) + v], &rb, &mb);
+    for (int k = 2; k < ZKB_N_STREAMS; k++)
+      zkb_codec::encode_records(k, w.s[k].data(), w.s[k].size() / rec_bytes[k], blob.data() + h.payload_offset[k] + offsets[(size_t)k * (n + 1) + v]);
+  }
 }
 
 int32_t orc_fetch_encoded(OrcBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes) {

@@ -119,11 +119,11 @@ def test_malformed_blobs_are_rejected(oracle_mod):
 
 
 def test_erc20_ratio(oracle_mod):
-    """the figure DESIGN.md / bench.py quote: the blob is ~30 % of the canonical bytes on the ERC-20 workload"""
+    """the figure DESIGN.md / bench.py quote: the blob is ~17 % of the canonical bytes on the ERC-20 workload (format v2)"""
     _, b = _oracle_run(oracle_mod, "erc20", dict(n_transfers=8), 64)
     blob = b.fetch_encoded()
     raw = sum(b.totals()[1])
-    assert 0.2 < blob.size / raw < 0.36, blob.size / raw
+    assert 0.12 < blob.size / raw < 0.20, blob.size / raw
 
 
 @pytest.mark.gpu
