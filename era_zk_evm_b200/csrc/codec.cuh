@@ -2,10 +2,13 @@
 // per VM; cycle rows and memory queries are coded jointly (encode_joint), the other streams record by record.
 //
 // The canonical streams stay in HBM (they are what the device-side consumers read); this kernel is the last step before
-// the PCIe link: it reads every record once per pass (HBM-read bound: two coalesced 128-byte loads per cycle row) and
-// writes ~30 % of the bytes.  Two passes over the same code (template WRITE): pass 1 only counts the encoded bytes of
-// every (VM, stream), a scan turns the counts into byte offsets, pass 2 writes -- so the blob layout is deterministic
-// (bit-identical to the scalar encoder in zkb_codec.h, which the tests check) and needs no atomics.
+// the PCIe link.  ONE encoding pass: every VM's payloads go to a staging area at worst-case offsets (known from the
+// record counts alone: record index x the longest encoding of a record), the pass also records their true sizes, a scan
+// turns those into the blob's byte offsets, and a copy kernel compacts staging -> blob and writes the blob's tables.  The
+// walk over a VM is a latency-bound dependent chain (~2 600 cycles per cycle row on 16 resident warps per SM), so it
+// runs once, not twice (round 2's first encoder counted in one pass and wrote in a second: 14.4 ms per 14 208-VM
+// sub-batch; this: see profiles/).  The blob layout is deterministic (bit-identical to the scalar encoder in
+// zkb_codec.h, which the tests check) and needs no atomics.
 #pragma once
 #include <stdint.h>
 
@@ -19,11 +22,24 @@ struct EncArgs {
   uint32_t* sizes;          // [6][n_vms] encoded bytes per VM and stream (pass 1 out, scan in)
   uint64_t* offsets;        // [6][n_vms + 1] exclusive prefix sums (scan out, pass 2 in)
   uint64_t* totals;         // [8] mapped pinned host memory: payload bytes per stream, [6] = raw canonical bytes
-  uint8_t* blob;            // pass 2: the device blob
+  uint8_t* blob;            // the device blob (compaction target)
+  uint8_t* stage;           // staging area of the encoding pass
+  uint64_t stage_base[ZKB_N_STREAMS];   // start of every stream's staging region
+  const uint64_t* canon;    // [6][n_vms + 1] canonical (packed) byte offsets of every VM: its first record's index x record size
   uint64_t counts_offset, offsets_offset;
   uint64_t payload_offset[ZKB_N_STREAMS];
   uint32_t kinds_mask;      // streams outside the mask are left out of the blob (their counts are still reported)
 };
+
+// longest encoding of one record of each stream (mask words + every word present) and the canonical record size
+__device__ __forceinline__ uint32_t enc_worst_bytes(int k) {
+  return k == ZKB_STREAM_ROWS ? 8u + ZKB_ROW_TX_WORDS * 4u : k == ZKB_STREAM_MEM ? 52u : k == ZKB_STREAM_LOG ? 132u : k == ZKB_STREAM_DECOMMIT ? 52u
+         : k == ZKB_STREAM_FRAME ? 132u : 8u;
+}
+__device__ __forceinline__ uint32_t* stage_slot(const EncArgs& A, int k, uint32_t vm, uint32_t n_vms) {
+  const uint64_t first_record = A.canon[(size_t)k * (n_vms + 1) + vm] / rec_bytes(k);
+  return reinterpret_cast<uint32_t*>(A.stage + A.stage_base[k] + first_record * enc_worst_bytes(k));
+}
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
@@ -267,8 +283,8 @@ __device__ __forceinline__ uint64_t encode_rec32(const uint32_t* __restrict__ re
   return words * 4;
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
+// the encoding pass: one warp per VM, payloads into the staging area, true sizes into A.sizes
+__global__ void __launch_bounds__(256, 4) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
   __shared__ uint32_t s_cache[8][ZKB_CW_SETS * ZKB_CW_WAYS * 8];   // the code-word cache of each warp's VM
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n_vms = B.n_vms;
@@ -277,24 +293,6 @@ __global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const
     uint32_t cnt[ZKB_N_STREAMS];
 #pragma unroll
     for (int k = 0; k < ZKB_N_STREAMS; k++) cnt[k] = ((A.kinds_mask >> k) & 1u) ? x[X_COUNT0 + k] : 0u;
-    uint32_t* outp[ZKB_N_STREAMS];
-#pragma unroll
-    for (int k = 0; k < ZKB_N_STREAMS; k++) outp[k] = nullptr;
-    if (WRITE) {
-      // the blob's tables: per-VM summary (same 8 words the host mirror holds) and this VM's offsets
-      uint32_t* counts = reinterpret_cast<uint32_t*>(A.blob + A.counts_offset) + (size_t)vm * 8;
-      const uint32_t status = x[X_STATUS];
-      const uint32_t st_out = (status == ZKB_VM_RUNNING && B.hot[vm].live[L_DEPTH - 40] == 0 && x[X_CYCLE] > 0) ? (uint32_t)ZKB_VM_ENDED : status;
-      if (lane < 8) counts[lane] = lane < 6 ? x[X_COUNT0 + lane] : lane == 6 ? st_out : x[X_CYCLE];
-      uint64_t* offs = reinterpret_cast<uint64_t*>(A.blob + A.offsets_offset);
-      if (lane < ZKB_N_STREAMS) {
-        offs[(size_t)lane * (n_vms + 1) + vm] = A.offsets[(size_t)lane * (n_vms + 1) + vm];
-        if (vm == n_vms - 1) offs[(size_t)lane * (n_vms + 1) + n_vms] = A.offsets[(size_t)lane * (n_vms + 1) + n_vms];
-      }
-#pragma unroll
-      for (int k = 0; k < ZKB_N_STREAMS; k++)
-        outp[k] = reinterpret_cast<uint32_t*>(A.blob + A.payload_offset[k] + A.offsets[(size_t)k * (n_vms + 1) + vm]);
-    }
     uint64_t sz[ZKB_N_STREAMS];
     const uint32_t* s0 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES);
@@ -302,26 +300,47 @@ __global__ void __launch_bounds__(256) zkb_encode_kernel(const DevBatch B, const
     J.cache = s_cache[warp];
     J.mems = s1;
     J.n_mem = cnt[1];
-    J.out_rows = outp[0];
-    J.out_mem = outp[1];
-    encode_joint<WRITE>(J, s0, cnt[0], lane);   // (a subset blob carries ROWS and MEM together or not at all)
+    J.out_rows = stage_slot(A, ZKB_STREAM_ROWS, vm, n_vms);
+    J.out_mem = stage_slot(A, ZKB_STREAM_MEM, vm, n_vms);
+    encode_joint<true>(J, s0, cnt[0], lane);   // (a subset blob carries ROWS and MEM together or not at all)
     sz[0] = J.rwords * 4;
     sz[1] = J.mwords * 4;
     const uint32_t* s2 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_LOG] + (size_t)vm * B.cap[ZKB_STREAM_LOG] * ZKB_LOG_BYTES);
-    sz[2] = encode_rec32<WRITE, ZKB_STREAM_LOG>(s2, cnt[2], outp[2], lane);
+    sz[2] = encode_rec32<true, ZKB_STREAM_LOG>(s2, cnt[2], stage_slot(A, ZKB_STREAM_LOG, vm, n_vms), lane);
     const uint32_t* s3 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_DECOMMIT] + (size_t)vm * B.cap[ZKB_STREAM_DECOMMIT] * ZKB_DECOMMIT_BYTES);
-    sz[3] = encode_rec12<WRITE, ZKB_STREAM_DECOMMIT>(s3, cnt[3], outp[3], lane);
+    sz[3] = encode_rec12<true, ZKB_STREAM_DECOMMIT>(s3, cnt[3], stage_slot(A, ZKB_STREAM_DECOMMIT, vm, n_vms), lane);
     const uint32_t* s4 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_FRAME] + (size_t)vm * B.cap[ZKB_STREAM_FRAME] * ZKB_FRAME_BYTES);
-    sz[4] = encode_rec32<WRITE, ZKB_STREAM_FRAME>(s4, cnt[4], outp[4], lane);
-    // REFUND: raw 8-byte records
-    sz[5] = (uint64_t)cnt[5] * ZKB_REFUND_BYTES;
-    if (WRITE) {
-      const uint32_t* s5 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_REFUND] + (size_t)vm * B.cap[ZKB_STREAM_REFUND] * ZKB_REFUND_BYTES);
-      for (uint32_t i = lane; i < cnt[5] * 2; i += 32) outp[5][i] = s5[i];
-    } else {
+    sz[4] = encode_rec32<true, ZKB_STREAM_FRAME>(s4, cnt[4], stage_slot(A, ZKB_STREAM_FRAME, vm, n_vms), lane);
+    sz[5] = (uint64_t)cnt[5] * ZKB_REFUND_BYTES;   // REFUND: raw 8-byte records, copied by the compaction straight from the stream
 #pragma unroll
-      for (int k = 0; k < ZKB_N_STREAMS; k++)
-        if (lane == (uint32_t)k) A.sizes[(size_t)k * n_vms + vm] = (uint32_t)sz[k];
+    for (int k = 0; k < ZKB_N_STREAMS; k++)
+      if (lane == (uint32_t)k) A.sizes[(size_t)k * n_vms + vm] = (uint32_t)sz[k];
+  }
+}
+
+// compaction: staging -> blob at the scanned offsets, plus the blob's per-VM tables.  One CTA per VM (grid-stride).
+__global__ void __launch_bounds__(128) zkb_encode_compact_kernel(const DevBatch B, const EncArgs A) {
+  const uint32_t n_vms = B.n_vms, t = threadIdx.x;
+  for (uint32_t vm = blockIdx.x; vm < n_vms; vm += gridDim.x) {
+    const uint32_t* x = B.hot[vm].x;
+    // the blob's tables: per-VM summary (same 8 words the host mirror holds) and this VM's offsets
+    uint32_t* counts = reinterpret_cast<uint32_t*>(A.blob + A.counts_offset) + (size_t)vm * 8;
+    const uint32_t status = x[X_STATUS];
+    const uint32_t st_out = (status == ZKB_VM_RUNNING && B.hot[vm].live[L_DEPTH - 40] == 0 && x[X_CYCLE] > 0) ? (uint32_t)ZKB_VM_ENDED : status;
+    if (t < 8) counts[t] = t < 6 ? x[X_COUNT0 + t] : t == 6 ? st_out : x[X_CYCLE];
+    uint64_t* offs = reinterpret_cast<uint64_t*>(A.blob + A.offsets_offset);
+    if (t < ZKB_N_STREAMS) {
+      offs[(size_t)t * (n_vms + 1) + vm] = A.offsets[(size_t)t * (n_vms + 1) + vm];
+      if (vm == n_vms - 1) offs[(size_t)t * (n_vms + 1) + n_vms] = A.offsets[(size_t)t * (n_vms + 1) + n_vms];
+    }
+#pragma unroll
+    for (int k = 0; k < ZKB_N_STREAMS; k++) {
+      const uint32_t words = A.sizes[(size_t)k * n_vms + vm] / 4u;
+      const uint32_t* src = k == ZKB_STREAM_REFUND
+                                ? reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_REFUND] + (size_t)vm * B.cap[ZKB_STREAM_REFUND] * ZKB_REFUND_BYTES)
+                                : stage_slot(A, k, vm, n_vms);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(A.blob + A.payload_offset[k] + A.offsets[(size_t)k * (n_vms + 1) + vm]);
+      for (uint32_t i = t; i < words; i += 128) dst[i] = src[i];
     }
   }
 }

@@ -542,6 +542,9 @@ struct ZkbBatch {
   // transport encoder (zkb_codec.h): per-(VM, stream) sizes, their prefix sums, the blob, totals in mapped host memory
   uint32_t* d_enc_sizes = nullptr;
   uint64_t* d_enc_offsets = nullptr;
+  uint64_t* d_enc_canon = nullptr;      // [6][n_vms + 1] canonical byte offsets (device copy of h_offsets)
+  uint8_t* d_enc_stage = nullptr;       // staging area of the encoding pass (grow-only)
+  uint64_t enc_stage_capacity = 0;
   uint64_t* h_enc_totals = nullptr;
   uint64_t* d_enc_totals = nullptr;
   uint8_t* d_enc = nullptr;
@@ -858,6 +861,7 @@ int32_t zkb_destroy(ZkbBatch* b) {
   if (b->h_fail) cudaFreeHost(b->h_fail);
   if (b->h_offsets[0]) cudaFreeHost(b->h_offsets[0]);
   if (b->d_enc) cudaFree(b->d_enc);
+  if (b->d_enc_stage) cudaFree(b->d_enc_stage);
   if (b->d_snap_pack) cudaFree(b->d_snap_pack);
   if (b->h_enc_totals) cudaFreeHost(b->h_enc_totals);
   if (b->ev_enc) cudaEventDestroy(b->ev_enc);
@@ -1386,18 +1390,21 @@ int32_t zkb_fetch_stream_packed(ZkbBatch* b, uint32_t kind, void* host_dst, uint
 }
 
 // ---- transport encoding (include/zkb_codec.h) ------------------------------------------------------------------
-// size pass + scan on `st`, then (after the host has read the totals from mapped memory and sized the blob) the write
-// pass.  Returns the device blob; it stays valid until the next encode / destroy.
+// encoding pass (payloads into a staging area at worst-case offsets, true sizes) + scan on the encoder's own stream, then
+// (after the host has read the totals from mapped memory and sized the blob) the compaction into the blob.  Returns the
+// device blob; it stays valid until the next encode / destroy.
 static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dptr, uint64_t* n_bytes, uint32_t kinds_mask = 63u) {
   CUDA_OK(cudaSetDevice(b->cfg.device));
   if (kinds_mask & 3u) kinds_mask |= 3u;   // cycle rows and memory queries are coded jointly (format v2): both or neither
   const uint32_t* c = nullptr;
   int32_t rc = summary(b, &c);  // waits for THIS batch's run only
   if (rc != ZKB_OK) return rc;
+  refresh_offsets(b);           // canonical (packed) byte offsets of every VM, in pinned host memory
   const size_t n = b->cfg.n_vms;
   if (!b->d_enc_sizes) {
     cudaError_t e = dalloc(b, &b->d_enc_sizes, n * ZKB_N_STREAMS, false);
     if (e == cudaSuccess) e = dalloc(b, &b->d_enc_offsets, (n + 1) * ZKB_N_STREAMS, false);
+    if (e == cudaSuccess) e = dalloc(b, &b->d_enc_canon, (n + 1) * ZKB_N_STREAMS, false);
     void* hp = nullptr;
     void* dp = nullptr;
     if (e == cudaSuccess) e = cudaHostAlloc(&hp, 64, cudaHostAllocMapped);
@@ -1414,14 +1421,35 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dpt
   a.sizes = b->d_enc_sizes;
   a.offsets = b->d_enc_offsets;
   a.totals = b->d_enc_totals;
+  a.canon = b->d_enc_canon;
   a.kinds_mask = kinds_mask & 63u;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8));
+  // staging area: every stream's region holds (records of the batch) x (longest encoding of one record)
+  static const uint32_t WORST[ZKB_N_STREAMS] = {8u + ZKB_ROW_TX_WORDS * 4u, 52u, 132u, 52u, 132u, 8u};
+  uint64_t stage_need = 0;
+  for (int k = 0; k < ZKB_N_STREAMS; k++) {
+    a.stage_base[k] = stage_need;
+    stage_need += (b->h_offsets[k][n] / REC_BYTES[k] * WORST[k] + 255) / 256 * 256;
+  }
   // The run has finished (summary() waited for it), so the passes need no dependency on the caller's stream -- and they
   // must not sit on it: in a pipelined host loop that stream still carries the previous sub-batch's D2H copy.
   cudaStream_t st = b->enc_stream;
-  zkb_encode_kernel<false><<<grid, 256, 0, st>>>(b->d, a);
+  if (stage_need > b->enc_stage_capacity) {
+    CUDA_OK(cudaStreamSynchronize(st));   // (the previous encode of this batch is long finished; its blob copy does not read staging)
+    if (b->d_enc_stage) CUDA_OK(cudaFree(b->d_enc_stage));
+    b->d_enc_stage = nullptr;
+    b->enc_stage_capacity = 0;
+    const uint64_t cap = stage_need + stage_need / 8 + 4096;
+    cudaError_t e = cudaMalloc(&b->d_enc_stage, cap);
+    if (e != cudaSuccess) return set_err(ZKB_ERR_OUT_OF_MEMORY, std::string("encoder staging cudaMalloc: ") + cudaGetErrorString(e));
+    b->enc_stage_capacity = cap;
+  }
+  a.stage = b->d_enc_stage;
+  for (int k = 0; k < ZKB_N_STREAMS; k++)
+    CUDA_OK(cudaMemcpyAsync(b->d_enc_canon + (size_t)k * (n + 1), b->h_offsets[k], (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->cfg.device);
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 7) / 8, (size_t)n_sm * 8));
+  zkb_encode_kernel<<<grid, 256, 0, st>>>(b->d, a);
   zkb_encode_scan_kernel<<<ZKB_N_STREAMS, 1024, 0, st>>>(b->d, a);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(b->ev_enc, st));
@@ -1459,7 +1487,7 @@ static int32_t encode_async(ZkbBatch* b, cudaStream_t user_stream, uint8_t** dpt
   a.offsets_offset = h.offsets_offset;
   if (b->blob_read_pending) CUDA_OK(cudaStreamWaitEvent(st, b->ev_blob_read, 0));  // the previous blob is still being copied out
   zkb_encode_header_kernel<<<1, 32, 0, st>>>(h, b->d_enc);
-  zkb_encode_kernel<true><<<grid, 256, 0, st>>>(b->d, a);
+  zkb_encode_compact_kernel<<<(int)std::max<size_t>(1, std::min<size_t>(n, (size_t)n_sm * 16)), 128, 0, st>>>(b->d, a);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(b->ev_enc_done, st));
   CUDA_OK(cudaStreamWaitEvent(user_stream, b->ev_enc_done, 0));   // whatever the caller queues next sees the finished blob
