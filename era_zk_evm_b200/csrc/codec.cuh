@@ -374,8 +374,15 @@ __global__ void __launch_bounds__(1024) zkb_encode_scan_kernel(const DevBatch B,
   }
 }
 
+// header + the alignment padding after every payload (each payload starts 16-byte aligned; the bytes in between are part
+// of the blob and must be deterministic: the blob is compared byte for byte with the scalar encoder's)
 __global__ void zkb_encode_header_kernel(ZkbEncodedHeader h, uint8_t* blob) {
-  if (threadIdx.x == 0) *reinterpret_cast<ZkbEncodedHeader*>(blob) = h;
+  const uint32_t t = threadIdx.x;
+  if (t == 0) *reinterpret_cast<ZkbEncodedHeader*>(blob) = h;
+  if (t < ZKB_N_STREAMS) {
+    const uint64_t lo = h.payload_offset[t] + h.payload_bytes[t], hi = t + 1 < ZKB_N_STREAMS ? h.payload_offset[t + 1] : h.total_bytes;
+    for (uint64_t i = lo; i < hi; i++) blob[i] = 0;
+  }
 }
 
 }  // namespace zkb

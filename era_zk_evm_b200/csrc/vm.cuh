@@ -97,6 +97,8 @@ struct DevBatch {
   const uint32_t* code_words;  // 8 u32 (LE limbs) per 256-bit code word, all bytecodes back to back
   const uint32_t* code_meta;   // per bytecode: offset_words, len_words, hash limbs[8]
   uint32_t n_codes;
+  const uint32_t* code_index;  // open-addressed hash index over code_meta: slot -> bytecode id or ZKB_NO_CODE
+  uint32_t code_index_mask;    // slots - 1 (power of two, >= 2 x n_codes)
   uint32_t default_aa[8];
   uint32_t zkporter;
   VmHot* hot;
@@ -1601,10 +1603,16 @@ __device__ __forceinline__ void Vm<KD>::op_far_call(uint32_t sub, u256l src0, u2
     mapped_code_page = ZK_UNMAPPED_PAGE;
   } else {
     // SimpleDecommitter::decommit_into_memory (decommitter.rs:32-99)
+    // lookup by hash: open-addressed index over the loaded bytecodes (built by the host at upload: power-of-two slots, at
+    // most half full, keyed by the hash's low limb) -- round 1 scanned all bytecodes linearly on every fresh far call
     int id = -1;
-    for (uint32_t c = 0; c < B.n_codes && id < 0; c++) {
-      uint32_t hw = B.code_meta[c * 10 + 2 + lane];
-      if (u_eq(hw, code_hash)) id = (int)c;
+    for (uint32_t slot = oshfl(code_hash, 0) & B.code_index_mask, probes = 0; probes <= B.code_index_mask; slot = (slot + 1u) & B.code_index_mask, probes++) {
+      const uint32_t c = B.code_index[slot];
+      if (c == ZKB_NO_CODE) break;
+      if (u_eq(B.code_meta[c * 10 + 2 + lane], code_hash)) {
+        id = (int)c;
+        break;
+      }
     }
     uint32_t* dec = B.dec + (size_t)vm * ZKB_DEC_ENTRIES * 2;
     // history is keyed by hash; entries created by populate_code are flagged (bit 31) and not part of it.

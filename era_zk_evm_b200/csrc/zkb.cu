@@ -496,6 +496,7 @@ struct ZkbBatch {
   bool codes_dirty = true;
   uint32_t* d_code_words = nullptr;
   uint32_t* d_code_meta = nullptr;
+  uint32_t* d_code_index = nullptr;   // open-addressed hash index over the loaded bytecodes (DevBatch.code_index)
   std::vector<int32_t> boot_code;  // per VM: code id bound by populate_code (page in boot_page)
   uint32_t* d_order = nullptr;     // schedule slot -> VM, VMs grouped by boot_code (nullptr while the identity is already grouped)
   bool order_dirty = true;
@@ -660,6 +661,21 @@ static int32_t upload(ZkbBatch* b) {
     b->d.code_words = b->d_code_words;
     b->d.code_meta = b->d_code_meta;
     b->d.n_codes = (uint32_t)b->codes.size();
+    // hash index for the decommitter's lookup (vm.cuh op_far_call): at most half full, linear probing from the low limb
+    uint32_t slots = 16;
+    while (slots < 2 * b->codes.size()) slots *= 2;
+    std::vector<uint32_t> index(slots, ZKB_NO_CODE);
+    for (size_t i = 0; i < b->codes.size(); i++) {
+      uint32_t s = b->codes[i].hash[0] & (slots - 1);
+      while (index[s] != ZKB_NO_CODE) s = (s + 1) & (slots - 1);
+      index[s] = (uint32_t)i;
+    }
+    if (b->d_code_index) cudaFree(b->d_code_index);
+    b->d_code_index = nullptr;
+    CUDA_OK(cudaMalloc(&b->d_code_index, (size_t)slots * 4));
+    CUDA_OK(cudaMemcpy(b->d_code_index, index.data(), (size_t)slots * 4, cudaMemcpyHostToDevice));
+    b->d.code_index = b->d_code_index;
+    b->d.code_index_mask = slots - 1;
     b->codes_dirty = false;
   }
   if (b->hot_dirty) {
@@ -850,6 +866,7 @@ int32_t zkb_destroy(ZkbBatch* b) {
   for (void* p : b->allocs) cudaFree(p);
   if (b->d_code_words) cudaFree(b->d_code_words);
   if (b->d_code_meta) cudaFree(b->d_code_meta);
+  if (b->d_code_index) cudaFree(b->d_code_index);
   if (b->d_pack) cudaFree(b->d_pack);
   for (auto& r : b->snap)
     if (r.saved) cudaFree(r.saved);
