@@ -13,7 +13,7 @@
 // With these a host loop needs only snapshots + commitments + the (encoded) query logs across PCIe; the full-stream
 // download stays available.
 //   K12 zkb_consume_state_kernel   one warp per VM, walks the rows once (HBM-read bound: 256 B per cycle)
-//   K13 zkb_consume_hash_kernel    one THREAD per (VM, queue): sequential chain per queue, parallel across VMs
+//   K13 zkb_consume_hash_kernel    one THREAD per (queue, VM): sequential chain per queue, parallel across VMs; a warp = one queue kind
 #pragma once
 #include <stdint.h>
 
@@ -258,9 +258,11 @@ __device__ __forceinline__ void sha256_compress_thread(uint32_t st[8], uint32_t 
 // i.e. message words are the byte-swapped little-endian record words), drops the chaining value into every snapshot
 // whose boundary count is reached, finalises with the standard sha256 padding.
 __global__ void __launch_bounds__(128) zkb_consume_hash_kernel(const DevBatch B, const ConsumeOut O) {
+  // thread t -> (queue t / n_vms, VM t % n_vms): the lanes of a warp hash the SAME queue of 32 neighbouring VMs, whose chains
+  // are about equally long (a (vm, queue) interleave left two thirds of every warp waiting for its memory-queue lanes)
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t vm = t / 3, q = t % 3;
-  if (vm >= B.n_vms) return;
+  if (t >= B.n_vms * 3u) return;
+  const uint32_t q = t / B.n_vms, vm = t % B.n_vms;
   const int kind = q == 0 ? ZKB_STREAM_MEM : q == 1 ? ZKB_STREAM_LOG : ZKB_STREAM_DECOMMIT;
   const uint32_t rec_words = q == 1 ? 32u : 12u;
   const uint32_t n = B.hot[vm].x[X_COUNT0 + kind];

@@ -184,3 +184,47 @@ def test_subset_blob_carries_only_the_requested_streams(oracle_mod):
             else:
                 assert len(got) == 0
         assert view.counts(vm)[0] == len(orc.read_stream(vm, 0))       # the true counts are still reported
+
+
+def test_midcycle_stop_round_trips(oracle_mod):
+    """a VM whose far call hits an unknown code hash stops in the MIDDLE of a cycle: records of that cycle without a row"""
+    from era_zk_evm_b200 import isa
+    from era_zk_evm_b200._binding import storage_entries
+    w = workloads.Erc20(n_transfers=2)
+    n = 9
+    b = oracle_mod.OracleBatch(w.config(n))
+    w.setup(b, np.arange(n))
+    fake = int.from_bytes(bytes([1, 0, 0, 1]) + bytes(range(28)), "big")       # well-formed versioned hash, never loaded
+    b.populate_storage(storage_entries([(0, isa.C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, workloads.TOKEN_ADDRESS, fake)]), vm_lo=0, vm_hi=5)
+    b.run_threads(0, 1)
+    st = b.vm_status()
+    assert (st[:5, 0] == 2).all() and (st[5:, 0] == 1).all()                     # ZKB_VM_UNKNOWN_CODE_HASH / ended
+    view = EncodedWitness(oracle_mod.lib(), "orc_", b.fetch_encoded())
+    for vm in range(n):
+        for kind in range(records.N_STREAMS):
+            assert view.read_stream(vm, kind).tobytes() == b.read_stream(vm, kind).tobytes()
+
+
+@pytest.mark.gpu
+def test_orphan_memory_queries_round_trip_on_the_gpu():
+    """a VM stopped by a stream capacity at row emission has already emitted that cycle's memory queries: queries no row
+    announces.  The CUDA encoder's blob must decode (host decoder) to exactly the batch's own canonical streams."""
+    from era_zk_evm_b200 import GpuVmBatch, load_library
+    w = workloads.Erc20(n_transfers=2)
+    n = 40
+    cfg = w.config(n)
+    cfg.cap_records[0] = 37                                                       # rows: every VM stops on ZKB_VM_CAP_STREAM
+    gpu = GpuVmBatch(cfg)
+    w.setup(gpu, np.arange(n))
+    gpu.run()
+    st = gpu.vm_status()
+    assert (st[:, 0] >= 16).all(), st[:3]                                        # ZKB_VM_CAP_*
+    view = EncodedWitness(load_library(), "zkb_", gpu.fetch_encoded())
+    orphans = 0
+    for vm in range(n):
+        rows, mem = gpu.read_stream(vm, records.STREAM_ROWS), gpu.read_stream(vm, records.STREAM_MEM)
+        orphans += len(mem) - int(rows["n_mem"].sum())
+        for kind in range(records.N_STREAMS):
+            assert view.read_stream(vm, kind).tobytes() == gpu.read_stream(vm, kind).tobytes(), (vm, kind)
+    assert orphans > 0
+
