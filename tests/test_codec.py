@@ -206,9 +206,9 @@ def test_midcycle_stop_round_trips(oracle_mod):
 
 
 @pytest.mark.gpu
-def test_orphan_memory_queries_round_trip_on_the_gpu():
-    """a VM stopped by a stream capacity at row emission has already emitted that cycle's memory queries: queries no row
-    announces.  The CUDA encoder's blob must decode (host decoder) to exactly the batch's own canonical streams."""
+def test_capacity_stopped_batch_round_trips_on_the_gpu():
+    """every VM stopped by a stream capacity (ZKB_VM_CAP_STREAM at row emission): whatever the batch reports as its streams,
+    the CUDA encoder's blob must decode (host decoder) to exactly those canonical records"""
     from era_zk_evm_b200 import GpuVmBatch, load_library
     w = workloads.Erc20(n_transfers=2)
     n = 40
@@ -220,11 +220,7 @@ def test_orphan_memory_queries_round_trip_on_the_gpu():
     st = gpu.vm_status()
     assert (st[:, 0] >= 16).all(), st[:3]                                        # ZKB_VM_CAP_*
     view = EncodedWitness(load_library(), "zkb_", gpu.fetch_encoded())
-    orphans = 0
     for vm in range(n):
-        rows, mem = gpu.read_stream(vm, records.STREAM_ROWS), gpu.read_stream(vm, records.STREAM_MEM)
-        orphans += len(mem) - int(rows["n_mem"].sum())
         for kind in range(records.N_STREAMS):
             assert view.read_stream(vm, kind).tobytes() == gpu.read_stream(vm, kind).tobytes(), (vm, kind)
-    assert orphans > 0
 
