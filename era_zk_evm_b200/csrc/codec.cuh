@@ -53,26 +53,11 @@ __device__ __constant__ uint32_t c_mem_flag_codes[16] = {0x00000004u, 0x00000001
 // ---- format v2: cycle rows and memory queries of one VM, coded jointly by one warp (zkb_codec.h JointCoder is the scalar
 // statement of the same walk; the blobs are bit-identical) -------------------------------------------------------------
 // Lane l owns words l and l + 32 of the current row (two coalesced 128-byte loads per row) and word l of the current
-// memory query (lanes 0..11).  Everything one lane needs from another goes through the warp's SCRATCH in shared memory
-// (the current and the previous row, the current and the previous query, the current code word, the FIFO pointers and
-// the 32-set x 4-way code-word cache: 4.7 KB per warp) -- a broadcast LDS instead of a shuffle: ptxas wraps every
-// shuffle / vote of this loop nest in a convergence guard (it cannot prove the data-dependent trip counts uniform), and
-// the first version of this walk spent most of its issue slots on ~50 guarded collectives per cycle.  Candidate
-// predictors are compared in ONE warp reduction: every lane packs its mismatch bits, 4 bits per candidate, and
-// __reduce_add_sync sums them (a count is at most 8, so the nibbles cannot carry into each other).
-struct JointScratch {
-  uint32_t row[2][64];        // current / previous row (index toggles)
-  uint32_t rec[2][12];        // current / previous memory query
-  uint32_t cw[8];             // current code word
-  uint32_t rr[ZKB_CW_SETS];   // FIFO pointer of every cache set
-  uint32_t cache[ZKB_CW_SETS * ZKB_CW_WAYS * 8];
-};
-
+// memory query (lanes 0..11); lanes 0..7 keep the current code word, lane s the FIFO pointer of cache set s; the
+// 32-set x 4-way code-word cache of the VM sits in shared memory (4 KB per warp).
 struct JointWarp {
-  JointScratch* S;
-  uint32_t cur, mcur;         // which row / rec buffer is current
-  uint32_t prev_lo, prev_hi;  // this lane's words of the previous row
-  uint32_t prevprev50;
+  uint32_t prev_lo, prev_hi, pm, cw, rr, prevprev50;
+  uint32_t* cache;            // [32 sets][4 ways][8] of this warp
   const uint32_t* mems;       // the VM's memory queries
   uint32_t n_mem, mi;
   uint32_t m_next;            // prefetched word `lane` of query mi
@@ -81,61 +66,59 @@ struct JointWarp {
   uint64_t rwords, mwords;
 };
 
-// one memory query (JointCoder::mem_record).  The cycle's row is S.row[J.cur] (a zero row for queries no row announces);
-// post: w3 (the raw opcode's immediates) may be used
+__device__ __forceinline__ uint32_t first_min8(const uint32_t* c) {
+  uint32_t best = c[0], sel = 0;
+#pragma unroll
+  for (uint32_t v = 1; v < 8; v++)
+    if (c[v] < best) {
+      best = c[v];
+      sel = v;
+    }
+  return sel;
+}
+
+// one memory query (JointCoder::mem_record).  w_lo / w_hi: the cycle's row; post: w3 (the raw opcode's immediates) may be used
 template <bool WRITE>
-__device__ __forceinline__ void joint_mem(JointWarp& J, uint32_t lane, uint32_t lt, bool post, bool fe, uint32_t j) {
-  JointScratch& S = *J.S;
+__device__ __forceinline__ void joint_mem(JointWarp& J, uint32_t lane, uint32_t lt, uint32_t w_lo, uint32_t w_hi, bool post, bool fe, uint32_t j) {
   const uint32_t w = J.m_next;
   J.mi++;
   if (J.mi < J.n_mem) J.m_next = lane < 12 ? __ldcs(J.mems + (size_t)J.mi * 12 + lane) : 0u;   // next query in flight
-  const uint32_t mc = J.mcur, mp = mc ^ 1u;
-  if (lane < 12) S.rec[mc][lane] = w;
-  __syncwarp();
-  const uint32_t* row = S.row[J.cur];
-  const uint32_t* prow = S.row[J.cur ^ 1u];
-  const uint32_t flags = S.rec[mc][3], index = S.rec[mc][2];
+  const uint32_t flags = __shfl_sync(0xffffffffu, w, 3), index = __shfl_sync(0xffffffffu, w, 2);
   const uint32_t type = flags & 0xFFu, rw = (flags >> 8) & 1u;
   const uint32_t fm = __ballot_sync(0xffffffffu, lane < 15 && c_mem_flag_codes[lane & 15u] == flags);
   const uint32_t fcode = fm ? (uint32_t)__ffs(fm) - 1u : 15u;
-  const uint32_t pm3 = S.rec[mp][3], pm2 = S.rec[mp][2];
-  const uint32_t pc_before = row[5] & 0xFFFFu, row_w3 = row[3];
-  const uint32_t p0 = row[1] + (rw ? 3u : 0u);
-  const uint32_t p1 = type == 4u ? prow[50] : type <= 2u ? prow[51] + 1u + type : row[9];
+  const uint32_t pm3 = __shfl_sync(0xffffffffu, J.pm, 3), pm2 = __shfl_sync(0xffffffffu, J.pm, 2);
+  const uint32_t row_ts = __shfl_sync(0xffffffffu, w_lo, 1), row_w3 = __shfl_sync(0xffffffffu, w_lo, 3), pc_before = __shfl_sync(0xffffffffu, w_lo, 5) & 0xFFFFu;
+  const uint32_t row_w8 = __shfl_sync(0xffffffffu, w_lo, 8), row_w9 = __shfl_sync(0xffffffffu, w_lo, 9), row_w10 = __shfl_sync(0xffffffffu, w_lo, 10);
+  const uint32_t prev50 = __shfl_sync(0xffffffffu, J.prev_hi, 18), prev51 = __shfl_sync(0xffffffffu, J.prev_hi, 19);
+  const uint32_t p0 = row_ts + (rw ? 3u : 0u);
+  const uint32_t p1 = type == 4u ? prev50 : type <= 2u ? prev51 + 1u + type : row_w9;
   uint32_t p2;
   if (j > 0 && pm3 == flags) p2 = pm2 + 1u;
   else if (type == 4u) p2 = ((j == 0 && fe) || !post) ? pc_before >> 2 : row_w3 & 0xFFFFu;
   else if (type == 0u) p2 = post ? (rw ? row_w3 >> 16 : row_w3 & 0xFFFFu) : 0u;
-  else if (type <= 2u) p2 = row[8] >> 5;
-  else p2 = (row[8] + row[10]) >> 5;
+  else if (type <= 2u) p2 = row_w8 >> 5;
+  else p2 = (row_w8 + row_w10) >> 5;
   // value candidates, on lanes 4..11 (limb k = lane - 4)
   const bool vl = lane >= 4 && lane < 12;
   const uint32_t k = (lane - 4u) & 7u, set = index % ZKB_CW_SETS;
-  const uint32_t* cset = S.cache + set * (ZKB_CW_WAYS * 8u);
   uint32_t cand[8];
   cand[0] = 0u;
-  cand[1] = row[8 + k];
-  cand[2] = row[16 + k];
-  cand[3] = row[24 + k];
+  cand[1] = __shfl_sync(0xffffffffu, w_lo, (lane + 4u) & 31u);
+  cand[2] = __shfl_sync(0xffffffffu, w_lo, (lane + 12u) & 31u);
+  cand[3] = __shfl_sync(0xffffffffu, w_lo, (lane + 20u) & 31u);
+  const uint32_t d1 = __shfl_sync(0xffffffffu, w_hi, (lane - 4u) & 31u);
+  const uint32_t* cset = J.cache + set * (ZKB_CW_WAYS * 8u);
 #pragma unroll
-  for (uint32_t v = 0; v < 4; v++) cand[4 + v] = type == 4u ? cset[v * 8u + k] : (v == 0 ? row[32 + k] : 0u);
-  uint32_t packed = 0;
+  for (uint32_t v = 0; v < 4; v++) cand[4 + v] = type == 4u ? cset[v * 8u + k] : (v == 0 ? d1 : 0u);
+  uint32_t cnt[8];
 #pragma unroll
-  for (uint32_t v = 0; v < 8; v++) packed |= (vl && w != cand[v]) ? 1u << (4u * v) : 0u;
-  const uint32_t tot = __reduce_add_sync(0xffffffffu, packed);   // nibble v = lanes on which candidate v misses (<= 8)
-  uint32_t vsel = 0, best = tot & 15u;
-#pragma unroll
-  for (uint32_t v = 1; v < 8; v++) {
-    const uint32_t c = (tot >> (4u * v)) & 15u;
-    if (c < best) {
-      best = c;
-      vsel = v;
-    }
-  }
+  for (uint32_t v = 0; v < 8; v++) cnt[v] = __popc(__ballot_sync(0xffffffffu, vl && w != cand[v]));
+  const uint32_t vsel = first_min8(cnt);
   uint32_t pv = cand[0];
 #pragma unroll
   for (uint32_t v = 1; v < 8; v++) pv = vsel == v ? cand[v] : pv;
-  const uint32_t pred = lane == 0 ? p0 : lane == 1 ? p1 : lane == 2 ? p2 : lane == 3 ? pm3 : pv;
+  const uint32_t pred = lane == 0 ? p0 : lane == 1 ? p1 : lane == 2 ? p2 : lane == 3 ? J.pm : pv;
   uint32_t x = lane < 12 ? (w ^ pred) : 0u;
   if (lane == 3 && fcode < 15u) x = 0u;
   const uint32_t pres = __ballot_sync(0xffffffffu, x != 0);
@@ -145,32 +128,30 @@ __device__ __forceinline__ void joint_mem(JointWarp& J, uint32_t lane, uint32_t 
     if (x) o[1 + __popc(pres & lt)] = x;
   }
   J.mwords += 1u + __popc(pres);
-  // state: code-word cache (FIFO per set), the current code word; the query becomes the previous one by toggling mcur
+  // state: code-word cache (FIFO per set), the current code word, the previous query
   if (type == 4u) {
-    const bool hit = ((tot >> 16) & 15u) == 0 || ((tot >> 20) & 15u) == 0 || ((tot >> 24) & 15u) == 0 || ((tot >> 28) & 15u) == 0;
-    __syncwarp();                                   // every lane has read its candidates
+    const bool hit = cnt[4] == 0 || cnt[5] == 0 || cnt[6] == 0 || cnt[7] == 0;
     if (!hit) {
-      const uint32_t way = S.rr[set];
+      const uint32_t way = __shfl_sync(0xffffffffu, J.rr, set);
       __syncwarp();
-      if (vl) S.cache[set * (ZKB_CW_WAYS * 8u) + way * 8u + k] = w;
-      if (lane == 0) S.rr[set] = (way + 1u) % ZKB_CW_WAYS;
+      if (vl) J.cache[set * (ZKB_CW_WAYS * 8u) + way * 8u + k] = w;
+      if (lane == set) J.rr = (J.rr + 1u) % ZKB_CW_WAYS;
+      __syncwarp();
     }
-    if (j == 0 && rw == 0 && index == pc_before >> 2 && vl) S.cw[k] = w;
-    __syncwarp();
+    const uint32_t v = __shfl_sync(0xffffffffu, w, (lane + 4u) & 31u);
+    if (j == 0 && rw == 0 && index == pc_before >> 2 && lane < 8) J.cw = v;
   }
-  J.mcur = mp;
+  J.pm = w;
 }
 
 template <bool WRITE>
 __device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __restrict__ rows, uint32_t n_rows, uint32_t lane) {
-  JointScratch& S = *J.S;
   const uint32_t lt = lanemask_lt();
-  J.prev_lo = J.prev_hi = J.prevprev50 = 0u;
-  J.cur = J.mcur = 0;
+  J.prev_lo = J.prev_hi = J.pm = J.cw = J.rr = J.prevprev50 = 0u;
   J.mi = 0;
   J.rwords = J.mwords = 0;
   __syncwarp();
-  for (uint32_t i = lane; i < sizeof(JointScratch) / 4; i += 32) reinterpret_cast<uint32_t*>(&S)[i] = 0u;
+  for (uint32_t i = lane; i < ZKB_CW_SETS * ZKB_CW_WAYS * 8u; i += 32) J.cache[i] = 0u;
   __syncwarp();
   J.m_next = (J.n_mem && lane < 12) ? __ldcs(J.mems + lane) : 0u;
   uint32_t nx_lo = 0, nx_hi = 0;
@@ -184,29 +165,23 @@ __device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __res
       nx_lo = __ldcs(rows + (size_t)(r + 1) * 64 + lane);
       nx_hi = __ldcs(rows + (size_t)(r + 1) * 64 + 32 + lane);
     }
-    J.cur ^= 1u;                                    // the buffer that held row r - 2 becomes row r; row r - 1 is the previous one
-    uint32_t* row = S.row[J.cur];
-    const uint32_t* prow = S.row[J.cur ^ 1u];
-    row[lane] = w_lo;
-    row[32 + lane] = w_hi;
-    __syncwarp();
-    const uint32_t pc_before = row[5] & 0xFFFFu;
-    const uint32_t prev48 = prow[48], prev50 = prow[50];
-    const uint32_t w43 = row[43];
-    // dst0 predictor (lanes 24..31 hold dst0 limb lane - 24; src0 / src1 limbs come from the scratch)
+    const uint32_t pc_before = __shfl_sync(0xffffffffu, w_lo, 5) & 0xFFFFu;
+    const uint32_t prev48 = __shfl_sync(0xffffffffu, J.prev_hi, 16), prev50 = __shfl_sync(0xffffffffu, J.prev_hi, 18);
+    const uint32_t w43 = __shfl_sync(0xffffffffu, w_hi, 11);
+    // dst0 predictor (lanes 24..31 hold dst0; src0 sits 16 lanes, src1 8 lanes below)
+    const uint32_t s0 = __shfl_sync(0xffffffffu, w_lo, (lane - 16u) & 31u), s1 = __shfl_sync(0xffffffffu, w_lo, (lane - 8u) & 31u);
     const bool dl = lane >= 24;
-    const uint32_t s0 = row[8 + (lane & 7u)], s1 = row[16 + (lane & 7u)];
     const uint32_t sum = s0 + s1, dif = s0 - s1;
     const uint32_t Ga = __ballot_sync(0xffffffffu, sum < s0) >> 24, Pa = __ballot_sync(0xffffffffu, sum == 0xFFFFFFFFu) >> 24;
     const uint32_t Gs = __ballot_sync(0xffffffffu, s0 < s1) >> 24, Ps = __ballot_sync(0xffffffffu, s0 == s1) >> 24;
     const uint32_t Ka = carry_chain(Ga, Pa), Ks = carry_chain(Gs, Ps);
     const uint32_t addv = sum + ((Ka >> (lane & 7u)) & 1u), subv = dif - ((Ks >> (lane & 7u)) & 1u);
-    const uint32_t dpack = dl ? ((w_lo != 0u ? 1u : 0u) | (w_lo != s0 ? 1u << 4 : 0u) | (w_lo != addv ? 1u << 8 : 0u) | (w_lo != subv ? 1u << 12 : 0u)) : 0u;
-    const uint32_t dtot = __reduce_add_sync(0xffffffffu, dpack);
-    uint32_t dsel = 0, best = dtot & 15u;
-    if (((dtot >> 4) & 15u) < best) { best = (dtot >> 4) & 15u; dsel = 1; }
-    if (((dtot >> 8) & 15u) < best) { best = (dtot >> 8) & 15u; dsel = 2; }
-    if (((dtot >> 12) & 15u) < best) { best = (dtot >> 12) & 15u; dsel = 3; }
+    const uint32_t c0 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != 0u)), c1 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != s0));
+    const uint32_t c2 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != addv)), c3 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != subv));
+    uint32_t dsel = 0, best = c0;
+    if (c1 < best) { best = c1; dsel = 1; }
+    if (c2 < best) { best = c2; dsel = 2; }
+    if (c3 < best) { best = c3; dsel = 3; }
     const uint32_t dpred = dsel == 0 ? 0u : dsel == 1 ? s0 : dsel == 2 ? addv : subv;
     const uint32_t ncode = w43 < 7u ? w43 : 7u;
     // the cycle's memory queries: the first one ahead of the opcode when an instruction fetch is expected
@@ -214,16 +189,17 @@ __device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __res
     const uint32_t nm = min(w43 & 0xFFFFu, J.n_mem - J.mi);
     uint32_t j = 0;
     if (fe && nm >= 1) {
-      joint_mem<WRITE>(J, lane, lt, false, fe, 0);
+      joint_mem<WRITE>(J, lane, lt, w_lo, w_hi, false, fe, 0);
       j = 1;
     }
     const uint32_t sub = pc_before & 3u;
-    const uint32_t vidx = row[2] & ((1u << ZK_VARIANT_BITS) - 1u);
+    const uint32_t cw_a = __shfl_sync(0xffffffffu, J.cw, 6u - 2u * sub), cw_b = __shfl_sync(0xffffffffu, J.cw, 7u - 2u * sub);
+    const uint32_t vidx = __shfl_sync(0xffffffffu, w_lo, 2) & ((1u << ZK_VARIANT_BITS) - 1u);
     uint32_t pred_lo = 0;
     if (lane == 0) pred_lo = J.prev_lo + 1u;
     else if (lane == 1) pred_lo = J.prev_lo + ZK_TIME_DELTA_PER_CYCLE;
-    else if (lane == 2) pred_lo = S.cw[6u - 2u * sub];
-    else if (lane == 3) pred_lo = S.cw[7u - 2u * sub];
+    else if (lane == 2) pred_lo = cw_a;
+    else if (lane == 3) pred_lo = cw_b;
     else if (lane == 4) pred_lo = vidx | 1u << 16;
     else if (lane == 5) {
       const uint32_t p = J.prev_lo >> 16;
@@ -246,23 +222,15 @@ __device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __res
       if (x_hi) o[2 + n_lo + __popc(p_hi & lt)] = x_hi;
     }
     J.rwords += 2u + n_lo + n_hi;
-    for (; j < nm; j++) joint_mem<WRITE>(J, lane, lt, true, fe, j);
+    for (; j < nm; j++) joint_mem<WRITE>(J, lane, lt, w_lo, w_hi, true, fe, j);
     J.prevprev50 = prev50;
     J.prev_lo = w_lo;
     J.prev_hi = w_hi;
-    __syncwarp();                                   // all reads of the row before before-previous buffer is overwritten
   }
-  // memory queries no row announces (a cycle that stopped the VM emits its queries but no row): zero row context, the last
-  // row stays the previous one
-  J.cur ^= 1u;
-  __syncwarp();
-  S.row[J.cur][lane] = 0u;
-  S.row[J.cur][32 + lane] = 0u;
-  __syncwarp();
-  for (uint32_t j = 0; J.mi < J.n_mem; j++) joint_mem<WRITE>(J, lane, lt, true, false, j);
+  // memory queries no row announces (a cycle that stopped the VM emits its queries but no row): zero row context
+  for (uint32_t j = 0; J.mi < J.n_mem; j++) joint_mem<WRITE>(J, lane, lt, 0u, 0u, true, false, j);
 }
 
-// 12-word records (DECOMMIT): two records per step, one per half-warp
 template <bool WRITE, int KIND>
 __device__ __forceinline__ uint64_t encode_rec12(const uint32_t* __restrict__ recs, uint32_t n, uint32_t* __restrict__ out, uint32_t lane) {
   const uint32_t g = lane >> 4, li = lane & 15u;
@@ -317,7 +285,7 @@ __device__ __forceinline__ uint64_t encode_rec32(const uint32_t* __restrict__ re
 
 // the encoding pass: one warp per VM, payloads into the staging area, true sizes into A.sizes
 __global__ void __launch_bounds__(256, 4) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
-  __shared__ JointScratch s_scratch[8];   // per warp: rows, queries, code word and code-word cache of its VM
+  __shared__ uint32_t s_cache[8][ZKB_CW_SETS * ZKB_CW_WAYS * 8];   // the code-word cache of each warp's VM
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n_vms = B.n_vms;
   for (uint32_t vm = blockIdx.x * 8 + warp; vm < n_vms; vm += gridDim.x * 8) {
@@ -329,7 +297,7 @@ __global__ void __launch_bounds__(256, 4) zkb_encode_kernel(const DevBatch B, co
     const uint32_t* s0 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_ROWS] + (size_t)vm * B.cap[ZKB_STREAM_ROWS] * ZKB_ROW_BYTES);
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(B.streams[ZKB_STREAM_MEM] + (size_t)vm * B.cap[ZKB_STREAM_MEM] * ZKB_MEM_BYTES);
     JointWarp J;
-    J.S = &s_scratch[warp];
+    J.cache = s_cache[warp];
     J.mems = s1;
     J.n_mem = cnt[1];
     J.out_rows = stage_slot(A, ZKB_STREAM_ROWS, vm, n_vms);
