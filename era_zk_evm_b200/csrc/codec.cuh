@@ -111,15 +111,9 @@ __device__ __forceinline__ void joint_mem(JointWarp& J, uint32_t lane, uint32_t 
   const uint32_t* cset = J.cache + set * (ZKB_CW_WAYS * 8u);
 #pragma unroll
   for (uint32_t v = 0; v < 4; v++) cand[4 + v] = type == 4u ? cset[v * 8u + k] : (v == 0 ? d1 : 0u);
-  // all eight candidates compared in ONE warp reduction: every lane packs its mismatch bits, 4 bits per candidate, and the
-  // sum's nibble v = number of limbs on which candidate v misses (<= 8, so the nibbles cannot carry into each other)
-  uint32_t packed = 0;
-#pragma unroll
-  for (uint32_t v = 0; v < 8; v++) packed |= (vl && w != cand[v]) ? 1u << (4u * v) : 0u;
-  const uint32_t tot = __reduce_add_sync(0xffffffffu, packed);
   uint32_t cnt[8];
 #pragma unroll
-  for (uint32_t v = 0; v < 8; v++) cnt[v] = (tot >> (4u * v)) & 15u;
+  for (uint32_t v = 0; v < 8; v++) cnt[v] = __popc(__ballot_sync(0xffffffffu, vl && w != cand[v]));
   const uint32_t vsel = first_min8(cnt);
   uint32_t pv = cand[0];
 #pragma unroll
@@ -182,9 +176,8 @@ __device__ __forceinline__ void encode_joint(JointWarp& J, const uint32_t* __res
     const uint32_t Gs = __ballot_sync(0xffffffffu, s0 < s1) >> 24, Ps = __ballot_sync(0xffffffffu, s0 == s1) >> 24;
     const uint32_t Ka = carry_chain(Ga, Pa), Ks = carry_chain(Gs, Ps);
     const uint32_t addv = sum + ((Ka >> (lane & 7u)) & 1u), subv = dif - ((Ks >> (lane & 7u)) & 1u);
-    const uint32_t dpack = dl ? ((w_lo != 0u ? 1u : 0u) | (w_lo != s0 ? 1u << 4 : 0u) | (w_lo != addv ? 1u << 8 : 0u) | (w_lo != subv ? 1u << 12 : 0u)) : 0u;
-    const uint32_t dtot = __reduce_add_sync(0xffffffffu, dpack);   // nibble v = limbs on which dst0 candidate v misses
-    const uint32_t c0 = dtot & 15u, c1 = (dtot >> 4) & 15u, c2 = (dtot >> 8) & 15u, c3 = (dtot >> 12) & 15u;
+    const uint32_t c0 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != 0u)), c1 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != s0));
+    const uint32_t c2 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != addv)), c3 = __popc(__ballot_sync(0xffffffffu, dl && w_lo != subv));
     uint32_t dsel = 0, best = c0;
     if (c1 < best) { best = c1; dsel = 1; }
     if (c2 < best) { best = c2; dsel = 2; }
