@@ -234,12 +234,13 @@ int32_t zkb_pack_stream_device(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t
  * concatenation of step k with the interpreter launch of step k+1) */
 int32_t zkb_pack_stream_device_async(ZkbBatch* b, uint32_t kind, void** dptr, uint64_t* n_bytes, void* cuda_stream);
 /* ---- encoded transport (include/zkb_codec.h): the six streams of every VM as ONE lossless, self-describing blob ------
- * The encoder runs on the device (XOR with a per-word prediction + presence bitmaps, ~30 % of the canonical bytes on the
- * ERC-20 workload), so a PCIe-bound host loop moves 3x fewer bytes; zkb_decode_stream (host, no GPU needed) and
- * zkb_codec::EncodedView give the canonical records back byte for byte.
- * _async: waits (on the host) for THIS batch's last run and for the encoder's size pass (~2 ms), then enqueues the
- * write pass + ONE D2H copy on `cuda_stream`; host_dst should be pinned; completion = stream sync.  host_dst == NULL:
- * only *n_bytes (the blob size for the current streams) is returned. */
+ * The encoder runs on the device (format v2: XOR with a per-word prediction + presence bitmaps, cycle rows and memory
+ * queries coded jointly; 16.5 % of the canonical bytes on the ERC-20 workload), so a PCIe-bound host loop moves 6x fewer
+ * bytes; zkb_decode_stream (host, no GPU needed) and zkb_codec::EncodedView give the canonical records back byte for byte.
+ * _async: waits (on the host) for THIS batch's last run and for the encoding pass (which also yields the blob's size), then
+ * enqueues the compaction + ONE D2H copy on `cuda_stream`; host_dst should be pinned; completion = stream sync.
+ * host_dst == NULL: only *n_bytes (the blob size for the current streams) is returned.  A subset blob carries ROWS and MEM
+ * together or not at all. */
 int32_t zkb_fetch_encoded_async(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes, void* cuda_stream);
 int32_t zkb_fetch_encoded(ZkbBatch* b, void* host_dst, uint64_t host_capacity, uint64_t* n_bytes);
 /* the same for a subset of the streams (bit k of kinds_mask = ZkbStreamKind k): what a host that runs zkb_consume on the
