@@ -266,3 +266,48 @@ def test_flattened_histories_match_the_oracle(name, kwargs, n, oracle_mod):
             n_rollbacks += int(a["rollback"].sum())
     if name != "erc20":
         assert n_rollbacks > 0
+
+
+def test_regrouped_schedule_emits_the_same_bytes(oracle_mod, monkeypatch):
+    """zkb_run schedules VMs in bootloader-code order (DESIGN.md §4 "Regrouping"); state and streams stay indexed by VM, so
+    the grouped and the ungrouped (ZKB_REGROUP=0) schedule must produce identical streams -- and both equal the oracle's"""
+    from era_zk_evm_b200 import GpuVmBatch
+    w = workloads.WORKLOADS["mixed_shuffled"](n_programs=12)
+    n = 12 * 9 + 5
+    vm_ids = list(range(n))
+    orc = oracle_mod.OracleBatch(w.config(n))
+    w.setup(orc, vm_ids)
+    orc.run_threads(0, 0)
+    blobs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ZKB_REGROUP", flag)            # read by zkb_create
+        gpu = GpuVmBatch(w.config(n))
+        w.setup(gpu, vm_ids)
+        gpu.run()
+        problems = compare_batches(gpu, orc)
+        assert not problems, f"ZKB_REGROUP={flag}\n" + "\n".join(problems)
+        blobs.append(gpu.fetch_encoded().tobytes())
+        gpu.close()
+    assert blobs[0] == blobs[1]
+
+
+def test_unknown_code_hash_stops_the_vm_like_the_reference(oracle_mod):
+    """the reference's only Err (decommitter.rs:50-56 -> far_call.rs:448): a far call to a well-formed code hash that was
+    never loaded.  On the device the lookup goes through the hash index over the loaded bytecodes (a miss ends at an empty
+    slot); status, cycle count and every record emitted before the stop must equal the oracle's"""
+    from era_zk_evm_b200 import isa
+    from era_zk_evm_b200._binding import storage_entries
+    w = workloads.Erc20(n_transfers=2)
+    n = 41
+    gpu, orc = _pair(w, list(range(n)), oracle_mod)
+    fake = int.from_bytes(bytes([1, 0, 0, 1]) + bytes(range(28)), "big")
+    for b in (gpu, orc):
+        b.populate_storage(storage_entries([(0, isa.C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS, workloads.TOKEN_ADDRESS, fake)]), vm_lo=3, vm_hi=29)
+    gpu.run()
+    orc.run_threads(0, 0)
+    gs, os_ = gpu.vm_status(), orc.vm_status()
+    assert (gs == os_).all()
+    assert (gs[3:29, 0] == 2).all() and (gs[:3, 0] == 1).all() and (gs[29:, 0] == 1).all()      # ZKB_VM_UNKNOWN_CODE_HASH
+    problems = compare_batches(gpu, orc)
+    assert not problems, "\n".join(problems)
+
