@@ -384,12 +384,9 @@ def main():
         if args.sub_batches > 0:
             n_sub = max(1, min(args.sub_batches, args.vms // 1024))
             bounds = [shard.partition(args.vms, n_sub, i) for i in range(n_sub)]
-        else:   # auto: whole waves of the persistent interpreter grid (148 SMs x 96 VMs) per sub-batch, so no launch runs a partial
-            # wave but the first and the last: a SHORT first sub-batch (a third of a wave) gets the first blob onto the link early
-            # -- nothing overlaps the first sub-batch's populate + run + encode -- and leaves a short last copy behind the loop
+        else:   # auto: whole waves of the persistent interpreter grid (148 SMs x 96 VMs) per sub-batch, so no launch runs a partial wave but the last
             wave = 148 * 96
-            first = min(args.vms, (wave // 3) // 96 * 96) if args.vms > 2 * wave else 0
-            cuts = ([0, first] if first else [0]) + list(range(first + wave, args.vms, wave)) + [args.vms]
+            cuts = list(range(0, args.vms, wave)) + [args.vms]
             bounds = list(zip(cuts[:-1], cuts[1:]))
             n_sub = len(bounds)
         subs, sub_ids = [], []
