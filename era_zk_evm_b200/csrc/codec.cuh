@@ -283,8 +283,11 @@ __device__ __forceinline__ uint64_t encode_rec32(const uint32_t* __restrict__ re
   return words * 4;
 }
 
-// the encoding pass: one warp per VM, payloads into the staging area, true sizes into A.sizes
-__global__ void __launch_bounds__(256, 4) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
+// the encoding pass: one warp per VM, payloads into the staging area, true sizes into A.sizes.  THREE CTAs per SM (80
+// registers): four would own the whole register file, and the small populate / memset kernels of the NEXT sub-batch (<= 32
+// registers x 128 threads) could not start underneath it -- the host thread that populates then sits in its stream syncs until
+// the encoder drains and the interpreter launch it queues afterwards leaves the GPU idle for the rest of its host work.
+__global__ void __launch_bounds__(256, 3) zkb_encode_kernel(const DevBatch B, const EncArgs A) {
   __shared__ uint32_t s_cache[8][ZKB_CW_SETS * ZKB_CW_WAYS * 8];   // the code-word cache of each warp's VM
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n_vms = B.n_vms;
