@@ -210,6 +210,7 @@ static inline uint64_t decode_records(uint32_t kind, const uint8_t* src, uint64_
     memcpy(m32, p, (size_t)mw * 4);
     p += (size_t)mw * 4;
     const uint64_t mask = (uint64_t)m32[0] | (uint64_t)m32[1] << 32;
+    if (nw < 64 && (mask >> nw)) return UINT64_MAX;   /* presence bits beyond the record (a 12-word record carries a 32-bit mask word) */
     if ((uint64_t)(end - p) < (uint64_t)__builtin_popcountll(mask) * 4) return UINT64_MAX;
     switch (kind) {
       case ZKB_STREAM_DECOMMIT:
