@@ -169,6 +169,21 @@ def test_decoders_under_address_sanitizer(oracle_mod, tmp_path):
         assert out.returncode == 0 and "decodes ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_wire_format_is_pinned(oracle_mod):
+    """tests/golden/codec_v2.json: the blob of three small seeded workloads, byte for byte (sha256).  The CUDA encoder is
+    checked against the scalar encoder on the GPU; this pins the scalar encoder -- i.e. the wire format -- itself."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "codec_v2.json")) as f:
+        golden = json.load(f)
+    for name, case in golden["cases"].items():
+        _, b = _oracle_run(oracle_mod, name, case["kwargs"], case["n_vms"])
+        blob = b.fetch_encoded()
+        assert blob.size == case["blob_bytes"] and sum(b.totals()[1]) == case["raw_bytes"], name
+        assert hashlib.sha256(blob.tobytes()).hexdigest() == case["blob_sha256"], name
+
+
 def test_erc20_ratio(oracle_mod):
     """the figure DESIGN.md / bench.py quote: the blob is ~17 % of the canonical bytes on the ERC-20 workload (format v2)"""
     _, b = _oracle_run(oracle_mod, "erc20", dict(n_transfers=8), 64)
