@@ -265,7 +265,9 @@ static inline uint32_t count_diff8(const uint32_t* a, const uint32_t* b) {
  * directions, so a prediction can never differ between the encoder and the decoder; what is checked from outside is
  * decode(encode(x)) == x against the oracle's streams and CUDA blob == this encoder's blob (tests/test_codec.py). */
 struct JointCoder {
-  uint32_t prev_row[64], prev_mem[12], cw[8], rr[ZKB_CW_SETS], cache[ZKB_CW_SETS][ZKB_CW_WAYS][8];
+  const uint32_t* prev_row;   /* the previous row / memory query, where they lie in the caller's canonical buffers (a zero record before the first) */
+  const uint32_t* prev_mem;
+  uint32_t cw[8], rr[ZKB_CW_SETS], cache[ZKB_CW_SETS][ZKB_CW_WAYS][8];
   uint32_t prevprev_w50;
   /* payload cursors */
   uint8_t* rp;        /* rows payload (written when ENC, read when !ENC) */
@@ -276,8 +278,8 @@ struct JointCoder {
   bool ok;
 
   void reset() {
-    memset(prev_row, 0, sizeof(prev_row));
-    memset(prev_mem, 0, sizeof(prev_mem));
+    static const uint32_t zero_record[64] = {0};
+    prev_row = prev_mem = zero_record;
     memset(cw, 0, sizeof(cw));
     memset(rr, 0, sizeof(rr));
     memset(cache, 0, sizeof(cache));
@@ -387,7 +389,7 @@ struct JointCoder {
       }
       if (j == 0 && rw == 0 && rec[2] == pc_before >> 2) memcpy(cw, rec + 4, 32);
     }
-    memcpy(prev_mem, rec, 48);
+    prev_mem = rec;
   }
 
   /* rows[n_rows][64], mem[n_mem][12]: canonical records (input when ENC, output otherwise) */
@@ -398,18 +400,21 @@ struct JointCoder {
       uint32_t* row = rows + r * 64;
       uint64_t mask = 0;
       uint32_t pred[64], dsel = 0, ncode = 7;
-      /* predictions that look at nothing of this row */
-      pred[0] = prev_row[0] + 1u;
-      pred[1] = prev_row[1] + ZK_TIME_DELTA_PER_CYCLE;
-      pred[2] = pred[3] = pred[4] = pred[7] = 0u;
       const uint32_t pc = prev_row[5] >> 16;
-      pred[5] = pc | ((pc + 1u) & 0xFFFFu) << 16;
-      pred[6] = prev_row[6];
-      memset(pred + 8, 0, 32 * 4);
-      memcpy(pred + 40, prev_row + 40, 15 * 4);
-      pred[43] = pred[48] = 0u;
-      memset(pred + 55, 0, 9 * 4);
-      if (!ENC) {
+      const uint32_t p0 = prev_row[0] + 1u, p1 = prev_row[1] + ZK_TIME_DELTA_PER_CYCLE, p5 = pc | ((pc + 1u) & 0xFFFFu) << 16;
+      uint32_t cand[4][8];
+      if (ENC) {
+        /* predictions that look at nothing of this row */
+        pred[0] = p0;
+        pred[1] = p1;
+        pred[2] = pred[3] = pred[4] = pred[7] = 0u;
+        pred[5] = p5;
+        pred[6] = prev_row[6];
+        memset(pred + 8, 0, 32 * 4);
+        memcpy(pred + 40, prev_row + 40, 15 * 4);
+        pred[43] = 0u;
+        memset(pred + 55, 0, 9 * 4);
+      } else {
         if ((uint64_t)(rend - rp) < 8) {
           ok = false;
           return;
@@ -425,19 +430,29 @@ struct JointCoder {
           ok = false;
           return;
         }
-        memcpy(row, pred, 256);
-        rp = (uint8_t*)apply_residuals(pres, rp, row);   /* deferred words hold their bare residual for now */
+        /* the same predictions written straight into the row; words whose prediction looks at the row itself (2, 3, 4, 7,
+         * dst0, 43, 48) start from zero and hold their bare residual until they are fixed up below */
+        row[0] = p0;
+        row[1] = p1;
+        row[2] = row[3] = row[4] = row[7] = 0u;
+        row[5] = p5;
+        row[6] = prev_row[6];
+        memset(row + 8, 0, 32 * 4);
+        memcpy(row + 40, prev_row + 40, 15 * 4);
+        row[43] = row[48] = 0u;
+        memset(row + 55, 0, 9 * 4);
+        rp = (uint8_t*)apply_residuals(pres, rp, row);
         if (ncode < 7) row[43] = ncode;
       }
       /* w48 looks at w5, dst0 at src0 / src1 */
       const uint32_t pc_before = row[5] & 0xFFFFu;
-      pred[48] = (prev_row[48] & 0xFFFFu) | (pc_before >> 2) << 16;
-      uint32_t cand[4][8];
-      memset(cand[0], 0, 32);
-      memcpy(cand[1], row + 8, 32);
-      limbs_add(row + 8, row + 16, cand[2]);
-      limbs_sub(row + 8, row + 16, cand[3]);
+      const uint32_t p48 = (prev_row[48] & 0xFFFFu) | (pc_before >> 2) << 16;
       if (ENC) {
+        pred[48] = p48;
+        memset(cand[0], 0, 32);
+        memcpy(cand[1], row + 8, 32);
+        limbs_add(row + 8, row + 16, cand[2]);
+        limbs_sub(row + 8, row + 16, cand[3]);
         uint32_t best = 9;
         for (uint32_t v = 0; v < 4; v++) {
           const uint32_t c = count_diff8(row + 24, cand[v]);
@@ -447,11 +462,17 @@ struct JointCoder {
           }
         }
         ncode = row[43] < 7u ? row[43] : 7u;
+        memcpy(pred + 24, cand[dsel], 32);
       } else {
-        row[48] ^= pred[48];
-        for (int i = 0; i < 8; i++) row[24 + i] ^= cand[dsel][i];
+        row[48] ^= p48;
+        if (dsel == 1) {
+          for (int i = 0; i < 8; i++) row[24 + i] ^= row[8 + i];
+        } else if (dsel >= 2) {   /* only the selected predictor is computed when decoding */
+          if (dsel == 2) limbs_add(row + 8, row + 16, cand[0]);
+          else limbs_sub(row + 8, row + 16, cand[0]);
+          for (int i = 0; i < 8; i++) row[24 + i] ^= cand[0][i];
+        }
       }
-      memcpy(pred + 24, cand[dsel], 32);
       /* the cycle's memory queries: the first one ahead of the opcode when an instruction fetch is expected */
       const bool fe = r == 0 || (pc_before >> 2) != (prev_row[48] >> 16) || prev_row[50] != prevprev_w50;
       const uint64_t nm = std::min<uint64_t>(row[43] & 0xFFFFu, n_mem - mi);
@@ -496,7 +517,7 @@ struct JointCoder {
       }
       for (; j < nm && ok; j++, mi++) mem_record<ENC>(mem + mi * 12, row, true, fe, j);
       prevprev_w50 = prev_row[50];
-      memcpy(prev_row, row, 256);
+      prev_row = row;
     }
     /* memory queries no row announces (a cycle that stopped the VM emits its queries but no row) */
     static const uint32_t zero_row[64] = {0};
