@@ -405,13 +405,24 @@ def main():
             """transport = "encoded": ONE lossless blob per sub-batch (device-side encoder, include/zkb_codec.h) crosses PCIe;
             "raw": the six canonical streams, packed.  Either way every witness byte the host needs lands in pinned host
             memory inside the timed region."""
-            if transport == "consumer":  # snapshots + digests, and the encoded query logs
-                n_sub_vms = [hi - lo for lo, hi in bounds]
-                pinned = [[torch.empty(int(sum(sbytes[k] for k in log_kinds) * sh * 0.7) + (1 << 20), dtype=torch.uint8, pin_memory=True),
-                           torch.empty(nv * ((w.max_cycles_hint // args.snapshot_period + 2) * 792 + 104) + 4096, dtype=torch.uint8, pin_memory=True)]
-                          for sh, nv in zip(share, n_sub_vms)]
-            elif transport == "encoded":   # pinned landing zones sized from the device-timed run's stream totals (+ slack)
-                pinned = [[torch.empty(int(sum(sbytes) * sh * 0.5) + (1 << 20), dtype=torch.uint8, pin_memory=True)] for sh in share]
+            if transport in ("consumer", "encoded"):
+                # pinned landing zones sized from a size query (untimed): every sub-batch is run once and asked how long its
+                # blob is -- the ratio depends on the workload (16 % on ERC-20, far more on random preimages)
+                kinds = log_kinds if transport == "consumer" else list(range(records.N_STREAMS))
+                sizes = []
+                for i, sb in enumerate(subs):
+                    sb.reset()
+                    w.setup(sb, sub_ids[i])
+                    sb.run()
+                    sizes.append(sb.fetch_encoded_kinds_async(kinds, None, 0))     # host_dst == NULL: the blob's size only
+                torch.cuda.synchronize()
+                if transport == "consumer":  # snapshots + digests, and the encoded query logs
+                    n_sub_vms = [hi - lo for lo, hi in bounds]
+                    pinned = [[torch.empty(int(nb * 1.02) + (1 << 16), dtype=torch.uint8, pin_memory=True),
+                               torch.empty(nv * ((w.max_cycles_hint // args.snapshot_period + 2) * 792 + 104) + 4096, dtype=torch.uint8, pin_memory=True)]
+                              for nb, nv in zip(sizes, n_sub_vms)]
+                else:
+                    pinned = [[torch.empty(int(nb * 1.02) + (1 << 16), dtype=torch.uint8, pin_memory=True)] for nb in sizes]
             else:
                 pinned = [[torch.empty(int(nb * sh * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) for nb in sbytes] for sh in share]
             phase = {"setup_s": 0.0, "wait_run_s": 0.0}
