@@ -968,6 +968,46 @@ def case_context_and_cycle_bookkeeping(B):
 ALL = [v for k, v in sorted(globals().items()) if k.startswith("case_")]
 
 
+def case_invalid_opcode_burns_the_frame(B):
+    """cycle.rs:142-144 an opcode whose variant is the explicit panic (index 0: what the zero padding behind the last
+    instruction of a code word decodes to) sets INVALID_OPCODE; cycle.rs:146-161 its table price is charged like any other
+    -- the invalid entry is priced u32::MAX (ISA datum, unpinned like the rest of the table), so the subtraction underflows:
+    ergs := 0 and NOT_ENOUGH_ERGS is set as well; cycle.rs:187-190 masks to ret.panic (condition Always, :212-217);
+    ret.rs:243-249,262-264 the frame returns its zero ergs, pc goes to the exception handler, LT is set."""
+    p = Program()
+    p.add(R(1), 2, 3)                    # pc 0; pc 1..3 of the word are zero = the invalid opcode
+    b = H.launch(B, p, 1, regs={1: 5, 2: 6}, ergs=1000)
+    r = H.rows(b)
+    assert len(r) == 2 and H.val(r[0]["dst0"]) == 11
+    assert int(r[1]["raw_opcode"]) == 0 and int(r[1]["pc_before"]) == 1
+    assert int(r[1]["error_flags"]) == 1 | 2 and int(r[1]["masked_variant"]) == isa.PANIC_VARIANT_IDX and int(r[1]["cond_resolved"]) == 1
+    assert int(r[1]["callstack_depth"]) == 0 and int(r[1]["ergs_after"]) == ROOT_ERGS - 1000      # nothing comes back (ret.rs:243)
+    assert int(r[1]["flags_after"]) == 1
+    assert b.vm_status()[0, 0] == 1                                                                # mod.rs:96-98
+    b.close()
+
+
+def case_jump_takes_the_low_16_bits_of_a_register(B):
+    """jump.rs:23-25 "we use lowest 16 bits of src0 as a jump destination": the destination comes from a full 256-bit
+    operand; everything above bit 15 is dropped.  The instruction fetch then follows the new pc (cycle.rs:59-100)."""
+    p = Program()
+    p.jump(R(1))                         # r1 = 2^200 + 2^16 + 5  -> pc 5
+    p.add(Imm(1), 0, 2)                  # skipped
+    p.add(Imm(2), 0, 2)
+    p.add(Imm(3), 0, 2)
+    p.add(Imm(4), 0, 2)                  # pc 4 (second code word), skipped
+    p.add(Imm(77), 0, 2)                 # pc 5
+    p.ret(isa.RET_OK, R(0))
+    b = H.launch(B, p, 1, regs={1: (1 << 200) | (1 << 16) | 5})
+    r = H.rows(b)
+    assert len(r) == 3
+    assert int(r[0]["pc_before"]) == 0 and int(r[0]["pc_after"]) == 5 and int(r[0]["bits"]) & 0xC0 == 0     # no dst written
+    assert int(r[1]["pc_before"]) == 5 and H.val(r[1]["dst0"]) == 77
+    mem = b.read_stream(0, records.STREAM_MEM)
+    assert [int(m["index"]) for m in mem if int(m["memory_type"]) == C.MEM_CODE] == [0, 1]                 # word 0, then word 1 (pc 5)
+    b.close()
+
+
 def case_flattened_histories_after_a_panicking_near_call(B):
     """The backends' own post-processing.  storage.rs:98-120 every write pushes a forward and a rollback
     query; storage.rs:156-180 / event_sink.rs:166-170 finish_frame(panicked) appends the frame's forward log and then its
