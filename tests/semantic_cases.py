@@ -1008,6 +1008,43 @@ def case_jump_takes_the_low_16_bits_of_a_register(B):
     b.close()
 
 
+def case_far_call_without_code_runs_the_default_aa(B):
+    """far_call.rs:131-158: the callee's code hash is READ from the deployer's storage (a LOG query, read_value as stored); a
+    ZERO hash at a non-kernel address is masked into block_properties.default_aa_code_hash -- the query still reports the
+    zero -- and it is the default AA's hash that is decommitted (helpers.rs:164-194) and its code that runs in the new
+    frame, whose this / code address are the CALLED address (far_call.rs:520-560)."""
+    from era_zk_evm_b200.asm import bytecode_hash
+    aa = Program()
+    aa.add(Imm(42), 0, 2)
+    aa.ret(isa.RET_OK, R(0))
+    aa_home, target = 0xAA00AA00, 0xDEAD5555          # the AA's bytecode is loaded by deploying it somewhere else; target has no code
+    p = Program()
+    p.const("abi", far_call_abi(1 << 16))
+    p.const("target", target)
+    p.add(Code("abi"), 0, 1)
+    p.add(Code("target"), 0, 2)
+    p.far_call(R(1), 2, "handler")
+    p.ret(isa.RET_OK, R(0))
+    p.label("handler")
+    p.ret(isa.RET_PANIC, R(0))
+    aa_hash = bytecode_hash(aa.bytecode())
+    b = H.launch(B, p, 1, ergs=1 << 20, contracts={aa_home: aa}, default_aa=aa_hash)
+    r = H.rows(b)
+    assert [H.family_of(x) for x in r] == ["add", "add", "far_call", "add", "ret", "ret"]
+    lg = b.read_stream(0, records.STREAM_LOG)
+    assert len(lg) == 1 and H.val(lg[0]["key"]) == target and H.val(lg[0]["read_value"]) == 0 and int(lg[0]["rw_flag"]) == 0
+    assert bytes(lg[0]["address"]) == C.DEPLOYER_SYSTEM_CONTRACT_ADDRESS.to_bytes(20, "big")
+    dec = b.read_stream(0, records.STREAM_DECOMMIT)
+    assert len(dec) == 1 and H.val(dec[0]["hash"]) == aa_hash and int(dec[0]["is_fresh"]) == 1
+    fr = b.read_stream(0, records.STREAM_FRAME)
+    call = [f for f in fr if int(f["kind"]) == 1][-1]
+    assert bytes(call["this_address"]) == target.to_bytes(20, "big") == bytes(call["code_address"])
+    assert H.val(r[3]["dst0"]) == 42 and int(r[3]["callstack_depth"]) == 2
+    assert int(r[4]["callstack_depth"]) == 1 and int(r[4]["pc_after"]) == 3            # normal return: back behind the call
+    assert int(r[5]["callstack_depth"]) == 0 and b.vm_status()[0, 0] == 1
+    b.close()
+
+
 def case_flattened_histories_after_a_panicking_near_call(B):
     """The backends' own post-processing.  storage.rs:98-120 every write pushes a forward and a rollback
     query; storage.rs:156-180 / event_sink.rs:166-170 finish_frame(panicked) appends the frame's forward log and then its
