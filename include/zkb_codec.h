@@ -542,16 +542,15 @@ static inline void encode_joint(const void* rows, uint64_t n_rows, const void* m
 /* canonical rows_out[n_rows * 256 bytes] / mem_out[n_mem * 48 bytes] from the two payload slices; false = malformed */
 static inline bool decode_joint(const uint8_t* rsrc, uint64_t rlen, uint64_t n_rows, const uint8_t* msrc, uint64_t mlen, uint64_t n_mem,
                                 void* rows_out, void* mem_out) {
-  JointCoder* jc = new JointCoder;
+  static thread_local JointCoder coder;
+  JointCoder* jc = &coder;
   jc->reset();
   jc->rp = (uint8_t*)rsrc;
   jc->rend = rsrc + rlen;
   jc->mp = (uint8_t*)msrc;
   jc->mend = msrc + mlen;
   jc->run<false>((uint32_t*)rows_out, n_rows, (uint32_t*)mem_out, n_mem);
-  const bool good = jc->ok && jc->rp == jc->rend && jc->mp == jc->mend;
-  delete jc;
-  return good;
+  return jc->ok && jc->rp == jc->rend && jc->mp == jc->mend;
 }
 
 /* a received blob: validates the header, gives per-VM access */
@@ -599,9 +598,11 @@ struct EncodedView {
     if (kind <= ZKB_STREAM_MEM) {
       if (n == 0 && !present(kind)) return 0;
       const uint32_t other = kind ^ 1u;
-      std::vector<uint8_t> tmp((size_t)counts(vm)[other] * ZKB_CODEC_REC_WORDS[other] * 4 + 1);
-      const bool good = kind == ZKB_STREAM_ROWS ? decode_rows_mem(vm, dst, max_bytes, tmp.data(), tmp.size())
-                                                : decode_rows_mem(vm, tmp.data(), tmp.size(), dst, max_bytes);
+      static thread_local std::vector<uint8_t> tmp;   /* the other stream of the walk: scratch, reused from VM to VM */
+      const size_t other_bytes = (size_t)counts(vm)[other] * ZKB_CODEC_REC_WORDS[other] * 4 + 1;
+      if (tmp.size() < other_bytes) tmp.resize(other_bytes);
+      const bool good = kind == ZKB_STREAM_ROWS ? decode_rows_mem(vm, dst, max_bytes, tmp.data(), other_bytes)
+                                                : decode_rows_mem(vm, tmp.data(), other_bytes, dst, max_bytes);
       return good ? need : UINT64_MAX;
     }
     const uint8_t* src;
